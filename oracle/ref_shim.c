@@ -1,0 +1,469 @@
+/*
+ * ref_shim.c - TEST INFRASTRUCTURE ONLY.
+ *
+ * Flat, ctypes-friendly entry points around the UNMODIFIED srsRAN 4G reference primitives, compiled by oracle/Makefile
+ * from the sources where they lie under /root/reference (nothing from the reference is copied into this repo; this
+ * file is our own glue and only *calls* reference functions). The resulting oracle/_ref/libsrsran_ref.so is used
+ *   - by tests/ to pin the clean-room restatement (oracle/turbo_oracle.c) and to generate tests/golden/ fixtures,
+ *   - by bench.py --impl reference / the cpu_baseline leg as the timed CPU baseline (AVX2 windowed decoder).
+ * It is never loaded by the product library (srsran_4g_b200/).
+ *
+ * Oracle definition: srsran_tdec_init_manual(.., SRSRAN_TDEC_GENERIC) + natural input layout
+ * (srsran_rm_turbo_rx_lut_(.., false)) + the decode_tb_cb loop semantics (lib/src/phy/phch/sch.c:371-494) +
+ * srsran_crc_checksum_byte.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "srsran/phy/fec/cbsegm.h"
+#include "srsran/phy/fec/crc.h"
+#include "srsran/phy/fec/softbuffer.h"
+#include "srsran/phy/fec/turbo/rm_turbo.h"
+#include "srsran/phy/fec/turbo/tc_interl.h"
+#include "srsran/phy/fec/turbo/turbocoder.h"
+#include "srsran/phy/fec/turbo/turbodecoder.h"
+#include "srsran/phy/fec/turbo/turbodecoder_gen.h"
+
+#define CRC24A 0x1864CFB
+#define CRC24B 0x1800063
+#define MAX_K 6144
+#define MAX_L (3 * MAX_K + 12)
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static int             g_init = 0;
+static srsran_tcod_t   g_tcod;
+static srsran_tdec_t   g_tdec_gen;
+
+int ref_init(void)
+{
+  pthread_mutex_lock(&g_lock);
+  if (!g_init) {
+    srsran_rm_turbo_gentables();
+    if (srsran_tcod_init(&g_tcod, MAX_K)) {
+      pthread_mutex_unlock(&g_lock);
+      return -1;
+    }
+    if (srsran_tdec_init_manual(&g_tdec_gen, MAX_K, SRSRAN_TDEC_GENERIC)) {
+      pthread_mutex_unlock(&g_lock);
+      return -1;
+    }
+    g_init = 1;
+  }
+  pthread_mutex_unlock(&g_lock);
+  return 0;
+}
+
+int ref_cbsize(uint32_t idx) { return srsran_cbsegm_cbsize(idx); }
+int ref_cbindex(uint32_t K) { return srsran_cbsegm_cbindex(K); }
+
+/* out[12] = F C K1 K2 K1_idx K2_idx C1 C2 tbs L_tb L_cb Z */
+int ref_cbsegm(uint32_t tbs, uint32_t* out)
+{
+  srsran_cbsegm_t s;
+  memset(&s, 0, sizeof(s));
+  int ret = srsran_cbsegm(&s, tbs);
+  out[0]  = s.F;
+  out[1]  = s.C;
+  out[2]  = s.K1;
+  out[3]  = s.K2;
+  out[4]  = s.K1_idx;
+  out[5]  = s.K2_idx;
+  out[6]  = s.C1;
+  out[7]  = s.C2;
+  out[8]  = s.tbs;
+  out[9]  = s.L_tb;
+  out[10] = s.L_cb;
+  out[11] = s.Z;
+  return ret;
+}
+
+int ref_qpp(uint32_t K, uint16_t* fwd, uint16_t* rev)
+{
+  srsran_tc_interl_t t;
+  if (srsran_tc_interl_init(&t, K)) {
+    return -1;
+  }
+  int ret = srsran_tc_interl_LTE_gen(&t, K);
+  if (!ret) {
+    memcpy(fwd, t.forward, sizeof(uint16_t) * K);
+    memcpy(rev, t.reverse, sizeof(uint16_t) * K);
+  }
+  srsran_tc_interl_free(&t);
+  return ret;
+}
+
+uint32_t ref_crc_bytes(uint32_t poly, int order, const uint8_t* data, int nbits)
+{
+  srsran_crc_t c;
+  srsran_crc_init(&c, poly, order);
+  return srsran_crc_checksum_byte(&c, data, nbits);
+}
+
+/* CRC over unpacked bits (one bit per byte), any length: srsran_crc_checksum (crc.c:94-144) */
+uint32_t ref_crc_bits(uint32_t poly, int order, uint8_t* bits, int nbits)
+{
+  srsran_crc_t c;
+  srsran_crc_init(&c, poly, order);
+  return srsran_crc_checksum(&c, bits, nbits);
+}
+
+/* natural-layout rate de-matching: output[T[i mod L]] += input[i] */
+int ref_rm_rx(int16_t* e, int16_t* buf, uint32_t E, uint32_t cb_idx, uint32_t rv)
+{
+  ref_init();
+  return srsran_rm_turbo_rx_lut_(e, buf, E, cb_idx, rv, false);
+}
+
+/* the reference's production (AUTO) layout */
+int ref_rm_rx_auto(int16_t* e, int16_t* buf, uint32_t E, uint32_t cb_idx, uint32_t rv)
+{
+  ref_init();
+  return srsran_rm_turbo_rx_lut(e, buf, E, cb_idx, rv);
+}
+
+/* Recover the natural de-rate-matching table T[0..L) by impulse response of the reference function. */
+int ref_rm_table(uint32_t cb_idx, uint32_t rv, uint16_t* table)
+{
+  ref_init();
+  int K = srsran_cbsegm_cbsize(cb_idx);
+  if (K < 0 || rv >= 4) {
+    return -1;
+  }
+  uint32_t L   = 3 * K + 12;
+  int16_t* e   = calloc(L + 64, sizeof(int16_t));
+  int16_t* buf = calloc(L + 256, sizeof(int16_t));
+  for (uint32_t i = 0; i < L; i++) {
+    e[i] = (int16_t)(i + 1);
+  }
+  int ret = srsran_rm_turbo_rx_lut_(e, buf, L, cb_idx, rv, false);
+  for (uint32_t i = 0; i < L; i++) {
+    table[i] = 0xffff;
+  }
+  for (uint32_t j = 0; j < L; j++) {
+    if (buf[j] <= 0) {
+      ret = -2; /* not a permutation */
+    } else {
+      table[buf[j] - 1] = (uint16_t)j;
+    }
+  }
+  free(e);
+  free(buf);
+  return ret;
+}
+
+/* bitwise encoder: in[K] bits -> out[3K+12] bits (natural order) */
+int ref_tcod_encode(uint8_t* in, uint8_t* out, uint32_t K)
+{
+  ref_init();
+  pthread_mutex_lock(&g_lock);
+  int r = srsran_tcod_encode(&g_tcod, in, out, K);
+  pthread_mutex_unlock(&g_lock);
+  return r;
+}
+
+/* bitwise rate matching (tx): coded[3K+12] bits -> e[E] bits */
+int ref_rm_tx(uint8_t* coded, uint32_t K, uint8_t* e, uint32_t E, uint32_t rv)
+{
+  /* the reference fills its circular buffer only when rv == 0 (rm_turbo.c:1016) and reuses it for later rv */
+  uint8_t* w = calloc(3 * (MAX_K + 64) + 64, 1);
+  int      r = srsran_rm_turbo_tx(w, 3 * (MAX_K + 64), coded, 3 * K + 12, e, E, 0);
+  if (!r && rv != 0) {
+    r = srsran_rm_turbo_tx(w, 3 * (MAX_K + 64), coded, 3 * K + 12, e, E, rv);
+  }
+  free(w);
+  return r;
+}
+
+static srsran_tdec_impl_type_t impl_of(int impl)
+{
+  switch (impl) {
+    case 1:
+      return SRSRAN_TDEC_GENERIC;
+    case 3:
+      return SRSRAN_TDEC_SSE_WINDOW;
+    case 5:
+      return SRSRAN_TDEC_AVX_WINDOW;
+    default:
+      return SRSRAN_TDEC_AUTO;
+  }
+}
+
+/*
+ * Run nof_iter half-iterations of one code block (natural input layout), recording the hard decision after every
+ * half-iteration (out_bytes[it][K/8]) and optionally the soft arrays of the generic decoder after every half-iteration
+ * (dump[it][3][K] = ext1, ext2, app1).
+ */
+int ref_tdec_trace(int impl, uint32_t K, int16_t* in, uint32_t nof_iter, uint8_t* out_bytes, int16_t* dump)
+{
+  srsran_tdec_t h;
+  if (srsran_tdec_init_manual(&h, K, impl_of(impl))) {
+    return -1;
+  }
+  srsran_tdec_force_not_sb(&h);
+  if (srsran_tdec_new_cb(&h, K)) {
+    srsran_tdec_free(&h);
+    return -2;
+  }
+  for (uint32_t it = 0; it < nof_iter; it++) {
+    srsran_tdec_iteration(&h, in, &out_bytes[it * (K / 8)]);
+    if (dump) {
+      memcpy(&dump[(it * 3 + 0) * K], h.ext1, sizeof(int16_t) * K);
+      memcpy(&dump[(it * 3 + 1) * K], h.ext2, sizeof(int16_t) * K);
+      memcpy(&dump[(it * 3 + 2) * K], h.app1, sizeof(int16_t) * K);
+    }
+  }
+  srsran_tdec_free(&h);
+  return 0;
+}
+
+/* srsran_tdec_run_all on one CB */
+int ref_tdec_run_all(int impl, uint32_t K, int16_t* in, uint32_t nof_iter, uint8_t* out_bytes)
+{
+  srsran_tdec_t h;
+  if (srsran_tdec_init_manual(&h, K, impl_of(impl))) {
+    return -1;
+  }
+  srsran_tdec_force_not_sb(&h);
+  int r = srsran_tdec_new_cb(&h, K);
+  if (!r) {
+    r = srsran_tdec_run_all(&h, in, out_bytes, nof_iter, K);
+  }
+  srsran_tdec_free(&h);
+  return r;
+}
+
+/* one MAP decode through the reference's vtable seam (turbodecoder_impl.h:54-60), generic impl */
+int ref_map_gen(uint32_t K, int16_t* input, int16_t* app, int16_t* parity, int16_t* output)
+{
+  void* hh = NULL;
+  if (tdec_gen_init(&hh, K) < 0) {
+    return -1;
+  }
+  tdec_gen_dec(hh, input, app, parity, output, K);
+  tdec_gen_free(hh);
+  return 0;
+}
+
+/*
+ * The decode_tb_cb / decode_tb semantics (sch.c:371-494, 509-573) with the oracle substitutions:
+ * GENERIC decoder + natural-layout rate de-matching. HARQ state is passed as flat arrays:
+ *   buffer_f[C][18600] int16, sb_data[C][18600/8] u8, cb_crc[C] u8 (in/out), tb_crc (out)
+ * Returns the decode_tb return code (0 ok, -1 CRC fail, -2 invalid). cb_noi[C] receives per-CB half-iterations run in
+ * this call (0 for CBs skipped because cb_crc was already set); *avg_iterations mirrors q->avg_iterations.
+ */
+int ref_decode_tb(uint32_t tbs,
+                  uint32_t Qm,
+                  uint32_t rv,
+                  uint32_t nof_e_bits,
+                  int16_t* e_bits,
+                  uint32_t max_iterations,
+                  int16_t* buffer_f,
+                  uint8_t* sb_data,
+                  uint8_t* cb_crc,
+                  uint8_t* tb_crc,
+                  uint8_t* data,
+                  uint32_t* cb_noi,
+                  float*   avg_iterations)
+{
+  ref_init();
+  srsran_cbsegm_t seg;
+  if (srsran_cbsegm(&seg, tbs)) {
+    return -1;
+  }
+  if (Qm == 0) {
+    return -2;
+  }
+  if (seg.tbs == 0 || seg.C == 0) {
+    return 0;
+  }
+  if (seg.F) {
+    return -2;
+  }
+  srsran_crc_t crc_tb, crc_cb;
+  srsran_crc_init(&crc_tb, CRC24A, 24);
+  srsran_crc_init(&crc_cb, CRC24B, 24);
+  if (max_iterations == 0) {
+    max_iterations = 10;
+  }
+
+  srsran_tdec_t* dec = &g_tdec_gen;
+  pthread_mutex_lock(&g_lock);
+  float avg = 0;
+  for (uint32_t cb_idx = 0; cb_idx < seg.C; cb_idx++) {
+    uint32_t cb_len = cb_idx < seg.C1 ? seg.K1 : seg.K2;
+    uint32_t rlen   = seg.C == 1 ? cb_len : (cb_len - 24);
+    cb_noi[cb_idx]  = 0;
+    if (!cb_crc[cb_idx]) {
+      uint32_t cb_len_idx = cb_idx < seg.C1 ? seg.K1_idx : seg.K2_idx;
+      uint32_t Gp         = nof_e_bits / Qm;
+      uint32_t gamma      = Gp % seg.C;
+      uint32_t n_e        = Qm * (Gp / seg.C);
+      uint32_t rp         = cb_idx * n_e;
+      uint32_t n_e2       = n_e;
+      if (cb_idx > seg.C - gamma) {
+        n_e2 = n_e + Qm;
+        rp   = (seg.C - gamma) * n_e + (cb_idx - (seg.C - gamma)) * n_e2;
+      }
+      int16_t* buf = &buffer_f[(size_t)cb_idx * SOFTBUFFER_SIZE];
+      srsran_rm_turbo_rx_lut_(&e_bits[rp], buf, n_e2, cb_len_idx, rv, false);
+      srsran_tdec_new_cb(dec, cb_len);
+      bool     early_stop = false;
+      uint32_t noi        = 0;
+      do {
+        srsran_tdec_iteration(dec, buf, &data[cb_idx * rlen / 8]);
+        avg++;
+        noi++;
+        uint32_t      len_crc = seg.C > 1 ? cb_len : seg.tbs + 24;
+        srsran_crc_t* crc_ptr = seg.C > 1 ? &crc_cb : &crc_tb;
+        if (!srsran_crc_checksum_byte(crc_ptr, &data[cb_idx * rlen / 8], len_crc) && noi >= 2) {
+          cb_crc[cb_idx] = 1;
+          early_stop     = true;
+        }
+      } while (noi < max_iterations && !early_stop);
+      cb_noi[cb_idx] = noi;
+    } else {
+      memcpy(&data[cb_idx * rlen / 8], &sb_data[(size_t)cb_idx * (SOFTBUFFER_SIZE / 8)], rlen / 8);
+    }
+  }
+  pthread_mutex_unlock(&g_lock);
+
+  bool tb_ok = true;
+  for (uint32_t i = 0; i < seg.C && tb_ok; i++) {
+    tb_ok = cb_crc[i];
+  }
+  *tb_crc = tb_ok;
+  if (!tb_ok) {
+    for (uint32_t i = 0; i < seg.C; i++) {
+      if (cb_crc[i]) {
+        uint32_t cb_len = i < seg.C1 ? seg.K1 : seg.K2;
+        uint32_t rlen   = seg.C == 1 ? cb_len : (cb_len - 24);
+        memcpy(&sb_data[(size_t)i * (SOFTBUFFER_SIZE / 8)], &data[i * rlen / 8], rlen / 8);
+      }
+    }
+  }
+  *avg_iterations = avg / (float)seg.C;
+  if (!tb_ok) {
+    return -1;
+  }
+  if (seg.C == 1) {
+    return 0;
+  }
+  if (srsran_crc_match_byte(&crc_tb, data, seg.tbs)) {
+    return 0;
+  }
+  for (uint32_t i = 0; i < seg.C; i++) {
+    cb_crc[i] = 0; /* srsran_softbuffer_rx_reset_cb_crc */
+  }
+  return -1;
+}
+
+/* ---------------- timed CPU baseline: batch of equal-K code blocks over pthreads ---------------- */
+typedef struct {
+  int       impl;
+  uint32_t  K;
+  int16_t*  in; /* [n][3K+12] natural layout */
+  uint8_t*  out; /* [n][K/8] */
+  uint8_t*  noi; /* [n] */
+  uint8_t*  crc_ok; /* [n] */
+  uint32_t  first, last;
+  uint32_t  max_iter;
+  int       early_stop; /* 0: run exactly max_iter; 1: CRC24B early stop, min 2 */
+  int       core;
+  double    secs;
+  int       err;
+} job_t;
+
+static double now_s(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void* job_run(void* arg)
+{
+  job_t* j = (job_t*)arg;
+  if (j->core >= 0) {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    CPU_SET(j->core, &set);
+    pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+  }
+  srsran_tdec_t h;
+  srsran_crc_t  crc;
+  srsran_crc_init(&crc, CRC24B, 24);
+  if (srsran_tdec_init_manual(&h, j->K, impl_of(j->impl))) {
+    j->err = -1;
+    return NULL;
+  }
+  srsran_tdec_force_not_sb(&h);
+  uint32_t L  = 3 * j->K + 12;
+  double   t0 = now_s();
+  for (uint32_t n = j->first; n < j->last; n++) {
+    int16_t* in  = &j->in[(size_t)n * L];
+    uint8_t* out = &j->out[(size_t)n * (j->K / 8)];
+    srsran_tdec_new_cb(&h, j->K);
+    uint32_t noi = 0;
+    int      ok  = 0;
+    if (!j->early_stop) {
+      srsran_tdec_run_all(&h, in, out, j->max_iter, j->K);
+      noi = j->max_iter;
+      ok  = srsran_crc_checksum_byte(&crc, out, j->K) == 0;
+    } else {
+      do {
+        srsran_tdec_iteration(&h, in, out);
+        noi++;
+        if (!srsran_crc_checksum_byte(&crc, out, j->K) && noi >= 2) {
+          ok = 1;
+        }
+      } while (noi < j->max_iter && !ok);
+    }
+    j->noi[n]    = (uint8_t)noi;
+    j->crc_ok[n] = (uint8_t)ok;
+  }
+  j->secs = now_s() - t0;
+  srsran_tdec_free(&h);
+  return NULL;
+}
+
+/* returns wall seconds for decoding n code blocks with nthreads pthreads (pinned to cores 0..nthreads-1 if pin) */
+double ref_tdec_batch(int       impl,
+                      uint32_t  K,
+                      int16_t*  in,
+                      uint32_t  n,
+                      uint32_t  max_iter,
+                      int       early_stop,
+                      int       nthreads,
+                      int       pin,
+                      uint8_t*  out,
+                      uint8_t*  noi,
+                      uint8_t*  crc_ok)
+{
+  ref_init();
+  if (nthreads < 1) {
+    nthreads = 1;
+  }
+  pthread_t* th   = calloc(nthreads, sizeof(pthread_t));
+  job_t*     jobs = calloc(nthreads, sizeof(job_t));
+  double     t0   = now_s();
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = (job_t){impl, K, in, out, noi, crc_ok, (uint32_t)((uint64_t)n * t / nthreads),
+                      (uint32_t)((uint64_t)n * (t + 1) / nthreads), max_iter, early_stop, pin ? t : -1, 0, 0};
+    pthread_create(&th[t], NULL, job_run, &jobs[t]);
+  }
+  int err = 0;
+  for (int t = 0; t < nthreads; t++) {
+    pthread_join(th[t], NULL);
+    err |= jobs[t].err;
+  }
+  double dt = now_s() - t0;
+  free(th);
+  free(jobs);
+  return err ? -1.0 : dt;
+}

@@ -1,0 +1,58 @@
+/*
+ * turbo_oracle.h - TEST INFRASTRUCTURE ONLY (see turbo_oracle.c).
+ *
+ * Clean-room CPU restatement of the srsRAN 4G LTE turbo-decode hot path (generic int16 decoder, natural layout):
+ * the bit-exact checker for the CUDA engine. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+ * load this library. Parity status: PINNED - checked against the compiled reference (oracle/_ref) over all 188 block
+ * sizes and against the reference's own known-answer vectors (tests/test_oracle_*.py, tests/golden/).
+ */
+#ifndef TURBO_ORACLE_H
+#define TURBO_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_NOF_CB_SIZES 188
+#define ORC_MAX_K 6144
+#define ORC_SOFTBUFFER_SIZE 18600
+#define ORC_CRC24A 0x1864CFBu
+#define ORC_CRC24B 0x1800063u
+
+/* code-block size table and QPP interleaver */
+int orc_cbsize(uint32_t idx);            /* K or -1 */
+int orc_cbindex(uint32_t K);             /* first idx with size >= K, or -1 */
+int orc_cbindex_exact(uint32_t K);       /* idx with size == K, or -1 */
+int orc_qpp(uint32_t K, uint16_t* fwd, uint16_t* rev);
+int orc_cbsegm(uint32_t tbs, uint32_t* out12); /* F C K1 K2 K1_idx K2_idx C1 C2 tbs L_tb L_cb Z ; 0 ok / -1 */
+
+/* CRC, MSB first, init 0 */
+uint32_t orc_crc_bytes(uint32_t poly, int order, const uint8_t* data, int nbits);
+uint32_t orc_crc_bits(uint32_t poly, int order, const uint8_t* bits, int nbits);
+
+/* encoder side (test-vector generation) */
+int orc_tcod_encode(const uint8_t* in_bits, uint8_t* out_bits, uint32_t K);
+int orc_rm_tx(const uint8_t* coded_bits, uint32_t K, uint8_t* e_bits, uint32_t E, uint32_t rv);
+
+/* rate de-matching */
+int orc_rm_table(uint32_t cb_idx, uint32_t rv, uint16_t* table);
+int orc_rm_rx(const int16_t* e, int16_t* buf, uint32_t E, uint32_t cb_idx, uint32_t rv);
+
+/* decoder */
+int orc_map_gen(uint32_t K, const int16_t* input, const int16_t* app, const int16_t* parity, int16_t* output);
+int orc_tdec_trace(uint32_t K, const int16_t* in, uint32_t nof_iter, uint8_t* out_bytes, int16_t* dump);
+int orc_tdec_run_all(uint32_t K, const int16_t* in, uint32_t nof_iter, uint8_t* out_bytes);
+double orc_tdec_batch(uint32_t K, const int16_t* in, uint32_t n, uint32_t max_iter, int early_stop, int nthreads,
+                      uint8_t* out, uint8_t* noi, uint8_t* crc_ok);
+
+/* transport-block loop */
+int orc_decode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, const int16_t* e_bits,
+                  uint32_t max_iterations, int16_t* buffer_f, uint8_t* sb_data, uint8_t* cb_crc, uint8_t* tb_crc,
+                  uint8_t* data, uint32_t* cb_noi, float* avg_iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

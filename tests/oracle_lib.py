@@ -1,0 +1,208 @@
+"""ctypes bindings for the test oracle (oracle/libturbo_oracle.so) and, when it has been built in the container,
+the compiled reference (oracle/_ref/libsrsran_ref.so). TEST INFRASTRUCTURE: imported only by tests/, smoke() and
+bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libturbo_oracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libsrsran_ref.so")
+
+CRC24A = 0x1864CFB
+CRC24B = 0x1800063
+SOFTBUFFER_SIZE = 18600
+
+i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+
+
+def build_oracle(force=False):
+    src = os.path.join(ORACLE_DIR, "turbo_oracle.c")
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+    return ORACLE_SO
+
+
+def build_ref():
+    """Compile the reference sources in place (container only: needs /root/reference)."""
+    if os.path.isdir(os.environ.get("SRSRAN_REF", "/root/reference")):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+    return REF_SO if os.path.exists(REF_SO) else None
+
+
+class _Lib:
+    """Common surface of the two libraries; `p` is the symbol prefix ('orc_' or 'ref_')."""
+
+    def __init__(self, path, p):
+        self.lib = C.CDLL(path)
+        self.p = p
+        L = self.lib
+        f = lambda n: getattr(L, p + n)
+        self._cbsize = f("cbsize"); self._cbsize.argtypes = [C.c_uint32]; self._cbsize.restype = C.c_int
+        self._cbindex = f("cbindex"); self._cbindex.argtypes = [C.c_uint32]; self._cbindex.restype = C.c_int
+        self._cbsegm = f("cbsegm"); self._cbsegm.argtypes = [C.c_uint32, u32p]; self._cbsegm.restype = C.c_int
+        self._qpp = f("qpp"); self._qpp.argtypes = [C.c_uint32, u16p, u16p]; self._qpp.restype = C.c_int
+        self._crc_bytes = f("crc_bytes"); self._crc_bytes.argtypes = [C.c_uint32, C.c_int, u8p, C.c_int]; self._crc_bytes.restype = C.c_uint32
+        self._crc_bits = f("crc_bits"); self._crc_bits.argtypes = [C.c_uint32, C.c_int, u8p, C.c_int]; self._crc_bits.restype = C.c_uint32
+        self._enc = f("tcod_encode"); self._enc.argtypes = [u8p, u8p, C.c_uint32]; self._enc.restype = C.c_int
+        self._rm_tx = f("rm_tx"); self._rm_tx.argtypes = [u8p, C.c_uint32, u8p, C.c_uint32, C.c_uint32]; self._rm_tx.restype = C.c_int
+        self._rm_table = f("rm_table"); self._rm_table.argtypes = [C.c_uint32, C.c_uint32, u16p]; self._rm_table.restype = C.c_int
+        self._rm_rx = f("rm_rx"); self._rm_rx.argtypes = [i16p, i16p, C.c_uint32, C.c_uint32, C.c_uint32]; self._rm_rx.restype = C.c_int
+        self._map = f("map_gen"); self._map.argtypes = [C.c_uint32, i16p, C.c_void_p, i16p, i16p]; self._map.restype = C.c_int
+        self._dec_tb = f("decode_tb")
+        self._dec_tb.argtypes = [C.c_uint32] * 4 + [i16p, C.c_uint32, i16p, u8p, u8p, u8p, u8p, u32p, C.POINTER(C.c_float)]
+        self._dec_tb.restype = C.c_int
+        if p == "ref_":
+            L.ref_init()
+            self._trace = L.ref_tdec_trace; self._trace.argtypes = [C.c_int, C.c_uint32, i16p, C.c_uint32, u8p, C.c_void_p]
+            self._run_all = L.ref_tdec_run_all; self._run_all.argtypes = [C.c_int, C.c_uint32, i16p, C.c_uint32, u8p]
+            self._batch = L.ref_tdec_batch
+            self._batch.argtypes = [C.c_int, C.c_uint32, i16p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, u8p, u8p, u8p]
+            self._rm_rx_auto = L.ref_rm_rx_auto; self._rm_rx_auto.argtypes = [i16p, i16p, C.c_uint32, C.c_uint32, C.c_uint32]
+        else:
+            self._trace = L.orc_tdec_trace; self._trace.argtypes = [C.c_uint32, i16p, C.c_uint32, u8p, C.c_void_p]
+            self._run_all = L.orc_tdec_run_all; self._run_all.argtypes = [C.c_uint32, i16p, C.c_uint32, u8p]
+            self._batch = L.orc_tdec_batch
+            self._batch.argtypes = [C.c_uint32, i16p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, u8p, u8p, u8p]
+        self._trace.restype = C.c_int
+        self._run_all.restype = C.c_int
+        self._batch.restype = C.c_double
+
+    # ---- tables
+    def cbsize(self, idx):
+        return self._cbsize(idx)
+
+    def cbindex(self, K):
+        return self._cbindex(K)
+
+    def cbsegm(self, tbs):
+        out = np.zeros(12, np.uint32)
+        ret = self._cbsegm(tbs, out)
+        keys = ["F", "C", "K1", "K2", "K1_idx", "K2_idx", "C1", "C2", "tbs", "L_tb", "L_cb", "Z"]
+        return ret, dict(zip(keys, (int(v) for v in out)))
+
+    def qpp(self, K):
+        f = np.zeros(K, np.uint16); r = np.zeros(K, np.uint16)
+        assert self._qpp(K, f, r) == 0
+        return f, r
+
+    def crc_bytes(self, poly, data, nbits, order=24):
+        return self._crc_bytes(poly, order, np.ascontiguousarray(data, np.uint8), nbits)
+
+    def crc_bits(self, poly, bits, order=24):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        return self._crc_bits(poly, order, bits, len(bits))
+
+    # ---- encoder chain
+    def encode(self, bits):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        K = len(bits)
+        out = np.zeros(3 * K + 12, np.uint8)
+        assert self._enc(bits, out, K) == 0
+        return out
+
+    def rm_tx(self, coded, K, E, rv):
+        e = np.zeros(E, np.uint8)
+        assert self._rm_tx(np.ascontiguousarray(coded, np.uint8), K, e, E, rv) == 0
+        return e
+
+    def rm_table(self, cb_idx, rv):
+        K = self.cbsize(cb_idx)
+        t = np.zeros(3 * K + 12, np.uint16)
+        ret = self._rm_table(cb_idx, rv, t)
+        assert ret == 0, ret
+        return t
+
+    def rm_rx(self, e, buf, cb_idx, rv):
+        """accumulates into buf (int16, at least 3K+12 (+slack for the reference's SIMD stores))"""
+        e = np.ascontiguousarray(e, np.int16)
+        return self._rm_rx(e, buf, len(e), cb_idx, rv)
+
+    # ---- decoder
+    def map_gen(self, K, inp, app, par):
+        out = np.zeros(K, np.int16)
+        inp = np.ascontiguousarray(inp, np.int16); par = np.ascontiguousarray(par, np.int16)
+        if app is not None:
+            app = np.ascontiguousarray(app, np.int16)
+            appp = app.ctypes.data_as(C.c_void_p)
+        else:
+            appp = None
+        assert self._map(K, inp, appp, par, out) == 0
+        return out
+
+    def tdec_trace(self, K, llr, nof_iter, dump=False, impl=1):
+        llr = np.ascontiguousarray(llr, np.int16)
+        out = np.zeros((nof_iter, K // 8), np.uint8)
+        d = np.zeros((nof_iter, 3, K), np.int16) if dump else None
+        dp = d.ctypes.data_as(C.c_void_p) if dump else None
+        if self.p == "ref_":
+            ret = self._trace(impl, K, llr, nof_iter, out, dp)
+        else:
+            ret = self._trace(K, llr, nof_iter, out, dp)
+        assert ret == 0, ret
+        return (out, d) if dump else out
+
+    def tdec_run_all(self, K, llr, nof_iter, impl=1):
+        llr = np.ascontiguousarray(llr, np.int16)
+        out = np.zeros(K // 8, np.uint8)
+        ret = self._run_all(impl, K, llr, nof_iter, out) if self.p == "ref_" else self._run_all(K, llr, nof_iter, out)
+        assert ret == 0, ret
+        return out
+
+    def tdec_batch(self, K, llr, max_iter, early_stop, nthreads=1, impl=1, pin=0):
+        """llr [n, 3K+12] int16 -> (seconds, out[n,K/8], noi[n], crc_ok[n])"""
+        llr = np.ascontiguousarray(llr, np.int16)
+        n = llr.shape[0]
+        out = np.zeros((n, K // 8), np.uint8); noi = np.zeros(n, np.uint8); ok = np.zeros(n, np.uint8)
+        if self.p == "ref_":
+            secs = self._batch(impl, K, llr, n, max_iter, int(early_stop), nthreads, pin, out, noi, ok)
+        else:
+            secs = self._batch(K, llr, n, max_iter, int(early_stop), nthreads, out, noi, ok)
+        return secs, out, noi, ok
+
+    # ---- transport block
+    def decode_tb(self, tbs, Qm, rv, e_bits, max_iterations, state=None, nof_e_bits=None):
+        """state = dict(buffer_f[C,18600] i16, sb_data[C,18600/8] u8, cb_crc[C] u8) persists across HARQ transmissions"""
+        _, seg = self.cbsegm(tbs)
+        Cn = max(seg["C"], 1)
+        if state is None:
+            state = new_tb_state(Cn)
+        e_bits = np.ascontiguousarray(e_bits, np.int16)
+        G = len(e_bits) if nof_e_bits is None else nof_e_bits
+        data = np.zeros(Cn * 768 + 8, np.uint8)
+        noi = np.zeros(Cn, np.uint32)
+        tb_crc = np.zeros(1, np.uint8)
+        avg = C.c_float(0)
+        ret = self._dec_tb(tbs, Qm, rv, G, e_bits, max_iterations, state["buffer_f"], state["sb_data"], state["cb_crc"],
+                           tb_crc, data, noi, C.byref(avg))
+        return dict(ret=ret, data=data, cb_noi=noi, tb_crc=int(tb_crc[0]), avg_iterations=avg.value, state=state, seg=seg)
+
+
+def new_tb_state(Cn):
+    return dict(buffer_f=np.zeros((Cn, SOFTBUFFER_SIZE), np.int16), sb_data=np.zeros((Cn, SOFTBUFFER_SIZE // 8), np.uint8),
+                cb_crc=np.zeros(Cn, np.uint8))
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        _oracle = _Lib(build_oracle(), "orc_")
+    return _oracle
+
+
+def ref():
+    """The compiled reference, or None when oracle/_ref has not been (cannot be) built."""
+    global _ref
+    if _ref is None and os.path.exists(REF_SO):
+        _ref = _Lib(REF_SO, "ref_")
+    return _ref

@@ -1,0 +1,86 @@
+"""The clean-room oracle against the committed golden fixtures (tests/golden/, generated from the compiled reference
+by tests/golden/make_golden.py) and the known-answer vectors of the reference's own unit tests. Runs anywhere (no
+/root/reference, no GPU)."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def o():
+    return ol.oracle()
+
+
+def test_kat_crc_words(o):
+    """lib/src/phy/fec/test/crc_test.h:37-38: srand(1), 5001 random bits -> CRC24A 0x1C5C97, CRC24B 0x36D1F0"""
+    k = np.load(os.path.join(G, "kat.npz"))
+    assert o.crc_bits(ol.CRC24A, k["crc_test_bits"]) == 0x1C5C97
+    assert o.crc_bits(ol.CRC24B, k["crc_test_bits"]) == 0x36D1F0
+
+
+def test_kat_encoder_known_data(o):
+    """lib/src/phy/fec/turbo/test/turbodecoder_test.h:70-125: pins trellis polynomials, QPP(504) and tail order"""
+    k = np.load(os.path.join(G, "kat.npz"))
+    assert (o.encode(k["known_data"]) == k["known_data_encoded"]).all()
+
+
+def test_tables_fingerprints(o):
+    t = np.load(os.path.join(G, "tables.npz"))
+    for idx in range(188):
+        K = o.cbsize(idx)
+        assert K == t["sizes"][idx]
+        f, r = o.qpp(K)
+        assert zlib.crc32(f.tobytes() + r.tobytes()) == t["qpp_fp"][idx]
+        for rv in range(4):
+            assert zlib.crc32(o.rm_table(idx, rv).tobytes()) == t["rm_fp"][idx, rv], (idx, rv)
+    for key in t.files:
+        if key.startswith("rm_"):
+            _, idx, rv = key.split("_")
+            assert (o.rm_table(int(idx), int(rv)) == t[key]).all()
+    for tbs, row in zip(t["tbs_list"], t["seg"]):
+        ret, seg = o.cbsegm(int(tbs))
+        assert ret == 0
+        assert [seg[k] for k in ("F", "C", "K1", "K2", "K1_idx", "K2_idx", "C1", "C2")] == row.tolist()
+
+
+def test_decoder_traces(o):
+    d = np.load(os.path.join(G, "decoder.npz"))
+    for n, (K, eb, scale) in enumerate(d["cases"]):
+        K = int(K)
+        hard, dump = o.tdec_trace(K, d["llr_%d" % n], 10, dump=True)
+        assert (hard == d["hard_%d" % n]).all(), (K, eb, scale)
+        assert (dump[3, 0] == d["ext1_it3_%d" % n]).all()
+        fp = d["softfp_%d" % n]
+        for it in range(10):
+            assert zlib.crc32(dump[it, 0].tobytes()) == fp[it, 0]
+            if it >= 1:  # ext2/app1 are undefined before the first DEC2 run
+                assert zlib.crc32(dump[it, 1].tobytes()) == fp[it, 1]
+                assert zlib.crc32(dump[it, 2].tobytes()) == fp[it, 2]
+
+
+def test_batch_early_stop(o):
+    b = np.load(os.path.join(G, "batch_k1024.npz"))
+    _, out, noi, ok = o.tdec_batch(1024, b["llr"], int(b["max_iter"]), True, nthreads=2)
+    assert (noi == b["noi"]).all() and (ok == b["ok"]).all() and (out == b["out"]).all()
+
+
+def test_tb_harq(o):
+    t = np.load(os.path.join(G, "tb_harq.npz"))
+    for n, (tbs, Gb, Qm, eb) in enumerate(t["cases"]):
+        st = None
+        for tx, rv in enumerate((0, 2, 3, 1)):
+            p = "tb%d_tx%d_" % (n, tx)
+            res = o.decode_tb(int(tbs), int(Qm), rv, t[p + "e"], 6, st)
+            st = res["state"]
+            assert res["ret"] == int(t[p + "ret"])
+            assert (res["data"] == t[p + "data"]).all()
+            assert (res["cb_noi"] == t[p + "noi"]).all()
+            assert (st["cb_crc"] == t[p + "cb_crc"]).all()
+            assert zlib.crc32(st["buffer_f"].tobytes()) == int(t[p + "buf_fp"])
+            assert np.float32(res["avg_iterations"]) == t[p + "avg"]

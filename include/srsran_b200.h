@@ -1,0 +1,158 @@
+/*
+ * srsran_b200.h - C ABI of the B200-native LTE turbo-decode engine (libsrsran_b200.so).
+ *
+ * Plain pointers and sizes only (no torch / C++ types). Two layers:
+ *
+ *  (1) Engine + batched entry points (NEW - the reference has no batched equivalent; its decode_tb_cb is a serial
+ *      per-code-block loop, lib/src/phy/phch/sch.c:390): every code block of a transport block, or of many transport
+ *      blocks across subframes and UEs, is submitted as ONE device launch.
+ *
+ *  (2) Per-object entry points with the reference's argument meaning and error behaviour, one per reference function
+ *      on the hot path. The reference-side binding (integration/srsran_b200_shim.c, built inside the reference tree
+ *      with the reference's own struct definitions) maps srsran_tdec_* / srsran_rm_turbo_rx_lut / decode_tb /
+ *      srsran_dlsch_decode2 / srsran_ulsch_decode onto them; see INTEGRATION.md.
+ *
+ * Results (hard bits, per-block half-iteration counts, CRC verdicts, soft-buffer contents) are bit-exact against the
+ * reference's generic int16 decoder (lib/src/phy/fec/turbo/turbodecoder_gen.c) with natural-order input.
+ *
+ * Error codes follow lib/include/srsran/config.h:57-59: 0 success, -1 error, -2 invalid inputs. There is NO CPU
+ * fallback: every compute entry point fails with SRSB200_ERROR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef SRSRAN_B200_H
+#define SRSRAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRSB200_SUCCESS 0
+#define SRSB200_ERROR -1
+#define SRSB200_ERROR_INVALID_INPUTS -2
+#define SRSB200_ERROR_NO_DEVICE -3
+
+#define SRSB200_NOF_CB_SIZES 188     /* lib/include/srsran/phy/fec/cbsegm.h: SRSRAN_NOF_TC_CB_SIZES */
+#define SRSB200_MAX_K 6144           /* SRSRAN_TCOD_MAX_LEN_CB, turbodecoder.h:44 */
+#define SRSB200_SOFTBUFFER_SIZE 18600 /* SOFTBUFFER_SIZE, lib/include/srsran/phy/fec/softbuffer.h:56 */
+#define SRSB200_MIN_TDEC_ITERS 2     /* SRSRAN_PDSCH_MIN_TDEC_ITERS, sch.c:35 */
+#define SRSB200_MAX_TDEC_ITERS 10    /* SRSRAN_PDSCH_MAX_TDEC_ITERS, sch.c:36 */
+
+/* which CRC ends a code block: multi-CB transport blocks use CRC24B per CB, single-CB ones CRC24A (sch.c:438-444) */
+#define SRSB200_CRC_NONE 0
+#define SRSB200_CRC_24A 1
+#define SRSB200_CRC_24B 2
+
+typedef struct srsb200_engine srsb200_engine_t;
+
+/* ------------------------------------------------------------------ engine */
+/* device < 0: use the current CUDA device. The engine owns one stream, its device tables and its workspace. */
+int  srsb200_engine_create(srsb200_engine_t** e, int device);
+void srsb200_engine_destroy(srsb200_engine_t* e);
+const char* srsb200_last_error(void);
+/* number of kernels launched by this engine since creation (bench.py's gpu_launches claim) */
+uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e);
+/* stream the engine launches on (cudaStream_t), so callers can time with events on the same stream */
+void* srsb200_engine_stream(const srsb200_engine_t* e);
+
+/* ------------------------------------------------------------------ host-side metadata (pure integer, no device) */
+/* replaces srsran_cbsegm_cbsize / srsran_cbsegm_cbindex (lib/src/phy/fec/cbsegm.c:119-140) */
+int srsb200_cbsize(uint32_t index);
+int srsb200_cbindex(uint32_t long_cb);
+/* replaces srsran_cbsegm (cbsegm.c:62-117). out[8] = F C K1 K2 K1_idx K2_idx C1 C2 */
+int srsb200_cbsegm(uint32_t tbs, uint32_t out[8]);
+/* replaces srsran_tdec_autoimp_get_subblocks[_8bit] (turbodecoder.c:381-393,410-424): always 0 = natural layout,
+ * which makes srsran_rm_turbo_rx_lut and the decoder agree on the generic decoder's input order. */
+uint32_t srsb200_tdec_autoimp_get_subblocks(uint32_t long_cb);
+
+/* ------------------------------------------------------------------ batched turbo decode (configs 1, 2, 4) */
+/*
+ * Decode n code blocks in one submission. Code block i has size K[i] (any of the 188 LTE sizes, mixed freely), its
+ * 3*K[i]+12 int16 LLRs in the reference's natural order (turbodecoder_gen.c:246-257) start at llr[llr_offset[i]]
+ * (offsets in int16 elements). For each block the reference loop of sch.c:426-456 is run:
+ *    do { half-iteration; noi++; } while (noi < max_iter && !(early_stop && noi >= min_iter && crc == 0))
+ * crc_kind[i] selects the CRC (NONE never stops early and reports crc_ok = 0). With early_stop == 0 this is
+ * srsran_tdec_run_all(h, in, out, max_iter, K) (turbodecoder.c:536-549; max_iter == 0 still runs one half-iteration).
+ * Outputs: out_bytes + out_offset[i] receives K[i]/8 bytes, MSB first (tdec_gen_decision_byte); noi[i] the number of
+ * half-iterations run; crc_ok[i] = 1 when the CRC over the K[i] decided bits is zero after the last one.
+ * Host-pointer variant: copies in, launches, copies out, returns when the results are in the host buffers.
+ */
+int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_t* K, const uint8_t* crc_kind, const int16_t* llr,
+                       const uint64_t* llr_offset, uint64_t llr_len, uint32_t max_iter, uint32_t min_iter, int early_stop,
+                       uint8_t* out_bytes, const uint64_t* out_offset, uint64_t out_len, uint8_t* noi, uint8_t* crc_ok);
+
+/*
+ * Device-resident variant for equal-size blocks: d_llr [n][3K+12] int16, d_out [n][K/8], d_noi [n], d_crc_ok [n] are
+ * DEVICE pointers; work is enqueued on the engine stream and NOT synchronised (time it with events on
+ * srsb200_engine_stream()). plan must come from srsb200_tdec_plan_uniform and can be reused for every launch of the
+ * same shape; it owns the device workspace.
+ */
+typedef struct srsb200_plan srsb200_plan_t;
+int  srsb200_tdec_plan_uniform(srsb200_engine_t* e, uint32_t n, uint32_t K, int crc_kind, srsb200_plan_t** plan);
+void srsb200_plan_destroy(srsb200_plan_t* plan);
+int  srsb200_tdec_run_plan_dev(srsb200_engine_t* e, srsb200_plan_t* plan, const int16_t* d_llr, uint32_t max_iter,
+                               uint32_t min_iter, int early_stop, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_crc_ok);
+int  srsb200_engine_sync(srsb200_engine_t* e);
+
+/* ------------------------------------------------------------------ per-object decoder: srsran_tdec_* */
+/*
+ * Handle-based mirror of srsran_tdec_t (lib/include/srsran/phy/fec/turbo/turbodecoder.h:63-116). The device keeps the
+ * decoder state (app1/app2/ext1/ext2 equivalents) between srsb200_tdec_iteration calls exactly as the reference keeps
+ * them in the object.
+ */
+typedef struct srsb200_tdec srsb200_tdec_t;
+int  srsb200_tdec_init(srsb200_tdec_t** h, srsb200_engine_t* e, uint32_t max_long_cb); /* srsran_tdec_init[_manual] :97-99 */
+void srsb200_tdec_free(srsb200_tdec_t* h);                                            /* srsran_tdec_free :101 */
+int  srsb200_tdec_new_cb(srsb200_tdec_t* h, uint32_t long_cb);        /* :105  -1 if K > max or not an LTE size */
+int  srsb200_tdec_get_nof_iterations(srsb200_tdec_t* h);              /* :107 */
+int  srsb200_tdec_iteration(srsb200_tdec_t* h, const int16_t* input, uint8_t* output); /* :113 one half-iteration + decision */
+int  srsb200_tdec_run_all(srsb200_tdec_t* h, const int16_t* input, uint8_t* output, uint32_t nof_iterations,
+                          uint32_t long_cb);                          /* :115-116 */
+
+/* ------------------------------------------------------------------ rate de-matching: srsran_rm_turbo_rx_lut */
+/* replaces srsran_rm_turbo_gentables / srsran_rm_turbo_free_tables (rm_turbo.h:54,56); idempotent, thread-safe */
+int  srsb200_rm_turbo_gentables(srsb200_engine_t* e);
+/* replaces srsran_rm_turbo_rx_lut / srsran_rm_turbo_rx_lut_ (rm_turbo.h:76-84): output[T[i mod (3K+12)]] += input[i],
+ * int16 wrap, natural layout; host buffers; -2 if rv_idx >= 4 or cb_idx >= 188 (rm_turbo.c:441-444) */
+int  srsb200_rm_turbo_rx_lut(srsb200_engine_t* e, const int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx,
+                             uint32_t rv_idx);
+/* the de-rate-matching index table itself (natural layout), 3K+12 entries - for inspection / tests */
+int  srsb200_rm_table(uint32_t cb_idx, uint32_t rv_idx, uint16_t* table);
+
+/* ------------------------------------------------------------------ transport blocks: decode_tb / srsran_*sch_decode */
+/*
+ * One transport-block decode request. Mirrors the arguments of decode_tb (sch.c:509-573) with the soft buffer
+ * (lib/include/srsran/phy/fec/softbuffer.h:41-48) passed as its three arrays:
+ *   buffer_f[r] -> int16[SRSB200_SOFTBUFFER_SIZE]  accumulating LLR buffer of code block r (in/out, host memory)
+ *   sb_data[r]  -> uint8[SRSB200_SOFTBUFFER_SIZE/8] cached bytes of already-decoded code blocks (in/out)
+ *   cb_crc[r]   -> per code block CRC flag (in/out); *tb_crc (out)
+ * On return: data holds the decoded bytes laid out as the reference does (CB r at byte r*rlen/8), ret is decode_tb's
+ * return code (0 ok, -1 CRC failure, -2 invalid inputs), cb_noi[r] the half-iterations run for CB r in this call
+ * (0 if skipped) and avg_iterations what srsran_sch_last_noi would report.
+ */
+typedef struct {
+  uint32_t  tbs;
+  uint32_t  Qm;          /* bits per symbol x layers, as passed to decode_tb */
+  uint32_t  rv;
+  uint32_t  nof_e_bits;  /* G */
+  const int16_t* e_bits; /* G int16 LLRs */
+  int16_t** buffer_f;
+  uint8_t** sb_data;
+  uint8_t*  cb_crc;      /* bool per CB */
+  uint8_t*  tb_crc;
+  uint32_t  max_cb;      /* softbuffer->max_cb */
+  uint8_t*  data;
+  uint32_t* cb_noi;      /* may be NULL */
+  float     avg_iterations;
+  int       ret;
+} srsb200_tb_t;
+
+/* decode n transport blocks (possibly of different UEs/cells/subframes) as one batched submission */
+int srsb200_decode_tb_batch(srsb200_engine_t* e, srsb200_tb_t* tbs, uint32_t n, uint32_t max_iterations);
+/* single transport block = decode_tb (sch.c:509); returns tb->ret */
+int srsb200_decode_tb(srsb200_engine_t* e, srsb200_tb_t* tb, uint32_t max_iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRSRAN_B200_H */

@@ -1,0 +1,269 @@
+"""ctypes binding of libsrsran_b200.so (the C ABI in include/srsran_b200.h)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+CRC_NONE, CRC_24A, CRC_24B = 0, 1, 2
+SOFTBUFFER_SIZE = 18600
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class SrsB200Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libsrsran_b200.so")
+
+
+def lib():
+    """Load the CUDA library; fails loudly when it has not been built (no silent fallback)."""
+    global _LIB
+    if _LIB is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise SrsB200Error("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % p)
+        L = C.CDLL(p)
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        L.srsb200_last_error.restype = C.c_char_p
+        L.srsb200_engine_create.argtypes = [C.POINTER(vp), i32]
+        L.srsb200_engine_destroy.argtypes = [vp]
+        L.srsb200_engine_destroy.restype = None
+        L.srsb200_engine_launch_count.argtypes = [vp]
+        L.srsb200_engine_launch_count.restype = u64
+        L.srsb200_engine_stream.argtypes = [vp]
+        L.srsb200_engine_stream.restype = vp
+        L.srsb200_engine_sync.argtypes = [vp]
+        L.srsb200_cbsize.argtypes = [u32]
+        L.srsb200_cbindex.argtypes = [u32]
+        L.srsb200_cbsegm.argtypes = [u32, C.POINTER(u32)]
+        L.srsb200_tdec_autoimp_get_subblocks.argtypes = [u32]
+        L.srsb200_tdec_autoimp_get_subblocks.restype = u32
+        L.srsb200_tdec_batch.argtypes = [vp, u32, vp, vp, vp, vp, u64, u32, u32, i32, vp, vp, u64, vp, vp]
+        L.srsb200_tdec_plan_uniform.argtypes = [vp, u32, u32, i32, C.POINTER(vp)]
+        L.srsb200_plan_destroy.argtypes = [vp]
+        L.srsb200_plan_destroy.restype = None
+        L.srsb200_tdec_run_plan_dev.argtypes = [vp, vp, vp, u32, u32, i32, vp, vp, vp]
+        L.srsb200_tdec_init.argtypes = [C.POINTER(vp), vp, u32]
+        L.srsb200_tdec_free.argtypes = [vp]
+        L.srsb200_tdec_free.restype = None
+        L.srsb200_tdec_new_cb.argtypes = [vp, u32]
+        L.srsb200_tdec_get_nof_iterations.argtypes = [vp]
+        L.srsb200_tdec_iteration.argtypes = [vp, vp, vp]
+        L.srsb200_tdec_run_all.argtypes = [vp, vp, vp, u32, u32]
+        L.srsb200_rm_turbo_gentables.argtypes = [vp]
+        L.srsb200_rm_turbo_rx_lut.argtypes = [vp, vp, vp, u32, u32, u32]
+        L.srsb200_rm_table.argtypes = [u32, u32, vp]
+        L.srsb200_decode_tb_batch.argtypes = [vp, vp, u32, u32]
+        L.srsb200_decode_tb.argtypes = [vp, vp, u32]
+        _LIB = L
+    return _LIB
+
+
+def _check(ret, what):
+    if ret != 0:
+        raise SrsB200Error("%s failed (%d): %s" % (what, ret, lib().srsb200_last_error().decode()))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---- host-side metadata (no device needed)
+def cbsize(idx):
+    return lib().srsb200_cbsize(idx)
+
+
+def cbindex(K):
+    return lib().srsb200_cbindex(K)
+
+
+def cbsegm(tbs):
+    out = (C.c_uint32 * 8)()
+    ret = lib().srsb200_cbsegm(tbs, out)
+    return ret, dict(zip(["F", "C", "K1", "K2", "K1_idx", "K2_idx", "C1", "C2"], [int(v) for v in out]))
+
+
+def rm_table(cb_idx, rv):
+    K = cbsize(cb_idx)
+    t = np.zeros(3 * K + 12, np.uint16)
+    _check(lib().srsb200_rm_table(cb_idx, rv, _ptr(t)), "srsb200_rm_table")
+    return t
+
+
+class _TbStruct(C.Structure):
+    _fields_ = [("tbs", C.c_uint32), ("Qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32), ("e_bits", C.c_void_p),
+                ("buffer_f", C.POINTER(C.c_void_p)), ("sb_data", C.POINTER(C.c_void_p)), ("cb_crc", C.c_void_p), ("tb_crc", C.c_void_p),
+                ("max_cb", C.c_uint32), ("data", C.c_void_p), ("cb_noi", C.c_void_p), ("avg_iterations", C.c_float), ("ret", C.c_int)]
+
+
+class TransportBlock:
+    """One decode_tb request + its HARQ soft buffer (srsran_softbuffer_rx_t: buffer_f / data / cb_crc / tb_crc)."""
+
+    def __init__(self, tbs, max_cb=None):
+        _, seg = cbsegm(tbs)
+        self.tbs, self.seg = tbs, seg
+        self.max_cb = max_cb if max_cb is not None else max(seg["C"], 1)
+        self.buffer_f = np.zeros((self.max_cb, SOFTBUFFER_SIZE), np.int16)
+        self.sb_data = np.zeros((self.max_cb, SOFTBUFFER_SIZE // 8), np.uint8)
+        self.cb_crc = np.zeros(self.max_cb, np.uint8)
+        self.tb_crc = np.zeros(1, np.uint8)
+        self.data = np.zeros(self.max_cb * 768 + 8, np.uint8)
+        self.cb_noi = np.zeros(self.max_cb, np.uint32)
+        self._bf = (C.c_void_p * self.max_cb)(*[self.buffer_f[i].ctypes.data for i in range(self.max_cb)])
+        self._sd = (C.c_void_p * self.max_cb)(*[self.sb_data[i].ctypes.data for i in range(self.max_cb)])
+        self.ret, self.avg_iterations = None, 0.0
+        self._e = None
+
+    def fill(self, s, Qm, rv, e_bits, nof_e_bits=None):
+        self._e = np.ascontiguousarray(e_bits, np.int16)
+        s.tbs, s.Qm, s.rv = self.tbs, Qm, rv
+        s.nof_e_bits = len(self._e) if nof_e_bits is None else nof_e_bits
+        s.e_bits = self._e.ctypes.data
+        s.buffer_f, s.sb_data = self._bf, self._sd
+        s.cb_crc, s.tb_crc = self.cb_crc.ctypes.data, self.tb_crc.ctypes.data
+        s.max_cb = self.max_cb
+        s.data, s.cb_noi = self.data.ctypes.data, self.cb_noi.ctypes.data
+
+
+class Engine:
+    """One engine per GPU (owns a stream, device tables and workspaces)."""
+
+    def __init__(self, device=-1):
+        self._h = C.c_void_p()
+        self._L = lib()
+        _check(self._L.srsb200_engine_create(C.byref(self._h), device), "srsb200_engine_create")
+
+    def close(self):
+        if self._h:
+            self._L.srsb200_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def launch_count(self):
+        return int(self._L.srsb200_engine_launch_count(self._h))
+
+    @property
+    def stream(self):
+        return self._L.srsb200_engine_stream(self._h)
+
+    def sync(self):
+        _check(self._L.srsb200_engine_sync(self._h), "srsb200_engine_sync")
+
+    # ---- batched decode, host buffers
+    def tdec_batch(self, K, llr, max_iter, early_stop=True, min_iter=2, crc_kind=CRC_24B):
+        """K: int or per-block sizes; llr: [n, 3K+12] int16 (uniform K) or list of int16 arrays.
+        -> (out list/array of K/8-byte rows, noi[n], crc_ok[n])"""
+        if np.isscalar(K):
+            llr = np.ascontiguousarray(llr, np.int16)
+            n = llr.shape[0]
+            Ks = np.full(n, K, np.uint32)
+            flat = llr.reshape(-1)
+            loff = np.arange(n, dtype=np.uint64) * np.uint64(3 * K + 12)
+        else:
+            Ks = np.ascontiguousarray(K, np.uint32)
+            n = len(Ks)
+            parts = [np.ascontiguousarray(a, np.int16).reshape(-1) for a in llr]
+            lens = np.array([len(p) for p in parts], np.uint64)
+            loff = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+            flat = np.concatenate(parts) if n else np.zeros(0, np.int16)
+        kinds = np.full(n, crc_kind, np.uint8) if np.isscalar(crc_kind) else np.ascontiguousarray(crc_kind, np.uint8)
+        obytes = (Ks // 8).astype(np.uint64)
+        ooff = np.concatenate([[0], np.cumsum(obytes)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+        out = np.zeros(int(obytes.sum()), np.uint8)
+        noi = np.zeros(n, np.uint8)
+        ok = np.zeros(n, np.uint8)
+        _check(self._L.srsb200_tdec_batch(self._h, n, _ptr(Ks), _ptr(kinds), _ptr(flat), _ptr(loff), len(flat), max_iter, min_iter,
+                                          int(early_stop), _ptr(out), _ptr(ooff), len(out), _ptr(noi), _ptr(ok)), "srsb200_tdec_batch")
+        if np.isscalar(K):
+            return out.reshape(n, K // 8), noi, ok
+        return [out[int(o):int(o) + int(b)] for o, b in zip(ooff, obytes)], noi, ok
+
+    # ---- device-resident plan API (raw device pointers, e.g. torch tensor .data_ptr())
+    def plan_uniform(self, n, K, crc_kind=CRC_24B):
+        p = C.c_void_p()
+        _check(self._L.srsb200_tdec_plan_uniform(self._h, n, K, crc_kind, C.byref(p)), "srsb200_tdec_plan_uniform")
+        return p
+
+    def plan_destroy(self, p):
+        self._L.srsb200_plan_destroy(p)
+
+    def run_plan_dev(self, plan, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok):
+        _check(self._L.srsb200_tdec_run_plan_dev(self._h, plan, d_llr, max_iter, min_iter, int(early_stop), d_out, d_noi, d_ok),
+               "srsb200_tdec_run_plan_dev")
+
+    # ---- rate de-matching (srsran_rm_turbo_rx_lut_ with natural layout)
+    def rm_turbo_rx_lut(self, e, buf, cb_idx, rv):
+        e = np.ascontiguousarray(e, np.int16)
+        assert buf.dtype == np.int16 and buf.flags.c_contiguous
+        return self._L.srsb200_rm_turbo_rx_lut(self._h, _ptr(e), _ptr(buf), len(e), cb_idx, rv)
+
+    # ---- transport blocks
+    def decode_tb_batch(self, reqs, max_iterations):
+        """reqs: list of (TransportBlock, Qm, rv, e_bits)"""
+        arr = (_TbStruct * len(reqs))()
+        for s, (tb, Qm, rv, e) in zip(arr, reqs):
+            tb.fill(s, Qm, rv, e)
+        ret = self._L.srsb200_decode_tb_batch(self._h, arr, len(reqs), max_iterations)
+        for s, (tb, _, _, _) in zip(arr, reqs):
+            tb.ret, tb.avg_iterations = s.ret, s.avg_iterations
+        return ret
+
+    def decode_tb(self, tb, Qm, rv, e_bits, max_iterations, nof_e_bits=None):
+        s = _TbStruct()
+        tb.fill(s, Qm, rv, e_bits, nof_e_bits)
+        ret = self._L.srsb200_decode_tb(self._h, C.byref(s), max_iterations)
+        tb.ret, tb.avg_iterations = s.ret, s.avg_iterations
+        return ret
+
+
+class Tdec:
+    """Mirror of srsran_tdec_t + srsran_tdec_* (lib/include/srsran/phy/fec/turbo/turbodecoder.h:63-116)."""
+
+    def __init__(self, engine, max_long_cb=6144):
+        self._L = lib()
+        self._h = C.c_void_p()
+        self.engine = engine
+        _check(self._L.srsb200_tdec_init(C.byref(self._h), engine.handle, max_long_cb), "srsb200_tdec_init")
+
+    def free(self):
+        if self._h:
+            self._L.srsb200_tdec_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def new_cb(self, long_cb):
+        return self._L.srsb200_tdec_new_cb(self._h, long_cb)
+
+    def get_nof_iterations(self):
+        return self._L.srsb200_tdec_get_nof_iterations(self._h)
+
+    def iteration(self, llr, K):
+        llr = np.ascontiguousarray(llr, np.int16)
+        out = np.zeros(K // 8, np.uint8)
+        _check(self._L.srsb200_tdec_iteration(self._h, _ptr(llr), _ptr(out)), "srsb200_tdec_iteration")
+        return out
+
+    def run_all(self, llr, nof_iterations, K):
+        llr = np.ascontiguousarray(llr, np.int16)
+        out = np.zeros(K // 8, np.uint8)
+        ret = self._L.srsb200_tdec_run_all(self._h, _ptr(llr), _ptr(out), nof_iterations, K)
+        return ret, out

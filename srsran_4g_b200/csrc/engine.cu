@@ -1,0 +1,621 @@
+/*
+ * engine.cu - host side of libsrsran_b200.so: device tables, batch planning, kernel launches and the C ABI declared in
+ * include/srsran_b200.h. C++ because the reference's host side is compiled code (C); no torch types anywhere.
+ * There is no CPU fallback: without a usable CUDA device every compute entry point returns SRSB200_ERROR_NO_DEVICE.
+ */
+#include "../../include/srsran_b200.h"
+#include "../../include/lte_qpp_params.h"
+#include "turbo_kernels.cuh"
+#include "rm_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace srsb200;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char* srsb200_last_error(void) { return g_err; }
+
+#define CUDA_TRY(expr)                                                                                                 \
+  do {                                                                                                                 \
+    cudaError_t _e = (expr);                                                                                           \
+    if (_e != cudaSuccess) {                                                                                           \
+      cudaGetLastError();                                                                                              \
+      return fail(SRSB200_ERROR, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);          \
+    }                                                                                                                  \
+  } while (0)
+
+// ------------------------------------------------------------------ host-side metadata
+extern "C" int srsb200_cbsize(uint32_t index)
+{
+  return index < LTE_NOF_CB_SIZES ? (int)lte_qpp_params[index].K : SRSB200_ERROR;
+}
+extern "C" int srsb200_cbindex(uint32_t long_cb)
+{
+  // first table entry >= long_cb (srsran_cbsegm_cbindex, cbsegm.c:119-130)
+  for (int i = 0; i < LTE_NOF_CB_SIZES; i++)
+    if (lte_qpp_params[i].K >= long_cb) return i;
+  return SRSB200_ERROR;
+}
+static int cbindex_exact(uint32_t K)
+{
+  int i = srsb200_cbindex(K);
+  return (i >= 0 && lte_qpp_params[i].K == K) ? i : -1;
+}
+extern "C" uint32_t srsb200_tdec_autoimp_get_subblocks(uint32_t) { return 0; }
+
+extern "C" int srsb200_cbsegm(uint32_t tbs, uint32_t o[8])
+{
+  // 36.212 5.1.2 as realised by srsran_cbsegm (cbsegm.c:62-117)
+  memset(o, 0, 8 * sizeof(uint32_t));
+  if (tbs == 0) return SRSB200_SUCCESS;
+  const uint32_t Z = SRSB200_MAX_K;
+  uint32_t       B = tbs + 24, C = 1, Bp = B;
+  if (B > Z) {
+    C  = (B + (Z - 24) - 1) / (Z - 24);
+    Bp = B + 24 * C;
+  }
+  int i1 = srsb200_cbindex((Bp - 1) / C + 1);
+  if (i1 < 0) return SRSB200_ERROR;
+  uint32_t K1 = lte_qpp_params[i1].K;
+  o[1] = C; o[2] = K1; o[4] = (uint32_t)i1;
+  if (C == 1) {
+    o[6] = 1;
+  } else {
+    uint32_t K2 = lte_qpp_params[i1 - 1].K;
+    o[3] = K2; o[5] = (uint32_t)(i1 - 1);
+    o[7] = (C * K1 - Bp) / (K1 - K2);
+    o[6] = C - o[7];
+  }
+  o[0] = o[6] * o[2] + o[7] * o[3] - Bp;
+  return SRSB200_SUCCESS;
+}
+
+// ------------------------------------------------------------------ tables
+static void qpp_tables(int kidx, std::vector<uint16_t>& fwd, std::vector<uint16_t>& rev)
+{
+  const uint32_t K = lte_qpp_params[kidx].K;
+  const uint64_t f1 = lte_qpp_params[kidx].f1, f2 = lte_qpp_params[kidx].f2;
+  fwd.resize(K);
+  rev.resize(K);
+  for (uint64_t i = 0; i < K; i++) {
+    uint32_t p = (uint32_t)((f1 * i + f2 * i * i) % K);
+    fwd[i]     = (uint16_t)p;
+    rev[p]     = (uint16_t)i;
+  }
+}
+
+// x^(m+24) mod g for m = 0..MAX_K-1: contribution of a set bit m positions before the end of the message to the
+// MSB-first, zero-init CRC of srsran_crc_checksum_byte (crc.c:147-161)
+static void crc_position_words(uint32_t poly, std::vector<uint32_t>& r)
+{
+  r.resize(SRSB200_MAX_K);
+  uint32_t v = 1;  // x^0
+  // advance to x^24
+  auto mulx = [&](uint32_t a) {
+    a <<= 1;
+    if (a & 0x1000000u) a ^= poly;
+    return a & 0xffffffu;
+  };
+  for (int i = 0; i < 24; i++) v = mulx(v);
+  for (uint32_t m = 0; m < SRSB200_MAX_K; m++) {
+    r[m] = v;
+    v    = mulx(v);
+  }
+}
+
+static const uint8_t RM_COLPERM[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
+                                       1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};
+
+// 36.212 5.1.4.1 sub-block interleaver + circular buffer walk: transmitted bit n of redundancy version rv is element
+// T[n] of the natural coded stream (what srsran_rm_turbo_gentable_receive builds, rm_turbo.c:175-248)
+static void rm_table_host(uint32_t cb_idx, uint32_t rv, std::vector<uint16_t>& T)
+{
+  const uint32_t K = lte_qpp_params[cb_idx].K, D = K + 4, Rr = (D - 1) / 32 + 1, Kp = 32 * Rr, Nd = Kp - D, Ncb = 3 * Kp, L = 3 * D;
+  std::vector<int32_t> w(Ncb, -1);
+  for (uint32_t i = 0; i < D; i++) {
+    uint32_t y = Nd + i, v = RM_COLPERM[y % 32] * Rr + y / 32;
+    w[v]          = (int32_t)(3 * i);
+    w[Kp + 2 * v] = (int32_t)(3 * i + 1);
+    uint32_t t = (y + Kp - 1) % Kp, v2 = RM_COLPERM[t % 32] * Rr + t / 32;
+    w[Kp + 2 * v2 + 1] = (int32_t)(3 * i + 2);
+  }
+  T.resize(L);
+  uint32_t k0 = Rr * (24 * rv + 2), n = 0;
+  for (uint32_t j = 0; n < L; j++) {
+    int32_t src = w[(k0 + j) % Ncb];
+    if (src >= 0) T[n++] = (uint16_t)src;
+  }
+}
+
+extern "C" int srsb200_rm_table(uint32_t cb_idx, uint32_t rv_idx, uint16_t* table)
+{
+  if (cb_idx >= LTE_NOF_CB_SIZES || rv_idx >= 4 || !table) return SRSB200_ERROR_INVALID_INPUTS;
+  std::vector<uint16_t> T;
+  rm_table_host(cb_idx, rv_idx, T);
+  memcpy(table, T.data(), T.size() * sizeof(uint16_t));
+  return SRSB200_SUCCESS;
+}
+
+// ------------------------------------------------------------------ engine
+struct srsb200_engine {
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t     launches = 0;
+  std::mutex   mtx;
+
+  // per-K device tables
+  KTable              h_ktab[LTE_NOF_CB_SIZES];
+  bool                have_k[LTE_NOF_CB_SIZES];
+  KTable*             d_ktab = nullptr;
+  std::vector<void*>  owned;  // device allocations freed at destroy
+  std::vector<uint32_t> crc_words[3];
+
+  // rate-matching tables [cb_idx][rv] (device, uint16[3K+12]) built lazily
+  uint16_t* d_rm[LTE_NOF_CB_SIZES][4];
+
+  // scratch for the host-pointer APIs (grown on demand)
+  void*  d_scratch[8]   = {nullptr};
+  size_t scratch_cap[8] = {0};
+};
+
+static int ensure_scratch(srsb200_engine* e, int slot, size_t bytes, void** out)
+{
+  if (e->scratch_cap[slot] < bytes) {
+    if (e->d_scratch[slot]) cudaFree(e->d_scratch[slot]);
+    e->d_scratch[slot]   = nullptr;
+    e->scratch_cap[slot] = 0;
+    size_t cap = bytes + bytes / 4 + 4096;
+    CUDA_TRY(cudaMalloc(&e->d_scratch[slot], cap));
+    e->scratch_cap[slot] = cap;
+  }
+  *out = e->d_scratch[slot];
+  return 0;
+}
+
+static int ensure_ktable(srsb200_engine* e, int kidx)
+{
+  if (e->have_k[kidx]) return 0;
+  const uint32_t K = lte_qpp_params[kidx].K;
+  const uint32_t R = ((K + 3 + W - 1) / W) * W;
+  std::vector<uint16_t> fwd, rev;
+  qpp_tables(kidx, fwd, rev);
+  KTable kt;
+  memset(&kt, 0, sizeof(kt));
+  for (int kind = 0; kind < 3; kind++) {
+    std::vector<uint2> t1(R), t2(R);
+    for (uint32_t i = 0; i < R; i++) {
+      t1[i] = make_uint2(0, 0);
+      t2[i] = make_uint2(0, 0);
+    }
+    for (uint32_t i = 0; i < K; i++) {
+      uint32_t w1 = kind ? e->crc_words[kind][K - 1 - i] : 0u;
+      uint32_t w2 = kind ? e->crc_words[kind][K - 1 - fwd[i]] : 0u;
+      t1[i]       = make_uint2(rev[i], w1);
+      t2[i]       = make_uint2(fwd[i], w2);
+    }
+    uint2 *d1, *d2;
+    CUDA_TRY(cudaMalloc(&d1, R * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&d2, R * sizeof(uint2)));
+    e->owned.push_back(d1);
+    e->owned.push_back(d2);
+    CUDA_TRY(cudaMemcpyAsync(d1, t1.data(), R * sizeof(uint2), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(d2, t2.data(), R * sizeof(uint2), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));  // the host vectors die at the end of this scope
+    kt.dec1[kind] = d1;
+    kt.dec2[kind] = d2;
+  }
+  uint16_t* drev;
+  CUDA_TRY(cudaMalloc(&drev, K * sizeof(uint16_t)));
+  e->owned.push_back(drev);
+  CUDA_TRY(cudaMemcpyAsync(drev, rev.data(), K * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
+  kt.rev = drev;
+  e->h_ktab[kidx] = kt;
+  CUDA_TRY(cudaMemcpyAsync(e->d_ktab + kidx, &e->h_ktab[kidx], sizeof(KTable), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->have_k[kidx] = true;
+  return 0;
+}
+
+static int ensure_rm_table(srsb200_engine* e, uint32_t cb_idx, uint32_t rv)
+{
+  if (e->d_rm[cb_idx][rv]) return 0;
+  std::vector<uint16_t> T;
+  rm_table_host(cb_idx, rv, T);
+  uint16_t* d;
+  CUDA_TRY(cudaMalloc(&d, T.size() * sizeof(uint16_t)));
+  e->owned.push_back(d);
+  CUDA_TRY(cudaMemcpyAsync(d, T.data(), T.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->d_rm[cb_idx][rv] = d;
+  return 0;
+}
+
+extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
+{
+  if (!out) return fail(SRSB200_ERROR_INVALID_INPUTS, "null engine pointer");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SRSB200_ERROR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) return fail(SRSB200_ERROR_NO_DEVICE, "cudaGetDevice failed");
+  }
+  if (device >= ndev) return fail(SRSB200_ERROR_INVALID_INPUTS, "device %d out of range (%d devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  srsb200_engine* e = new srsb200_engine();
+  e->device         = device;
+  memset(e->have_k, 0, sizeof(e->have_k));
+  memset(e->d_rm, 0, sizeof(e->d_rm));
+  memset(e->h_ktab, 0, sizeof(e->h_ktab));
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&e->d_ktab, sizeof(KTable) * LTE_NOF_CB_SIZES));
+  CUDA_TRY(cudaMemset(e->d_ktab, 0, sizeof(KTable) * LTE_NOF_CB_SIZES));
+  crc_position_words(0x1864CFBu, e->crc_words[SRSB200_CRC_24A]);
+  crc_position_words(0x1800063u, e->crc_words[SRSB200_CRC_24B]);
+  CUDA_TRY(cudaFuncSetAttribute(tdec_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
+  *out = e;
+  return SRSB200_SUCCESS;
+}
+
+extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
+{
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (void* p : e->owned) cudaFree(p);
+  for (int i = 0; i < 8; i++)
+    if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);
+  cudaFree(e->d_ktab);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+extern "C" uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e) { return e ? e->launches : 0; }
+extern "C" void*    srsb200_engine_stream(const srsb200_engine_t* e) { return e ? (void*)e->stream : nullptr; }
+extern "C" int      srsb200_engine_sync(srsb200_engine_t* e)
+{
+  if (!e) return SRSB200_ERROR_INVALID_INPUTS;
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return SRSB200_SUCCESS;
+}
+
+// ------------------------------------------------------------------ plans: code blocks -> groups
+struct srsb200_plan {
+  srsb200_engine* e = nullptr;
+  uint32_t n_cb = 0, n_groups = 0, max_R = 0;
+  std::vector<Group> h_groups;
+  Group*    d_groups = nullptr;
+  uint8_t*  d_ws = nullptr;
+  uint64_t  ws_bytes = 0;
+  uint64_t* d_llr_off = nullptr;
+  uint64_t* d_out_off = nullptr;
+  bool      uniform = false;
+};
+
+// cbs sorted into groups of <= 64 equal (K, crc_kind) blocks
+static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const uint8_t* crc_kind, uint32_t uniform_K, int uniform_kind,
+                      const uint64_t* llr_off, const uint64_t* out_off, srsb200_plan** out)
+{
+  std::map<std::pair<uint32_t, uint32_t>, std::vector<int32_t>> buckets;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t k    = K ? K[i] : uniform_K;
+    uint32_t kind = crc_kind ? crc_kind[i] : (uint32_t)uniform_kind;
+    if (cbindex_exact(k) < 0) return fail(SRSB200_ERROR_INVALID_INPUTS, "code block %u: K=%u is not an LTE turbo block size", i, k);
+    if (kind > 2) return fail(SRSB200_ERROR_INVALID_INPUTS, "code block %u: bad crc kind %u", i, kind);
+    buckets[{k, kind}].push_back((int32_t)i);
+  }
+  srsb200_plan* p = new srsb200_plan();
+  p->e            = e;
+  p->n_cb         = n;
+  uint64_t off    = 0;
+  for (auto& kv : buckets) {
+    const uint32_t k = kv.first.first, kind = kv.first.second;
+    const int kidx = cbindex_exact(k);
+    if (ensure_ktable(e, kidx)) {
+      delete p;
+      return SRSB200_ERROR;
+    }
+    const uint32_t R = ((k + 3 + W - 1) / W) * W;
+    p->max_R = std::max(p->max_R, R);
+    const std::vector<int32_t>& ids = kv.second;
+    for (size_t s = 0; s < ids.size(); s += 64) {
+      Group g;
+      g.K = k; g.R = R; g.kidx = (uint32_t)kidx; g.crc_kind = kind; g.ws_off = off;
+      size_t cnt = std::min<size_t>(64, ids.size() - s);
+      // fill low halves first so that a half-empty group still uses all lanes
+      for (int j = 0; j < 64; j++) g.cb[j] = -1;
+      size_t nlo = std::min<size_t>(32, cnt);
+      // spread: first ceil(cnt/2) blocks in the low halves, the rest in the high halves of the same lanes
+      size_t half = (cnt + 1) / 2;
+      (void)nlo;
+      for (size_t j = 0; j < cnt; j++) {
+        if (j < half) g.cb[j] = ids[s + j];
+        else g.cb[32 + (j - half)] = ids[s + j];
+      }
+      off += ((group_ws_words(R) * 4 + 255) / 256) * 256;
+      p->h_groups.push_back(g);
+    }
+  }
+  p->n_groups = (uint32_t)p->h_groups.size();
+  p->ws_bytes = off;
+  cudaError_t ce;
+  if ((ce = cudaMalloc(&p->d_groups, sizeof(Group) * std::max<uint32_t>(1, p->n_groups))) != cudaSuccess ||
+      (ce = cudaMalloc(&p->d_ws, std::max<uint64_t>(256, p->ws_bytes))) != cudaSuccess ||
+      (ce = cudaMalloc(&p->d_llr_off, sizeof(uint64_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
+      (ce = cudaMalloc(&p->d_out_off, sizeof(uint64_t) * std::max<uint32_t>(1, n))) != cudaSuccess) {
+    cudaGetLastError();
+    srsb200_plan_destroy(p);
+    return fail(SRSB200_ERROR, "plan allocation failed: %s", cudaGetErrorString(ce));
+  }
+  std::vector<uint64_t> lo(n), oo(n);
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t k = K ? K[i] : uniform_K;
+    lo[i]      = llr_off ? llr_off[i] : (uint64_t)i * (3ull * k + 12);
+    oo[i]      = out_off ? out_off[i] : (uint64_t)i * (k / 8);
+  }
+  if (n) {
+    cudaMemcpyAsync(p->d_groups, p->h_groups.data(), sizeof(Group) * p->n_groups, cudaMemcpyHostToDevice, e->stream);
+    cudaMemcpyAsync(p->d_llr_off, lo.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream);
+    cudaMemcpyAsync(p->d_out_off, oo.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream);
+  }
+  ce = cudaStreamSynchronize(e->stream);
+  if (ce != cudaSuccess) {
+    srsb200_plan_destroy(p);
+    return fail(SRSB200_ERROR, "plan upload failed: %s", cudaGetErrorString(ce));
+  }
+  *out = p;
+  return SRSB200_SUCCESS;
+}
+
+extern "C" void srsb200_plan_destroy(srsb200_plan_t* p)
+{
+  if (!p) return;
+  if (p->e) cudaSetDevice(p->e->device);
+  cudaFree(p->d_groups);
+  cudaFree(p->d_ws);
+  cudaFree(p->d_llr_off);
+  cudaFree(p->d_out_off);
+  delete p;
+}
+
+extern "C" int srsb200_tdec_plan_uniform(srsb200_engine_t* e, uint32_t n, uint32_t K, int crc_kind, srsb200_plan_t** plan)
+{
+  if (!e || !plan) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  int r = build_plan(e, n, nullptr, nullptr, K, crc_kind, nullptr, nullptr, plan);
+  if (r == SRSB200_SUCCESS) (*plan)->uniform = true;
+  return r;
+}
+
+// enqueue extract + decode + emit for a plan; all pointers are device pointers
+static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr, uint32_t max_iter, uint32_t min_iter, int early_stop,
+                       uint32_t start_iter, bool do_extract, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok)
+{
+  if (p->n_groups == 0) return SRSB200_SUCCESS;
+  if (do_extract) {
+    dim3 grid(p->max_R / 32, p->n_groups);
+    extract_kernel<<<grid, 256, 0, e->stream>>>(p->d_groups, p->d_ws, d_llr, p->d_llr_off);
+    e->launches++;
+  }
+  tdec_group_kernel<<<p->n_groups, 32, sizeof(WarpSmem), e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, d_noi, d_ok, max_iter, min_iter,
+                                                                     early_stop, start_iter, nullptr);
+  e->launches++;
+  dim3 egrid((SRSB200_MAX_K / 32 + 127) / 128, p->n_groups * 64);
+  egrid.x = (p->max_R / 32 + 127) / 128;
+  emit_kernel<<<egrid, 128, 0, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SRSB200_SUCCESS;
+}
+
+extern "C" int srsb200_tdec_run_plan_dev(srsb200_engine_t* e, srsb200_plan_t* plan, const int16_t* d_llr, uint32_t max_iter,
+                                         uint32_t min_iter, int early_stop, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_crc_ok)
+{
+  if (!e || !plan || !d_llr || !d_out || !d_noi || !d_crc_ok) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  return launch_plan(e, plan, d_llr, max_iter, min_iter, early_stop, 0, true, d_out, d_noi, d_crc_ok);
+}
+
+extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_t* K, const uint8_t* crc_kind, const int16_t* llr,
+                                  const uint64_t* llr_offset, uint64_t llr_len, uint32_t max_iter, uint32_t min_iter, int early_stop,
+                                  uint8_t* out_bytes, const uint64_t* out_offset, uint64_t out_len, uint8_t* noi, uint8_t* crc_ok)
+{
+  if (!e) return fail(SRSB200_ERROR_NO_DEVICE, "no engine (no CUDA device?)");
+  if (n == 0) return SRSB200_SUCCESS;
+  if (!K || !llr || !llr_offset || !out_bytes || !out_offset || !noi || !crc_ok) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
+  for (uint32_t i = 0; i < n; i++) {
+    if (cbindex_exact(K[i]) < 0) return fail(SRSB200_ERROR_INVALID_INPUTS, "code block %u: K=%u is not an LTE turbo block size", i, K[i]);
+    if (llr_offset[i] + 3ull * K[i] + 12 > llr_len) return fail(SRSB200_ERROR_INVALID_INPUTS, "code block %u: LLR range exceeds llr_len", i);
+    if (out_offset[i] + K[i] / 8 > out_len) return fail(SRSB200_ERROR_INVALID_INPUTS, "code block %u: output range exceeds out_len", i);
+  }
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  srsb200_plan* p = nullptr;
+  int r = build_plan(e, n, K, crc_kind, 0, SRSB200_CRC_NONE, llr_offset, out_offset, &p);
+  if (r) return r;
+  void *d_llr, *d_out, *d_noi, *d_ok;
+  if (ensure_scratch(e, 0, llr_len * sizeof(int16_t), &d_llr) || ensure_scratch(e, 1, out_len, &d_out) || ensure_scratch(e, 2, n, &d_noi) ||
+      ensure_scratch(e, 3, n, &d_ok)) {
+    srsb200_plan_destroy(p);
+    return SRSB200_ERROR;
+  }
+  cudaError_t ce = cudaMemcpyAsync(d_llr, llr, llr_len * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream);
+  if (ce == cudaSuccess) {
+    r = launch_plan(e, p, (const int16_t*)d_llr, max_iter, min_iter, early_stop, 0, true, (uint8_t*)d_out, (uint8_t*)d_noi, (uint8_t*)d_ok);
+  }
+  if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(out_bytes, d_out, out_len, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(noi, d_noi, n, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(crc_ok, d_ok, n, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess && r == 0) ce = cudaStreamSynchronize(e->stream);
+  srsb200_plan_destroy(p);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SRSB200_ERROR, "batch decode failed: %s", cudaGetErrorString(ce));
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------ per-object decoder (srsran_tdec_*)
+struct srsb200_tdec {
+  srsb200_engine* e = nullptr;
+  uint32_t max_long_cb = 0;
+  int      current_cbidx = -1;
+  uint32_t current_long_cb = 0;
+  int      n_iter = 0;
+  srsb200_plan* plan = nullptr;
+  int16_t* d_in = nullptr;
+  uint8_t *d_out = nullptr, *d_noi = nullptr, *d_ok = nullptr;
+};
+
+extern "C" int srsb200_tdec_init(srsb200_tdec_t** h, srsb200_engine_t* e, uint32_t max_long_cb)
+{
+  if (!h) return SRSB200_ERROR_INVALID_INPUTS;
+  *h = nullptr;
+  if (!e) return fail(SRSB200_ERROR_NO_DEVICE, "no engine (no CUDA device?)");
+  if (max_long_cb > SRSB200_MAX_K) return fail(SRSB200_ERROR, "max_long_cb %u exceeds %d", max_long_cb, SRSB200_MAX_K);
+  srsb200_tdec* t = new srsb200_tdec();
+  t->e            = e;
+  t->max_long_cb  = max_long_cb;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  cudaSetDevice(e->device);
+  if (cudaMalloc(&t->d_in, (3 * SRSB200_MAX_K + 12) * sizeof(int16_t)) != cudaSuccess || cudaMalloc(&t->d_out, SRSB200_MAX_K / 8) != cudaSuccess ||
+      cudaMalloc(&t->d_noi, 4) != cudaSuccess || cudaMalloc(&t->d_ok, 4) != cudaSuccess) {
+    cudaGetLastError();
+    delete t;
+    return fail(SRSB200_ERROR, "tdec allocation failed");
+  }
+  *h = t;
+  return SRSB200_SUCCESS;
+}
+
+extern "C" void srsb200_tdec_free(srsb200_tdec_t* t)
+{
+  if (!t) return;
+  cudaSetDevice(t->e->device);
+  if (t->plan) srsb200_plan_destroy(t->plan);
+  cudaFree(t->d_in);
+  cudaFree(t->d_out);
+  cudaFree(t->d_noi);
+  cudaFree(t->d_ok);
+  delete t;
+}
+
+extern "C" int srsb200_tdec_new_cb(srsb200_tdec_t* t, uint32_t long_cb)
+{
+  if (!t) return SRSB200_ERROR;
+  if (long_cb > t->max_long_cb) return fail(SRSB200_ERROR, "TDEC was initialized for max_long_cb=%u", t->max_long_cb);
+  int idx = cbindex_exact(long_cb);
+  if (idx < 0) return fail(SRSB200_ERROR, "Invalid code block size %u", long_cb);
+  t->n_iter = 0;
+  if (t->current_long_cb != long_cb || !t->plan) {
+    std::lock_guard<std::mutex> lk(t->e->mtx);
+    cudaSetDevice(t->e->device);
+    if (t->plan) srsb200_plan_destroy(t->plan);
+    t->plan = nullptr;
+    int r = build_plan(t->e, 1, nullptr, nullptr, long_cb, SRSB200_CRC_NONE, nullptr, nullptr, &t->plan);
+    if (r) return SRSB200_ERROR;
+  }
+  t->current_cbidx   = idx;
+  t->current_long_cb = long_cb;
+  return SRSB200_SUCCESS;
+}
+
+extern "C" int srsb200_tdec_get_nof_iterations(srsb200_tdec_t* t) { return t ? t->n_iter : 0; }
+
+extern "C" int srsb200_tdec_iteration(srsb200_tdec_t* t, const int16_t* input, uint8_t* output)
+{
+  if (!t || !input || !output) return SRSB200_ERROR_INVALID_INPUTS;
+  if (t->current_cbidx < 0) return fail(SRSB200_ERROR, "Error CB index not set (call srsb200_tdec_new_cb() first");
+  srsb200_engine* e = t->e;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  const uint32_t K = t->current_long_cb;
+  bool first = t->n_iter == 0;
+  if (first) CUDA_TRY(cudaMemcpyAsync(t->d_in, input, (3 * K + 12) * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
+  int r = launch_plan(e, t->plan, t->d_in, (uint32_t)t->n_iter + 1, 1, 0, (uint32_t)t->n_iter, first, t->d_out, t->d_noi, t->d_ok);
+  if (r) return r;
+  CUDA_TRY(cudaMemcpyAsync(output, t->d_out, K / 8, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  t->n_iter++;
+  return SRSB200_SUCCESS;
+}
+
+extern "C" int srsb200_tdec_run_all(srsb200_tdec_t* t, const int16_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb)
+{
+  if (!t || !input || !output) return SRSB200_ERROR_INVALID_INPUTS;
+  if (srsb200_tdec_new_cb(t, long_cb)) return SRSB200_ERROR;
+  srsb200_engine* e = t->e;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaMemcpyAsync(t->d_in, input, (3 * long_cb + 12) * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
+  uint32_t iters = nof_iterations ? nof_iterations : 1;  // do-while: at least one (turbodecoder.c:542-546)
+  int r = launch_plan(e, t->plan, t->d_in, iters, 1, 0, 0, true, t->d_out, t->d_noi, t->d_ok);
+  if (r) return r;
+  CUDA_TRY(cudaMemcpyAsync(output, t->d_out, long_cb / 8, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  t->n_iter = (int)iters;
+  return SRSB200_SUCCESS;
+}
+
+// ------------------------------------------------------------------ rate de-matching
+extern "C" int srsb200_rm_turbo_gentables(srsb200_engine_t* e)
+{
+  // tables are built lazily per (cb_idx, rv) on first use; kept for API symmetry with srsran_rm_turbo_gentables
+  return e ? SRSB200_SUCCESS : SRSB200_ERROR_NO_DEVICE;
+}
+
+extern "C" int srsb200_rm_turbo_rx_lut(srsb200_engine_t* e, const int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx,
+                                       uint32_t rv_idx)
+{
+  if (rv_idx >= 4 || cb_idx >= LTE_NOF_CB_SIZES) {
+    printf("Invalid inputs rv_idx=%d, cb_idx=%d\n", rv_idx, cb_idx);
+    return SRSB200_ERROR_INVALID_INPUTS;
+  }
+  if (!e) return fail(SRSB200_ERROR_NO_DEVICE, "no engine (no CUDA device?)");
+  if (!input || !output) return SRSB200_ERROR_INVALID_INPUTS;
+  if (in_len == 0) return SRSB200_SUCCESS;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (ensure_rm_table(e, cb_idx, rv_idx)) return SRSB200_ERROR;
+  const uint32_t L = 3 * lte_qpp_params[cb_idx].K + 12;
+  void *d_e, *d_buf;
+  if (ensure_scratch(e, 4, (size_t)in_len * 2, &d_e) || ensure_scratch(e, 5, (size_t)L * 2, &d_buf)) return SRSB200_ERROR;
+  CUDA_TRY(cudaMemcpyAsync(d_e, input, (size_t)in_len * 2, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_buf, output, (size_t)L * 2, cudaMemcpyHostToDevice, e->stream));
+  RmJob job;
+  job.e = (const int16_t*)d_e; job.buf = (int16_t*)d_buf; job.table = e->d_rm[cb_idx][rv_idx]; job.E = in_len; job.L = L;
+  void* d_job;
+  if (ensure_scratch(e, 6, sizeof(RmJob), &d_job)) return SRSB200_ERROR;
+  CUDA_TRY(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, e->stream));
+  rm_rx_kernel<<<dim3((L + 255) / 256, 1), 256, 0, e->stream>>>((const RmJob*)d_job);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(output, d_buf, (size_t)L * 2, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return SRSB200_SUCCESS;
+}
+
+// ------------------------------------------------------------------ transport blocks (decode_tb)
+#include "tb_decode.inc"

@@ -1,0 +1,62 @@
+/*
+ * rm_kernels.cuh - rate de-matching + HARQ soft combining (srsran_rm_turbo_rx_lut, lib/src/phy/fec/turbo/rm_turbo.c:390-445)
+ * and transport-block CRC24A (decode_tb, lib/src/phy/phch/sch.c:563) as sm_100a kernels.
+ *
+ * The reference computes  output[T[i mod L]] += input[i]  for i < E  (L = 3K+12, int16 wrap). T is a permutation of
+ * 0..L-1, so thread n < L owns every received LLR that lands on soft-buffer position T[n]:
+ *     sum_n = e[n] + e[n+L] + e[n+2L] + ...   (repetition when E > L),   buf[T[n]] += sum_n
+ * Loads of e are coalesced, the read-modify-write of the soft buffer is conflict-free without atomics, and the result is
+ * the reference's bit for bit because 16-bit wrapping addition is associative.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace srsb200 {
+
+struct RmJob {
+  const int16_t*  e;      // first received LLR of this code block (device)
+  int16_t*        buf;    // soft buffer of this code block, natural layout (device)
+  const uint16_t* table;  // T[0..L)
+  uint32_t        E;
+  uint32_t        L;
+};
+
+// grid = (ceil(maxL/256), n_jobs), block = 256
+__global__ void __launch_bounds__(256) rm_rx_kernel(const RmJob* __restrict__ jobs)
+{
+  const RmJob    j = jobs[blockIdx.y];
+  const uint32_t n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= j.L || n >= j.E) return;
+  uint32_t sum = 0;
+  for (uint32_t i = n; i < j.E; i += j.L) sum += (uint16_t)j.e[i];
+  const uint32_t t = j.table[n];
+  j.buf[t] = (int16_t)(uint16_t)((uint16_t)j.buf[t] + sum);
+}
+
+/*
+ * CRC of a byte string by linearity: crc = XOR over set bits of x^(nbits-1-pos+24) mod g. words[m] = x^(m+24) mod g.
+ * One block per job; crc_out[job] must be zero on entry (atomicXor accumulation).
+ */
+struct CrcJob {
+  const uint8_t* data;
+  uint32_t       nbits;  // multiple of 8
+};
+__global__ void __launch_bounds__(256) crc_bytes_kernel(const CrcJob* __restrict__ jobs, const uint32_t* __restrict__ words, uint32_t* __restrict__ crc_out)
+{
+  const CrcJob j   = jobs[blockIdx.y];
+  uint32_t     acc = 0;
+  for (uint32_t byte = blockIdx.x * 256 + threadIdx.x; byte < j.nbits / 8; byte += gridDim.x * 256) {
+    uint32_t v = j.data[byte];
+    while (v) {
+      int      b   = 31 - __clz(v);        // bit b of the byte (b = 7 is the earliest bit)
+      uint32_t pos = byte * 8 + (7 - b);   // position in the message
+      acc ^= words[j.nbits - 1 - pos];
+      v &= ~(1u << b);
+    }
+  }
+  acc = __reduce_xor_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicXor(&crc_out[blockIdx.y], acc);
+}
+
+}  // namespace srsb200

@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py - decoded information throughput of the batched LTE turbo decoder (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): 16384 code blocks of K=6144, synthetic BPSK/AWGN LLRs at true Eb/N0 = 1.5 dB,
+LLR scale 100, CRC24B early stop (min 2), at most 8 half-iterations (= 4 full turbo iterations; the reference API counts
+half-iterations). One "step" = one pass of the hot path (de-multiplex -> turbo decode with fused
+CRC early stop -> hard-bit emit) over the whole batch.
+
+  value : whole-job decoded info Mbit/s with the LLRs already resident in HBM (CUDA events on the engine stream,
+          max over ranks)
+  e2e   : the same metric through the host-pointer C-ABI call (srsb200_tdec_batch) with pinned HOST buffers:
+          H2D of the LLRs and D2H of bits / iteration counts / CRC flags inside the timed region
+  roofline / roofline_int : the dominant kernel (tdec_group_kernel) against the HBM copy peak (algorithmic bytes) and
+          against the measured packed-int16x2 issue peak (algorithmic op count) - SURVEY.md section 8(d)
+  cpu_baseline : the reference's AVX2 windowed decoder compiled from the reference sources (oracle/_ref), all host
+          cores, on a bounded sample of the same workload (N=1, rank 0 only)
+
+--impl reference times that CPU implementation alone (rank 0 only under torchrun).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 6144
+N_CB = 16384
+EBN0_DB = 1.5
+LLR_SCALE = 100
+MAX_ITER = 8
+MIN_ITER = 2
+# 40.25 packed-s16x2 instructions per info bit per half-iteration (generic algorithm op count)
+ALG_OPS_PER_BIT_HALFITER = 40.25
+# measured by tools/microbench/int16x2_issue.cu on this pool's B200 (profiles/r01_int16x2_issue.txt): the two integer
+# pipes together sustain 2 x 64 packed lanes/clk/SM -> 148 SM x 128 x 1.965 GHz
+INT_PEAK_TOPS = 36.8
+WORKLOAD = ("16384 code blocks x K=6144, true Eb/N0 1.5 dB BPSK/AWGN, int16 LLR scale 100, CRC24B early stop (min 2), "
+            "max 8 half-iterations (= 4 full turbo iterations)")
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons of one GPU during the timed region (pynvml, ~10 ms period)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2, "sync_boost": 0x10}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_decoder():
+    """(library wrapper, kind, impl id): oracle/_ref (the compiled reference, AVX2 windowed decoder) when it travelled
+    with the repo, else the clean-room port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    r = ol.ref()
+    if r is not None:
+        return r, "reference", 5  # SRSRAN_TDEC_AVX_WINDOW
+    return ol.oracle(), "port", 1
+
+
+def run_cpu(sample_cbs, min_seconds, seed):
+    """times the CPU decoder on a bounded sample with all host threads; returns dict for cpu_baseline"""
+    from srsran_4g_b200 import synth
+    lib, kind, impl = cpu_decoder()
+    cores = len(os.sched_getaffinity(0))
+    n = max(sample_cbs, cores * 8)
+    _, llr = synth.make_llr_batch(K, n, EBN0_DB, seed, LLR_SCALE, n_distinct=64)
+    lib.tdec_batch(K, llr[: cores * 2], MAX_ITER, True, nthreads=cores, impl=impl)  # warm-up (tables, page-in)
+    total_bits, total_s, reps, noi_all = 0, 0.0, 0, None
+    while total_s < min_seconds or reps < 2:
+        secs, _, noi, ok = lib.tdec_batch(K, llr, MAX_ITER, True, nthreads=cores, impl=impl, pin=1) if kind == "reference" else \
+            lib.tdec_batch(K, llr, MAX_ITER, True, nthreads=cores)
+        total_s += secs
+        total_bits += n * K
+        reps += 1
+        noi_all = noi
+    name = "srsRAN AVX2 windowed int16 decoder (SRSRAN_TDEC_AVX_WINDOW, turbodecoder_win.h) compiled from the reference tree" \
+        if kind == "reference" else "clean-room generic int16 port (oracle/turbo_oracle.c)"
+    return {"value": total_bits / total_s / 1e6, "unit": "Mbit/s", "cores": cores, "kind": kind,
+            "sample": "%d code blocks of the same workload x %d passes (%.1f s), %s, %d pthreads pinned" % (n, reps, total_s, name, cores),
+            "mean_half_iterations": float(np.mean(noi_all))}, n, reps, total_s
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-cb", type=int, default=N_CB, help="code blocks per GPU (default: the BASELINE config)")
+    ap.add_argument("--max-iter", type=int, default=MAX_ITER)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    peaks, peak_src = measured_peaks()
+
+    # ------------------------------------------------------------------ reference arm: the CPU implementation alone
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = len(os.sched_getaffinity(0))
+        from srsran_4g_b200 import synth
+        lib, kind, impl = cpu_decoder()
+        per_thread = 64
+        n = cores * per_thread
+        _, llr = synth.make_llr_batch(K, n, EBN0_DB, 1234, LLR_SCALE, n_distinct=64)
+        run = (lambda: lib.tdec_batch(K, llr, args.max_iter, True, nthreads=cores, impl=impl, pin=1)) if kind == "reference" else \
+            (lambda: lib.tdec_batch(K, llr, args.max_iter, True, nthreads=cores))
+        for _ in range(args.warmup):
+            run()
+        dt = 0.0
+        for _ in range(args.steps):
+            dt += run()[0]  # decode time inside the library: decoder objects are built before its start barrier
+        val = n * K * args.steps / dt / 1e6
+        sample = "each step = %d code blocks (%d per thread) of the workload, %d pthreads pinned" % (n, per_thread, cores)
+        print(json.dumps({
+            "impl": "reference", "metric": "turbo-decoded info Mbit/s (K=6144, 4 iter)", "value": val, "unit": "Mbit/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "decoder": "AVX2 windowed int16 (reference production decoder for K=6144)" if kind == "reference"
+                       else "generic int16 port", "bounded_sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import srsran_4g_b200 as sb
+    from srsran_4g_b200 import synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_cb = args.n_cb
+    eng = sb.Engine(local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    bits, llr = synth.make_llr_batch(K, n_cb, EBN0_DB, 1000 + rank, LLR_SCALE, n_distinct=256, device=dev)
+    torch.cuda.synchronize()
+    d_out = torch.zeros((n_cb, K // 8), dtype=torch.uint8, device=dev)
+    d_noi = torch.zeros(n_cb, dtype=torch.uint8, device=dev)
+    d_ok = torch.zeros(n_cb, dtype=torch.uint8, device=dev)
+    plan = eng.plan_uniform(n_cb, K, sb.CRC_24B)
+
+    def step():
+        eng.run_plan_dev(plan, llr.data_ptr(), args.max_iter, MIN_ITER, True, d_out.data_ptr(), d_noi.data_ptr(), d_ok.data_ptr())
+
+    for _ in range(warmup):
+        step()
+    eng.sync()
+    # correctness gate on this rank's batch (not timed): CRC-passing blocks must equal the transmitted payloads
+    noi = d_noi.cpu().numpy()
+    ok = d_ok.cpu().numpy()
+    tx = np.packbits(bits, axis=1)
+    got = d_out.cpu().numpy()
+    idx = np.arange(n_cb) % len(bits)
+    good = ok == 1
+    if not (got[good] == tx[idx[good]]).all():
+        raise SystemExit("decoded bits differ from the transmitted payload on CRC-passing blocks")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.profile(True)
+    eng.profile_read()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    eng.sync()
+    l0 = eng.launch_count
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    launches = eng.launch_count - l0
+    prof = eng.profile_read()
+    eng.profile(False)
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.result()
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    bits_per_step = float(n_cb) * K * world
+    value = bits_per_step * args.steps / (ms * 1e-3) / 1e6
+
+    # ------------------------------------------------------------------ end to end through the host-pointer C ABI
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        L = sb.lib()
+        h_llr = torch.empty((n_cb, 3 * K + 12), dtype=torch.int16, pin_memory=True)
+        h_llr.copy_(llr)
+        h_out = torch.empty((n_cb, K // 8), dtype=torch.uint8, pin_memory=True)
+        h_noi = torch.empty(n_cb, dtype=torch.uint8, pin_memory=True)
+        h_ok = torch.empty(n_cb, dtype=torch.uint8, pin_memory=True)
+        Ks = np.full(n_cb, K, np.uint32)
+        kinds = np.full(n_cb, sb.CRC_24B, np.uint8)
+        loff = (np.arange(n_cb, dtype=np.uint64) * np.uint64(3 * K + 12))
+        ooff = (np.arange(n_cb, dtype=np.uint64) * np.uint64(K // 8))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+        def e2e_step():
+            r = L.srsb200_tdec_batch(eng.handle, n_cb, vp(Ks), vp(kinds), C.c_void_p(h_llr.data_ptr()), vp(loff), n_cb * (3 * K + 12),
+                                     args.max_iter, MIN_ITER, 1, C.c_void_p(h_out.data_ptr()), vp(ooff), n_cb * (K // 8),
+                                     C.c_void_p(h_noi.data_ptr()), C.c_void_p(h_ok.data_ptr()))
+            if r != 0:
+                raise SystemExit("srsb200_tdec_batch failed: %s" % L.srsb200_last_error().decode())
+
+        for _ in range(2):
+            e2e_step()
+        if not (h_noi.numpy() == noi).all():
+            raise SystemExit("host-path iteration counts differ from the device-resident path")
+        e_steps = max(3, min(args.steps, 10))
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()  # synchronous: results are in the host buffers on return
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": bits_per_step * e_steps / dt / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": int(n_cb * (3 * K + 12) * 2),
+               "d2h_bytes_per_step": int(n_cb * (K // 8) + 2 * n_cb), "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
+               "api": "srsb200_tdec_batch (host pointers, pinned), wall clock around synchronous calls"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    dec_ms, dec_n = prof["decode"]
+    per_launch_ms = dec_ms / max(dec_n, 1)
+    half_iters = float(noi.astype(np.float64).sum())  # executed half-iterations of this rank's batch (per launch)
+    alg_bytes = n_cb * (2 * (3 * K + 12) + K // 8 + 2)  # LLRs in once, hard bits + flags out once
+    hbm_achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+    alg_ops = ALG_OPS_PER_BIT_HALFITER * K * half_iters
+    int_achieved = alg_ops / (per_launch_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            traffic = json.load(f).get("tdec_group_kernel_bytes_per_launch")
+    except Exception:
+        pass
+    out = {
+        "metric": "turbo-decoded info Mbit/s (K=6144, 4 iter)", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16", "data": "synthetic",
+        "config": {"workload": WORKLOAD if (n_cb == N_CB and args.max_iter == MAX_ITER) else "NON-DEFAULT: %d CB, max_iter %d" % (n_cb, args.max_iter),
+                   "code_blocks_per_gpu": n_cb, "K": K, "max_half_iterations": args.max_iter, "sharding": "independent code-block batches per GPU, no collective",
+                   "l2": "inputs (%.0f MB LLRs + %.0f MB streams per step) exceed the 126 MB L2" % (n_cb * (3 * K + 12) * 2 / 1e6, n_cb * 5 * (K + 32) * 2 / 1e6)},
+        "mean_half_iterations": float(noi.mean()), "crc_ok_fraction": float(ok.mean()),
+        "noi_hist": {str(int(k)): int(v) for k, v in zip(*np.unique(noi, return_counts=True))},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
+        "roofline": {"bound": "hbm", "kernel": "tdec_group_kernel", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (%s)" % peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
+                     "note": "compulsory bytes (6.13 B/info bit); the kernel is integer-issue bound, see roofline_int"},
+        "roofline_int": {"bound": "int16x2 issue (VIADD/VIMNMX/VIADDMNMX .16x2, two pipes)", "kernel": "tdec_group_kernel", "achieved": int_achieved,
+                         "peak": INT_PEAK_TOPS, "unit": "T packed-instr/s", "frac": int_achieved / INT_PEAK_TOPS,
+                         "algorithmic_ops_per_launch": alg_ops, "executed_half_iterations_per_launch": half_iters,
+                         "peak_source": "tools/microbench/int16x2_issue.cu on this pool (profiles/r01_int16x2_issue.txt)"},
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        cb, _, _, _ = run_cpu(0, 10.0, 4321)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

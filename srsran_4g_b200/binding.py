@@ -37,6 +37,8 @@ def lib():
         L.srsb200_engine_stream.argtypes = [vp]
         L.srsb200_engine_stream.restype = vp
         L.srsb200_engine_sync.argtypes = [vp]
+        L.srsb200_engine_profile.argtypes = [vp, i32]
+        L.srsb200_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
         L.srsb200_cbsize.argtypes = [u32]
         L.srsb200_cbindex.argtypes = [u32]
         L.srsb200_cbsegm.argtypes = [u32, C.POINTER(u32)]
@@ -162,6 +164,17 @@ class Engine:
 
     def sync(self):
         _check(self._L.srsb200_engine_sync(self._h), "srsb200_engine_sync")
+
+    def profile(self, enable):
+        _check(self._L.srsb200_engine_profile(self._h, int(enable)), "srsb200_engine_profile")
+
+    def profile_read(self):
+        """-> {kernel kind: (summed ms, launches)} since the last read; kinds: extract, decode, emit, rm, tbcrc"""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_uint64 * 8)()
+        _check(self._L.srsb200_engine_profile_read(self._h, ms, cnt), "srsb200_engine_profile_read")
+        names = ["extract", "decode", "emit", "rm", "tbcrc"]
+        return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names)}
 
     # ---- batched decode, host buffers
     def tdec_batch(self, K, llr, max_iter, early_stop=True, min_iter=2, crc_kind=CRC_24B):

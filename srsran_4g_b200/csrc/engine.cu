@@ -173,6 +173,36 @@ struct srsb200_engine {
   // scratch for the host-pointer APIs (grown on demand)
   void*  d_scratch[8]   = {nullptr};
   size_t scratch_cap[8] = {0};
+
+  // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
+  bool profiling = false;
+  struct ProfEv { cudaEvent_t a, b; int kind; };
+  std::vector<ProfEv> prof;
+
+  // last plan built by srsb200_tdec_batch, reused when the next submission has the same shape
+  struct srsb200_plan* cached_plan = nullptr;
+  std::vector<uint32_t> cached_K;
+  std::vector<uint8_t>  cached_kind;
+  std::vector<uint64_t> cached_loff, cached_ooff;
+};
+
+struct ProfScope {
+  srsb200_engine* e; int kind; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(srsb200_engine* e_, int k) : e(e_), kind(k)
+  {
+    if (e->profiling) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, e->stream);
+    }
+  }
+  ~ProfScope()
+  {
+    if (a) {
+      cudaEventRecord(b, e->stream);
+      e->prof.push_back({a, b, kind});
+    }
+  }
 };
 
 static int ensure_scratch(srsb200_engine* e, int slot, size_t bytes, void** out)
@@ -281,12 +311,38 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  if (e->cached_plan) srsb200_plan_destroy(e->cached_plan);
   for (void* p : e->owned) cudaFree(p);
   for (int i = 0; i < 8; i++)
     if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);
   cudaFree(e->d_ktab);
   cudaStreamDestroy(e->stream);
   delete e;
+}
+
+extern "C" int srsb200_engine_profile(srsb200_engine_t* e, int enable)
+{
+  if (!e) return SRSB200_ERROR_INVALID_INPUTS;
+  e->profiling = enable != 0;
+  return SRSB200_SUCCESS;
+}
+// ms[kind] += elapsed, cnt[kind] += launches; kinds: 0 extract, 1 decode, 2 emit, 3 rate-dematch, 4 tb-crc. Synchronises.
+extern "C" int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[8])
+{
+  if (!e) return SRSB200_ERROR_INVALID_INPUTS;
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < 8; i++) { ms[i] = 0; cnt[i] = 0; }
+  for (auto& p : e->prof) {
+    float t = 0;
+    cudaEventElapsedTime(&t, p.a, p.b);
+    ms[p.kind & 7] += t;
+    cnt[p.kind & 7]++;
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  e->prof.clear();
+  return SRSB200_SUCCESS;
 }
 
 extern "C" uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e) { return e ? e->launches : 0; }
@@ -414,17 +470,23 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
 {
   if (p->n_groups == 0) return SRSB200_SUCCESS;
   if (do_extract) {
+    ProfScope ps(e, 0);
     dim3 grid(p->max_R / 32, p->n_groups);
     extract_kernel<<<grid, 256, 0, e->stream>>>(p->d_groups, p->d_ws, d_llr, p->d_llr_off);
     e->launches++;
   }
-  tdec_group_kernel<<<p->n_groups, 32, sizeof(WarpSmem), e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, d_noi, d_ok, max_iter, min_iter,
-                                                                     early_stop, start_iter, nullptr);
-  e->launches++;
-  dim3 egrid((SRSB200_MAX_K / 32 + 127) / 128, p->n_groups * 64);
-  egrid.x = (p->max_R / 32 + 127) / 128;
-  emit_kernel<<<egrid, 128, 0, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off);
-  e->launches++;
+  {
+    ProfScope ps(e, 1);
+    tdec_group_kernel<<<p->n_groups, 32, sizeof(WarpSmem), e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, d_noi, d_ok, max_iter, min_iter,
+                                                                       early_stop, start_iter, nullptr);
+    e->launches++;
+  }
+  {
+    ProfScope ps(e, 2);
+    dim3 egrid((p->max_R / 32 + 127) / 128, p->n_groups * 64);
+    emit_kernel<<<egrid, 128, 0, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off);
+    e->launches++;
+  }
   CUDA_TRY(cudaGetLastError());
   return SRSB200_SUCCESS;
 }
@@ -453,12 +515,32 @@ extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
   srsb200_plan* p = nullptr;
-  int r = build_plan(e, n, K, crc_kind, 0, SRSB200_CRC_NONE, llr_offset, out_offset, &p);
-  if (r) return r;
+  int r = 0;
+  {
+    // same shape as the previous submission -> reuse its plan (group table + workspace)
+    bool same = e->cached_plan && e->cached_K.size() == n && memcmp(e->cached_K.data(), K, n * sizeof(uint32_t)) == 0 &&
+                memcmp(e->cached_loff.data(), llr_offset, n * sizeof(uint64_t)) == 0 &&
+                memcmp(e->cached_ooff.data(), out_offset, n * sizeof(uint64_t)) == 0;
+    if (same) {
+      for (uint32_t i = 0; i < n && same; i++) same = e->cached_kind[i] == (crc_kind ? crc_kind[i] : (uint8_t)SRSB200_CRC_NONE);
+    }
+    if (!same) {
+      if (e->cached_plan) srsb200_plan_destroy(e->cached_plan);
+      e->cached_plan = nullptr;
+      r = build_plan(e, n, K, crc_kind, 0, SRSB200_CRC_NONE, llr_offset, out_offset, &p);
+      if (r) return r;
+      e->cached_plan = p;
+      e->cached_K.assign(K, K + n);
+      e->cached_kind.resize(n);
+      for (uint32_t i = 0; i < n; i++) e->cached_kind[i] = crc_kind ? crc_kind[i] : (uint8_t)SRSB200_CRC_NONE;
+      e->cached_loff.assign(llr_offset, llr_offset + n);
+      e->cached_ooff.assign(out_offset, out_offset + n);
+    }
+    p = e->cached_plan;
+  }
   void *d_llr, *d_out, *d_noi, *d_ok;
   if (ensure_scratch(e, 0, llr_len * sizeof(int16_t), &d_llr) || ensure_scratch(e, 1, out_len, &d_out) || ensure_scratch(e, 2, n, &d_noi) ||
       ensure_scratch(e, 3, n, &d_ok)) {
-    srsb200_plan_destroy(p);
     return SRSB200_ERROR;
   }
   cudaError_t ce = cudaMemcpyAsync(d_llr, llr, llr_len * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream);
@@ -469,7 +551,6 @@ extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_
   if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(noi, d_noi, n, cudaMemcpyDeviceToHost, e->stream);
   if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(crc_ok, d_ok, n, cudaMemcpyDeviceToHost, e->stream);
   if (ce == cudaSuccess && r == 0) ce = cudaStreamSynchronize(e->stream);
-  srsb200_plan_destroy(p);
   if (ce != cudaSuccess) {
     cudaGetLastError();
     return fail(SRSB200_ERROR, "batch decode failed: %s", cudaGetErrorString(ce));

@@ -301,7 +301,9 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   CUDA_TRY(cudaMemset(e->d_ktab, 0, sizeof(KTable) * LTE_NOF_CB_SIZES));
   crc_position_words(0x1864CFBu, e->crc_words[SRSB200_CRC_24A]);
   crc_position_words(0x1800063u, e->crc_words[SRSB200_CRC_24B]);
-  CUDA_TRY(cudaFuncSetAttribute(tdec_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
   *out = e;
   return SRSB200_SUCCESS;
 }
@@ -365,6 +367,10 @@ struct srsb200_plan {
   uint64_t  ws_bytes = 0;
   uint64_t* d_llr_off = nullptr;
   uint64_t* d_out_off = nullptr;
+  // decode state that lives across the launches of one decode (and across srsb200_tdec_iteration calls)
+  uint32_t* d_crc_acc = nullptr;  // [n_cb] running CRC of the current half-iteration
+  uint8_t*  d_done = nullptr;     // [n_cb]
+  uint8_t*  d_active = nullptr;   // [n_groups]
   bool      uniform = false;
 };
 
@@ -418,7 +424,10 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
   if ((ce = cudaMalloc(&p->d_groups, sizeof(Group) * std::max<uint32_t>(1, p->n_groups))) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_ws, std::max<uint64_t>(256, p->ws_bytes))) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_llr_off, sizeof(uint64_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
-      (ce = cudaMalloc(&p->d_out_off, sizeof(uint64_t) * std::max<uint32_t>(1, n))) != cudaSuccess) {
+      (ce = cudaMalloc(&p->d_out_off, sizeof(uint64_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
+      (ce = cudaMalloc(&p->d_crc_acc, sizeof(uint32_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
+      (ce = cudaMalloc(&p->d_done, std::max<uint32_t>(1, n))) != cudaSuccess ||
+      (ce = cudaMalloc(&p->d_active, std::max<uint32_t>(1, p->n_groups))) != cudaSuccess) {
     cudaGetLastError();
     srsb200_plan_destroy(p);
     return fail(SRSB200_ERROR, "plan allocation failed: %s", cudaGetErrorString(ce));
@@ -451,6 +460,9 @@ extern "C" void srsb200_plan_destroy(srsb200_plan_t* p)
   cudaFree(p->d_ws);
   cudaFree(p->d_llr_off);
   cudaFree(p->d_out_off);
+  cudaFree(p->d_crc_acc);
+  cudaFree(p->d_done);
+  cudaFree(p->d_active);
   delete p;
 }
 
@@ -475,11 +487,33 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     extract_kernel<<<grid, 256, 0, e->stream>>>(p->d_groups, p->d_ws, d_llr, p->d_llr_off);
     e->launches++;
   }
+  if (max_iter == 0) max_iter = 1;  // run_all is a do-while (turbodecoder.c:542-546)
+  if (start_iter == 0) {
+    CUDA_TRY(cudaMemsetAsync(p->d_crc_acc, 0, sizeof(uint32_t) * p->n_cb, e->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_done, 0, p->n_cb, e->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_active, 1, p->n_groups, e->stream));
+  }
   {
+    // every half-iteration up to max_iter is enqueued; groups whose code blocks are all done exit at once
     ProfScope ps(e, 1);
-    tdec_group_kernel<<<p->n_groups, 32, sizeof(WarpSmem), e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, d_noi, d_ok, max_iter, min_iter,
-                                                                       early_stop, start_iter, nullptr);
-    e->launches++;
+    const uint32_t nwin_max = (p->max_R + WC - 1) / WC;
+    const dim3 sgrid(p->n_groups, 2), jgrid((nwin_max + 4 * WPJ - 1) / (4 * WPJ), p->n_groups);
+    const size_t ssm = sizeof(ScanSmem), jsm = 4 * sizeof(JobWarpSmem);
+    for (uint32_t n = start_iter; n < max_iter; n++) {
+      if (n == 0) {
+        scan_kernel<0><<<sgrid, 32, ssm, e->stream>>>(p->d_groups, p->d_ws, p->d_active);
+        job_kernel<0><<<jgrid, 128, jsm, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, p->d_active, p->d_done, p->d_crc_acc);
+      } else if ((n & 1u) == 0) {
+        scan_kernel<1><<<sgrid, 32, ssm, e->stream>>>(p->d_groups, p->d_ws, p->d_active);
+        job_kernel<1><<<jgrid, 128, jsm, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, p->d_active, p->d_done, p->d_crc_acc);
+      } else {
+        scan_kernel<2><<<sgrid, 32, ssm, e->stream>>>(p->d_groups, p->d_ws, p->d_active);
+        job_kernel<2><<<jgrid, 128, jsm, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, p->d_active, p->d_done, p->d_crc_acc);
+      }
+      status_kernel<<<p->n_groups, 64, 0, e->stream>>>(p->d_groups, p->d_crc_acc, d_noi, d_ok, p->d_done, p->d_active, n + 1, max_iter, min_iter,
+                                                       early_stop);
+      e->launches += 3;
+    }
   }
   {
     ProfScope ps(e, 2);
@@ -635,6 +669,11 @@ extern "C" int srsb200_tdec_iteration(srsb200_tdec_t* t, const int16_t* input, u
   const uint32_t K = t->current_long_cb;
   bool first = t->n_iter == 0;
   if (first) CUDA_TRY(cudaMemcpyAsync(t->d_in, input, (3 * K + 12) * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
+  if (!first) {
+    // the previous call marked the block done at its own max_iter; re-arm it for one more half-iteration
+    CUDA_TRY(cudaMemsetAsync(t->plan->d_done, 0, t->plan->n_cb, e->stream));
+    CUDA_TRY(cudaMemsetAsync(t->plan->d_active, 1, t->plan->n_groups, e->stream));
+  }
   int r = launch_plan(e, t->plan, t->d_in, (uint32_t)t->n_iter + 1, 1, 0, (uint32_t)t->n_iter, first, t->d_out, t->d_noi, t->d_ok);
   if (r) return r;
   CUDA_TRY(cudaMemcpyAsync(output, t->d_out, K / 8, cudaMemcpyDeviceToHost, e->stream));

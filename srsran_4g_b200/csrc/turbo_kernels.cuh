@@ -4,19 +4,23 @@
  * Design (DESIGN.md has the long form):
  *   - bit-exactness against the reference's generic int16 decoder (turbodecoder_gen.c) forbids windowed/warm-up
  *     recursions: every alpha/beta recursion runs exactly and sequentially in k, with 16-bit WRAPPING arithmetic.
- *   - parallelism comes from the batch: one thread = TWO code blocks packed in the halves of a 32-bit register
- *     (VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2 wrap exactly like the reference's int16 stores - verified by
- *     tools/microbench/int16x2_issue.cu), one warp = a "group" of up to 64 code blocks of equal K in lock-step.
- *   - all soft streams of a group live in HBM as [row k][32 lanes] packed words, so every access of the warp is one
+ *   - one thread = TWO code blocks packed in the halves of a 32-bit register (VIADD.16x2 / VIMNMX.S16x2 /
+ *     VIADDMNMX.S16x2 wrap exactly like the reference's int16 stores - verified by tools/microbench/int16x2_issue.cu);
+ *     one warp = a "group" of up to 64 code blocks of equal K in lock-step.
+ *   - all soft streams of a group live in HBM as [row k][32 lanes] packed words, so every access of a warp is one
  *     coalesced 128-byte row and the QPP (de)interleaver is a *row* move with a warp-uniform row index.
- *   - beta is not stored (98 KB per block): the backward pass keeps the un-normalised state every W steps
- *     (checkpoints), the forward pass recomputes one window of beta into shared memory and then runs alpha + LLR
- *     over that window - bit-identical because the recursion is deterministic from the checkpoint.
- *   - input windows are staged HBM -> shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier,
- *     SASS UBLKCP), double-buffered, so the warp spends no issue slots on loads.
- *   - hard decision, CRC24A/B (by linearity: crc ^= bit ? x^(K-1-pos+24) mod g : 0, position table is warp-uniform)
- *     and the per-code-block early-stop decision are fused into the forward pass; a warp leaves the half-iteration
- *     loop when all of its code blocks are done. The whole turbo decode of a group is ONE kernel launch.
+ *   - a half-iteration (one constituent MAP decode + glue) is three launches:
+ *       scan_kernel   : the two inherently sequential recursions, alpha forward and beta backward, one warp each per
+ *                       group, storing only the state every WC steps (checkpoints). Exact by construction.
+ *       job_kernel    : window-parallel. A warp takes a window of WC steps, its alpha checkpoint at the start and its
+ *                       beta checkpoint at the end, recomputes beta of the window into REGISTERS (8 steps at a time),
+ *                       runs alpha + LLR + extrinsic/QPP write-back + hard decision + CRC (by linearity) over it.
+ *                       Bit-identical because the recursions are deterministic from the checkpointed states. This
+ *                       is where ~75% of the instructions are, spread over K/WC x more warps than code-block groups.
+ *       status_kernel : per-code-block CRC verdict, half-iteration count and early-stop flag; groups whose blocks
+ *                       are all done make the later launches exit immediately.
+ *   - input windows are staged HBM -> shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier, SASS
+ *     UBLKCP), double-buffered per warp, so warps spend no issue slots on loads.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -24,7 +28,9 @@
 
 namespace srsb200 {
 
-constexpr int W        = 32;  // window / checkpoint spacing (trellis steps); multiple of 8
+constexpr int W        = 32;  // rows per staged chunk of the scan kernels; streams are padded to a multiple of W rows
+constexpr int WC       = 16;  // checkpoint spacing = window of one job = one hard-bit word
+constexpr int WPJ      = 8;   // windows per job warp
 constexpr int LANES    = 32;
 constexpr int NEG_INF2 = 0xD8F0D8F0;  // two int16 of -10000 (turbodecoder_gen.c:37)
 
@@ -46,14 +52,14 @@ struct Group {
 };
 
 // workspace layout of one group (all uint32 [rows][32]):
-//   syst[R] par0[R] par1[R] app1p[R] app2[R] ckpt[(R/W+1)*8] bits1[R/16] bits2[R/16]
+//   syst[R] par0[R] par1[R] app1p[R] app2[R] ckA[(R/WC+1)*8] ckB[(R/WC+1)*8] bits1[R/16] bits2[R/16]
 __host__ __device__ inline uint64_t group_ws_words(uint32_t R)
 {
-  return (uint64_t)LANES * (5ull * R + (R / W + 1) * 8ull + 2ull * (R / 16));
+  return (uint64_t)LANES * (5ull * R + 2ull * (R / WC + 1) * 8ull + 2ull * (R / 16));
 }
 
 struct GroupPtrs {
-  uint32_t *syst, *par0, *par1, *app1p, *app2, *ckpt, *bits1, *bits2;
+  uint32_t *syst, *par0, *par1, *app1p, *app2, *ckA, *ckB, *bits1, *bits2;
 };
 __host__ __device__ inline GroupPtrs group_ptrs(uint8_t* ws, const Group& g)
 {
@@ -65,8 +71,9 @@ __host__ __device__ inline GroupPtrs group_ptrs(uint8_t* ws, const Group& g)
   p.par1      = b + 2 * s;
   p.app1p     = b + 3 * s;
   p.app2      = b + 4 * s;
-  p.ckpt      = b + 5 * s;
-  p.bits1     = p.ckpt + (uint64_t)(g.R / W + 1) * 8 * LANES;
+  p.ckA       = b + 5 * s;
+  p.ckB       = p.ckA + (uint64_t)(g.R / WC + 1) * 8 * LANES;
+  p.bits1     = p.ckB + (uint64_t)(g.R / WC + 1) * 8 * LANES;
   p.bits2     = p.bits1 + (uint64_t)(g.R / 16) * LANES;
   return p;
 }
@@ -159,45 +166,55 @@ __device__ __forceinline__ void fence_proxy_async()
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-// ---------------------------------------------------------------- shared-memory image of one warp
-struct Stage {
-  uint32_t s[3][W][LANES];  // up to three input streams, W rows each
-  uint2    tab[W];          // (scatter row, CRC position word) per step
+// forward recursion step without LLR (alpha part of map_gen_alpha, turbodecoder_gen.c:148-191)
+__device__ __forceinline__ void alpha_step(uint32_t (&a)[8], uint32_t x, uint32_t y)
+{
+  uint32_t xy = padd(x, y);
+  uint32_t n0 = paddmax(a[1], xy, a[0]);
+  uint32_t n1 = paddmax(a[3], y, padd(a[2], x));
+  uint32_t n2 = paddmax(a[4], y, padd(a[5], x));
+  uint32_t n3 = paddmax(a[6], xy, a[7]);
+  uint32_t n4 = paddmax(a[0], xy, a[1]);
+  uint32_t n5 = paddmax(a[2], y, padd(a[3], x));
+  uint32_t n6 = paddmax(a[5], y, padd(a[4], x));
+  uint32_t n7 = paddmax(a[7], xy, a[6]);
+  a[0] = n0; a[1] = n1; a[2] = n2; a[3] = n3; a[4] = n4; a[5] = n5; a[6] = n6; a[7] = n7;
+}
+
+// hard decision of both halves: bit 15 / bit 31 set iff the int16 is > 0  (tdec_gen_decision_byte: app > 0)
+__device__ __forceinline__ uint32_t positive_mask(uint32_t v)
+{
+  return padd(pmax(v, 0u), 0x7fff7fffu) & 0x80008000u;
+}
+
+// ---------------------------------------------------------------- scan kernel: sequential alpha / beta recursions
+struct ScanStage {
+  uint32_t s[3][W][LANES];
 };
-struct WarpSmem {
-  Stage    st[2];
-  uint4    beta[W][2][LANES];  // recomputed beta window: [k - lo - 1][state half][lane] (conflict-free 128-bit)
-  uint64_t bar[2];
+struct ScanSmem {
+  ScanStage st[2];
+  uint64_t  bar[2];
 };
 
-struct Pipe {
-  // double-buffered chunk loader; all members are warp-uniform scalars (no dynamically indexed arrays -> no stack)
-  WarpSmem*       sm;
+struct ScanPipe {
+  // double-buffered chunk loader (chunks of W rows); all members are warp-uniform scalars
+  ScanSmem*       sm;
   const uint32_t *src0, *src1, *src2;
-  const uint2*    tab;
   int             held0, held1;
   bool            pend0, pend1;
   uint32_t        phase0, phase1;
 
-  __device__ __forceinline__ void reset(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint2* t)
-  {
-    src0 = a; src1 = b; src2 = c; tab = t;
-    held0 = held1 = -1;
-    pend0 = pend1 = false;
-  }
   __device__ __forceinline__ void issue(int c)
   {
     const int s = c & 1;
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
-      Stage&    st    = sm->st[s];
-      uint64_t* bar   = &sm->bar[s];
-      uint32_t  bytes = (src2 ? 3u : 2u) * W * LANES * 4 + W * 8;
-      mbar_expect_tx(bar, bytes);
+      ScanStage& st  = sm->st[s];
+      uint64_t*  bar = &sm->bar[s];
+      mbar_expect_tx(bar, (src2 ? 3u : 2u) * W * LANES * 4);
       bulk_g2s(&st.s[0][0][0], src0 + (size_t)c * W * LANES, W * LANES * 4, bar);
       bulk_g2s(&st.s[1][0][0], src1 + (size_t)c * W * LANES, W * LANES * 4, bar);
       if (src2) bulk_g2s(&st.s[2][0][0], src2 + (size_t)c * W * LANES, W * LANES * 4, bar);
-      bulk_g2s(&st.tab[0], tab + (size_t)c * W, W * 8, bar);
     }
     if (s) { held1 = c; pend1 = true; } else { held0 = c; pend0 = true; }
   }
@@ -205,7 +222,7 @@ struct Pipe {
   {
     if (c >= 0 && ((c & 1) ? held1 : held0) != c) issue(c);
   }
-  __device__ __forceinline__ const Stage& acquire(int c)
+  __device__ __forceinline__ const ScanStage& acquire(int c)
   {
     const int s = c & 1;
     if ((s ? held1 : held0) != c) issue(c);
@@ -217,41 +234,6 @@ struct Pipe {
   }
 };
 
-// hard decision of both halves: bit 15 / bit 31 set iff the int16 is > 0  (tdec_gen_decision_byte: app > 0)
-__device__ __forceinline__ uint32_t positive_mask(uint32_t v)
-{
-  return padd(pmax(v, 0u), 0x7fff7fffu) & 0x80008000u;
-}
-
-struct LaneState {
-  uint32_t crc_lo, crc_hi;    // running CRC (linear accumulation) of the two code blocks
-  uint32_t bitacc;            // 16 decisions of each code block (LSB = earliest step)
-};
-
-/*
- * One half-iteration (one constituent MAP decode + glue) for the warp's group.
- * MODE 0: DEC1 on the first half-iteration (no a-priori)     x = syst,          y = par0, writes app2[rev[i]] = L
- * MODE 1: DEC1 with a-priori                                  x = syst + app1p,  y = par0, writes app2[rev[i]] = L - app1p
- * MODE 2: DEC2                                                x = app2,          y = par1, writes app1p[fwd[i]] = L - app2
- * (turbodecoder_iter.h:104-128 with the two vec_sub + vec_lut glue steps folded into the write-back)
- */
-template <int MODE>
-__device__ __forceinline__ void half_iteration(WarpSmem* sm, Pipe& pipe, const GroupPtrs& gp, const Group& g, const KTable& kt,
-                                               uint32_t keep_mask, LaneState& ls)
-{
-  const int      lane = threadIdx.x & 31;
-  const uint32_t K    = g.K;
-  const int      cK   = (int)(K / W);          // chunk holding rows K..K+2
-  const int      nwin = (int)((K + W - 1) / W);
-
-  const uint32_t* in0 = (MODE == 2) ? gp.app2 : gp.syst;
-  const uint32_t* in1 = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
-  const uint32_t* in2 = (MODE == 1) ? gp.par0 : nullptr;
-  const uint2*    tab = (MODE == 2) ? kt.dec2[g.crc_kind] : kt.dec1[g.crc_kind];
-  uint32_t*       dst = (MODE == 2) ? gp.app1p : gp.app2;
-  uint32_t*       bits = (MODE == 2) ? gp.bits2 : gp.bits1;
-  pipe.reset(in0, in1, in2, tab);
-
 #define LOAD_XY(st, r)                                                   \
   uint32_t x = (st).s[0][(r)][lane];                                     \
   uint32_t y;                                                            \
@@ -262,38 +244,73 @@ __device__ __forceinline__ void half_iteration(WarpSmem* sm, Pipe& pipe, const G
     y = (st).s[1][(r)][lane];                                            \
   }
 
-  // ---------------- backward pass: checkpoints of un-normalised beta at k = multiples of W and k = K
-  {
-    uint32_t b[8];
+/*
+ * MODE 0: DEC1 on the first half-iteration (no a-priori)   x = syst,          y = par0
+ * MODE 1: DEC1 with a-priori                                x = syst + app1p,  y = par0
+ * MODE 2: DEC2                                              x = app2,          y = par1
+ * grid = (n_groups, 2): blockIdx.y == 0 runs the backward (beta) recursion, 1 the forward (alpha) recursion.
+ * Checkpoints: ckB[ceil(k/WC)] = un-normalised beta[k] for k = multiples of WC and k = K (what alpha step k consumes);
+ *              ckA[k/WC] = alpha state entering step k+1 (post-normalisation) for k = multiples of WC.
+ */
+template <int MODE>
+__global__ void __launch_bounds__(32) scan_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const uint8_t* __restrict__ group_active)
+{
+  if (!group_active[blockIdx.x]) return;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ScanSmem*       sm   = reinterpret_cast<ScanSmem*>(smem_raw);
+  const int       lane = threadIdx.x;
+  const Group&    g    = groups[blockIdx.x];
+  const GroupPtrs gp   = group_ptrs(ws, g);
+  const uint32_t  K    = g.K;
+  if (lane == 0) {
+    mbar_init(&sm->bar[0], 1);
+    mbar_init(&sm->bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  ScanPipe pipe;
+  pipe.sm     = sm;
+  pipe.phase0 = pipe.phase1 = 0;
+  pipe.held0 = pipe.held1 = -1;
+  pipe.pend0 = pipe.pend1 = false;
+  pipe.src0 = (MODE == 2) ? gp.app2 : gp.syst;
+  pipe.src1 = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
+  pipe.src2 = (MODE == 1) ? gp.par0 : nullptr;
+  const int nwin = (int)((K + WC - 1) / WC);
+
+  if (blockIdx.y == 0) {
+    // ---------------- backward recursion (map_gen_beta)
+    const int cK = (int)(K / W);  // chunk holding rows K..K+2
+    uint32_t  b[8];
     b[0] = 0u;
 #pragma unroll
     for (int i = 1; i < 8; i++) b[i] = NEG_INF2;
     pipe.prefetch(cK);
     pipe.prefetch(cK - 1);
     for (int c = cK; c >= 0; c--) {
-      const Stage& st = pipe.acquire(c);
+      const ScanStage& st = pipe.acquire(c);
       if (c == cK) {
-        // termination steps k = K+2, K+1, K (rows beyond K carry no a-priori: app1p rows >= K stay zero)
+        // termination steps k = K+2, K+1, K (no a-priori there: app1p rows >= K stay zero); no normalisation at k = K
 #pragma unroll
         for (int r = 2; r >= 0; r--) {
           LOAD_XY(st, (K - (uint32_t)cK * W) + r);
           beta_step(b, x, y);
         }
-        uint32_t* ck = gp.ckpt + (size_t)nwin * 8 * LANES + lane;
+        uint32_t* ck = gp.ckB + (size_t)nwin * 8 * LANES + lane;
 #pragma unroll
         for (int i = 0; i < 8; i++) ck[i * LANES] = b[i];
       }
-      int top = (int)min(K, (uint32_t)(c + 1) * W) - 4;
+      const int top = (int)min(K, (uint32_t)(c + 1) * W) - 4;
       for (int kb = top; kb >= c * W; kb -= 4) {
-        int r = kb - c * W;
+        const int r = kb - c * W;
 #pragma unroll
         for (int j = 3; j >= 0; j--) {
           LOAD_XY(st, r + j);
           beta_step(b, x, y);
         }
         // kb % 4 == 0 and kb < K: checkpoint first (un-normalised, like beta[8*k+i]), then normalise
-        if ((kb % W) == 0 && kb > 0) {
-          uint32_t* ck = gp.ckpt + (size_t)(kb / W) * 8 * LANES + lane;
+        if ((kb % WC) == 0 && kb > 0) {
+          uint32_t* ck = gp.ckB + (size_t)(kb / WC) * 8 * LANES + lane;
 #pragma unroll
           for (int i = 0; i < 8; i++) ck[i * LANES] = b[i];
         }
@@ -301,99 +318,99 @@ __device__ __forceinline__ void half_iteration(WarpSmem* sm, Pipe& pipe, const G
       }
       pipe.prefetch(c - 2);
     }
-  }
-
-  // ---------------- forward pass: per window recompute beta into shared memory, then alpha + LLR + glue
-  {
-    uint32_t a[8];
+  } else {
+    // ---------------- forward recursion (alpha part of map_gen_alpha)
+    const int nch = (int)((K + W - 1) / W);
+    uint32_t  a[8];
     a[0] = 0u;
 #pragma unroll
     for (int i = 1; i < 8; i++) a[i] = NEG_INF2;
-    ls.crc_lo = ls.crc_hi = 0u;
-    ls.bitacc = 0u;
     pipe.prefetch(0);
-    pipe.prefetch(1 < nwin ? 1 : -1);
-    for (int w = 0; w < nwin; w++) {
-      const int lo = w * W;
-      const int hi = (int)min((uint32_t)lo + W, K);
-      const int nq = (hi - lo) / 4;
-      uint32_t  b[8];
-      {
-        const uint32_t* ck = gp.ckpt + (size_t)(w + 1) * 8 * LANES + lane;
+    pipe.prefetch(1 < nch ? 1 : -1);
+    for (int c = 0; c < nch; c++) {
+      const ScanStage& st  = pipe.acquire(c);
+      const int        len = (int)min((uint32_t)W, K - (uint32_t)c * W);
+      for (int r = 0; r < len; r += 4) {
+        if ((r % WC) == 0) {
+          uint32_t* ck = gp.ckA + (size_t)((c * W + r) / WC) * 8 * LANES + lane;
 #pragma unroll
-        for (int i = 0; i < 8; i++) b[i] = ck[i * LANES];
-      }
-      const Stage& st = pipe.acquire(w);
-      // beta[hi] (un-normalised) is what alpha step k = hi consumes
-      sm->beta[hi - lo - 1][0][lane] = make_uint4(b[0], b[1], b[2], b[3]);
-      sm->beta[hi - lo - 1][1][lane] = make_uint4(b[4], b[5], b[6], b[7]);
-      if ((uint32_t)hi < K) normalise(b);  // hi % 4 == 0 always
-      for (int q = nq - 1; q >= 0; q--) {
-        int r = 4 * q;
-#pragma unroll
-        for (int j = 3; j >= 1; j--) {
-          LOAD_XY(st, r + j);
-          beta_step(b, x, y);
-          sm->beta[r + j - 1][0][lane] = make_uint4(b[0], b[1], b[2], b[3]);
-          sm->beta[r + j - 1][1][lane] = make_uint4(b[4], b[5], b[6], b[7]);
+          for (int i = 0; i < 8; i++) ck[i * LANES] = a[i];
         }
-        if (q > 0) {
-          LOAD_XY(st, r);
-          beta_step(b, x, y);
-          sm->beta[r - 1][0][lane] = make_uint4(b[0], b[1], b[2], b[3]);
-          sm->beta[r - 1][1][lane] = make_uint4(b[4], b[5], b[6], b[7]);
-          normalise(b);
-        }
-      }
-      // alpha steps k = lo+1 .. hi  (trellis step index i = k-1 = lo + r)
-      for (int q = 0; q < nq; q++) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const int r = 4 * q + j;
-          LOAD_XY(st, r);
-          uint32_t ap = (MODE == 1) ? st.s[1][r][lane] : (MODE == 2 ? st.s[0][r][lane] : 0u);
-          uint4    bl = sm->beta[r][0][lane], bh = sm->beta[r][1][lane];
-          uint32_t L  = alpha_llr_step(a, bl, bh, x, y);
-          if (j == 3) normalise(a);
-          uint2 t = st.tab[r];
-          dst[(size_t)t.x * LANES + lane] = (MODE == 0) ? L : psub(L, ap);
-          uint32_t pos = positive_mask(L);
-          ls.crc_lo ^= (pos & 0x8000u) ? t.y : 0u;
-          ls.crc_hi ^= (pos & 0x80000000u) ? t.y : 0u;
-          ls.bitacc = ((ls.bitacc >> 1) & 0x7fff7fffu) | pos;
-          if (((lo + r) & 15) == 15) {
-            uint32_t* bw  = bits + (size_t)((lo + r) >> 4) * LANES + lane;
-            uint32_t  old = *bw;
-            *bw           = (ls.bitacc & ~keep_mask) | (old & keep_mask);
-          }
+          LOAD_XY(st, r + j);
+          alpha_step(a, x, y);
         }
+        normalise(a);  // k = c*W + r + 4 is a multiple of 4
       }
-      pipe.prefetch(w + 2 < nwin ? w + 2 : -1);
-    }
-    if (K & 15u) {
-      // K = 8 mod 16: the last eight decisions sit in the upper byte of each half
-      uint32_t* bw  = bits + (size_t)(K >> 4) * LANES + lane;
-      uint32_t  old = *bw;
-      *bw           = (((ls.bitacc >> 8) & 0x00ff00ffu) & ~keep_mask) | (old & keep_mask);
+      pipe.prefetch(c + 2 < nch ? c + 2 : -1);
     }
   }
-#undef LOAD_XY
+}
+
+// ---------------------------------------------------------------- job kernel: window-parallel recompute + LLR + glue
+struct JobStage {
+  uint32_t s[3][WC][LANES];
+  uint2    tab[WC];
+};
+struct JobWarpSmem {
+  JobStage st[2];
+  uint64_t bar[2];
+};
+
+// forward recursion + LLR step (map_gen_alpha, turbodecoder_gen.c:135-194) with beta[k] in registers; returns m1 - m0
+__device__ __forceinline__ uint32_t alpha_llr_step(uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t x, uint32_t y)
+{
+  uint32_t xy = padd(x, y);
+  // information bit 0 branches into state i (m_b[i]) and information bit 1 branches (new[i])
+  uint32_t z0 = a[0], z1 = padd(a[3], y), z2 = padd(a[4], y), z3 = a[7];
+  uint32_t z4 = a[1], z5 = padd(a[2], y), z6 = padd(a[5], y), z7 = a[6];
+  uint32_t o0 = padd(a[1], xy), o1 = padd(a[2], x), o2 = padd(a[5], x), o3 = padd(a[6], xy);
+  uint32_t o4 = padd(a[0], xy), o5 = padd(a[3], x), o6 = padd(a[4], x), o7 = padd(a[7], xy);
+  // two chains per maximum keep the dependent depth short
+  uint32_t m0a = padd(z0, b[0]), m0b = padd(z4, b[4]);
+  m0a = paddmax(z1, b[1], m0a); m0b = paddmax(z5, b[5], m0b);
+  m0a = paddmax(z2, b[2], m0a); m0b = paddmax(z6, b[6], m0b);
+  m0a = paddmax(z3, b[3], m0a); m0b = paddmax(z7, b[7], m0b);
+  uint32_t m1a = padd(o0, b[0]), m1b = padd(o4, b[4]);
+  m1a = paddmax(o1, b[1], m1a); m1b = paddmax(o5, b[5], m1b);
+  m1a = paddmax(o2, b[2], m1a); m1b = paddmax(o6, b[6], m1b);
+  m1a = paddmax(o3, b[3], m1a); m1b = paddmax(o7, b[7], m1b);
+  a[0] = pmax(z0, o0); a[1] = pmax(z1, o1); a[2] = pmax(z2, o2); a[3] = pmax(z3, o3);
+  a[4] = pmax(z4, o4); a[5] = pmax(z5, o5); a[6] = pmax(z6, o6); a[7] = pmax(z7, o7);
+  return psub(pmax(m1a, m1b), pmax(m0a, m0b));
 }
 
 /*
- * The whole turbo decode of one group: one warp, one launch. status arrays are per code block.
+ * grid = (ceil(nwin_max / (4*WPJ)), n_groups), block = 128 (4 warps). Warp j of block bx handles windows
+ * [(4*bx + j)*WPJ, +WPJ) of its group. Write-back (turbodecoder_iter.h:104-128 with the vec_sub / vec_lut glue folded in):
+ *   MODE 0: app2[rev[i]]  = L            MODE 1: app2[rev[i]] = L - app1p[i]          MODE 2: app1p[fwd[i]] = L - app2[i]
  */
-__global__ void __launch_bounds__(32, 1)
-tdec_group_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws, uint8_t* __restrict__ noi_out,
-                  uint8_t* __restrict__ ok_out, uint32_t max_iter, uint32_t min_iter, int early_stop, uint32_t start_iter,
-                  uint32_t* __restrict__ resume_state)
+template <int MODE>
+__global__ void __launch_bounds__(128) job_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws,
+                                                  const uint8_t* __restrict__ group_active, const uint8_t* __restrict__ done,
+                                                  uint32_t* __restrict__ crc_acc)
 {
+  if (!group_active[blockIdx.y]) return;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  WarpSmem*      sm   = reinterpret_cast<WarpSmem*>(smem_raw);
-  const int      lane = threadIdx.x;
-  const Group&   g    = groups[blockIdx.x];
-  const KTable&  kt   = ktabs[g.kidx];
-  const GroupPtrs gp  = group_ptrs(ws, g);
+  const int       wid  = threadIdx.x >> 5;
+  const int       lane = threadIdx.x & 31;
+  JobWarpSmem*    sm   = reinterpret_cast<JobWarpSmem*>(smem_raw) + wid;
+  const Group&    g    = groups[blockIdx.y];
+  const uint32_t  K    = g.K;
+  const int       nwin = (int)((K + WC - 1) / WC);
+  const int       w0   = (int)(blockIdx.x * 4 + wid) * WPJ;
+  if (w0 >= nwin) return;
+  const int       w1   = min(w0 + WPJ, nwin);
+  const GroupPtrs gp   = group_ptrs(ws, g);
+  const KTable&   kt   = ktabs[g.kidx];
+
+  const uint32_t* in0  = (MODE == 2) ? gp.app2 : gp.syst;
+  const uint32_t* in1  = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
+  const uint32_t* in2  = (MODE == 1) ? gp.par0 : nullptr;
+  const uint2*    tab  = (MODE == 2) ? kt.dec2[g.crc_kind] : kt.dec1[g.crc_kind];
+  uint32_t*       dst  = (MODE == 2) ? gp.app1p : gp.app2;
+  uint32_t*       bits = (MODE == 2) ? gp.bits2 : gp.bits1;
 
   if (lane == 0) {
     mbar_init(&sm->bar[0], 1);
@@ -401,56 +418,129 @@ tdec_group_kernel(const Group* __restrict__ groups, const KTable* __restrict__ k
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  Pipe pipe;
-  pipe.sm       = sm;
-  pipe.phase0 = pipe.phase1 = 0;
+  auto issue = [&](int w) {
+    // rows [w*WC, w*WC + WC) of each stream (streams are padded to a multiple of W >= WC rows) + the step table
+    if (lane == 0) {
+      JobStage& st  = sm->st[w & 1];
+      uint64_t* bar = &sm->bar[w & 1];
+      mbar_expect_tx(bar, (MODE == 1 ? 3u : 2u) * WC * LANES * 4 + WC * 8);
+      bulk_g2s(&st.s[0][0][0], in0 + (size_t)w * WC * LANES, WC * LANES * 4, bar);
+      bulk_g2s(&st.s[1][0][0], in1 + (size_t)w * WC * LANES, WC * LANES * 4, bar);
+      if (MODE == 1) bulk_g2s(&st.s[2][0][0], in2 + (size_t)w * WC * LANES, WC * LANES * 4, bar);
+      bulk_g2s(&st.tab[0], tab + (size_t)w * WC, WC * 8, bar);
+    }
+  };
+  issue(w0);
 
   const int cb_lo = g.cb[lane], cb_hi = g.cb[32 + lane];
-  // bit0: low-half code block finished, bit1: high-half
-  uint32_t done = (cb_lo < 0 ? 1u : 0u) | (cb_hi < 0 ? 2u : 0u);
-  uint32_t noi_lo = 0, noi_hi = 0, ok_lo = 0, ok_hi = 0;
-  if (start_iter > 0) {
-    // per-object API (srsran_tdec_iteration): continue a decode whose state lives in the workspace
-    noi_lo = noi_hi = start_iter;
-  }
-  if (max_iter == 0) max_iter = 1;  // run_all is a do-while (turbodecoder.c:542-546)
+  uint32_t  keep  = 0;
+  if (cb_lo < 0 || done[cb_lo]) keep |= 0x0000ffffu;
+  if (cb_hi < 0 || done[cb_hi]) keep |= 0xffff0000u;
+  uint32_t crc_lo = 0, crc_hi = 0;
+  uint32_t ph0 = 0, ph1 = 0;
 
-  for (uint32_t n = start_iter; n < max_iter; n++) {
-    uint32_t  keep = ((done & 1u) ? 0x0000ffffu : 0u) | ((done & 2u) ? 0xffff0000u : 0u);
-    LaneState ls;
-    if (n == 0) {
-      half_iteration<0>(sm, pipe, gp, g, kt, keep, ls);
-    } else if ((n & 1u) == 0) {
-      half_iteration<1>(sm, pipe, gp, g, kt, keep, ls);
-    } else {
-      half_iteration<2>(sm, pipe, gp, g, kt, keep, ls);
+  for (int w = w0; w < w1; w++) {
+    const int lo = w * WC;
+    const int hi = (int)min((uint32_t)lo + WC, K);
+    if (w + 1 < w1) {
+      __syncwarp();  // every lane has finished reading the stage the next copy overwrites (window w-1)
+      issue(w + 1);
     }
-    // the scattered rows are read back by bulk async copies (async proxy) in the next half-iteration
-    __threadfence_block();
-    fence_proxy_async();
-    __syncwarp();
-    const uint32_t cnt = n + 1;
-    if (!(done & 1u)) {
-      noi_lo = cnt;
-      ok_lo  = (g.crc_kind != 0 && ls.crc_lo == 0u) ? 1u : 0u;
-      if ((early_stop && ok_lo && cnt >= min_iter) || cnt >= max_iter) done |= 1u;
+    uint32_t a[8], bt[8];
+    {
+      const uint32_t* ca = gp.ckA + (size_t)w * 8 * LANES + lane;
+      const uint32_t* cb = gp.ckB + (size_t)(w + 1) * 8 * LANES + lane;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        a[i]  = ca[i * LANES];
+        bt[i] = cb[i * LANES];
+      }
     }
-    if (!(done & 2u)) {
-      noi_hi = cnt;
-      ok_hi  = (g.crc_kind != 0 && ls.crc_hi == 0u) ? 1u : 0u;
-      if ((early_stop && ok_hi && cnt >= min_iter) || cnt >= max_iter) done |= 2u;
+    if (w & 1) { mbar_wait(&sm->bar[1], ph1 & 1u); ph1++; } else { mbar_wait(&sm->bar[0], ph0 & 1u); ph0++; }
+    const JobStage& st = sm->st[w & 1];
+
+    // coarse pass (only for full windows): un-normalised beta[lo+8]
+    uint32_t  bmid[8];
+    const int nsub = (hi - lo) / 8;
+    if (nsub == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) bmid[i] = bt[i];
+      if ((uint32_t)hi < K) normalise(bmid);
+#pragma unroll
+      for (int r = 15; r >= 8; r--) {
+        LOAD_XY(st, r);
+        beta_step(bmid, x, y);
+        if (r == 12) normalise(bmid);  // k = lo + 12
+      }
     }
-    if (__all_sync(0xffffffffu, done == 3u)) break;
+    uint32_t bitacc = 0;
+#pragma unroll 1
+    for (int s = 0; s < nsub; s++) {
+      uint32_t B[8][8], cur[8];
+      const bool last = (s == nsub - 1);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        cur[i]  = last ? bt[i] : bmid[i];
+        B[7][i] = cur[i];
+      }
+      if ((uint32_t)(lo + 8 * s + 8) < K) normalise(cur);
+#pragma unroll
+      for (int j = 6; j >= 0; j--) {
+        LOAD_XY(st, 8 * s + 1 + j);
+        beta_step(cur, x, y);
+#pragma unroll
+        for (int i = 0; i < 8; i++) B[j][i] = cur[i];
+        if (j == 3) normalise(cur);  // k = lo + 8s + 4
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int r = 8 * s + j;
+        LOAD_XY(st, r);
+        uint32_t ap = (MODE == 1) ? st.s[1][r][lane] : (MODE == 2 ? st.s[0][r][lane] : 0u);
+        uint32_t L  = alpha_llr_step(a, B[j], x, y);
+        if (j == 3 || j == 7) normalise(a);
+        const uint2 t = st.tab[r];
+        dst[(size_t)t.x * LANES + lane] = (MODE == 0) ? L : psub(L, ap);
+        const uint32_t pos = positive_mask(L);
+        crc_lo ^= (pos & 0x8000u) ? t.y : 0u;
+        crc_hi ^= (pos & 0x80000000u) ? t.y : 0u;
+        bitacc = ((bitacc >> 1) & 0x7fff7fffu) | pos;
+      }
+    }
+    if (nsub == 1) bitacc = (bitacc >> 8) & 0x00ff00ffu;  // K = 8 mod 16: the last word holds eight decisions
+    uint32_t* bw = bits + (size_t)w * LANES + lane;
+    if (keep) bitacc = (bitacc & ~keep) | (*bw & keep);  // finished code blocks keep their final decisions
+    *bw = bitacc;
   }
-  if (cb_lo >= 0) {
-    noi_out[cb_lo] = (uint8_t)noi_lo;
-    ok_out[cb_lo]  = (uint8_t)ok_lo;
+  if (cb_lo >= 0 && !(keep & 0xffffu) && crc_lo) atomicXor(&crc_acc[cb_lo], crc_lo);
+  if (cb_hi >= 0 && !(keep & 0xffff0000u) && crc_hi) atomicXor(&crc_acc[cb_hi], crc_hi);
+}
+#undef LOAD_XY
+
+/*
+ * Per-code-block verdict after half-iteration number cnt (1-based): the loop condition of decode_tb_cb
+ * (lib/src/phy/phch/sch.c:426-456). grid = n_groups, block = 64.
+ */
+__global__ void __launch_bounds__(64) status_kernel(const Group* __restrict__ groups, uint32_t* __restrict__ crc_acc, uint8_t* __restrict__ noi,
+                                                    uint8_t* __restrict__ ok, uint8_t* __restrict__ done, uint8_t* __restrict__ group_active,
+                                                    uint32_t cnt, uint32_t max_iter, uint32_t min_iter, int early_stop)
+{
+  const Group& g = groups[blockIdx.x];
+  if (!group_active[blockIdx.x]) return;
+  const int cb     = g.cb[threadIdx.x];
+  int       active = 0;
+  if (cb >= 0) {
+    if (!done[cb]) {
+      const uint32_t okv = (g.crc_kind != 0 && crc_acc[cb] == 0u) ? 1u : 0u;
+      noi[cb] = (uint8_t)cnt;
+      ok[cb]  = (uint8_t)okv;
+      if ((early_stop && okv && cnt >= min_iter) || cnt >= max_iter) done[cb] = 1;
+      else active = 1;
+    }
+    crc_acc[cb] = 0u;
   }
-  if (cb_hi >= 0) {
-    noi_out[cb_hi] = (uint8_t)noi_hi;
-    ok_out[cb_hi]  = (uint8_t)ok_hi;
-  }
-  (void)resume_state;
+  active = __syncthreads_or(active);
+  if (threadIdx.x == 0) group_active[blockIdx.x] = (uint8_t)(active ? 1 : 0);
 }
 
 /*

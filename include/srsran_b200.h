@@ -53,10 +53,13 @@ const char* srsb200_last_error(void);
 /* number of kernels launched by this engine since creation (bench.py's gpu_launches claim) */
 uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e);
 /* per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg). profile_read synchronises and
- * returns, per kernel kind (0 extract, 1 turbo decode, 2 emit, 3 rate de-match, 4 TB CRC), the summed milliseconds and
- * launch counts since the previous read. */
+ * returns, per kernel kind (0 extract, 2 emit, 3 rate de-match, 4 TB CRC, 5 alpha/beta scan, 6 window jobs, 7 status), the
+ * summed milliseconds and launch counts since the previous read. While profiling is enabled a decode runs as one chain
+ * of launches (the sub-batch overlap of srsb200_engine_set_subbatches is off) so the durations are not inflated. */
 int srsb200_engine_profile(srsb200_engine_t* e, int enable);
 int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[8]);
+/* number of sub-batches whose launch chains overlap on separate streams (default 4, env SRSB200_SUBBATCHES; 1 = off) */
+int srsb200_engine_set_subbatches(srsb200_engine_t* e, int n);
 /* stream the engine launches on (cudaStream_t), so callers can time with events on the same stream */
 void* srsb200_engine_stream(const srsb200_engine_t* e);
 

@@ -38,6 +38,7 @@ def lib():
         L.srsb200_engine_stream.restype = vp
         L.srsb200_engine_sync.argtypes = [vp]
         L.srsb200_engine_profile.argtypes = [vp, i32]
+        L.srsb200_engine_set_subbatches.argtypes = [vp, i32]
         L.srsb200_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
         L.srsb200_cbsize.argtypes = [u32]
         L.srsb200_cbindex.argtypes = [u32]
@@ -165,6 +166,9 @@ class Engine:
     def sync(self):
         _check(self._L.srsb200_engine_sync(self._h), "srsb200_engine_sync")
 
+    def set_subbatches(self, n):
+        _check(self._L.srsb200_engine_set_subbatches(self._h, n), "srsb200_engine_set_subbatches")
+
     def profile(self, enable):
         _check(self._L.srsb200_engine_profile(self._h, int(enable)), "srsb200_engine_profile")
 
@@ -173,7 +177,7 @@ class Engine:
         ms = (C.c_double * 8)()
         cnt = (C.c_uint64 * 8)()
         _check(self._L.srsb200_engine_profile_read(self._h, ms, cnt), "srsb200_engine_profile_read")
-        names = ["extract", "decode", "emit", "rm", "tbcrc"]
+        names = ["extract", "decode", "emit", "rm", "tbcrc", "scan", "job", "status"]
         return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names)}
 
     # ---- batched decode, host buffers

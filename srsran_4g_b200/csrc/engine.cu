@@ -174,6 +174,14 @@ struct srsb200_engine {
   void*  d_scratch[8]   = {nullptr};
   size_t scratch_cap[8] = {0};
 
+  // sub-batch streams (see launch_plan)
+  static const int MAX_SUB = 8;
+  int          n_sub = 4;
+  cudaStream_t sub[MAX_SUB] = {nullptr};
+  cudaEvent_t  ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
+  static const int N_TOKEN = 2 * MAX_SUB * SRSB200_MAX_TDEC_ITERS;
+  cudaEvent_t  ev_token[N_TOKEN] = {nullptr};
+
   // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
   bool profiling = false;
   struct ProfEv { cudaEvent_t a, b; int kind; };
@@ -187,19 +195,19 @@ struct srsb200_engine {
 };
 
 struct ProfScope {
-  srsb200_engine* e; int kind; cudaEvent_t a = nullptr, b = nullptr;
-  ProfScope(srsb200_engine* e_, int k) : e(e_), kind(k)
+  srsb200_engine* e; int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(srsb200_engine* e_, int k, cudaStream_t s = nullptr) : e(e_), kind(k), st(s ? s : e_->stream)
   {
     if (e->profiling) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
-      cudaEventRecord(a, e->stream);
+      cudaEventRecord(a, st);
     }
   }
   ~ProfScope()
   {
     if (a) {
-      cudaEventRecord(b, e->stream);
+      cudaEventRecord(b, st);
       e->prof.push_back({a, b, kind});
     }
   }
@@ -297,10 +305,22 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   memset(e->d_rm, 0, sizeof(e->d_rm));
   memset(e->h_ktab, 0, sizeof(e->h_ktab));
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  if (const char* env = getenv("SRSB200_SUBBATCHES")) e->n_sub = std::max(1, std::min((int)srsb200_engine::MAX_SUB, atoi(env)));
+  for (int i = 0; i < srsb200_engine::MAX_SUB; i++) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->sub[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < srsb200_engine::N_TOKEN; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_token[i], cudaEventDisableTiming));
   CUDA_TRY(cudaMalloc(&e->d_ktab, sizeof(KTable) * LTE_NOF_CB_SIZES));
   CUDA_TRY(cudaMemset(e->d_ktab, 0, sizeof(KTable) * LTE_NOF_CB_SIZES));
   crc_position_words(0x1864CFBu, e->crc_words[SRSB200_CRC_24A]);
   crc_position_words(0x1800063u, e->crc_words[SRSB200_CRC_24B]);
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)emit_smem_bytes(((SRSB200_MAX_K + 3 + W - 1) / W) * W, SRSB200_MAX_K + 64)));
   CUDA_TRY(cudaFuncSetAttribute(job_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
   CUDA_TRY(cudaFuncSetAttribute(job_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
   CUDA_TRY(cudaFuncSetAttribute(job_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
@@ -318,6 +338,13 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
   for (int i = 0; i < 8; i++)
     if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);
   cudaFree(e->d_ktab);
+  for (int i = 0; i < srsb200_engine::MAX_SUB; i++) {
+    if (e->sub[i]) cudaStreamDestroy(e->sub[i]);
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  for (int i = 0; i < srsb200_engine::N_TOKEN; i++)
+    if (e->ev_token[i]) cudaEventDestroy(e->ev_token[i]);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -328,7 +355,8 @@ extern "C" int srsb200_engine_profile(srsb200_engine_t* e, int enable)
   e->profiling = enable != 0;
   return SRSB200_SUCCESS;
 }
-// ms[kind] += elapsed, cnt[kind] += launches; kinds: 0 extract, 1 decode, 2 emit, 3 rate-dematch, 4 tb-crc. Synchronises.
+// ms[kind] += elapsed, cnt[kind] += launches; kinds: 0 extract, 2 emit, 3 rate-dematch, 4 tb-crc, 5 scan, 6 job, 7 status.
+// Synchronises. While profiling is on, decodes run as a single chain (no sub-batch overlap).
 extern "C" int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[8])
 {
   if (!e) return SRSB200_ERROR_INVALID_INPUTS;
@@ -344,6 +372,13 @@ extern "C" int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], ui
     cudaEventDestroy(p.b);
   }
   e->prof.clear();
+  return SRSB200_SUCCESS;
+}
+
+extern "C" int srsb200_engine_set_subbatches(srsb200_engine_t* e, int n)
+{
+  if (!e || n < 1 || n > srsb200_engine::MAX_SUB) return SRSB200_ERROR_INVALID_INPUTS;
+  e->n_sub = n;
   return SRSB200_SUCCESS;
 }
 
@@ -476,50 +511,106 @@ extern "C" int srsb200_tdec_plan_uniform(srsb200_engine_t* e, uint32_t n, uint32
   return r;
 }
 
-// enqueue extract + decode + emit for a plan; all pointers are device pointers
+struct RangeArgs {
+  uint32_t       g0, g1;
+  cudaStream_t   st;
+};
+
+// one launch of the decode chain of a group range; kind: 0 extract, 1 scan, 2 job, 3 status, 4 emit
+static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, int kind, uint32_t n, const int16_t* d_llr, uint32_t max_iter,
+                       uint32_t min_iter, int early_stop, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok)
+{
+  const uint32_t ng = r.g1 - r.g0;
+  const Group*   dg = p->d_groups + r.g0;
+  uint8_t*       da = p->d_active + r.g0;
+  cudaStream_t   st = r.st;
+  const int      mode = (n == 0) ? 0 : ((n & 1u) ? 2 : 1);
+  const uint32_t nwin_max = (p->max_R + WC - 1) / WC;
+  const dim3     sgrid(ng, 2), jgrid((nwin_max + 4 * WPJ - 1) / (4 * WPJ), ng);
+  const size_t   ssm = sizeof(ScanSmem), jsm = 4 * sizeof(JobWarpSmem);
+  switch (kind) {
+    case 0: {
+      ProfScope ps(e, 0, st);
+      extract_kernel<<<dim3(p->max_R / XT, ng), 256, 0, st>>>(dg, p->d_ws, d_llr, p->d_llr_off);
+    } break;
+    case 1: {
+      ProfScope ps(e, 5, st);
+      if (mode == 0) scan_kernel<0><<<sgrid, 32, ssm, st>>>(dg, p->d_ws, da);
+      else if (mode == 1) scan_kernel<1><<<sgrid, 32, ssm, st>>>(dg, p->d_ws, da);
+      else scan_kernel<2><<<sgrid, 32, ssm, st>>>(dg, p->d_ws, da);
+    } break;
+    case 2: {
+      ProfScope ps(e, 6, st);
+      if (mode == 0) job_kernel<0><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc);
+      else if (mode == 1) job_kernel<1><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc);
+      else job_kernel<2><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc);
+    } break;
+    case 3: {
+      ProfScope ps(e, 7, st);
+      status_kernel<<<ng, 64, 0, st>>>(dg, p->d_crc_acc, d_noi, d_ok, p->d_done, da, n + 1, max_iter, min_iter, early_stop);
+    } break;
+    default: {
+      ProfScope ps(e, 2, st);
+      emit_kernel<<<ng, 256, emit_smem_bytes(p->max_R, p->max_R), st>>>(dg, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off);
+    } break;
+  }
+  e->launches++;
+}
+
+/*
+ * A decode is a chain of dependent launches: extract, then per half-iteration {scan, job, status}, then emit. Every
+ * half-iteration up to max_iter is enqueued; groups whose code blocks are all done exit at once.
+ * The alpha/beta scans are latency-bound (one lone warp per recursion, ~6144 x 47 cycles whatever the batch size), the
+ * window jobs are throughput-bound. So the groups are split into S sub-batches with one stream each, and a token (an event
+ * chain) makes the job kernels take turns: while the jobs of one sub-batch fill the machine, the other sub-batches run
+ * their scans in the shadow. Per-kernel profiling forces a single chain so that the event-timed durations are not
+ * inflated by co-running kernels.
+ */
 static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr, uint32_t max_iter, uint32_t min_iter, int early_stop,
                        uint32_t start_iter, bool do_extract, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok)
 {
   if (p->n_groups == 0) return SRSB200_SUCCESS;
-  if (do_extract) {
-    ProfScope ps(e, 0);
-    dim3 grid(p->max_R / 32, p->n_groups);
-    extract_kernel<<<grid, 256, 0, e->stream>>>(p->d_groups, p->d_ws, d_llr, p->d_llr_off);
-    e->launches++;
-  }
   if (max_iter == 0) max_iter = 1;  // run_all is a do-while (turbodecoder.c:542-546)
   if (start_iter == 0) {
     CUDA_TRY(cudaMemsetAsync(p->d_crc_acc, 0, sizeof(uint32_t) * p->n_cb, e->stream));
     CUDA_TRY(cudaMemsetAsync(p->d_done, 0, p->n_cb, e->stream));
     CUDA_TRY(cudaMemsetAsync(p->d_active, 1, p->n_groups, e->stream));
   }
-  {
-    // every half-iteration up to max_iter is enqueued; groups whose code blocks are all done exit at once
-    ProfScope ps(e, 1);
-    const uint32_t nwin_max = (p->max_R + WC - 1) / WC;
-    const dim3 sgrid(p->n_groups, 2), jgrid((nwin_max + 4 * WPJ - 1) / (4 * WPJ), p->n_groups);
-    const size_t ssm = sizeof(ScanSmem), jsm = 4 * sizeof(JobWarpSmem);
-    for (uint32_t n = start_iter; n < max_iter; n++) {
-      if (n == 0) {
-        scan_kernel<0><<<sgrid, 32, ssm, e->stream>>>(p->d_groups, p->d_ws, p->d_active);
-        job_kernel<0><<<jgrid, 128, jsm, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, p->d_active, p->d_done, p->d_crc_acc);
-      } else if ((n & 1u) == 0) {
-        scan_kernel<1><<<sgrid, 32, ssm, e->stream>>>(p->d_groups, p->d_ws, p->d_active);
-        job_kernel<1><<<jgrid, 128, jsm, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, p->d_active, p->d_done, p->d_crc_acc);
-      } else {
-        scan_kernel<2><<<sgrid, 32, ssm, e->stream>>>(p->d_groups, p->d_ws, p->d_active);
-        job_kernel<2><<<jgrid, 128, jsm, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, p->d_active, p->d_done, p->d_crc_acc);
+  uint32_t S = e->profiling ? 1u : (uint32_t)e->n_sub;
+  // sub-batches only pay off when each still fills a good part of the machine with window jobs
+  S = std::max(1u, std::min(S, p->n_groups / 16u));
+  RangeArgs rg[srsb200_engine::MAX_SUB];
+  for (uint32_t s = 0; s < S; s++) {
+    rg[s].g0 = (uint32_t)((uint64_t)p->n_groups * s / S);
+    rg[s].g1 = (uint32_t)((uint64_t)p->n_groups * (s + 1) / S);
+    rg[s].st = (S == 1) ? e->stream : e->sub[s];
+  }
+  if (S > 1) {
+    CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
+    for (uint32_t s = 0; s < S; s++) CUDA_TRY(cudaStreamWaitEvent(e->sub[s], e->ev_fork, 0));
+  }
+  if (do_extract)
+    for (uint32_t s = 0; s < S; s++) launch_one(e, p, rg[s], 0, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+  cudaEvent_t token = nullptr;  // completion of the most recently enqueued job kernel
+  uint32_t    tk = 0;
+  for (uint32_t n = start_iter; n < max_iter; n++) {
+    for (uint32_t s = 0; s < S; s++) {
+      launch_one(e, p, rg[s], 1, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+      if (S > 1 && token) CUDA_TRY(cudaStreamWaitEvent(rg[s].st, token, 0));
+      launch_one(e, p, rg[s], 2, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+      if (S > 1) {
+        token = e->ev_token[tk++ % srsb200_engine::N_TOKEN];
+        CUDA_TRY(cudaEventRecord(token, rg[s].st));
       }
-      status_kernel<<<p->n_groups, 64, 0, e->stream>>>(p->d_groups, p->d_crc_acc, d_noi, d_ok, p->d_done, p->d_active, n + 1, max_iter, min_iter,
-                                                       early_stop);
-      e->launches += 3;
+      launch_one(e, p, rg[s], 3, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
     }
   }
-  {
-    ProfScope ps(e, 2);
-    dim3 egrid((p->max_R / 32 + 127) / 128, p->n_groups * 64);
-    emit_kernel<<<egrid, 128, 0, e->stream>>>(p->d_groups, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off);
-    e->launches++;
+  for (uint32_t s = 0; s < S; s++) launch_one(e, p, rg[s], 4, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+  if (S > 1) {
+    for (uint32_t s = 0; s < S; s++) {
+      CUDA_TRY(cudaEventRecord(e->ev_join[s], e->sub[s]));
+      CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[s], 0));
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return SRSB200_SUCCESS;

@@ -31,6 +31,7 @@ namespace srsb200 {
 constexpr int W        = 32;  // rows per staged chunk of the scan kernels; streams are padded to a multiple of W rows
 constexpr int WC       = 16;  // checkpoint spacing = window of one job = one hard-bit word
 constexpr int WPJ      = 8;   // windows per job warp
+constexpr int CKB      = 8;   // spacing of the beta checkpoints (one per 8-step register window of the job kernel)
 constexpr int LANES    = 32;
 constexpr int NEG_INF2 = 0xD8F0D8F0;  // two int16 of -10000 (turbodecoder_gen.c:37)
 
@@ -52,10 +53,10 @@ struct Group {
 };
 
 // workspace layout of one group (all uint32 [rows][32]):
-//   syst[R] par0[R] par1[R] app1p[R] app2[R] ckA[(R/WC+1)*8] ckB[(R/WC+1)*8] bits1[R/16] bits2[R/16]
+//   syst[R] par0[R] par1[R] app1p[R] app2[R] ckA[(R/(WC*WPJ)+1)*8] ckB[(R/CKB+1)*8] bits1[R/16] bits2[R/16]
 __host__ __device__ inline uint64_t group_ws_words(uint32_t R)
 {
-  return (uint64_t)LANES * (5ull * R + 2ull * (R / WC + 1) * 8ull + 2ull * (R / 16));
+  return (uint64_t)LANES * (5ull * R + (R / (WC * WPJ) + 1) * 8ull + (R / CKB + 1) * 8ull + 2ull * (R / 16));
 }
 
 struct GroupPtrs {
@@ -72,8 +73,8 @@ __host__ __device__ inline GroupPtrs group_ptrs(uint8_t* ws, const Group& g)
   p.app1p     = b + 3 * s;
   p.app2      = b + 4 * s;
   p.ckA       = b + 5 * s;
-  p.ckB       = p.ckA + (uint64_t)(g.R / WC + 1) * 8 * LANES;
-  p.bits1     = p.ckB + (uint64_t)(g.R / WC + 1) * 8 * LANES;
+  p.ckB       = p.ckA + (uint64_t)(g.R / (WC * WPJ) + 1) * 8 * LANES;
+  p.bits1     = p.ckB + (uint64_t)(g.R / CKB + 1) * 8 * LANES;
   p.bits2     = p.bits1 + (uint64_t)(g.R / 16) * LANES;
   return p;
 }
@@ -93,42 +94,22 @@ __device__ __forceinline__ void normalise(uint32_t (&s)[8])
   s[0] = 0u;
 }
 
-// backward recursion step (map_gen_beta, turbodecoder_gen.c:71-103): b <- beta[k] (un-normalised)
+// backward recursion step (map_gen_beta, turbodecoder_gen.c:71-103): b <- beta[k] (un-normalised).
+// Statement order matters for a lone in-order warp: all adds (FMA pipe) first, then the maxes (ALU pipe) whose add
+// operand is oldest, so that no instruction issues within 5 cycles of its producer (measured dependent latency 4-5).
 __device__ __forceinline__ void beta_step(uint32_t (&b)[8], uint32_t x, uint32_t y)
 {
-  uint32_t xy = padd(x, y);
-  uint32_t n0 = paddmax(b[4], xy, b[0]);
-  uint32_t n1 = paddmax(b[0], xy, b[4]);
-  uint32_t n2 = paddmax(b[5], y, padd(b[1], x));
-  uint32_t n3 = paddmax(b[5], x, padd(b[1], y));
-  uint32_t n4 = paddmax(b[6], x, padd(b[2], y));
-  uint32_t n5 = paddmax(b[6], y, padd(b[2], x));
-  uint32_t n6 = paddmax(b[3], xy, b[7]);
-  uint32_t n7 = paddmax(b[7], xy, b[3]);
+  const uint32_t xy = padd(x, y);
+  const uint32_t t2 = padd(b[1], x), t3 = padd(b[1], y), t4 = padd(b[2], y), t5 = padd(b[2], x);
+  const uint32_t n1 = paddmax(b[0], xy, b[4]);
+  const uint32_t n0 = paddmax(b[4], xy, b[0]);
+  const uint32_t n6 = paddmax(b[3], xy, b[7]);
+  const uint32_t n7 = paddmax(b[7], xy, b[3]);
+  const uint32_t n2 = paddmax(b[5], y, t2);
+  const uint32_t n3 = paddmax(b[5], x, t3);
+  const uint32_t n4 = paddmax(b[6], x, t4);
+  const uint32_t n5 = paddmax(b[6], y, t5);
   b[0] = n0; b[1] = n1; b[2] = n2; b[3] = n3; b[4] = n4; b[5] = n5; b[6] = n6; b[7] = n7;
-}
-
-// forward recursion + LLR step (map_gen_alpha, turbodecoder_gen.c:135-194); returns m1 - m0
-__device__ __forceinline__ uint32_t alpha_llr_step(uint32_t (&a)[8], const uint4 bl, const uint4 bh, uint32_t x, uint32_t y)
-{
-  uint32_t xy = padd(x, y);
-  // information bit 0 branches into state i (m_b[i]) and information bit 1 branches (new[i])
-  uint32_t z0 = a[0], z1 = padd(a[3], y), z2 = padd(a[4], y), z3 = a[7];
-  uint32_t z4 = a[1], z5 = padd(a[2], y), z6 = padd(a[5], y), z7 = a[6];
-  uint32_t o0 = padd(a[1], xy), o1 = padd(a[2], x), o2 = padd(a[5], x), o3 = padd(a[6], xy);
-  uint32_t o4 = padd(a[0], xy), o5 = padd(a[3], x), o6 = padd(a[4], x), o7 = padd(a[7], xy);
-  // two chains per maximum keep the dependent depth short
-  uint32_t m0a = padd(z0, bl.x), m0b = padd(z4, bh.x);
-  m0a = paddmax(z1, bl.y, m0a); m0b = paddmax(z5, bh.y, m0b);
-  m0a = paddmax(z2, bl.z, m0a); m0b = paddmax(z6, bh.z, m0b);
-  m0a = paddmax(z3, bl.w, m0a); m0b = paddmax(z7, bh.w, m0b);
-  uint32_t m1a = padd(o0, bl.x), m1b = padd(o4, bh.x);
-  m1a = paddmax(o1, bl.y, m1a); m1b = paddmax(o5, bh.y, m1b);
-  m1a = paddmax(o2, bl.z, m1a); m1b = paddmax(o6, bh.z, m1b);
-  m1a = paddmax(o3, bl.w, m1a); m1b = paddmax(o7, bh.w, m1b);
-  a[0] = pmax(z0, o0); a[1] = pmax(z1, o1); a[2] = pmax(z2, o2); a[3] = pmax(z3, o3);
-  a[4] = pmax(z4, o4); a[5] = pmax(z5, o5); a[6] = pmax(z6, o6); a[7] = pmax(z7, o7);
-  return psub(pmax(m1a, m1b), pmax(m0a, m0b));
 }
 
 // ---------------------------------------------------------------- bulk async copy + mbarrier (sm_90+/sm_100a PTX)
@@ -166,19 +147,66 @@ __device__ __forceinline__ void fence_proxy_async()
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-// forward recursion step without LLR (alpha part of map_gen_alpha, turbodecoder_gen.c:148-191)
+// forward recursion step without LLR (alpha part of map_gen_alpha, turbodecoder_gen.c:148-191); same ordering rule
 __device__ __forceinline__ void alpha_step(uint32_t (&a)[8], uint32_t x, uint32_t y)
 {
-  uint32_t xy = padd(x, y);
-  uint32_t n0 = paddmax(a[1], xy, a[0]);
-  uint32_t n1 = paddmax(a[3], y, padd(a[2], x));
-  uint32_t n2 = paddmax(a[4], y, padd(a[5], x));
-  uint32_t n3 = paddmax(a[6], xy, a[7]);
-  uint32_t n4 = paddmax(a[0], xy, a[1]);
-  uint32_t n5 = paddmax(a[2], y, padd(a[3], x));
-  uint32_t n6 = paddmax(a[5], y, padd(a[4], x));
-  uint32_t n7 = paddmax(a[7], xy, a[6]);
+  const uint32_t xy = padd(x, y);
+  const uint32_t t1 = padd(a[2], x), t2 = padd(a[5], x), t5 = padd(a[3], x), t6 = padd(a[4], x);
+  const uint32_t n0 = paddmax(a[1], xy, a[0]);
+  const uint32_t n3 = paddmax(a[6], xy, a[7]);
+  const uint32_t n4 = paddmax(a[0], xy, a[1]);
+  const uint32_t n7 = paddmax(a[7], xy, a[6]);
+  const uint32_t n1 = paddmax(a[3], y, t1);
+  const uint32_t n2 = paddmax(a[4], y, t2);
+  const uint32_t n5 = paddmax(a[2], y, t5);
+  const uint32_t n6 = paddmax(a[5], y, t6);
   a[0] = n0; a[1] = n1; a[2] = n2; a[3] = n3; a[4] = n4; a[5] = n5; a[6] = n6; a[7] = n7;
+}
+
+// one backward step of chain b and one forward step of chain a with their statements interleaved: two independent
+// dependency chains in one instruction stream (a lone in-order warp needs >= 5 cycles between dependent instructions)
+__device__ __forceinline__ void beta_alpha_step(uint32_t (&b)[8], uint32_t xb, uint32_t yb, uint32_t (&a)[8], uint32_t xa, uint32_t ya)
+{
+  const uint32_t xyb = padd(xb, yb);
+  const uint32_t xya = padd(xa, ya);
+  const uint32_t tb2 = padd(b[1], xb);
+  const uint32_t ta1 = padd(a[2], xa);
+  const uint32_t tb3 = padd(b[1], yb);
+  const uint32_t ta2 = padd(a[5], xa);
+  const uint32_t tb4 = padd(b[2], yb);
+  const uint32_t ta5 = padd(a[3], xa);
+  const uint32_t tb5 = padd(b[2], xb);
+  const uint32_t ta6 = padd(a[4], xa);
+  const uint32_t nb1 = paddmax(b[0], xyb, b[4]);
+  const uint32_t na0 = paddmax(a[1], xya, a[0]);
+  const uint32_t nb0 = paddmax(b[4], xyb, b[0]);
+  const uint32_t na3 = paddmax(a[6], xya, a[7]);
+  const uint32_t nb6 = paddmax(b[3], xyb, b[7]);
+  const uint32_t na4 = paddmax(a[0], xya, a[1]);
+  const uint32_t nb7 = paddmax(b[7], xyb, b[3]);
+  const uint32_t na7 = paddmax(a[7], xya, a[6]);
+  const uint32_t nb2 = paddmax(b[5], yb, tb2);
+  const uint32_t na1 = paddmax(a[3], ya, ta1);
+  const uint32_t nb3 = paddmax(b[5], xb, tb3);
+  const uint32_t na2 = paddmax(a[4], ya, ta2);
+  const uint32_t nb4 = paddmax(b[6], xb, tb4);
+  const uint32_t na5 = paddmax(a[2], ya, ta5);
+  const uint32_t nb5 = paddmax(b[6], yb, tb5);
+  const uint32_t na6 = paddmax(a[5], ya, ta6);
+  b[0] = nb0; b[1] = nb1; b[2] = nb2; b[3] = nb3; b[4] = nb4; b[5] = nb5; b[6] = nb6; b[7] = nb7;
+  a[0] = na0; a[1] = na1; a[2] = na2; a[3] = na3; a[4] = na4; a[5] = na5; a[6] = na6; a[7] = na7;
+}
+
+__device__ __forceinline__ void normalise2(uint32_t (&s)[8], uint32_t (&t)[8])
+{
+  const uint32_t ns = psub(0u, s[0]), nt = psub(0u, t[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    s[i] = padd(s[i], ns);
+    t[i] = padd(t[i], nt);
+  }
+  s[0] = 0u;
+  t[0] = 0u;
 }
 
 // hard decision of both halves: bit 15 / bit 31 set iff the int16 is > 0  (tdec_gen_decision_byte: app > 0)
@@ -188,49 +216,36 @@ __device__ __forceinline__ uint32_t positive_mask(uint32_t v)
 }
 
 // ---------------------------------------------------------------- scan kernel: sequential alpha / beta recursions
+constexpr int NS = 4;  // staged chunks in flight per scan warp (bulk copies run NS-1 chunks ahead of the recursion)
 struct ScanStage {
   uint32_t s[3][W][LANES];
 };
 struct ScanSmem {
-  ScanStage st[2];
-  uint64_t  bar[2];
+  ScanStage st[NS];
+  uint64_t  bar[NS];
 };
 
 struct ScanPipe {
-  // double-buffered chunk loader (chunks of W rows); all members are warp-uniform scalars
+  // chunks are consumed in a fixed order (it = 0, 1, 2, ...); stage = it % NS, mbarrier parity = (it / NS) & 1
   ScanSmem*       sm;
   const uint32_t *src0, *src1, *src2;
-  int             held0, held1;
-  bool            pend0, pend1;
-  uint32_t        phase0, phase1;
 
-  __device__ __forceinline__ void issue(int c)
+  __device__ __forceinline__ void issue(int it, int chunk)
   {
-    const int s = c & 1;
-    __syncwarp();
+    __syncwarp();  // every lane is done with the stage this copy overwrites
     if ((threadIdx.x & 31) == 0) {
-      ScanStage& st  = sm->st[s];
-      uint64_t*  bar = &sm->bar[s];
+      ScanStage& st  = sm->st[it % NS];
+      uint64_t*  bar = &sm->bar[it % NS];
       mbar_expect_tx(bar, (src2 ? 3u : 2u) * W * LANES * 4);
-      bulk_g2s(&st.s[0][0][0], src0 + (size_t)c * W * LANES, W * LANES * 4, bar);
-      bulk_g2s(&st.s[1][0][0], src1 + (size_t)c * W * LANES, W * LANES * 4, bar);
-      if (src2) bulk_g2s(&st.s[2][0][0], src2 + (size_t)c * W * LANES, W * LANES * 4, bar);
+      bulk_g2s(&st.s[0][0][0], src0 + (size_t)chunk * W * LANES, W * LANES * 4, bar);
+      bulk_g2s(&st.s[1][0][0], src1 + (size_t)chunk * W * LANES, W * LANES * 4, bar);
+      if (src2) bulk_g2s(&st.s[2][0][0], src2 + (size_t)chunk * W * LANES, W * LANES * 4, bar);
     }
-    if (s) { held1 = c; pend1 = true; } else { held0 = c; pend0 = true; }
   }
-  __device__ __forceinline__ void prefetch(int c)
+  __device__ __forceinline__ const ScanStage& wait(int it)
   {
-    if (c >= 0 && ((c & 1) ? held1 : held0) != c) issue(c);
-  }
-  __device__ __forceinline__ const ScanStage& acquire(int c)
-  {
-    const int s = c & 1;
-    if ((s ? held1 : held0) != c) issue(c);
-    if (s ? pend1 : pend0) {
-      mbar_wait(&sm->bar[s], (s ? phase1 : phase0) & 1u);
-      if (s) { phase1++; pend1 = false; } else { phase0++; pend0 = false; }
-    }
-    return sm->st[s];
+    mbar_wait(&sm->bar[it % NS], (uint32_t)(it / NS) & 1u);
+    return sm->st[it % NS];
   }
 };
 
@@ -244,13 +259,69 @@ struct ScanPipe {
     y = (st).s[1][(r)][lane];                                            \
   }
 
+// A lone warp issues roughly one instruction every two cycles (tools/microbench/lone_warp_step.cu: 22.7 cycles per
+// 13-instruction step), so the scans are written to execute as few instructions per trellis step as possible:
+// fully unrolled blocks of N steps whose x / y are fetched from shared memory up front, one checkpoint test per block.
+template <int MODE, int N>
+__device__ __forceinline__ void beta_block(const ScanStage& st, int r0, int k0, uint32_t (&b)[8], uint32_t* ckB, int lane)
+{
+  // steps k = k0+N-1 .. k0 (rows r0+N-1 .. r0 of the staged chunk); k0 is a multiple of 8
+  uint32_t xs[N], ys[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    LOAD_XY(st, r0 + j);
+    xs[j] = x;
+    ys[j] = y;
+  }
+#pragma unroll
+  for (int j = N - 1; j >= 0; j--) {
+    beta_step(b, xs[j], ys[j]);
+    if ((j & 3) == 0) {
+      // k % 4 == 0 and k < K: checkpoint first (un-normalised, like beta[8*k+i]), then normalise
+      if ((j & 7) == 0 && k0 + j > 0) {
+        // layout [slot][lane][8]: two 128-bit stores per lane, 1 KB contiguous per warp
+        uint4* ck = reinterpret_cast<uint4*>(ckB + ((size_t)((k0 + j) / CKB) * LANES + lane) * 8);
+        ck[0]     = make_uint4(b[0], b[1], b[2], b[3]);
+        ck[1]     = make_uint4(b[4], b[5], b[6], b[7]);
+      }
+      normalise(b);
+    }
+  }
+}
+
+template <int MODE, int N>
+__device__ __forceinline__ void alpha_block(const ScanStage& st, int r0, int k0, uint32_t (&a)[8], uint32_t* ckA, int lane)
+{
+  // steps k = k0+1 .. k0+N (rows r0 .. r0+N-1); k0 is a multiple of 8
+  uint32_t xs[N], ys[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    LOAD_XY(st, r0 + j);
+    xs[j] = x;
+    ys[j] = y;
+  }
+  // a job warp only needs the alpha state at its first window: one checkpoint per WPJ windows
+  if ((k0 % (WC * WPJ)) == 0) {
+    uint4* ck = reinterpret_cast<uint4*>(ckA + ((size_t)(k0 / (WC * WPJ)) * LANES + lane) * 8);
+    ck[0]     = make_uint4(a[0], a[1], a[2], a[3]);
+    ck[1]     = make_uint4(a[4], a[5], a[6], a[7]);
+  }
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    alpha_step(a, xs[j], ys[j]);
+    if ((j & 3) == 3) normalise(a);  // k = k0 + j + 1 is a multiple of 4
+  }
+}
+
 /*
  * MODE 0: DEC1 on the first half-iteration (no a-priori)   x = syst,          y = par0
  * MODE 1: DEC1 with a-priori                                x = syst + app1p,  y = par0
  * MODE 2: DEC2                                              x = app2,          y = par1
- * grid = (n_groups, 2): blockIdx.y == 0 runs the backward (beta) recursion, 1 the forward (alpha) recursion.
- * Checkpoints: ckB[ceil(k/WC)] = un-normalised beta[k] for k = multiples of WC and k = K (what alpha step k consumes);
- *              ckA[k/WC] = alpha state entering step k+1 (post-normalisation) for k = multiples of WC.
+ * grid = (n_groups, 2), block = 32: blockIdx.y == 0 runs the backward (beta) recursion, 1 the forward (alpha) one.
+ * (Running both recursions in ONE warp doubles the time - measured 365 us vs 185 us per launch: a lone warp is
+ * issue-limited, not dependency-limited. They stay in separate warps.)
+ * Checkpoints: ckB[k/CKB] = un-normalised beta[k] for k = CKB, 2 CKB, ..., K (what alpha step k consumes);
+ *              ckA[k/(WC*WPJ)] = alpha state entering step k+1 (post-normalisation) for k = multiples of WC*WPJ.
  */
 template <int MODE>
 __global__ void __launch_bounds__(32) scan_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const uint8_t* __restrict__ group_active)
@@ -261,102 +332,99 @@ __global__ void __launch_bounds__(32) scan_kernel(const Group* __restrict__ grou
   const int       lane = threadIdx.x;
   const Group&    g    = groups[blockIdx.x];
   const GroupPtrs gp   = group_ptrs(ws, g);
-  const uint32_t  K    = g.K;
+  const int       K    = (int)g.K;
   if (lane == 0) {
-    mbar_init(&sm->bar[0], 1);
-    mbar_init(&sm->bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < NS; i++) mbar_init(&sm->bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
   ScanPipe pipe;
-  pipe.sm     = sm;
-  pipe.phase0 = pipe.phase1 = 0;
-  pipe.held0 = pipe.held1 = -1;
-  pipe.pend0 = pipe.pend1 = false;
+  pipe.sm   = sm;
   pipe.src0 = (MODE == 2) ? gp.app2 : gp.syst;
   pipe.src1 = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
   pipe.src2 = (MODE == 1) ? gp.par0 : nullptr;
-  const int nwin = (int)((K + WC - 1) / WC);
 
   if (blockIdx.y == 0) {
-    // ---------------- backward recursion (map_gen_beta)
-    const int cK = (int)(K / W);  // chunk holding rows K..K+2
+    // ---------------- backward recursion (map_gen_beta): chunks cK, cK-1, ..., 0
+    const int cK = K / W;  // chunk holding rows K..K+2
     uint32_t  b[8];
     b[0] = 0u;
 #pragma unroll
     for (int i = 1; i < 8; i++) b[i] = NEG_INF2;
-    pipe.prefetch(cK);
-    pipe.prefetch(cK - 1);
-    for (int c = cK; c >= 0; c--) {
-      const ScanStage& st = pipe.acquire(c);
+    for (int it = 0; it < NS - 1 && it <= cK; it++) pipe.issue(it, cK - it);
+    for (int it = 0; it <= cK; it++) {
+      const int c = cK - it;
+      if (it + NS - 1 <= cK) pipe.issue(it + NS - 1, c - (NS - 1));
+      const ScanStage& st = pipe.wait(it);
       if (c == cK) {
         // termination steps k = K+2, K+1, K (no a-priori there: app1p rows >= K stay zero); no normalisation at k = K
 #pragma unroll
         for (int r = 2; r >= 0; r--) {
-          LOAD_XY(st, (K - (uint32_t)cK * W) + r);
+          LOAD_XY(st, (K - cK * W) + r);
           beta_step(b, x, y);
         }
-        uint32_t* ck = gp.ckB + (size_t)nwin * 8 * LANES + lane;
-#pragma unroll
-        for (int i = 0; i < 8; i++) ck[i * LANES] = b[i];
+        uint4* ck = reinterpret_cast<uint4*>(gp.ckB + ((size_t)(K / CKB) * LANES + lane) * 8);
+        ck[0]     = make_uint4(b[0], b[1], b[2], b[3]);
+        ck[1]     = make_uint4(b[4], b[5], b[6], b[7]);
       }
-      const int top = (int)min(K, (uint32_t)(c + 1) * W) - 4;
-      for (int kb = top; kb >= c * W; kb -= 4) {
-        const int r = kb - c * W;
-#pragma unroll
-        for (int j = 3; j >= 0; j--) {
-          LOAD_XY(st, r + j);
-          beta_step(b, x, y);
-        }
-        // kb % 4 == 0 and kb < K: checkpoint first (un-normalised, like beta[8*k+i]), then normalise
-        if ((kb % WC) == 0 && kb > 0) {
-          uint32_t* ck = gp.ckB + (size_t)(kb / WC) * 8 * LANES + lane;
-#pragma unroll
-          for (int i = 0; i < 8; i++) ck[i * LANES] = b[i];
-        }
-        normalise(b);
+      int top = min(K, (c + 1) * W);  // trellis steps of this chunk: k in [c*W, top)
+      if (top & 8) {
+        top -= 8;
+        beta_block<MODE, 8>(st, top - c * W, top, b, gp.ckB, lane);
       }
-      pipe.prefetch(c - 2);
+      for (; top > c * W; top -= 16) beta_block<MODE, 16>(st, top - 16 - c * W, top - 16, b, gp.ckB, lane);
     }
   } else {
-    // ---------------- forward recursion (alpha part of map_gen_alpha)
-    const int nch = (int)((K + W - 1) / W);
+    // ---------------- forward recursion (alpha part of map_gen_alpha): chunks 0, 1, ...
+    const int nch = (K + W - 1) / W;
     uint32_t  a[8];
     a[0] = 0u;
 #pragma unroll
     for (int i = 1; i < 8; i++) a[i] = NEG_INF2;
-    pipe.prefetch(0);
-    pipe.prefetch(1 < nch ? 1 : -1);
+    for (int it = 0; it < NS - 1 && it < nch; it++) pipe.issue(it, it);
     for (int c = 0; c < nch; c++) {
-      const ScanStage& st  = pipe.acquire(c);
-      const int        len = (int)min((uint32_t)W, K - (uint32_t)c * W);
-      for (int r = 0; r < len; r += 4) {
-        if ((r % WC) == 0) {
-          uint32_t* ck = gp.ckA + (size_t)((c * W + r) / WC) * 8 * LANES + lane;
-#pragma unroll
-          for (int i = 0; i < 8; i++) ck[i * LANES] = a[i];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          LOAD_XY(st, r + j);
-          alpha_step(a, x, y);
-        }
-        normalise(a);  // k = c*W + r + 4 is a multiple of 4
-      }
-      pipe.prefetch(c + 2 < nch ? c + 2 : -1);
+      if (c + NS - 1 < nch) pipe.issue(c + NS - 1, c + NS - 1);
+      const ScanStage& st  = pipe.wait(c);
+      const int        end = min(K, (c + 1) * W);
+      int              k0  = c * W;
+      for (; k0 + 16 <= end; k0 += 16) alpha_block<MODE, 16>(st, k0 - c * W, k0, a, gp.ckA, lane);
+      if (k0 < end) alpha_block<MODE, 8>(st, k0 - c * W, k0, a, gp.ckA, lane);
     }
   }
 }
 
 // ---------------------------------------------------------------- job kernel: window-parallel recompute + LLR + glue
 struct JobStage {
-  uint32_t s[3][WC][LANES];
-  uint2    tab[WC];
+  uint32_t s[3][WC][LANES];     // input rows of the window
+  uint32_t ck[2][LANES][8];     // un-normalised beta at the top of its two 8-step halves (checkpoints 2w+1, 2w+2)
+  uint2    tab[WC];             // (scatter row, CRC position word) per step
 };
 struct JobWarpSmem {
   JobStage st[2];
   uint64_t bar[2];
 };
+
+// pure form of the backward step: d = beta[k] from s = beta[k+1] (possibly normalised)
+__device__ __forceinline__ void beta_step_to(uint32_t (&d)[8], const uint32_t (&s)[8], uint32_t x, uint32_t y)
+{
+  const uint32_t xy = padd(x, y);
+  d[0] = paddmax(s[4], xy, s[0]);
+  d[1] = paddmax(s[0], xy, s[4]);
+  d[2] = paddmax(s[5], y, padd(s[1], x));
+  d[3] = paddmax(s[5], x, padd(s[1], y));
+  d[4] = paddmax(s[6], x, padd(s[2], y));
+  d[5] = paddmax(s[6], y, padd(s[2], x));
+  d[6] = paddmax(s[3], xy, s[7]);
+  d[7] = paddmax(s[7], xy, s[3]);
+}
+__device__ __forceinline__ void normalise_to(uint32_t (&d)[8], const uint32_t (&s)[8])
+{
+  const uint32_t neg = psub(0u, s[0]);
+  d[0] = 0u;
+#pragma unroll
+  for (int i = 1; i < 8; i++) d[i] = padd(s[i], neg);
+}
 
 // forward recursion + LLR step (map_gen_alpha, turbodecoder_gen.c:135-194) with beta[k] in registers; returns m1 - m0
 __device__ __forceinline__ uint32_t alpha_llr_step(uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t x, uint32_t y)
@@ -385,11 +453,13 @@ __device__ __forceinline__ uint32_t alpha_llr_step(uint32_t (&a)[8], const uint3
  * grid = (ceil(nwin_max / (4*WPJ)), n_groups), block = 128 (4 warps). Warp j of block bx handles windows
  * [(4*bx + j)*WPJ, +WPJ) of its group. Write-back (turbodecoder_iter.h:104-128 with the vec_sub / vec_lut glue folded in):
  *   MODE 0: app2[rev[i]]  = L            MODE 1: app2[rev[i]] = L - app1p[i]          MODE 2: app1p[fwd[i]] = L - app2[i]
+ * Everything a window needs - its input rows, its two beta checkpoints, its step table - arrives in shared memory through
+ * one group of bulk asynchronous copies issued one window ahead; the loop itself performs no global loads.
  */
 template <int MODE>
-__global__ void __launch_bounds__(128) job_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws,
-                                                  const uint8_t* __restrict__ group_active, const uint8_t* __restrict__ done,
-                                                  uint32_t* __restrict__ crc_acc)
+__global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws,
+                                            const uint8_t* __restrict__ group_active, const uint8_t* __restrict__ done,
+                                            uint32_t* __restrict__ crc_acc)
 {
   if (!group_active[blockIdx.y]) return;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -419,14 +489,16 @@ __global__ void __launch_bounds__(128) job_kernel(const Group* __restrict__ grou
   }
   __syncwarp();
   auto issue = [&](int w) {
-    // rows [w*WC, w*WC + WC) of each stream (streams are padded to a multiple of W >= WC rows) + the step table
+    // rows [w*WC, w*WC + WC) of each stream (streams are padded to a multiple of W >= WC rows), beta checkpoints
+    // 2w+1 and 2w+2 (adjacent), and the step table
     if (lane == 0) {
       JobStage& st  = sm->st[w & 1];
       uint64_t* bar = &sm->bar[w & 1];
-      mbar_expect_tx(bar, (MODE == 1 ? 3u : 2u) * WC * LANES * 4 + WC * 8);
+      mbar_expect_tx(bar, (MODE == 1 ? 3u : 2u) * WC * LANES * 4 + 2 * 8 * LANES * 4 + WC * 8);
       bulk_g2s(&st.s[0][0][0], in0 + (size_t)w * WC * LANES, WC * LANES * 4, bar);
       bulk_g2s(&st.s[1][0][0], in1 + (size_t)w * WC * LANES, WC * LANES * 4, bar);
       if (MODE == 1) bulk_g2s(&st.s[2][0][0], in2 + (size_t)w * WC * LANES, WC * LANES * 4, bar);
+      bulk_g2s(&st.ck[0][0][0], gp.ckB + (size_t)(2 * w + 1) * 8 * LANES, 2 * 8 * LANES * 4, bar);
       bulk_g2s(&st.tab[0], tab + (size_t)w * WC, WC * 8, bar);
     }
   };
@@ -438,6 +510,14 @@ __global__ void __launch_bounds__(128) job_kernel(const Group* __restrict__ grou
   if (cb_hi < 0 || done[cb_hi]) keep |= 0xffff0000u;
   uint32_t crc_lo = 0, crc_hi = 0;
   uint32_t ph0 = 0, ph1 = 0;
+  // alpha state entering the first window (the windows of this warp are consecutive, so it simply carries on)
+  uint32_t a[8];
+  {
+    const uint4* ca = reinterpret_cast<const uint4*>(gp.ckA + ((size_t)(w0 / WPJ) * LANES + lane) * 8);
+    const uint4  c0 = ca[0], c1 = ca[1];
+    a[0] = c0.x; a[1] = c0.y; a[2] = c0.z; a[3] = c0.w;
+    a[4] = c1.x; a[5] = c1.y; a[6] = c1.z; a[7] = c1.w;
+  }
 
   for (int w = w0; w < w1; w++) {
     const int lo = w * WC;
@@ -446,51 +526,48 @@ __global__ void __launch_bounds__(128) job_kernel(const Group* __restrict__ grou
       __syncwarp();  // every lane has finished reading the stage the next copy overwrites (window w-1)
       issue(w + 1);
     }
-    uint32_t a[8], bt[8];
-    {
-      const uint32_t* ca = gp.ckA + (size_t)w * 8 * LANES + lane;
-      const uint32_t* cb = gp.ckB + (size_t)(w + 1) * 8 * LANES + lane;
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        a[i]  = ca[i * LANES];
-        bt[i] = cb[i * LANES];
-      }
-    }
     if (w & 1) { mbar_wait(&sm->bar[1], ph1 & 1u); ph1++; } else { mbar_wait(&sm->bar[0], ph0 & 1u); ph0++; }
-    const JobStage& st = sm->st[w & 1];
-
-    // coarse pass (only for full windows): un-normalised beta[lo+8]
-    uint32_t  bmid[8];
-    const int nsub = (hi - lo) / 8;
-    if (nsub == 2) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) bmid[i] = bt[i];
-      if ((uint32_t)hi < K) normalise(bmid);
-#pragma unroll
-      for (int r = 15; r >= 8; r--) {
-        LOAD_XY(st, r);
-        beta_step(bmid, x, y);
-        if (r == 12) normalise(bmid);  // k = lo + 12
-      }
-    }
-    uint32_t bitacc = 0;
+    const JobStage& st   = sm->st[w & 1];
+    const int       nsub = (hi - lo) / 8;
+    uint32_t        bitacc = 0;
 #pragma unroll 1
     for (int s = 0; s < nsub; s++) {
-      uint32_t B[8][8], cur[8];
-      const bool last = (s == nsub - 1);
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        cur[i]  = last ? bt[i] : bmid[i];
-        B[7][i] = cur[i];
+      // recompute beta[k] for the eight steps k = lo+8s+1 .. lo+8s+8 into registers: B[j] = beta[lo+8s+1+j]
+      uint32_t B[8][8];
+      {
+        const uint4* c  = reinterpret_cast<const uint4*>(&st.ck[s][lane][0]);
+        const uint4  c0 = c[0], c1 = c[1];
+        B[7][0] = c0.x; B[7][1] = c0.y; B[7][2] = c0.z; B[7][3] = c0.w;
+        B[7][4] = c1.x; B[7][5] = c1.y; B[7][6] = c1.z; B[7][7] = c1.w;
       }
-      if ((uint32_t)(lo + 8 * s + 8) < K) normalise(cur);
+      {
+        uint32_t t[8];
+        if ((uint32_t)(lo + 8 * s + 8) < K) {
+          normalise_to(t, B[7]);  // the recursion continues from the normalised state (k % 4 == 0 and k < K)
+        } else {
 #pragma unroll
-      for (int j = 6; j >= 0; j--) {
+          for (int i = 0; i < 8; i++) t[i] = B[7][i];
+        }
+        {
+          LOAD_XY(st, 8 * s + 7);
+          beta_step_to(B[6], t, x, y);
+        }
+      }
+#pragma unroll
+      for (int j = 5; j >= 3; j--) {
         LOAD_XY(st, 8 * s + 1 + j);
-        beta_step(cur, x, y);
+        beta_step_to(B[j], B[j + 1], x, y);
+      }
+      {
+        uint32_t t[8];
+        normalise_to(t, B[3]);  // k = lo + 8s + 4
+        LOAD_XY(st, 8 * s + 3);
+        beta_step_to(B[2], t, x, y);
+      }
 #pragma unroll
-        for (int i = 0; i < 8; i++) B[j][i] = cur[i];
-        if (j == 3) normalise(cur);  // k = lo + 8s + 4
+      for (int j = 1; j >= 0; j--) {
+        LOAD_XY(st, 8 * s + 1 + j);
+        beta_step_to(B[j], B[j + 1], x, y);
       }
 #pragma unroll
       for (int j = 0; j < 8; j++) {
@@ -545,44 +622,69 @@ __global__ void __launch_bounds__(64) status_kernel(const Group* __restrict__ gr
 
 /*
  * De-multiplex natural-order LLRs (tdec_gen_extract_input, turbodecoder_gen.c:238-258) of up to 64 code blocks into the
- * group's packed [row][lane] streams. grid = (ceil(R / 32), n_groups), block = 256.
+ * group's packed [row][lane] streams. grid = (R / XT, n_groups), block = 256. HBM-bound: every LLR is read once
+ * (coalesced 192-byte runs per code block) and written once (coalesced 128-byte rows); only the three channel streams are
+ * written (app1p / app2 rows < K are produced by the decoder before they are read).
  * llr_off[cb] = element offset of the code block's 3K+12 int16 in llr.
  */
+constexpr int XT = 32;  // rows per tile
 __global__ void __launch_bounds__(256)
 extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const int16_t* __restrict__ llr, const uint64_t* __restrict__ llr_off)
 {
-  __shared__ int16_t tile[64][3 * 32 + 2];
+  constexpr int ROWW = 3 * XT / 2 + 1;      // words per tile row: 96 int16 + pad (odd => conflict-free column reads)
+  __shared__ uint32_t tile[64][ROWW];
   const Group&    g  = groups[blockIdx.y];
-  const GroupPtrs gp = group_ptrs(ws, g);
   const uint32_t  K  = g.K;
-  const uint32_t  k0 = blockIdx.x * 32;  // first row of this tile
+  const uint32_t  k0 = blockIdx.x * XT;  // first row of this tile
   if (k0 >= g.R) return;
-  const int tid = threadIdx.x;
-  // body rows k0..k0+31 (< K): 96 consecutive int16 per code block
-  const uint32_t nbody = (k0 < K) ? min(32u, K - k0) : 0u;
-  for (int idx = tid; idx < 64 * 96; idx += 256) {
-    int     cbl = idx / 96, e = idx % 96;
-    int     cb  = g.cb[cbl];
-    int16_t v   = 0;
-    if (cb >= 0 && (uint32_t)e < 3 * nbody) v = llr[llr_off[cb] + 3ull * k0 + e];
-    tile[cbl][e] = v;
+  const GroupPtrs gp   = group_ptrs(ws, g);
+  const int       tid  = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const uint32_t  nbody = (k0 < K) ? min((uint32_t)XT, K - k0) : 0u;  // rows of this tile that are trellis steps (multiple of 8)
+  // ---- load: warp w takes code blocks w, w+8, ...; 3*nbody int16 = 1.5*nbody words, contiguous
+  const uint32_t nwords = 3 * nbody / 2;
+  if (nbody) {
+#pragma unroll
+    for (int c8 = 0; c8 < 8; c8++) {
+      const int cbl = wid + 8 * c8;
+      const int cb  = g.cb[cbl];
+      if (cb < 0) {
+        for (uint32_t i = lane; i < nwords; i += 32) tile[cbl][i] = 0u;
+      } else {
+        const uint64_t off = llr_off[cb] + 3ull * k0;
+        if ((off & 1ull) == 0) {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(llr + off);
+          for (uint32_t i = lane; i < nwords; i += 32) tile[cbl][i] = __ldg(src + i);
+        } else {
+          const uint16_t* src = reinterpret_cast<const uint16_t*>(llr + off);
+          for (uint32_t i = lane; i < nwords; i += 32) tile[cbl][i] = (uint32_t)src[2 * i] | ((uint32_t)src[2 * i + 1] << 16);
+        }
+      }
+    }
   }
   __syncthreads();
-  for (int idx = tid; idx < 32 * 32; idx += 256) {
-    int      r = idx / 32, l = idx % 32;
-    uint32_t k = k0 + r;
-    if (k >= g.R) continue;
-    uint32_t s = 0, p0 = 0, p1 = 0, a2 = 0;
-    if (k < K) {
-      s  = (uint16_t)tile[l][3 * r] | ((uint32_t)(uint16_t)tile[32 + l][3 * r] << 16);
-      p0 = (uint16_t)tile[l][3 * r + 1] | ((uint32_t)(uint16_t)tile[32 + l][3 * r + 1] << 16);
-      p1 = (uint16_t)tile[l][3 * r + 2] | ((uint32_t)(uint16_t)tile[32 + l][3 * r + 2] << 16);
-    } else if (k < K + 3) {
-      // termination: syst/par0 from the first six tail values, app2/par1 from the last six
-      uint32_t j = k - K;
-      uint16_t v[2][4];
+  // ---- store: warp w writes rows w, w+8, ...: lane l packs code blocks l (low half) and 32+l (high half)
+  const uint16_t* tlo = reinterpret_cast<const uint16_t*>(&tile[lane][0]);
+  const uint16_t* thi = reinterpret_cast<const uint16_t*>(&tile[32 + lane][0]);
+  for (uint32_t r = wid; r < nbody; r += 8) {
+    const uint32_t v0 = (uint32_t)tlo[3 * r] | ((uint32_t)thi[3 * r] << 16);
+    const uint32_t v1 = (uint32_t)tlo[3 * r + 1] | ((uint32_t)thi[3 * r + 1] << 16);
+    const uint32_t v2 = (uint32_t)tlo[3 * r + 2] | ((uint32_t)thi[3 * r + 2] << 16);
+    const size_t   o  = (size_t)(k0 + r) * LANES + lane;
+    gp.syst[o] = v0;
+    gp.par0[o] = v1;
+    gp.par1[o] = v2;
+  }
+  // ---- rows >= K of this tile: termination values and zero padding (a handful of rows per group)
+  for (uint32_t idx = tid; idx < (XT - nbody) * 32; idx += 256) {
+    const uint32_t l = idx & 31, k = k0 + nbody + (idx >> 5);
+    if (k >= g.R) break;
+    uint32_t sv = 0, p0 = 0, p1 = 0, a2 = 0;
+    if (k < K + 3) {
+      // syst/par0 from the first six tail values, app2/par1 from the last six
+      const uint32_t j = k - K;
+      uint16_t       v[2][4];
       for (int h = 0; h < 2; h++) {
-        int cb = g.cb[32 * h + l];
+        const int cb = g.cb[32 * h + l];
         if (cb >= 0) {
           const int16_t* t = llr + llr_off[cb] + 3ull * K;
           v[h][0] = (uint16_t)t[2 * j];
@@ -593,58 +695,85 @@ extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const
           v[h][0] = v[h][1] = v[h][2] = v[h][3] = 0;
         }
       }
-      s  = v[0][0] | ((uint32_t)v[1][0] << 16);
+      sv = v[0][0] | ((uint32_t)v[1][0] << 16);
       p0 = v[0][1] | ((uint32_t)v[1][1] << 16);
       a2 = v[0][2] | ((uint32_t)v[1][2] << 16);
       p1 = v[0][3] | ((uint32_t)v[1][3] << 16);
     }
-    size_t o    = (size_t)k * LANES + l;
-    gp.syst[o]  = s;
+    const size_t o = (size_t)k * LANES + l;
+    gp.syst[o]  = sv;
     gp.par0[o]  = p0;
     gp.par1[o]  = p1;
     gp.app1p[o] = 0;   // rows >= K must stay zero (no a-priori on the termination steps)
-    gp.app2[o]  = a2;  // rows < K are overwritten by DEC1 before DEC2 reads them
+    gp.app2[o]  = a2;  // second encoder's termination systematic values
   }
 }
 
 /*
- * Final hard-decision bytes (tdec_gen_decision_byte, MSB first) of every code block: bits of the last half-iteration
- * it ran; after a DEC2 half-iteration they are gathered through the QPP permutation (app1[fwd[i]] = ext2[i]).
- * grid = (ceil(K/32/128), n_groups*64), block = 128 : one thread per 32 output bits.
+ * Final hard-decision bytes (tdec_gen_decision_byte, MSB first) of every code block of a group: the decisions of the
+ * last half-iteration each block ran; after a DEC2 half-iteration they are gathered through the QPP permutation
+ * (app1[fwd[i]] = ext2[i], decision on app1). grid = n_groups, block = 256, dynamic smem = emit_smem_bytes(R, K).
+ * The group's two decision arrays are transposed into shared memory ([code block][16-bit piece]), then each warp
+ * produces 32 consecutive output words of one code block (coalesced 128-byte stores).
  */
-__global__ void __launch_bounds__(128)
+__host__ __device__ inline size_t emit_smem_bytes(uint32_t R, uint32_t K)
+{
+  const uint32_t P = R / 16 + 2;  // 16-bit pieces per code block, padded so that a row is an odd number of words
+  return (size_t)2 * 64 * (P | 2u) * 2 + ((K + 63) & ~63u) * 2;
+}
+__global__ void __launch_bounds__(256)
 emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws, const uint8_t* __restrict__ noi,
             uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off)
 {
-  const Group& g   = groups[blockIdx.y >> 6];
-  const int    cbl = blockIdx.y & 63;
-  const int    cb  = g.cb[cbl];
-  if (cb < 0) return;
-  const uint32_t word = blockIdx.x * 128 + threadIdx.x;  // 32-bit word of the output
-  if (word * 32 >= g.K) return;
+  extern __shared__ __align__(16) uint8_t esm[];
+  const Group&    g    = groups[blockIdx.x];
   const GroupPtrs gp   = group_ptrs(ws, g);
-  const int       lane = cbl & 31, sh = (cbl >> 5) * 16;
-  const uint32_t  n    = noi[cb];
-  uint32_t        v    = 0;
-  if (n & 1u) {
-    // natural order: two 16-bit pieces
-    uint32_t w0 = (gp.bits1[(size_t)(2 * word) * LANES + lane] >> sh) & 0xffffu;
-    uint32_t w1 = (gp.bits1[(size_t)(2 * word + 1) * LANES + lane] >> sh) & 0xffffu;
-    v           = w0 | (w1 << 16);  // bit t of v = decision of step 32*word + t
-  } else {
-    const uint16_t* rev = ktabs[g.kidx].rev;
-    const int nt = (int)min(32u, g.K - word * 32);
-    for (int t = 0; t < nt; t++) {
-      uint32_t i = rev[word * 32 + t];
-      uint32_t b = (gp.bits2[(size_t)(i >> 4) * LANES + lane] >> (sh + (i & 15))) & 1u;
-      v |= b << t;
+  const uint32_t  K    = g.K;
+  const uint32_t  NP   = (K + 15) / 16;             // pieces actually used
+  const uint32_t  P    = (g.R / 16 + 2) | 2u;       // row pitch in int16; P/2 is odd => conflict-free transposed stores
+  uint16_t*       T1   = reinterpret_cast<uint16_t*>(esm);
+  uint16_t*       T2   = T1 + 64 * P;
+  uint16_t*       srev = T2 + 64 * P;
+  const int       tid  = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  for (uint32_t p = wid; p < NP; p += 8) {
+    const uint32_t w1 = gp.bits1[(size_t)p * LANES + lane], w2 = gp.bits2[(size_t)p * LANES + lane];
+    T1[lane * P + p]        = (uint16_t)w1;
+    T1[(32 + lane) * P + p] = (uint16_t)(w1 >> 16);
+    T2[lane * P + p]        = (uint16_t)w2;
+    T2[(32 + lane) * P + p] = (uint16_t)(w2 >> 16);
+  }
+  const uint16_t* rev = ktabs[g.kidx].rev;
+  for (uint32_t i = tid; i < K; i += 256) srev[i] = rev[i];
+  __syncthreads();
+  const uint32_t nwords = (K + 31) / 32, nchunk = (nwords + 31) / 32;
+  for (uint32_t task = wid; task < 64 * nchunk; task += 8) {
+    const uint32_t cbl = task / nchunk, word = (task % nchunk) * 32 + lane;
+    const int      cb  = g.cb[cbl];
+    if (cb < 0 || word >= nwords) continue;
+    const uint32_t nt = min(32u, K - word * 32);  // K is a multiple of 8 but not always of 32
+    uint32_t       v  = 0;
+    if (noi[cb] & 1u) {
+      // last half-iteration was a DEC1: natural order, two 16-bit pieces
+      v = (uint32_t)T1[cbl * P + 2 * word] | (nt > 16 ? ((uint32_t)T1[cbl * P + 2 * word + 1] << 16) : 0u);
+    } else {
+      const uint16_t* t2 = T2 + cbl * P;
+#pragma unroll 8
+      for (uint32_t t = 0; t < 32; t++) {
+        const uint32_t tt = (t + lane) & 31u;  // rotate so that the lanes of a warp hit different banks
+        if (tt < nt) {
+          const uint32_t i = srev[word * 32 + tt];
+          v |= (((uint32_t)t2[i >> 4] >> (i & 15u)) & 1u) << tt;
+        }
+      }
+    }
+    v = __brev(v);  // bit 31 = step 32*word : MSB-first bytes
+    uint8_t* o = out + out_off[cb] + 4ull * word;
+    if (nt == 32 && ((out_off[cb] & 3ull) == 0)) {
+      *reinterpret_cast<uint32_t*>(o) = __byte_perm(v, 0, 0x0123);
+    } else {
+      for (uint32_t b = 0; b < nt / 8; b++) o[b] = (uint8_t)(v >> (24 - 8 * b));
     }
   }
-  // MSB-first bytes; K is a multiple of 8 but not always of 32
-  v = __brev(v);  // bit 31 = step 32*word
-  uint8_t*       o      = out + out_off[cb] + 4ull * word;
-  const uint32_t nbytes = min(4u, g.K / 8 - 4 * word);
-  for (uint32_t b = 0; b < nbytes; b++) o[b] = (uint8_t)(v >> (24 - 8 * b));
 }
 
 }  // namespace srsb200

@@ -167,6 +167,10 @@ struct srsb200_engine {
   std::vector<void*>  owned;  // device allocations freed at destroy
   std::vector<uint32_t> crc_words[3];
 
+  // x^(m+24) mod g24A for the transport-block CRC kernel, grown on demand
+  uint32_t* d_tb_crc_words = nullptr;
+  uint32_t  tb_crc_words_n = 0;
+
   // rate-matching tables [cb_idx][rv] (device, uint16[3K+12]) built lazily
   uint16_t* d_rm[LTE_NOF_CB_SIZES][4];
 
@@ -285,6 +289,32 @@ static int ensure_rm_table(srsb200_engine* e, uint32_t cb_idx, uint32_t rv)
   return 0;
 }
 
+static int ensure_tb_crc_words(srsb200_engine* e, uint32_t nbits)
+{
+  if (e->tb_crc_words_n >= nbits) return 0;
+  uint32_t n = std::max(nbits, 160000u);
+  std::vector<uint32_t> w(n);
+  uint32_t v = 1;
+  auto mulx = [](uint32_t a) {
+    a <<= 1;
+    if (a & 0x1000000u) a ^= 0x1864CFBu;
+    return a & 0xffffffu;
+  };
+  for (int i = 0; i < 24; i++) v = mulx(v);
+  for (uint32_t m = 0; m < n; m++) {
+    w[m] = v;
+    v    = mulx(v);
+  }
+  if (e->d_tb_crc_words) cudaFree(e->d_tb_crc_words);
+  e->d_tb_crc_words = nullptr;
+  e->tb_crc_words_n = 0;
+  CUDA_TRY(cudaMalloc(&e->d_tb_crc_words, sizeof(uint32_t) * n));
+  CUDA_TRY(cudaMemcpyAsync(e->d_tb_crc_words, w.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->tb_crc_words_n = n;
+  return 0;
+}
+
 extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
 {
   if (!out) return fail(SRSB200_ERROR_INVALID_INPUTS, "null engine pointer");
@@ -338,6 +368,7 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
   for (int i = 0; i < 8; i++)
     if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);
   cudaFree(e->d_ktab);
+  if (e->d_tb_crc_words) cudaFree(e->d_tb_crc_words);
   for (int i = 0; i < srsb200_engine::MAX_SUB; i++) {
     if (e->sub[i]) cudaStreamDestroy(e->sub[i]);
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
@@ -402,6 +433,7 @@ struct srsb200_plan {
   uint64_t  ws_bytes = 0;
   uint64_t* d_llr_off = nullptr;
   uint64_t* d_out_off = nullptr;
+  uint32_t* d_out_len = nullptr;  // optional [n_cb] bytes to emit per code block (nullptr: K/8)
   // decode state that lives across the launches of one decode (and across srsb200_tdec_iteration calls)
   uint32_t* d_crc_acc = nullptr;  // [n_cb] running CRC of the current half-iteration
   uint8_t*  d_done = nullptr;     // [n_cb]
@@ -495,6 +527,7 @@ extern "C" void srsb200_plan_destroy(srsb200_plan_t* p)
   cudaFree(p->d_ws);
   cudaFree(p->d_llr_off);
   cudaFree(p->d_out_off);
+  cudaFree(p->d_out_len);
   cudaFree(p->d_crc_acc);
   cudaFree(p->d_done);
   cudaFree(p->d_active);
@@ -551,7 +584,7 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
     } break;
     default: {
       ProfScope ps(e, 2, st);
-      emit_kernel<<<ng, 256, emit_smem_bytes(p->max_R, p->max_R), st>>>(dg, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off);
+      emit_kernel<<<ng, 256, emit_smem_bytes(p->max_R, p->max_R), st>>>(dg, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off, p->d_out_len);
     } break;
   }
   e->launches++;

@@ -723,7 +723,7 @@ __host__ __device__ inline size_t emit_smem_bytes(uint32_t R, uint32_t K)
 }
 __global__ void __launch_bounds__(256)
 emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws, const uint8_t* __restrict__ noi,
-            uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off)
+            uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_len)
 {
   extern __shared__ __align__(16) uint8_t esm[];
   const Group&    g    = groups[blockIdx.x];
@@ -768,10 +768,14 @@ emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, 
     }
     v = __brev(v);  // bit 31 = step 32*word : MSB-first bytes
     uint8_t* o = out + out_off[cb] + 4ull * word;
-    if (nt == 32 && ((out_off[cb] & 3ull) == 0)) {
+    // out_len: bytes of this code block the caller wants (a transport block keeps K/8 - 3 bytes of every code block but
+    // the last, because the next block's bytes overwrite the 24 CRC bits: sch.c:430 writes at cb_idx * rlen / 8)
+    const uint32_t total = out_len ? out_len[cb] : K / 8;
+    const uint32_t nb    = (4 * word >= total) ? 0u : min(nt / 8, total - 4 * word);
+    if (nb == 4 && ((out_off[cb] & 3ull) == 0)) {
       *reinterpret_cast<uint32_t*>(o) = __byte_perm(v, 0, 0x0123);
     } else {
-      for (uint32_t b = 0; b < nt / 8; b++) o[b] = (uint8_t)(v >> (24 - 8 * b));
+      for (uint32_t b = 0; b < nb; b++) o[b] = (uint8_t)(v >> (24 - 8 * b));
     }
   }
 }

@@ -1,0 +1,307 @@
+/*
+ * srsran_b200_shim.c - the reference-side binding: srsRAN 4G's own symbols for the turbo-decode hot path, implemented on
+ * top of the C ABI of libsrsran_b200.so (include/srsran_b200.h).
+ *
+ * This file is compiled INSIDE the reference tree (it includes the reference's own headers for the struct layouts, so
+ * sizeof(srsran_tdec_t) / sizeof(srsran_sch_t) stay what already-compiled callers expect) and replaces the objects
+ *   lib/src/phy/fec/turbo/turbodecoder.c      (srsran_tdec_*)
+ *   the rx half of lib/src/phy/fec/turbo/rm_turbo.c (srsran_rm_turbo_rx_lut[_])
+ * and provides srsran_b200_decode_tb(), which lib/src/phy/phch/sch.c:decode_tb calls instead of its serial
+ * decode_tb_cb loop (two-line patch). Everything above decode_tb (srsran_dlsch_decode[2],
+ * srsran_ulsch_decode with its UCI de-multiplexing) is untouched and funnels into it exactly as before.
+ *
+ * The device handle lives in fields the reference already has: h->dec16_hdlr[0] (srsb200_tdec_t*). One engine per
+ * process, created on first use (device = $SRSRAN_B200_DEVICE or 0); the C ABI serialises calls per engine, so any
+ * number of PHY worker threads may call concurrently, like the lock-free reference objects.
+ *
+ * Layout contract: srsran_tdec_autoimp_get_subblocks() returns 0 for every size, which makes srsran_rm_turbo_rx_lut and
+ * the decoder agree on the natural (generic decoder) input order - SURVEY.md section 8(b).
+ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+
+#include "srsran/phy/fec/cbsegm.h"
+#include "srsran/phy/fec/softbuffer.h"
+#include "srsran/phy/fec/turbo/rm_turbo.h"
+#include "srsran/phy/fec/turbo/turbodecoder.h"
+#include "srsran/phy/phch/sch.h"
+#include "srsran/phy/utils/debug.h"
+
+#include "srsran_b200.h"
+
+static pthread_once_t    g_once   = PTHREAD_ONCE_INIT;
+static srsb200_engine_t* g_engine = NULL;
+
+static void engine_create_once(void)
+{
+  const char* dev = getenv("SRSRAN_B200_DEVICE");
+  if (srsb200_engine_create(&g_engine, dev ? atoi(dev) : 0) != SRSB200_SUCCESS) {
+    ERROR("srsran_b200: %s", srsb200_last_error());
+    g_engine = NULL;
+  }
+}
+static srsb200_engine_t* engine(void)
+{
+  pthread_once(&g_once, engine_create_once);
+  return g_engine;
+}
+
+/* ------------------------------------------------------------------ srsran_tdec_* (turbodecoder.h:97-116) */
+int srsran_tdec_init(srsran_tdec_t* h, uint32_t max_long_cb)
+{
+  return srsran_tdec_init_manual(h, max_long_cb, SRSRAN_TDEC_AUTO);
+}
+
+int srsran_tdec_init_manual(srsran_tdec_t* h, uint32_t max_long_cb, srsran_tdec_impl_type_t dec_type)
+{
+  bzero(h, sizeof(srsran_tdec_t));
+  h->dec_type    = dec_type; /* every implementation type maps to the one bit-exact device decoder */
+  h->max_long_cb = max_long_cb;
+  srsb200_tdec_t* d = NULL;
+  if (srsb200_tdec_init(&d, engine(), max_long_cb) != SRSB200_SUCCESS) {
+    ERROR("srsran_b200: %s", srsb200_last_error());
+    return SRSRAN_ERROR;
+  }
+  h->dec16_hdlr[0]    = d;
+  h->current_llr_type = SRSRAN_TDEC_16;
+  h->current_cbidx    = -1;
+  return SRSRAN_SUCCESS;
+}
+
+void srsran_tdec_free(srsran_tdec_t* h)
+{
+  if (h->dec16_hdlr[0]) {
+    srsb200_tdec_free((srsb200_tdec_t*)h->dec16_hdlr[0]);
+  }
+  bzero(h, sizeof(srsran_tdec_t));
+}
+
+void srsran_tdec_force_not_sb(srsran_tdec_t* h)
+{
+  h->force_not_sb = true; /* the device decoder always takes the natural layout */
+}
+
+int srsran_tdec_new_cb(srsran_tdec_t* h, uint32_t long_cb)
+{
+  if (srsb200_tdec_new_cb((srsb200_tdec_t*)h->dec16_hdlr[0], long_cb) != SRSB200_SUCCESS) {
+    ERROR("%s", srsb200_last_error());
+    return SRSRAN_ERROR;
+  }
+  h->n_iter          = 0;
+  h->current_long_cb = long_cb;
+  h->current_cbidx   = srsran_cbsegm_cbindex(long_cb);
+  return SRSRAN_SUCCESS;
+}
+
+int srsran_tdec_get_nof_iterations(srsran_tdec_t* h)
+{
+  return h->n_iter;
+}
+
+uint32_t srsran_tdec_autoimp_get_subblocks(uint32_t long_cb)
+{
+  return srsb200_tdec_autoimp_get_subblocks(long_cb);
+}
+
+uint32_t srsran_tdec_autoimp_get_subblocks_8bit(uint32_t long_cb)
+{
+  return srsb200_tdec_autoimp_get_subblocks(long_cb);
+}
+
+void srsran_tdec_iteration(srsran_tdec_t* h, int16_t* input, uint8_t* output)
+{
+  if (h->current_cbidx < 0) {
+    ERROR("Error CB index not set (call srsran_tdec_new_cb() first");
+    return;
+  }
+  if (srsb200_tdec_iteration((srsb200_tdec_t*)h->dec16_hdlr[0], input, output) != SRSB200_SUCCESS) {
+    ERROR("srsran_b200: %s", srsb200_last_error());
+    return;
+  }
+  h->n_iter++;
+}
+
+int srsran_tdec_run_all(srsran_tdec_t* h, int16_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb)
+{
+  if (srsran_tdec_new_cb(h, long_cb)) {
+    return SRSRAN_ERROR;
+  }
+  if (srsb200_tdec_run_all((srsb200_tdec_t*)h->dec16_hdlr[0], input, output, nof_iterations, long_cb) != SRSB200_SUCCESS) {
+    ERROR("srsran_b200: %s", srsb200_last_error());
+    return SRSRAN_ERROR;
+  }
+  h->n_iter = srsb200_tdec_get_nof_iterations((srsb200_tdec_t*)h->dec16_hdlr[0]);
+  return SRSRAN_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ srsran_rm_turbo_rx_lut (rm_turbo.h:54-84), rx half */
+void srsran_b200_rm_turbo_gentables(void)
+{
+  srsb200_rm_turbo_gentables(engine());
+}
+
+int srsran_rm_turbo_rx_lut_(int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx, bool enable_input_tdec)
+{
+  (void)enable_input_tdec; /* natural layout in both cases (autoimp_get_subblocks == 0) */
+  return srsb200_rm_turbo_rx_lut(engine(), input, output, in_len, cb_idx, rv_idx);
+}
+
+int srsran_rm_turbo_rx_lut(int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx)
+{
+  return srsran_rm_turbo_rx_lut_(input, output, in_len, cb_idx, rv_idx, true);
+}
+
+/* ------------------------------------------------------------------ decode_tb (sch.c:509-573) */
+/*
+ * Drop-in body of sch.c's static decode_tb(): same arguments, same return codes (0 ok, -1 CRC failure, -2 invalid
+ * inputs), same side effects on the soft buffer (buffer_f accumulation, cb_crc / tb_crc, cached bytes) and on
+ * q->avg_iterations. All code blocks of the transport block go to the device as one batched submission.
+ */
+int srsran_b200_decode_tb(srsran_sch_t*           q,
+                          srsran_softbuffer_rx_t* softbuffer,
+                          srsran_cbsegm_t*        cb_segm,
+                          uint32_t                Qm,
+                          uint32_t                rv,
+                          uint32_t                nof_e_bits,
+                          int16_t*                e_bits,
+                          uint8_t*                data)
+{
+  if (q == NULL || data == NULL || softbuffer == NULL || e_bits == NULL || cb_segm == NULL || Qm == 0) {
+    ERROR("Missing inputs: data=%d, softbuffer=%d, e_bits=%d, cb_segm=%d Qm=%d", data != 0, softbuffer != 0, e_bits != 0, cb_segm != 0, Qm);
+    return SRSRAN_ERROR_INVALID_INPUTS;
+  }
+  if (q->llr_is_8bit) {
+    ERROR("srsran_b200: 8-bit LLR mode is not offloaded (int16 path only)");
+    return SRSRAN_ERROR_INVALID_INPUTS;
+  }
+  uint8_t      tb_crc = 0;
+  srsb200_tb_t tb;
+  memset(&tb, 0, sizeof(tb));
+  tb.tbs        = cb_segm->tbs;
+  tb.Qm         = Qm;
+  tb.rv         = rv;
+  tb.nof_e_bits = nof_e_bits;
+  tb.e_bits     = e_bits;
+  tb.buffer_f   = softbuffer->buffer_f;
+  tb.sb_data    = softbuffer->data;
+  tb.cb_crc     = (uint8_t*)softbuffer->cb_crc; /* bool[] */
+  tb.tb_crc     = &tb_crc;
+  tb.max_cb     = softbuffer->max_cb;
+  tb.data       = data;
+  tb.cb_noi     = NULL;
+  int ret = srsb200_decode_tb(engine(), &tb, q->max_iterations);
+  if (ret == SRSB200_ERROR_NO_DEVICE) {
+    ERROR("srsran_b200: %s", srsb200_last_error());
+    return SRSRAN_ERROR;
+  }
+  if (cb_segm->tbs != 0 && cb_segm->C != 0 && ret != SRSRAN_ERROR_INVALID_INPUTS) {
+    softbuffer->tb_crc = tb_crc != 0;
+    q->avg_iterations  = tb.avg_iterations;
+  }
+  return ret;
+}
+
+/*
+ * Batched entry point for callers that hold several transport blocks at once (both codewords of a PDSCH, all PUSCH
+ * grants of a subframe, several cells): one device submission for all of them. results[i] receives decode_tb's code.
+ */
+int srsran_b200_decode_tb_batch(srsran_sch_t**           q,
+                                srsran_softbuffer_rx_t** softbuffer,
+                                srsran_cbsegm_t*         cb_segm,
+                                const uint32_t*          Qm,
+                                const uint32_t*          rv,
+                                const uint32_t*          nof_e_bits,
+                                int16_t**                e_bits,
+                                uint8_t**                data,
+                                uint32_t                 n,
+                                int*                     results)
+{
+  srsb200_tb_t* tb     = calloc(n, sizeof(srsb200_tb_t));
+  uint8_t*      tb_crc = calloc(n, 1);
+  if (!tb || !tb_crc) {
+    free(tb);
+    free(tb_crc);
+    return SRSRAN_ERROR;
+  }
+  uint32_t max_it = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    tb[i].tbs        = cb_segm[i].tbs;
+    tb[i].Qm         = Qm[i];
+    tb[i].rv         = rv[i];
+    tb[i].nof_e_bits = nof_e_bits[i];
+    tb[i].e_bits     = e_bits[i];
+    tb[i].buffer_f   = softbuffer[i]->buffer_f;
+    tb[i].sb_data    = softbuffer[i]->data;
+    tb[i].cb_crc     = (uint8_t*)softbuffer[i]->cb_crc;
+    tb[i].tb_crc     = &tb_crc[i];
+    tb[i].max_cb     = softbuffer[i]->max_cb;
+    tb[i].data       = data[i];
+    if (q[i]->max_iterations > max_it) {
+      max_it = q[i]->max_iterations;
+    }
+  }
+  int ret = srsb200_decode_tb_batch(engine(), tb, n, max_it);
+  for (uint32_t i = 0; i < n && ret == SRSB200_SUCCESS; i++) {
+    results[i] = tb[i].ret;
+    if (cb_segm[i].tbs != 0 && cb_segm[i].C != 0 && tb[i].ret != SRSRAN_ERROR_INVALID_INPUTS) {
+      softbuffer[i]->tb_crc = tb_crc[i] != 0;
+      q[i]->avg_iterations  = tb[i].avg_iterations;
+    }
+  }
+  free(tb);
+  free(tb_crc);
+  return ret == SRSB200_SUCCESS ? SRSRAN_SUCCESS : SRSRAN_ERROR;
+}
+
+/* ------------------------------------------------------------------ self-test hook (tests/test_shim.py, ctypes) */
+/*
+ * Runs srsran_b200_decode_tb through REAL reference structs (srsran_sch_t, srsran_softbuffer_rx_t, srsran_cbsegm_t built
+ * by the reference's own srsran_cbsegm is not linked here, so the caller passes C/K1/... as computed by the library).
+ * Soft-buffer arrays are passed flat: buffer_f[max_cb][SOFTBUFFER_SIZE], sb_data[max_cb][SOFTBUFFER_SIZE/8].
+ */
+int srsran_b200_selftest_decode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, int16_t* e_bits, uint32_t max_iterations,
+                                   uint32_t max_cb, int16_t* buffer_f, uint8_t* sb_data, uint8_t* cb_crc, uint8_t* tb_crc, uint8_t* data,
+                                   float* avg_iterations)
+{
+  srsran_sch_t* q = calloc(1, sizeof(srsran_sch_t));
+  if (!q) {
+    return SRSRAN_ERROR;
+  }
+  q->max_iterations = max_iterations ? max_iterations : 10;
+  srsran_softbuffer_rx_t sb;
+  memset(&sb, 0, sizeof(sb));
+  sb.max_cb      = max_cb;
+  sb.max_cb_size = SOFTBUFFER_SIZE;
+  sb.buffer_f    = calloc(max_cb, sizeof(int16_t*));
+  sb.data        = calloc(max_cb, sizeof(uint8_t*));
+  sb.cb_crc      = calloc(max_cb, sizeof(bool));
+  for (uint32_t i = 0; i < max_cb; i++) {
+    sb.buffer_f[i] = &buffer_f[(size_t)i * SOFTBUFFER_SIZE];
+    sb.data[i]     = &sb_data[(size_t)i * (SOFTBUFFER_SIZE / 8)];
+    sb.cb_crc[i]   = cb_crc[i] != 0;
+  }
+  uint32_t        sg[8];
+  srsran_cbsegm_t seg;
+  memset(&seg, 0, sizeof(seg));
+  srsb200_cbsegm(tbs, sg);
+  seg.F = sg[0]; seg.C = sg[1]; seg.K1 = sg[2]; seg.K2 = sg[3]; seg.K1_idx = sg[4]; seg.K2_idx = sg[5]; seg.C1 = sg[6]; seg.C2 = sg[7];
+  seg.tbs = tbs; seg.L_tb = 24; seg.L_cb = 24;
+  int ret = srsran_b200_decode_tb(q, &sb, &seg, Qm, rv, nof_e_bits, e_bits, data);
+  for (uint32_t i = 0; i < max_cb; i++) {
+    cb_crc[i] = sb.cb_crc[i] ? 1 : 0;
+  }
+  *tb_crc         = sb.tb_crc ? 1 : 0;
+  *avg_iterations = q->avg_iterations;
+  free(sb.buffer_f);
+  free(sb.data);
+  free(sb.cb_crc);
+  free(q);
+  return ret;
+}
+
+size_t srsran_b200_selftest_sizeof_tdec(void)
+{
+  return sizeof(srsran_tdec_t);
+}

@@ -1,0 +1,84 @@
+"""The reference-side binding (integration/srsran_b200_shim.c): built against the reference's own headers in the
+container, exercised on the GPU through the reference's symbol names and struct layouts."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import vecgen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "integration", "_build", "libsrsran_b200_shim.so")
+
+
+@pytest.mark.ref
+def test_shim_builds_against_reference_headers():
+    if not os.path.isdir(os.environ.get("SRSRAN_REF", "/root/reference")):
+        pytest.skip("no reference tree")
+    import __graft_entry__ as g
+    g.build()
+    out = subprocess.check_output(["make", "-s", "-C", os.path.join(ROOT, "integration"), "check"]).decode()
+    assert "exports all 14" in out
+
+
+@pytest.fixture(scope="module")
+def shim():
+    if not os.path.exists(SHIM):
+        pytest.skip("shim not built (needs the reference headers; built in the container and shipped with the repo)")
+    return C.CDLL(SHIM)
+
+
+@pytest.mark.gpu
+def test_shim_tdec_symbols(shim):
+    """srsran_tdec_init / new_cb / iteration / run_all / get_nof_iterations / free on a real srsran_tdec_t"""
+    o = ol.oracle()
+    shim.srsran_b200_selftest_sizeof_tdec.restype = C.c_size_t
+    h = C.create_string_buffer(shim.srsran_b200_selftest_sizeof_tdec() + 64)
+    assert shim.srsran_tdec_init(h, 6144) == 0
+    assert shim.srsran_tdec_autoimp_get_subblocks(6144) == 0
+    assert shim.srsran_tdec_new_cb(h, 41) == -1
+    for K in (40, 6144):
+        _, llr = vecgen.make_cb(K, 1.5, 5 + K)
+        hard = o.tdec_trace(K, llr, 4)
+        out = np.zeros(K // 8, np.uint8)
+        assert shim.srsran_tdec_new_cb(h, K) == 0
+        for it in range(4):
+            shim.srsran_tdec_iteration(h, llr.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+            assert (out == hard[it]).all()
+            assert shim.srsran_tdec_get_nof_iterations(h) == it + 1
+        assert shim.srsran_tdec_run_all(h, llr.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 3, K) == 0
+        assert (out == hard[2]).all()
+    shim.srsran_tdec_free(h)
+
+
+@pytest.mark.gpu
+def test_shim_rm_and_decode_tb(shim):
+    o = ol.oracle()
+    rng = np.random.default_rng(1)
+    e = rng.integers(-3000, 3000, 6646).astype(np.int16)
+    bo = np.zeros(ol.SOFTBUFFER_SIZE, np.int16); bg = bo.copy()
+    o.rm_rx(e, bo, 187, 2)
+    assert shim.srsran_rm_turbo_rx_lut(e.ctypes.data_as(C.c_void_p), bg.ctypes.data_as(C.c_void_p), len(e), 187, 2) == 0
+    assert (bo == bg).all()
+    assert shim.srsran_rm_turbo_rx_lut(e.ctypes.data_as(C.c_void_p), bg.ctypes.data_as(C.c_void_p), len(e), 188, 0) == -2
+    # decode_tb through srsran_sch_t / srsran_softbuffer_rx_t / srsran_cbsegm_t, two HARQ transmissions
+    tbs, G, Qm = 12216, 19200, 6
+    st = None
+    Cn = 2
+    buf = np.zeros((Cn, ol.SOFTBUFFER_SIZE), np.int16); sbd = np.zeros((Cn, ol.SOFTBUFFER_SIZE // 8), np.uint8)
+    cbc = np.zeros(Cn, np.uint8); tbc = np.zeros(1, np.uint8); avg = C.c_float(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for rv in (0, 2):
+        _, eb = vecgen.make_tb(tbs, G, Qm, rv, 0.8, 41, scale=100)
+        res = o.decode_tb(tbs, Qm, rv, eb, 6, st); st = res["state"]
+        data = np.zeros(Cn * 768 + 8, np.uint8)
+        ret = shim.srsran_b200_selftest_decode_tb(tbs, Qm, rv, G, p(eb), 6, Cn, p(buf), p(sbd), p(cbc), p(tbc), p(data), C.byref(avg))
+        assert ret == res["ret"] and int(tbc[0]) == res["tb_crc"] and (cbc == st["cb_crc"]).all()
+        assert np.float32(avg.value) == np.float32(res["avg_iterations"])
+        assert (buf == st["buffer_f"]).all() and (sbd == st["sb_data"]).all()
+        K1 = res["seg"]["K1"]
+        nb = (K1 - 24) // 8 + K1 // 8
+        assert (data[:nb] == res["data"][:nb]).all()

@@ -58,7 +58,8 @@ uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e);
  * of launches (the sub-batch overlap of srsb200_engine_set_subbatches is off) so the durations are not inflated. */
 int srsb200_engine_profile(srsb200_engine_t* e, int enable);
 int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[8]);
-/* number of sub-batches whose launch chains overlap on separate streams (default 4, env SRSB200_SUBBATCHES; 1 = off) */
+/* host-pointer submissions of a contiguous equal-size batch are cut into this many ranges whose H2D / decode / D2H
+ * overlap on separate streams (default 8, env SRSB200_SUBBATCHES; 1 = off) */
 int srsb200_engine_set_subbatches(srsb200_engine_t* e, int n);
 /* stream the engine launches on (cudaStream_t), so callers can time with events on the same stream */
 void* srsb200_engine_stream(const srsb200_engine_t* e);

@@ -180,11 +180,9 @@ struct srsb200_engine {
 
   // sub-batch streams (see launch_plan)
   static const int MAX_SUB = 8;
-  int          n_sub = 4;
+  int          n_sub = 8;
   cudaStream_t sub[MAX_SUB] = {nullptr};
   cudaEvent_t  ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
-  static const int N_TOKEN = 2 * MAX_SUB * SRSB200_MAX_TDEC_ITERS;
-  cudaEvent_t  ev_token[N_TOKEN] = {nullptr};
 
   // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
   bool profiling = false;
@@ -341,14 +339,13 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
   }
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-  for (int i = 0; i < srsb200_engine::N_TOKEN; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_token[i], cudaEventDisableTiming));
   CUDA_TRY(cudaMalloc(&e->d_ktab, sizeof(KTable) * LTE_NOF_CB_SIZES));
   CUDA_TRY(cudaMemset(e->d_ktab, 0, sizeof(KTable) * LTE_NOF_CB_SIZES));
   crc_position_words(0x1864CFBu, e->crc_words[SRSB200_CRC_24A]);
   crc_position_words(0x1800063u, e->crc_words[SRSB200_CRC_24B]);
-  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
-  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmem))));
   CUDA_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)emit_smem_bytes(((SRSB200_MAX_K + 3 + W - 1) / W) * W, SRSB200_MAX_K + 64)));
   CUDA_TRY(cudaFuncSetAttribute(job_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
@@ -374,8 +371,6 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  for (int i = 0; i < srsb200_engine::N_TOKEN; i++)
-    if (e->ev_token[i]) cudaEventDestroy(e->ev_token[i]);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -439,6 +434,7 @@ struct srsb200_plan {
   uint8_t*  d_done = nullptr;     // [n_cb]
   uint8_t*  d_active = nullptr;   // [n_groups]
   bool      uniform = false;
+  bool      contiguous = false;  // one (K, crc) bucket and code block i at llr offset i*(3K+12), output offset i*K/8
 };
 
 // cbs sorted into groups of <= 64 equal (K, crc_kind) blocks
@@ -487,6 +483,11 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
   }
   p->n_groups = (uint32_t)p->h_groups.size();
   p->ws_bytes = off;
+  p->contiguous = buckets.size() == 1;
+  for (uint32_t i = 0; i < n && p->contiguous; i++) {
+    const uint32_t k = K ? K[i] : uniform_K;
+    if ((llr_off && llr_off[i] != (uint64_t)i * (3ull * k + 12)) || (out_off && out_off[i] != (uint64_t)i * (k / 8))) p->contiguous = false;
+  }
   cudaError_t ce;
   if ((ce = cudaMalloc(&p->d_groups, sizeof(Group) * std::max<uint32_t>(1, p->n_groups))) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_ws, std::max<uint64_t>(256, p->ws_bytes))) != cudaSuccess ||
@@ -559,8 +560,8 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
   cudaStream_t   st = r.st;
   const int      mode = (n == 0) ? 0 : ((n & 1u) ? 2 : 1);
   const uint32_t nwin_max = (p->max_R + WC - 1) / WC;
-  const dim3     sgrid(ng, 2), jgrid((nwin_max + 4 * WPJ - 1) / (4 * WPJ), ng);
-  const size_t   ssm = sizeof(ScanSmem), jsm = 4 * sizeof(JobWarpSmem);
+  const dim3     sgrid((ng + 1) / 2), jgrid((nwin_max + 4 * WPJ - 1) / (4 * WPJ), ng);
+  const size_t   ssm = 4 * sizeof(ScanSmem), jsm = 4 * sizeof(JobWarpSmem);
   switch (kind) {
     case 0: {
       ProfScope ps(e, 0, st);
@@ -568,9 +569,9 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
     } break;
     case 1: {
       ProfScope ps(e, 5, st);
-      if (mode == 0) scan_kernel<0><<<sgrid, 32, ssm, st>>>(dg, p->d_ws, da);
-      else if (mode == 1) scan_kernel<1><<<sgrid, 32, ssm, st>>>(dg, p->d_ws, da);
-      else scan_kernel<2><<<sgrid, 32, ssm, st>>>(dg, p->d_ws, da);
+      if (mode == 0) scan_kernel<0><<<sgrid, 128, ssm, st>>>(dg, p->d_ws, da, ng);
+      else if (mode == 1) scan_kernel<1><<<sgrid, 128, ssm, st>>>(dg, p->d_ws, da, ng);
+      else scan_kernel<2><<<sgrid, 128, ssm, st>>>(dg, p->d_ws, da, ng);
     } break;
     case 2: {
       ProfScope ps(e, 6, st);
@@ -593,14 +594,21 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
 /*
  * A decode is a chain of dependent launches: extract, then per half-iteration {scan, job, status}, then emit. Every
  * half-iteration up to max_iter is enqueued; groups whose code blocks are all done exit at once.
- * The alpha/beta scans are latency-bound (one lone warp per recursion, ~6144 x 47 cycles whatever the batch size), the
- * window jobs are throughput-bound. So the groups are split into S sub-batches with one stream each, and a token (an event
- * chain) makes the job kernels take turns: while the jobs of one sub-batch fill the machine, the other sub-batches run
- * their scans in the shadow. Per-kernel profiling forces a single chain so that the event-timed durations are not
- * inflated by co-running kernels.
+ *
+ * Host-pointer submissions of a contiguous equal-size batch are cut into S ranges of groups, each with its own stream:
+ * H2D of range s+1 overlaps the decode of range s, and its D2H overlaps the decode of range s+2 (the PCIe copies are
+ * the long pole of the end-to-end path: 6.1 bytes per information bit). Device-resident submissions run as one chain:
+ * overlapping the latency-bound scans of one range with the window jobs of another was measured and does not pay
+ * (scan warps sharing a sub-partition with job warps slow down as much as the overlap gains; profiles/r01_notes.md).
  */
+struct HostIO {
+  const int16_t* h_llr = nullptr;
+  uint8_t *      h_out = nullptr, *h_noi = nullptr, *h_ok = nullptr;
+  uint32_t       L = 0, KB = 0;  // int16 per code block in, bytes per code block out
+};
+
 static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr, uint32_t max_iter, uint32_t min_iter, int early_stop,
-                       uint32_t start_iter, bool do_extract, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok)
+                       uint32_t start_iter, bool do_extract, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok, const HostIO* io = nullptr)
 {
   if (p->n_groups == 0) return SRSB200_SUCCESS;
   if (max_iter == 0) max_iter = 1;  // run_all is a do-while (turbodecoder.c:542-546)
@@ -609,9 +617,8 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     CUDA_TRY(cudaMemsetAsync(p->d_done, 0, p->n_cb, e->stream));
     CUDA_TRY(cudaMemsetAsync(p->d_active, 1, p->n_groups, e->stream));
   }
-  uint32_t S = e->profiling ? 1u : (uint32_t)e->n_sub;
-  // sub-batches only pay off when each still fills a good part of the machine with window jobs
-  S = std::max(1u, std::min(S, p->n_groups / 16u));
+  uint32_t S = 1;
+  if (io && !e->profiling) S = std::max(1u, std::min((uint32_t)e->n_sub, p->n_groups / 16u));
   RangeArgs rg[srsb200_engine::MAX_SUB];
   for (uint32_t s = 0; s < S; s++) {
     rg[s].g0 = (uint32_t)((uint64_t)p->n_groups * s / S);
@@ -622,23 +629,25 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
     for (uint32_t s = 0; s < S; s++) CUDA_TRY(cudaStreamWaitEvent(e->sub[s], e->ev_fork, 0));
   }
-  if (do_extract)
-    for (uint32_t s = 0; s < S; s++) launch_one(e, p, rg[s], 0, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
-  cudaEvent_t token = nullptr;  // completion of the most recently enqueued job kernel
-  uint32_t    tk = 0;
-  for (uint32_t n = start_iter; n < max_iter; n++) {
-    for (uint32_t s = 0; s < S; s++) {
+  for (uint32_t s = 0; s < S; s++) {
+    // group g of a contiguous plan holds code blocks [64 g, 64 g + 64)
+    const uint64_t c0 = 64ull * rg[s].g0, c1 = std::min<uint64_t>(64ull * rg[s].g1, p->n_cb);
+    if (io)
+      CUDA_TRY(cudaMemcpyAsync(const_cast<int16_t*>(d_llr) + c0 * io->L, io->h_llr + c0 * io->L, (c1 - c0) * io->L * sizeof(int16_t),
+                               cudaMemcpyHostToDevice, rg[s].st));
+    if (do_extract) launch_one(e, p, rg[s], 0, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+    for (uint32_t n = start_iter; n < max_iter; n++) {
       launch_one(e, p, rg[s], 1, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
-      if (S > 1 && token) CUDA_TRY(cudaStreamWaitEvent(rg[s].st, token, 0));
       launch_one(e, p, rg[s], 2, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
-      if (S > 1) {
-        token = e->ev_token[tk++ % srsb200_engine::N_TOKEN];
-        CUDA_TRY(cudaEventRecord(token, rg[s].st));
-      }
       launch_one(e, p, rg[s], 3, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
     }
+    launch_one(e, p, rg[s], 4, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+    if (io) {
+      CUDA_TRY(cudaMemcpyAsync(io->h_out + c0 * io->KB, d_out + c0 * io->KB, (c1 - c0) * io->KB, cudaMemcpyDeviceToHost, rg[s].st));
+      CUDA_TRY(cudaMemcpyAsync(io->h_noi + c0, d_noi + c0, c1 - c0, cudaMemcpyDeviceToHost, rg[s].st));
+      CUDA_TRY(cudaMemcpyAsync(io->h_ok + c0, d_ok + c0, c1 - c0, cudaMemcpyDeviceToHost, rg[s].st));
+    }
   }
-  for (uint32_t s = 0; s < S; s++) launch_one(e, p, rg[s], 4, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
   if (S > 1) {
     for (uint32_t s = 0; s < S; s++) {
       CUDA_TRY(cudaEventRecord(e->ev_join[s], e->sub[s]));
@@ -701,13 +710,21 @@ extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_
       ensure_scratch(e, 3, n, &d_ok)) {
     return SRSB200_ERROR;
   }
-  cudaError_t ce = cudaMemcpyAsync(d_llr, llr, llr_len * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream);
-  if (ce == cudaSuccess) {
-    r = launch_plan(e, p, (const int16_t*)d_llr, max_iter, min_iter, early_stop, 0, true, (uint8_t*)d_out, (uint8_t*)d_noi, (uint8_t*)d_ok);
+  cudaError_t ce = cudaSuccess;
+  if (p->contiguous && llr_len == (uint64_t)n * (3ull * K[0] + 12) && out_len == (uint64_t)n * (K[0] / 8)) {
+    // chunked copies overlapped with the decode of the neighbouring ranges
+    HostIO io;
+    io.h_llr = llr; io.h_out = out_bytes; io.h_noi = noi; io.h_ok = crc_ok;
+    io.L = 3 * K[0] + 12; io.KB = K[0] / 8;
+    r = launch_plan(e, p, (const int16_t*)d_llr, max_iter, min_iter, early_stop, 0, true, (uint8_t*)d_out, (uint8_t*)d_noi, (uint8_t*)d_ok, &io);
+  } else {
+    ce = cudaMemcpyAsync(d_llr, llr, llr_len * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess)
+      r = launch_plan(e, p, (const int16_t*)d_llr, max_iter, min_iter, early_stop, 0, true, (uint8_t*)d_out, (uint8_t*)d_noi, (uint8_t*)d_ok);
+    if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(out_bytes, d_out, out_len, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(noi, d_noi, n, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(crc_ok, d_ok, n, cudaMemcpyDeviceToHost, e->stream);
   }
-  if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(out_bytes, d_out, out_len, cudaMemcpyDeviceToHost, e->stream);
-  if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(noi, d_noi, n, cudaMemcpyDeviceToHost, e->stream);
-  if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(crc_ok, d_ok, n, cudaMemcpyDeviceToHost, e->stream);
   if (ce == cudaSuccess && r == 0) ce = cudaStreamSynchronize(e->stream);
   if (ce != cudaSuccess) {
     cudaGetLastError();

@@ -216,11 +216,11 @@ __device__ __forceinline__ uint32_t positive_mask(uint32_t v)
 }
 
 // ---------------------------------------------------------------- scan kernel: sequential alpha / beta recursions
-constexpr int NS = 4;  // staged chunks in flight per scan warp (bulk copies run NS-1 chunks ahead of the recursion)
+constexpr int NS = 3;  // staged chunks in flight per scan warp (bulk copies run NS-1 chunks ahead of the recursion)
 struct ScanStage {
   uint32_t s[3][W][LANES];
 };
-struct ScanSmem {
+struct alignas(128) ScanSmem {
   ScanStage st[NS];
   uint64_t  bar[NS];
 };
@@ -317,20 +317,26 @@ __device__ __forceinline__ void alpha_block(const ScanStage& st, int r0, int k0,
  * MODE 0: DEC1 on the first half-iteration (no a-priori)   x = syst,          y = par0
  * MODE 1: DEC1 with a-priori                                x = syst + app1p,  y = par0
  * MODE 2: DEC2                                              x = app2,          y = par1
- * grid = (n_groups, 2), block = 32: blockIdx.y == 0 runs the backward (beta) recursion, 1 the forward (alpha) one.
- * (Running both recursions in ONE warp doubles the time - measured 365 us vs 185 us per launch: a lone warp is
- * issue-limited, not dependency-limited. They stay in separate warps.)
+ * grid = ceil(n_groups / 2), block = 128: the four warps of a block are the backward (beta) and forward (alpha) recursions
+ * of two groups. FOUR warps per block on purpose: a warp's SM sub-partition is its index within the block modulo 4, so
+ * one-warp blocks all pile up on sub-partition 0 of their SM and share its issue port (measured: 56 cycles per step with
+ * 32-thread blocks against 23-28 for a warp that has its sub-partition to itself - tools/microbench/lone_warp_step.cu).
+ * (Running both recursions in ONE warp is no alternative: a lone warp is issue-limited, not dependency-limited.)
  * Checkpoints: ckB[k/CKB] = un-normalised beta[k] for k = CKB, 2 CKB, ..., K (what alpha step k consumes);
  *              ckA[k/(WC*WPJ)] = alpha state entering step k+1 (post-normalisation) for k = multiples of WC*WPJ.
  */
 template <int MODE>
-__global__ void __launch_bounds__(32) scan_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const uint8_t* __restrict__ group_active)
+__global__ void __launch_bounds__(128) scan_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const uint8_t* __restrict__ group_active,
+                                                   uint32_t n_groups)
 {
-  if (!group_active[blockIdx.x]) return;
+  const int      wid = threadIdx.x >> 5;
+  const uint32_t gi  = blockIdx.x * 2 + (wid >> 1);
+  const int      dir = wid & 1;  // 0 = backward (beta), 1 = forward (alpha)
+  if (gi >= n_groups || !group_active[gi]) return;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  ScanSmem*       sm   = reinterpret_cast<ScanSmem*>(smem_raw);
-  const int       lane = threadIdx.x;
-  const Group&    g    = groups[blockIdx.x];
+  ScanSmem*       sm   = reinterpret_cast<ScanSmem*>(smem_raw) + wid;
+  const int       lane = threadIdx.x & 31;
+  const Group&    g    = groups[gi];
   const GroupPtrs gp   = group_ptrs(ws, g);
   const int       K    = (int)g.K;
   if (lane == 0) {
@@ -345,7 +351,7 @@ __global__ void __launch_bounds__(32) scan_kernel(const Group* __restrict__ grou
   pipe.src1 = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
   pipe.src2 = (MODE == 1) ? gp.par0 : nullptr;
 
-  if (blockIdx.y == 0) {
+  if (dir == 0) {
     // ---------------- backward recursion (map_gen_beta): chunks cK, cK-1, ..., 0
     const int cK = K / W;  // chunk holding rows K..K+2
     uint32_t  b[8];
@@ -400,7 +406,7 @@ struct JobStage {
   uint32_t ck[2][LANES][8];     // un-normalised beta at the top of its two 8-step halves (checkpoints 2w+1, 2w+2)
   uint2    tab[WC];             // (scatter row, CRC position word) per step
 };
-struct JobWarpSmem {
+struct alignas(128) JobWarpSmem {
   JobStage st[2];
   uint64_t bar[2];
 };

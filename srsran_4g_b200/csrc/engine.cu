@@ -343,9 +343,9 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   CUDA_TRY(cudaMemset(e->d_ktab, 0, sizeof(KTable) * LTE_NOF_CB_SIZES));
   crc_position_words(0x1864CFBu, e->crc_words[SRSB200_CRC_24A]);
   crc_position_words(0x1800063u, e->crc_words[SRSB200_CRC_24B]);
-  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmem))));
-  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmem))));
-  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmemT<0>))));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmemT<1>))));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmemT<2>))));
   CUDA_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)emit_smem_bytes(((SRSB200_MAX_K + 3 + W - 1) / W) * W, SRSB200_MAX_K + 64)));
   CUDA_TRY(cudaFuncSetAttribute(job_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
@@ -561,7 +561,8 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
   const int      mode = (n == 0) ? 0 : ((n & 1u) ? 2 : 1);
   const uint32_t nwin_max = (p->max_R + WC - 1) / WC;
   const dim3     sgrid((ng + 1) / 2), jgrid((nwin_max + 4 * WPJ - 1) / (4 * WPJ), ng);
-  const size_t   ssm = 4 * sizeof(ScanSmem), jsm = 4 * sizeof(JobWarpSmem);
+  const size_t   ssm = 4 * sizeof(ScanSmemT<0>), jsm = 4 * sizeof(JobWarpSmem);
+  static_assert(sizeof(ScanSmemT<0>) == sizeof(ScanSmemT<1>) && sizeof(ScanSmemT<0>) == sizeof(ScanSmemT<2>), "scan smem");
   switch (kind) {
     case 0: {
       ProfScope ps(e, 0, st);

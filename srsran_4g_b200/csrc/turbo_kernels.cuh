@@ -28,7 +28,7 @@
 
 namespace srsb200 {
 
-constexpr int W        = 32;  // rows per staged chunk of the scan kernels; streams are padded to a multiple of W rows
+constexpr int W        = 64;  // rows per staged chunk of the scan kernels; streams are padded to a multiple of W rows
 constexpr int WC       = 16;  // checkpoint spacing = window of one job = one hard-bit word
 constexpr int WPJ      = 8;   // windows per job warp
 constexpr int CKB      = 8;   // spacing of the beta checkpoints (one per 8-step register window of the job kernel)
@@ -83,6 +83,7 @@ __host__ __device__ inline GroupPtrs group_ptrs(uint8_t* ws, const Group& g)
 __device__ __forceinline__ uint32_t padd(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 __device__ __forceinline__ uint32_t psub(uint32_t a, uint32_t b) { return __vsub2(a, b); }
 __device__ __forceinline__ uint32_t pmax(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+__device__ __forceinline__ uint32_t pmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 // max(a + b, c) with a wrapping add: one VIADDMNMX.S16x2
 __device__ __forceinline__ uint32_t paddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
 
@@ -216,35 +217,67 @@ __device__ __forceinline__ uint32_t positive_mask(uint32_t v)
 }
 
 // ---------------------------------------------------------------- scan kernel: sequential alpha / beta recursions
-constexpr int NS = 3;  // staged chunks in flight per scan warp (bulk copies run NS-1 chunks ahead of the recursion)
-struct ScanStage {
-  uint32_t s[3][W][LANES];
+#ifdef SCAN_PROBE
+__device__ long long g_probe_cycles[1024];
+#endif
+// staged chunks in flight per scan warp (bulk copies run NS-1 chunks ahead of the recursion), sized so that the four
+// warps of a block fit in one SM's shared memory: 2 streams x 3 stages or 3 streams x 2 stages of 8 KB each = 48 KB
+template <int MODE> struct ScanCfg {
+  static constexpr int NSTR = (MODE == 1) ? 3 : 2;
+  static constexpr int NS   = (MODE == 1) ? 2 : 3;
 };
-struct alignas(128) ScanSmem {
-  ScanStage st[NS];
-  uint64_t  bar[NS];
+template <int MODE> struct ScanStageT {
+  uint32_t s[ScanCfg<MODE>::NSTR][W][LANES];
+};
+template <int MODE> struct alignas(128) ScanSmemT {
+  ScanStageT<MODE> st[ScanCfg<MODE>::NS];
+  uint64_t         bar[ScanCfg<MODE>::NS];
 };
 
-struct ScanPipe {
+template <int MODE> struct ScanPipe {
   // chunks are consumed in a fixed order (it = 0, 1, 2, ...); stage = it % NS, mbarrier parity = (it / NS) & 1
-  ScanSmem*       sm;
+  static constexpr int NS = ScanCfg<MODE>::NS, NSTR = ScanCfg<MODE>::NSTR;
+  ScanSmemT<MODE>* sm;
   const uint32_t *src0, *src1, *src2;
 
   __device__ __forceinline__ void issue(int it, int chunk)
   {
+#ifdef PROBE_NO_PIPE
+    return;
+#endif
     __syncwarp();  // every lane is done with the stage this copy overwrites
-    if ((threadIdx.x & 31) == 0) {
-      ScanStage& st  = sm->st[it % NS];
-      uint64_t*  bar = &sm->bar[it % NS];
-      mbar_expect_tx(bar, (src2 ? 3u : 2u) * W * LANES * 4);
-      bulk_g2s(&st.s[0][0][0], src0 + (size_t)chunk * W * LANES, W * LANES * 4, bar);
-      bulk_g2s(&st.s[1][0][0], src1 + (size_t)chunk * W * LANES, W * LANES * 4, bar);
-      if (src2) bulk_g2s(&st.s[2][0][0], src2 + (size_t)chunk * W * LANES, W * LANES * 4, bar);
+    // one elected lane arms the barrier and issues the bulk copies; a single predicated asm block keeps the warp
+    // convergent (a C++ `if (lane == 0)` around separate asm statements costs a divergence region per copy)
+    const uint32_t bar = smem_u32(&sm->bar[it % NS]);
+    const uint32_t d0  = smem_u32(&sm->st[it % NS].s[0][0][0]);
+    const size_t   off = (size_t)chunk * W * LANES;
+    constexpr uint32_t BYTES = W * LANES * 4;
+    if (NSTR == 3) {
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "elect.sync _|p, 0xffffffff;\n"
+          "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %4, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%6], %4, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%8], [%7], %4, [%0];\n}"
+          ::"r"(bar), "r"(3u * BYTES), "r"(d0), "r"(d0 + BYTES), "r"(BYTES), "l"(src0 + off), "l"(src1 + off), "l"(src2 + off), "r"(d0 + 2 * BYTES)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "elect.sync _|p, 0xffffffff;\n"
+          "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %4, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%6], %4, [%0];\n}"
+          ::"r"(bar), "r"(2u * BYTES), "r"(d0), "r"(d0 + BYTES), "r"(BYTES), "l"(src0 + off), "l"(src1 + off)
+          : "memory");
     }
   }
-  __device__ __forceinline__ const ScanStage& wait(int it)
+  __device__ __forceinline__ const ScanStageT<MODE>& wait(int it)
   {
+#ifndef PROBE_NO_PIPE
     mbar_wait(&sm->bar[it % NS], (uint32_t)(it / NS) & 1u);
+#endif
     return sm->st[it % NS];
   }
 };
@@ -263,7 +296,7 @@ struct ScanPipe {
 // 13-instruction step), so the scans are written to execute as few instructions per trellis step as possible:
 // fully unrolled blocks of N steps whose x / y are fetched from shared memory up front, one checkpoint test per block.
 template <int MODE, int N>
-__device__ __forceinline__ void beta_block(const ScanStage& st, int r0, int k0, uint32_t (&b)[8], uint32_t* ckB, int lane)
+__device__ __forceinline__ void beta_block(const ScanStageT<MODE>& st, int r0, int k0, uint32_t (&b)[8], uint32_t* ckB, int lane)
 {
   // steps k = k0+N-1 .. k0 (rows r0+N-1 .. r0 of the staged chunk); k0 is a multiple of 8
   uint32_t xs[N], ys[N];
@@ -278,19 +311,21 @@ __device__ __forceinline__ void beta_block(const ScanStage& st, int r0, int k0, 
     beta_step(b, xs[j], ys[j]);
     if ((j & 3) == 0) {
       // k % 4 == 0 and k < K: checkpoint first (un-normalised, like beta[8*k+i]), then normalise
+#ifndef PROBE_NO_CKPT
       if ((j & 7) == 0 && k0 + j > 0) {
         // layout [slot][lane][8]: two 128-bit stores per lane, 1 KB contiguous per warp
         uint4* ck = reinterpret_cast<uint4*>(ckB + ((size_t)((k0 + j) / CKB) * LANES + lane) * 8);
         ck[0]     = make_uint4(b[0], b[1], b[2], b[3]);
         ck[1]     = make_uint4(b[4], b[5], b[6], b[7]);
       }
+#endif
       normalise(b);
     }
   }
 }
 
 template <int MODE, int N>
-__device__ __forceinline__ void alpha_block(const ScanStage& st, int r0, int k0, uint32_t (&a)[8], uint32_t* ckA, int lane)
+__device__ __forceinline__ void alpha_block(const ScanStageT<MODE>& st, int r0, int k0, uint32_t (&a)[8], uint32_t* ckA, int lane)
 {
   // steps k = k0+1 .. k0+N (rows r0 .. r0+N-1); k0 is a multiple of 8
   uint32_t xs[N], ys[N];
@@ -333,8 +368,12 @@ __global__ void __launch_bounds__(128) scan_kernel(const Group* __restrict__ gro
   const uint32_t gi  = blockIdx.x * 2 + (wid >> 1);
   const int      dir = wid & 1;  // 0 = backward (beta), 1 = forward (alpha)
   if (gi >= n_groups || !group_active[gi]) return;
+#ifdef SCAN_PROBE
+  const long long probe_t0 = clock64();
+#endif
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  ScanSmem*       sm   = reinterpret_cast<ScanSmem*>(smem_raw) + wid;
+  ScanSmemT<MODE>* sm  = reinterpret_cast<ScanSmemT<MODE>*>(smem_raw) + wid;
+  constexpr int   NS   = ScanCfg<MODE>::NS;
   const int       lane = threadIdx.x & 31;
   const Group&    g    = groups[gi];
   const GroupPtrs gp   = group_ptrs(ws, g);
@@ -345,7 +384,7 @@ __global__ void __launch_bounds__(128) scan_kernel(const Group* __restrict__ gro
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  ScanPipe pipe;
+  ScanPipe<MODE> pipe;
   pipe.sm   = sm;
   pipe.src0 = (MODE == 2) ? gp.app2 : gp.syst;
   pipe.src1 = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
@@ -362,7 +401,7 @@ __global__ void __launch_bounds__(128) scan_kernel(const Group* __restrict__ gro
     for (int it = 0; it <= cK; it++) {
       const int c = cK - it;
       if (it + NS - 1 <= cK) pipe.issue(it + NS - 1, c - (NS - 1));
-      const ScanStage& st = pipe.wait(it);
+      const ScanStageT<MODE>& st = pipe.wait(it);
       if (c == cK) {
         // termination steps k = K+2, K+1, K (no a-priori there: app1p rows >= K stay zero); no normalisation at k = K
 #pragma unroll
@@ -391,13 +430,16 @@ __global__ void __launch_bounds__(128) scan_kernel(const Group* __restrict__ gro
     for (int it = 0; it < NS - 1 && it < nch; it++) pipe.issue(it, it);
     for (int c = 0; c < nch; c++) {
       if (c + NS - 1 < nch) pipe.issue(c + NS - 1, c + NS - 1);
-      const ScanStage& st  = pipe.wait(c);
+      const ScanStageT<MODE>& st = pipe.wait(c);
       const int        end = min(K, (c + 1) * W);
       int              k0  = c * W;
       for (; k0 + 16 <= end; k0 += 16) alpha_block<MODE, 16>(st, k0 - c * W, k0, a, gp.ckA, lane);
       if (k0 < end) alpha_block<MODE, 8>(st, k0 - c * W, k0, a, gp.ckA, lane);
     }
   }
+#ifdef SCAN_PROBE
+  if (lane == 0) g_probe_cycles[gi * 2 + dir] = clock64() - probe_t0;
+#endif
 }
 
 // ---------------------------------------------------------------- job kernel: window-parallel recompute + LLR + glue
@@ -441,18 +483,19 @@ __device__ __forceinline__ uint32_t alpha_llr_step(uint32_t (&a)[8], const uint3
   uint32_t z4 = a[1], z5 = padd(a[2], y), z6 = padd(a[5], y), z7 = a[6];
   uint32_t o0 = padd(a[1], xy), o1 = padd(a[2], x), o2 = padd(a[5], x), o3 = padd(a[6], xy);
   uint32_t o4 = padd(a[0], xy), o5 = padd(a[3], x), o6 = padd(a[4], x), o7 = padd(a[7], xy);
-  // two chains per maximum keep the dependent depth short
-  uint32_t m0a = padd(z0, b[0]), m0b = padd(z4, b[4]);
-  m0a = paddmax(z1, b[1], m0a); m0b = paddmax(z5, b[5], m0b);
-  m0a = paddmax(z2, b[2], m0a); m0b = paddmax(z6, b[6], m0b);
-  m0a = paddmax(z3, b[3], m0a); m0b = paddmax(z7, b[7], m0b);
-  uint32_t m1a = padd(o0, b[0]), m1b = padd(o4, b[4]);
-  m1a = paddmax(o1, b[1], m1a); m1b = paddmax(o5, b[5], m1b);
-  m1a = paddmax(o2, b[2], m1a); m1b = paddmax(o6, b[6], m1b);
-  m1a = paddmax(o3, b[3], m1a); m1b = paddmax(o7, b[7], m1b);
+  // The job kernel is bound by the ALU pipe (max-class instructions), the FMA pipe (adds) has room: form the sixteen
+  // branch sums with plain adds and reduce them with three-input maxima (VIMNMX3.S16x2): 8 ALU-pipe instructions for
+  // the two 8-way maxima instead of 14 with add-max chains.
+  const uint32_t p0 = padd(z0, b[0]), p1 = padd(z1, b[1]), p2 = padd(z2, b[2]), p3 = padd(z3, b[3]);
+  const uint32_t p4 = padd(z4, b[4]), p5 = padd(z5, b[5]), p6 = padd(z6, b[6]), p7 = padd(z7, b[7]);
+  const uint32_t q0 = padd(o0, b[0]), q1 = padd(o1, b[1]), q2 = padd(o2, b[2]), q3 = padd(o3, b[3]);
+  const uint32_t q4 = padd(o4, b[4]), q5 = padd(o5, b[5]), q6 = padd(o6, b[6]), q7 = padd(o7, b[7]);
+  // (every three-input maximum takes sums only, so ptxas cannot fold an add back into a VIADDMNMX on the ALU pipe)
+  const uint32_t m0  = pmax(pmax3(pmax3(p0, p1, p2), p6, p7), pmax3(p3, p4, p5));
+  const uint32_t m1  = pmax(pmax3(pmax3(q0, q1, q2), q6, q7), pmax3(q3, q4, q5));
   a[0] = pmax(z0, o0); a[1] = pmax(z1, o1); a[2] = pmax(z2, o2); a[3] = pmax(z3, o3);
   a[4] = pmax(z4, o4); a[5] = pmax(z5, o5); a[6] = pmax(z6, o6); a[7] = pmax(z7, o7);
-  return psub(pmax(m1a, m1b), pmax(m0a, m0b));
+  return psub(m1, m0);
 }
 
 /*
@@ -496,16 +539,40 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   __syncwarp();
   auto issue = [&](int w) {
     // rows [w*WC, w*WC + WC) of each stream (streams are padded to a multiple of W >= WC rows), beta checkpoints
-    // 2w+1 and 2w+2 (adjacent), and the step table
-    if (lane == 0) {
-      JobStage& st  = sm->st[w & 1];
-      uint64_t* bar = &sm->bar[w & 1];
-      mbar_expect_tx(bar, (MODE == 1 ? 3u : 2u) * WC * LANES * 4 + 2 * 8 * LANES * 4 + WC * 8);
-      bulk_g2s(&st.s[0][0][0], in0 + (size_t)w * WC * LANES, WC * LANES * 4, bar);
-      bulk_g2s(&st.s[1][0][0], in1 + (size_t)w * WC * LANES, WC * LANES * 4, bar);
-      if (MODE == 1) bulk_g2s(&st.s[2][0][0], in2 + (size_t)w * WC * LANES, WC * LANES * 4, bar);
-      bulk_g2s(&st.ck[0][0][0], gp.ckB + (size_t)(2 * w + 1) * 8 * LANES, 2 * 8 * LANES * 4, bar);
-      bulk_g2s(&st.tab[0], tab + (size_t)w * WC, WC * 8, bar);
+    // 2w+1 and 2w+2 (adjacent), and the step table: one elected lane, one predicated asm block (warp stays convergent)
+    JobStage&          st    = sm->st[w & 1];
+    const uint32_t     bar   = smem_u32(&sm->bar[w & 1]);
+    const uint32_t     d0    = smem_u32(&st.s[0][0][0]);
+    const size_t       off   = (size_t)w * WC * LANES;
+    constexpr uint32_t BYTES = WC * LANES * 4, CKBYTES = 2 * 8 * LANES * 4, TABBYTES = WC * 8;
+    const uint32_t*    ck    = gp.ckB + (size_t)(2 * w + 1) * 8 * LANES;
+    const uint2*       tb    = tab + (size_t)w * WC;
+    if (MODE == 1) {
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "elect.sync _|p, 0xffffffff;\n"
+          "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %3, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%6], %3, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%7], [%8], %3, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%9], [%10], %11, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%12], [%13], %14, [%0];\n}"
+          ::"r"(bar), "r"(3u * BYTES + CKBYTES + TABBYTES), "r"(d0), "r"(BYTES), "r"(d0 + BYTES), "l"(in0 + off), "l"(in1 + off),
+            "r"(d0 + 2 * BYTES), "l"(in2 + off), "r"(smem_u32(&st.ck[0][0][0])), "l"(ck), "r"(CKBYTES), "r"(smem_u32(&st.tab[0])), "l"(tb),
+            "r"(TABBYTES)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "elect.sync _|p, 0xffffffff;\n"
+          "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %3, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%6], %3, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%7], [%8], %9, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%10], [%11], %12, [%0];\n}"
+          ::"r"(bar), "r"(2u * BYTES + CKBYTES + TABBYTES), "r"(d0), "r"(BYTES), "r"(d0 + BYTES), "l"(in0 + off), "l"(in1 + off),
+            "r"(smem_u32(&st.ck[0][0][0])), "l"(ck), "r"(CKBYTES), "r"(smem_u32(&st.tab[0])), "l"(tb), "r"(TABBYTES)
+          : "memory");
     }
   };
   issue(w0);

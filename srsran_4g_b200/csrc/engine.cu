@@ -343,9 +343,9 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   CUDA_TRY(cudaMemset(e->d_ktab, 0, sizeof(KTable) * LTE_NOF_CB_SIZES));
   crc_position_words(0x1864CFBu, e->crc_words[SRSB200_CRC_24A]);
   crc_position_words(0x1800063u, e->crc_words[SRSB200_CRC_24B]);
-  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmemT<0>))));
-  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmemT<1>))));
-  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(ScanSmemT<2>))));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<0>)));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<1>)));
+  CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<2>)));
   CUDA_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)emit_smem_bytes(((SRSB200_MAX_K + 3 + W - 1) / W) * W, SRSB200_MAX_K + 64)));
   CUDA_TRY(cudaFuncSetAttribute(job_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
@@ -561,8 +561,7 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
   const int      mode = (n == 0) ? 0 : ((n & 1u) ? 2 : 1);
   const uint32_t nwin_max = (p->max_R + WC - 1) / WC;
   const dim3     sgrid((ng + 1) / 2), jgrid((nwin_max + 4 * WPJ - 1) / (4 * WPJ), ng);
-  const size_t   ssm = 4 * sizeof(ScanSmemT<0>), jsm = 4 * sizeof(JobWarpSmem);
-  static_assert(sizeof(ScanSmemT<0>) == sizeof(ScanSmemT<1>) && sizeof(ScanSmemT<0>) == sizeof(ScanSmemT<2>), "scan smem");
+  const size_t   jsm = 4 * sizeof(JobWarpSmem);
   switch (kind) {
     case 0: {
       ProfScope ps(e, 0, st);
@@ -570,9 +569,9 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
     } break;
     case 1: {
       ProfScope ps(e, 5, st);
-      if (mode == 0) scan_kernel<0><<<sgrid, 128, ssm, st>>>(dg, p->d_ws, da, ng);
-      else if (mode == 1) scan_kernel<1><<<sgrid, 128, ssm, st>>>(dg, p->d_ws, da, ng);
-      else scan_kernel<2><<<sgrid, 128, ssm, st>>>(dg, p->d_ws, da, ng);
+      if (mode == 0) scan_kernel<0><<<sgrid, 160, sizeof(ScanSmemT<0>), st>>>(dg, p->d_ws, da, ng);
+      else if (mode == 1) scan_kernel<1><<<sgrid, 160, sizeof(ScanSmemT<1>), st>>>(dg, p->d_ws, da, ng);
+      else scan_kernel<2><<<sgrid, 160, sizeof(ScanSmemT<2>), st>>>(dg, p->d_ws, da, ng);
     } break;
     case 2: {
       ProfScope ps(e, 6, st);

@@ -229,58 +229,30 @@ template <int MODE> struct ScanCfg {
 template <int MODE> struct ScanStageT {
   uint32_t s[ScanCfg<MODE>::NSTR][W][LANES];
 };
+// shared memory of one scan block: four recursion warps (two groups x {beta, alpha}) + one producer warp
 template <int MODE> struct alignas(128) ScanSmemT {
-  ScanStageT<MODE> st[ScanCfg<MODE>::NS];
-  uint64_t         bar[ScanCfg<MODE>::NS];
+  ScanStageT<MODE> st[4][ScanCfg<MODE>::NS];     // input chunks in flight per recursion warp
+  uint32_t         ck[2][2][W / CKB][LANES][8];  // per beta warp: double-buffered checkpoint staging (one bulk flush per chunk)
+  uint64_t         full[4][ScanCfg<MODE>::NS];   // producer -> recursion warp: chunk landed (bulk copy complete_tx)
+  uint64_t         empty[4][ScanCfg<MODE>::NS];  // recursion warp -> producer: stage may be overwritten
 };
 
-template <int MODE> struct ScanPipe {
-  // chunks are consumed in a fixed order (it = 0, 1, 2, ...); stage = it % NS, mbarrier parity = (it / NS) & 1
-  static constexpr int NS = ScanCfg<MODE>::NS, NSTR = ScanCfg<MODE>::NSTR;
-  ScanSmemT<MODE>* sm;
-  const uint32_t *src0, *src1, *src2;
-
-  __device__ __forceinline__ void issue(int it, int chunk)
-  {
-#ifdef PROBE_NO_PIPE
-    return;
-#endif
-    __syncwarp();  // every lane is done with the stage this copy overwrites
-    // one elected lane arms the barrier and issues the bulk copies; a single predicated asm block keeps the warp
-    // convergent (a C++ `if (lane == 0)` around separate asm statements costs a divergence region per copy)
-    const uint32_t bar = smem_u32(&sm->bar[it % NS]);
-    const uint32_t d0  = smem_u32(&sm->st[it % NS].s[0][0][0]);
-    const size_t   off = (size_t)chunk * W * LANES;
-    constexpr uint32_t BYTES = W * LANES * 4;
-    if (NSTR == 3) {
-      asm volatile(
-          "{\n.reg .pred p;\n"
-          "elect.sync _|p, 0xffffffff;\n"
-          "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %4, [%0];\n"
-          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%6], %4, [%0];\n"
-          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%8], [%7], %4, [%0];\n}"
-          ::"r"(bar), "r"(3u * BYTES), "r"(d0), "r"(d0 + BYTES), "r"(BYTES), "l"(src0 + off), "l"(src1 + off), "l"(src2 + off), "r"(d0 + 2 * BYTES)
-          : "memory");
-    } else {
-      asm volatile(
-          "{\n.reg .pred p;\n"
-          "elect.sync _|p, 0xffffffff;\n"
-          "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %4, [%0];\n"
-          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%6], %4, [%0];\n}"
-          ::"r"(bar), "r"(2u * BYTES), "r"(d0), "r"(d0 + BYTES), "r"(BYTES), "l"(src0 + off), "l"(src1 + off)
-          : "memory");
-    }
-  }
-  __device__ __forceinline__ const ScanStageT<MODE>& wait(int it)
-  {
-#ifndef PROBE_NO_PIPE
-    mbar_wait(&sm->bar[it % NS], (uint32_t)(it / NS) & 1u);
-#endif
-    return sm->st[it % NS];
-  }
-};
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 #define LOAD_XY(st, r)                                                   \
   uint32_t x = (st).s[0][(r)][lane];                                     \
@@ -296,9 +268,9 @@ template <int MODE> struct ScanPipe {
 // 13-instruction step), so the scans are written to execute as few instructions per trellis step as possible:
 // fully unrolled blocks of N steps whose x / y are fetched from shared memory up front, one checkpoint test per block.
 template <int MODE, int N>
-__device__ __forceinline__ void beta_block(const ScanStageT<MODE>& st, int r0, int k0, uint32_t (&b)[8], uint32_t* ckB, int lane)
+__device__ __forceinline__ void beta_block(const ScanStageT<MODE>& st, int r0, uint32_t (&b)[8], uint32_t (*ck)[LANES][8], int lane)
 {
-  // steps k = k0+N-1 .. k0 (rows r0+N-1 .. r0 of the staged chunk); k0 is a multiple of 8
+  // steps k = chunk base + r0+N-1 .. r0 (rows r0+N-1 .. r0 of the staged chunk); r0 is a multiple of 8
   uint32_t xs[N], ys[N];
 #pragma unroll
   for (int j = 0; j < N; j++) {
@@ -312,11 +284,13 @@ __device__ __forceinline__ void beta_block(const ScanStageT<MODE>& st, int r0, i
     if ((j & 3) == 0) {
       // k % 4 == 0 and k < K: checkpoint first (un-normalised, like beta[8*k+i]), then normalise
 #ifndef PROBE_NO_CKPT
-      if ((j & 7) == 0 && k0 + j > 0) {
-        // layout [slot][lane][8]: two 128-bit stores per lane, 1 KB contiguous per warp
-        uint4* ck = reinterpret_cast<uint4*>(ckB + ((size_t)((k0 + j) / CKB) * LANES + lane) * 8);
-        ck[0]     = make_uint4(b[0], b[1], b[2], b[3]);
-        ck[1]     = make_uint4(b[4], b[5], b[6], b[7]);
+      if ((j & 7) == 0) {
+        // Into shared memory, not global: a global store keeps its source registers busy until it has read them, and
+        // normalise() overwrites them right away - a lone in-order warp then stalls ~100 cycles per checkpoint
+        // (measured 39.6 vs 27.9 cycles per step, tools/microbench/block_probe.cu). Layout [slot][lane][8].
+        uint4* c4 = reinterpret_cast<uint4*>(&ck[(r0 + j) / CKB][lane][0]);
+        c4[0]     = make_uint4(b[0], b[1], b[2], b[3]);
+        c4[1]     = make_uint4(b[4], b[5], b[6], b[7]);
       }
 #endif
       normalise(b);
@@ -352,43 +326,130 @@ __device__ __forceinline__ void alpha_block(const ScanStageT<MODE>& st, int r0, 
  * MODE 0: DEC1 on the first half-iteration (no a-priori)   x = syst,          y = par0
  * MODE 1: DEC1 with a-priori                                x = syst + app1p,  y = par0
  * MODE 2: DEC2                                              x = app2,          y = par1
- * grid = ceil(n_groups / 2), block = 128: the four warps of a block are the backward (beta) and forward (alpha) recursions
- * of two groups. FOUR warps per block on purpose: a warp's SM sub-partition is its index within the block modulo 4, so
- * one-warp blocks all pile up on sub-partition 0 of their SM and share its issue port (measured: 56 cycles per step with
- * 32-thread blocks against 23-28 for a warp that has its sub-partition to itself - tools/microbench/lone_warp_step.cu).
+ * grid = ceil(n_groups / 2), block = 160 = five warps: warps 0-3 are the backward (beta) and forward (alpha) recursions of
+ * two groups, warp 4 is the PRODUCER that issues every bulk copy (HBM -> shared memory) for them.
+ *  - a recursion warp is a lone, issue-limited instruction stream (tools/microbench/lone_warp_step.cu: ~28 cycles per step
+ *    for the bare recursion), so everything that is not the recursion is moved off it: the copies are issued by the
+ *    producer (full/empty mbarrier pairs per stage), the "has my next chunk landed?" test is issued one chunk early so
+ *    its latency hides behind 64 steps of work, checkpoints go to shared memory and leave with one bulk store per chunk.
+ *  - four recursion warps per block on purpose: consecutive warps of a block sit on different SM sub-partitions.
  * (Running both recursions in ONE warp is no alternative: a lone warp is issue-limited, not dependency-limited.)
  * Checkpoints: ckB[k/CKB] = un-normalised beta[k] for k = CKB, 2 CKB, ..., K (what alpha step k consumes);
  *              ckA[k/(WC*WPJ)] = alpha state entering step k+1 (post-normalisation) for k = multiples of WC*WPJ.
  */
 template <int MODE>
-__global__ void __launch_bounds__(128) scan_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const uint8_t* __restrict__ group_active,
+__global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const uint8_t* __restrict__ group_active,
                                                    uint32_t n_groups)
 {
-  const int      wid = threadIdx.x >> 5;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ScanSmemT<MODE>* sm   = reinterpret_cast<ScanSmemT<MODE>*>(smem_raw);
+  constexpr int    NS   = ScanCfg<MODE>::NS;
+  const int        wid  = threadIdx.x >> 5;
+  const int        lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 4; w++)
+      for (int i = 0; i < NS; i++) {
+        mbar_init(&sm->full[w][i], 1);
+        mbar_init(&sm->empty[w][i], 1);
+      }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (wid == 4) {
+    // ---------------- producer: round-robin over the four recursion warps, NS chunks ahead of each
+    const uint32_t* src[4][3];
+    int             nchunk[4], cK4[4];
+    for (int w = 0; w < 4; w++) {
+      const uint32_t gi = blockIdx.x * 2 + (w >> 1);
+      nchunk[w] = 0;
+      cK4[w]    = 0;
+      if (gi < n_groups && group_active[gi]) {
+        const Group&    g  = groups[gi];
+        const GroupPtrs gp = group_ptrs(ws, g);
+        src[w][0] = (MODE == 2) ? gp.app2 : gp.syst;
+        src[w][1] = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
+        src[w][2] = (MODE == 1) ? gp.par0 : nullptr;
+        cK4[w]    = (int)g.K / W;
+        nchunk[w] = (w & 1) ? ((int)g.K + W - 1) / W : cK4[w] + 1;
+      }
+    }
+    const int maxc = max(max(nchunk[0], nchunk[1]), max(nchunk[2], nchunk[3]));
+    constexpr uint32_t BYTES = W * LANES * 4;
+    for (int it = 0; it < maxc; it++) {
+#pragma unroll
+      for (int w = 0; w < 4; w++) {
+        if (it >= nchunk[w]) continue;
+        const int s = it % NS;
+        if (it >= NS) mbar_wait(&sm->empty[w][s], (uint32_t)(it / NS - 1) & 1u);
+        const int      chunk = (w & 1) ? it : cK4[w] - it;
+        const size_t   off   = (size_t)chunk * W * LANES;
+        const uint32_t bar   = smem_u32(&sm->full[w][s]);
+        const uint32_t d0    = smem_u32(&sm->st[w][s].s[0][0][0]);
+        if (MODE == 1) {
+          asm volatile(
+              "{\n.reg .pred p;\n"
+              "elect.sync _|p, 0xffffffff;\n"
+              "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+              "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %4, [%0];\n"
+              "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%6], %4, [%0];\n"
+              "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%8], [%7], %4, [%0];\n}"
+              ::"r"(bar), "r"(3u * BYTES), "r"(d0), "r"(d0 + BYTES), "r"(BYTES), "l"(src[w][0] + off), "l"(src[w][1] + off),
+                "l"(src[w][2] + off), "r"(d0 + 2 * BYTES)
+              : "memory");
+        } else {
+          asm volatile(
+              "{\n.reg .pred p;\n"
+              "elect.sync _|p, 0xffffffff;\n"
+              "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+              "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %4, [%0];\n"
+              "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%6], %4, [%0];\n}"
+              ::"r"(bar), "r"(2u * BYTES), "r"(d0), "r"(d0 + BYTES), "r"(BYTES), "l"(src[w][0] + off), "l"(src[w][1] + off)
+              : "memory");
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- recursion warps
   const uint32_t gi  = blockIdx.x * 2 + (wid >> 1);
   const int      dir = wid & 1;  // 0 = backward (beta), 1 = forward (alpha)
   if (gi >= n_groups || !group_active[gi]) return;
 #ifdef SCAN_PROBE
   const long long probe_t0 = clock64();
 #endif
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  ScanSmemT<MODE>* sm  = reinterpret_cast<ScanSmemT<MODE>*>(smem_raw) + wid;
-  constexpr int   NS   = ScanCfg<MODE>::NS;
-  const int       lane = threadIdx.x & 31;
-  const Group&    g    = groups[gi];
-  const GroupPtrs gp   = group_ptrs(ws, g);
-  const int       K    = (int)g.K;
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < NS; i++) mbar_init(&sm->bar[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  ScanPipe<MODE> pipe;
-  pipe.sm   = sm;
-  pipe.src0 = (MODE == 2) ? gp.app2 : gp.syst;
-  pipe.src1 = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
-  pipe.src2 = (MODE == 1) ? gp.par0 : nullptr;
+  const Group&    g  = groups[gi];
+  const GroupPtrs gp = group_ptrs(ws, g);
+  const int       K  = (int)g.K;
+  uint64_t*       full  = sm->full[wid];
+  uint64_t*       empty = sm->empty[wid];
+  const int       nch   = dir ? (K + W - 1) / W : K / W + 1;
+  // chunk it lives in stage it % NS; `ready` = result of the early test for the chunk about to be consumed
+  uint32_t ready = 0;
+#ifdef SCAN_PROBE
+  long long probe_wait = 0;
+  int       probe_nwait = 0;
+#endif
+  auto acquire = [&](int it) -> const ScanStageT<MODE>& {
+#ifdef SCAN_PROBE
+    if (!ready) {
+      long long w0 = clock64();
+      mbar_wait(&full[it % NS], (uint32_t)(it / NS) & 1u);
+      probe_wait += clock64() - w0;
+      probe_nwait++;
+    }
+#else
+    if (!ready) mbar_wait(&full[it % NS], (uint32_t)(it / NS) & 1u);
+#endif
+    // test the NEXT chunk now; the answer is only looked at after this chunk's 64 steps
+    ready = (it + 1 < nch) ? mbar_test(&full[(it + 1) % NS], (uint32_t)((it + 1) / NS) & 1u) : 0u;
+    return sm->st[wid][it % NS];
+  };
+  auto release = [&](int it) {
+    __syncwarp();  // every lane is done reading the stage
+    if (lane == 0) mbar_arrive(&empty[it % NS]);
+  };
 
   if (dir == 0) {
     // ---------------- backward recursion (map_gen_beta): chunks cK, cK-1, ..., 0
@@ -397,11 +458,14 @@ __global__ void __launch_bounds__(128) scan_kernel(const Group* __restrict__ gro
     b[0] = 0u;
 #pragma unroll
     for (int i = 1; i < 8; i++) b[i] = NEG_INF2;
-    for (int it = 0; it < NS - 1 && it <= cK; it++) pipe.issue(it, cK - it);
     for (int it = 0; it <= cK; it++) {
-      const int c = cK - it;
-      if (it + NS - 1 <= cK) pipe.issue(it + NS - 1, c - (NS - 1));
-      const ScanStageT<MODE>& st = pipe.wait(it);
+      const int               c  = cK - it;
+      const ScanStageT<MODE>& st = acquire(it);
+      uint32_t(*ck)[LANES][8]    = sm->ck[wid >> 1][it & 1];
+      // the flush of two chunks ago (same staging buffer) must have finished reading shared memory
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      int nslot = W / CKB;
       if (c == cK) {
         // termination steps k = K+2, K+1, K (no a-priori there: app1p rows >= K stay zero); no normalisation at k = K
 #pragma unroll
@@ -409,36 +473,60 @@ __global__ void __launch_bounds__(128) scan_kernel(const Group* __restrict__ gro
           LOAD_XY(st, (K - cK * W) + r);
           beta_step(b, x, y);
         }
-        uint4* ck = reinterpret_cast<uint4*>(gp.ckB + ((size_t)(K / CKB) * LANES + lane) * 8);
-        ck[0]     = make_uint4(b[0], b[1], b[2], b[3]);
-        ck[1]     = make_uint4(b[4], b[5], b[6], b[7]);
+        nslot     = (K - cK * W) / CKB + 1;
+        uint4* c4 = reinterpret_cast<uint4*>(&ck[nslot - 1][lane][0]);
+        c4[0]     = make_uint4(b[0], b[1], b[2], b[3]);
+        c4[1]     = make_uint4(b[4], b[5], b[6], b[7]);
       }
       int top = min(K, (c + 1) * W);  // trellis steps of this chunk: k in [c*W, top)
       if (top & 8) {
         top -= 8;
-        beta_block<MODE, 8>(st, top - c * W, top, b, gp.ckB, lane);
+        beta_block<MODE, 8>(st, top - c * W, b, ck, lane);
       }
-      for (; top > c * W; top -= 16) beta_block<MODE, 16>(st, top - 16 - c * W, top - 16, b, gp.ckB, lane);
+#ifdef SCAN_PROBE
+      long long pb0 = clock64();
+#endif
+#ifdef PROBE_B8
+      for (; top > c * W; top -= 8) beta_block<MODE, 8>(st, top - 8 - c * W, b, ck, lane);
+#else
+      for (; top > c * W; top -= 16) beta_block<MODE, 16>(st, top - 16 - c * W, b, ck, lane);
+#endif
+#ifdef SCAN_PROBE
+      probe_wait += clock64() - pb0;  // (reported in the "waited" column for the beta warp: time inside the 16-step blocks)
+#endif
+      release(it);
+      // flush this chunk's checkpoints (slots 8c .. 8c+nslot-1 are adjacent in ckB) with one bulk store
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;" ::"l"(
+                         gp.ckB + (size_t)c * (W / CKB) * LANES * 8),
+                     "r"(smem_u32(&ck[0][0][0])), "r"((uint32_t)nslot * LANES * 8 * 4)
+                     : "memory");
+      }
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ---------------- forward recursion (alpha part of map_gen_alpha): chunks 0, 1, ...
-    const int nch = (K + W - 1) / W;
-    uint32_t  a[8];
+    uint32_t a[8];
     a[0] = 0u;
 #pragma unroll
     for (int i = 1; i < 8; i++) a[i] = NEG_INF2;
-    for (int it = 0; it < NS - 1 && it < nch; it++) pipe.issue(it, it);
     for (int c = 0; c < nch; c++) {
-      if (c + NS - 1 < nch) pipe.issue(c + NS - 1, c + NS - 1);
-      const ScanStageT<MODE>& st = pipe.wait(c);
-      const int        end = min(K, (c + 1) * W);
-      int              k0  = c * W;
+      const ScanStageT<MODE>& st  = acquire(c);
+      const int               end = min(K, (c + 1) * W);
+      int                     k0  = c * W;
       for (; k0 + 16 <= end; k0 += 16) alpha_block<MODE, 16>(st, k0 - c * W, k0, a, gp.ckA, lane);
       if (k0 < end) alpha_block<MODE, 8>(st, k0 - c * W, k0, a, gp.ckA, lane);
+      release(c);
     }
   }
 #ifdef SCAN_PROBE
-  if (lane == 0) g_probe_cycles[gi * 2 + dir] = clock64() - probe_t0;
+  if (lane == 0) {
+    g_probe_cycles[gi * 2 + dir]       = clock64() - probe_t0;
+    g_probe_cycles[512 + gi * 2 + dir] = probe_wait;
+    g_probe_cycles[768 + gi * 2 + dir] = probe_nwait;
+  }
 #endif
 }
 

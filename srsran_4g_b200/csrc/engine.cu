@@ -180,7 +180,8 @@ struct srsb200_engine {
 
   // sub-batch streams (see launch_plan)
   static const int MAX_SUB = 8;
-  int          n_sub = 8;
+  int          n_sub = 8;      // ranges of a host-pointer submission (copy/compute overlap)
+  int          n_sub_dev = 4;  // ranges of a device-resident submission (their launch chains overlap a little: +3-4 %)
   cudaStream_t sub[MAX_SUB] = {nullptr};
   cudaEvent_t  ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
 
@@ -334,6 +335,7 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   memset(e->h_ktab, 0, sizeof(e->h_ktab));
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   if (const char* env = getenv("SRSB200_SUBBATCHES")) e->n_sub = std::max(1, std::min((int)srsb200_engine::MAX_SUB, atoi(env)));
+  if (const char* env = getenv("SRSB200_SUBBATCHES_DEV")) e->n_sub_dev = std::max(1, std::min((int)srsb200_engine::MAX_SUB, atoi(env)));
   for (int i = 0; i < srsb200_engine::MAX_SUB; i++) {
     CUDA_TRY(cudaStreamCreateWithFlags(&e->sub[i], cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
@@ -618,7 +620,7 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     CUDA_TRY(cudaMemsetAsync(p->d_active, 1, p->n_groups, e->stream));
   }
   uint32_t S = 1;
-  if (io && !e->profiling) S = std::max(1u, std::min((uint32_t)e->n_sub, p->n_groups / 16u));
+  if (!e->profiling) S = std::max(1u, std::min((uint32_t)(io ? e->n_sub : e->n_sub_dev), p->n_groups / 16u));
   RangeArgs rg[srsb200_engine::MAX_SUB];
   for (uint32_t s = 0; s < S; s++) {
     rg[s].g0 = (uint32_t)((uint64_t)p->n_groups * s / S);

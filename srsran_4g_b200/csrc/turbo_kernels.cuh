@@ -386,6 +386,10 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
         const size_t   off   = (size_t)chunk * W * LANES;
         const uint32_t bar   = smem_u32(&sm->full[w][s]);
         const uint32_t d0    = smem_u32(&sm->st[w][s].s[0][0][0]);
+#ifdef PROBE_NO_COPY
+        if (lane == 0) mbar_arrive(&sm->full[w][s]);
+        continue;
+#endif
         if (MODE == 1) {
           asm volatile(
               "{\n.reg .pred p;\n"
@@ -496,6 +500,9 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
 #endif
       release(it);
       // flush this chunk's checkpoints (slots 8c .. 8c+nslot-1 are adjacent in ckB) with one bulk store
+#ifdef PROBE_NO_CKPT
+      continue;
+#endif
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
@@ -801,23 +808,28 @@ extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const
   const GroupPtrs gp   = group_ptrs(ws, g);
   const int       tid  = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const uint32_t  nbody = (k0 < K) ? min((uint32_t)XT, K - k0) : 0u;  // rows of this tile that are trellis steps (multiple of 8)
-  // ---- load: warp w takes code blocks w, w+8, ...; 3*nbody int16 = 1.5*nbody words, contiguous
-  const uint32_t nwords = 3 * nbody / 2;
+  // ---- load: 3*nbody int16 = 1.5*nbody words per code block, contiguous; 8-byte loads (a code block starts on an
+  //      8-byte boundary whenever its LLR offset is a multiple of 4 elements: 3K+12 is), four code blocks per warp pass
+  const uint32_t nwords = 3 * nbody / 2, npairs = nwords / 2;  // nbody % 8 == 0 => nwords % 12 == 0
   if (nbody) {
-#pragma unroll
-    for (int c8 = 0; c8 < 8; c8++) {
-      const int cbl = wid + 8 * c8;
+    const int sub = lane >> 3, l8 = lane & 7;  // 4 code blocks x 8 lanes
+    for (int pass = 0; pass < 2; pass++) {
+      const int cbl = wid * 8 + pass * 4 + sub;
       const int cb  = g.cb[cbl];
       if (cb < 0) {
-        for (uint32_t i = lane; i < nwords; i += 32) tile[cbl][i] = 0u;
+        for (uint32_t i = l8; i < nwords; i += 8) tile[cbl][i] = 0u;
       } else {
         const uint64_t off = llr_off[cb] + 3ull * k0;
-        if ((off & 1ull) == 0) {
-          const uint32_t* src = reinterpret_cast<const uint32_t*>(llr + off);
-          for (uint32_t i = lane; i < nwords; i += 32) tile[cbl][i] = __ldg(src + i);
+        if ((off & 3ull) == 0) {
+          const uint2* src = reinterpret_cast<const uint2*>(llr + off);
+          for (uint32_t i = l8; i < npairs; i += 8) {
+            const uint2 v = __ldg(src + i);
+            tile[cbl][2 * i]     = v.x;
+            tile[cbl][2 * i + 1] = v.y;
+          }
         } else {
           const uint16_t* src = reinterpret_cast<const uint16_t*>(llr + off);
-          for (uint32_t i = lane; i < nwords; i += 32) tile[cbl][i] = (uint32_t)src[2 * i] | ((uint32_t)src[2 * i + 1] << 16);
+          for (uint32_t i = l8; i < nwords; i += 8) tile[cbl][i] = (uint32_t)src[2 * i] | ((uint32_t)src[2 * i + 1] << 16);
         }
       }
     }
@@ -826,14 +838,18 @@ extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const
   // ---- store: warp w writes rows w, w+8, ...: lane l packs code blocks l (low half) and 32+l (high half)
   const uint16_t* tlo = reinterpret_cast<const uint16_t*>(&tile[lane][0]);
   const uint16_t* thi = reinterpret_cast<const uint16_t*>(&tile[32 + lane][0]);
-  for (uint32_t r = wid; r < nbody; r += 8) {
-    const uint32_t v0 = (uint32_t)tlo[3 * r] | ((uint32_t)thi[3 * r] << 16);
-    const uint32_t v1 = (uint32_t)tlo[3 * r + 1] | ((uint32_t)thi[3 * r + 1] << 16);
-    const uint32_t v2 = (uint32_t)tlo[3 * r + 2] | ((uint32_t)thi[3 * r + 2] << 16);
-    const size_t   o  = (size_t)(k0 + r) * LANES + lane;
-    gp.syst[o] = v0;
-    gp.par0[o] = v1;
-    gp.par1[o] = v2;
+#pragma unroll
+  for (uint32_t rr = 0; rr < XT / 8; rr++) {
+    const uint32_t r = wid + 8 * rr;
+    if (r < nbody) {
+      const uint32_t v0 = (uint32_t)tlo[3 * r] | ((uint32_t)thi[3 * r] << 16);
+      const uint32_t v1 = (uint32_t)tlo[3 * r + 1] | ((uint32_t)thi[3 * r + 1] << 16);
+      const uint32_t v2 = (uint32_t)tlo[3 * r + 2] | ((uint32_t)thi[3 * r + 2] << 16);
+      const size_t   o  = (size_t)(k0 + r) * LANES + lane;
+      gp.syst[o] = v0;
+      gp.par0[o] = v1;
+      gp.par1[o] = v2;
+    }
   }
   // ---- rows >= K of this tile: termination values and zero padding (a handful of rows per group)
   for (uint32_t idx = tid; idx < (XT - nbody) * 32; idx += 256) {

@@ -15,7 +15,11 @@ __global__ void k(uint32_t* out, long long* cyc, uint32_t* ck, int iters)
   uint32_t* myck = ck + (size_t)(blockIdx.x * 4 + wid) * 1024 * 256;
   long long t0 = clock64();
   for (int it = 0; it < iters; it++) {
-    if (VAR == 0) {  // production beta blocks over a 64-row chunk
+    if (VAR == 3) {  // production beta block, row offset varies with the iteration so the loads cannot be hoisted
+      beta_block<2, 16>(st, (it * 16) & 48, b, ckb[wid], lane);
+    } else if (VAR == 4) {
+      beta_block<2, 8>(st, (it * 8) & 56, b, ckb[wid], lane);
+    } else if (VAR == 0) {  // production beta blocks over a 64-row chunk
       for (int top = 64; top > 0; top -= 16) beta_block<2, 16>(st, top - 16, b, ckb[wid], lane);
     } else if (VAR == 1) {  // alpha blocks
       for (int k0 = 0; k0 < 64; k0 += 16) alpha_block<2, 16>(st, k0, (it & 7) * 64 + k0 + 8, b, myck, lane);
@@ -37,12 +41,14 @@ template <int VAR> void run(const char* what, int warps)
   k<VAR><<<148, 32 * warps>>>(out, cyc, ck, 2000);
   long long h[148]; cudaMemcpy(h, cyc, 8 * 148, cudaMemcpyDeviceToHost);
   double m = 0; for (int i = 0; i < 148; i++) m += h[i]; m /= 148;
-  printf("%-46s warps/block=%d : %.1f cycles per step  (%s)\n", what, warps, m / (2000.0 * 64), cudaGetErrorString(cudaGetLastError()));
+  const double steps = (VAR == 3) ? 16 : (VAR == 4 ? 8 : 64);
+  printf("%-46s warps/block=%d : %.1f cycles per step  (%s)\n", what, warps, m / (2000.0 * steps), cudaGetErrorString(cudaGetLastError()));
   cudaFree(out); cudaFree(cyc); cudaFree(ck);
 }
 int main()
 {
   run<0>("beta_block<16> x4 per 64-row chunk", 4); run<0>("beta_block<16> x4 per 64-row chunk", 1);
   run<1>("alpha_block<16> x4", 4); run<2>("beta_block<8> x8", 4);
+  run<3>("beta_block<16>, varying rows (no hoisting)", 4); run<4>("beta_block<8>, varying rows (no hoisting)", 4);
   return 0;
 }

@@ -156,6 +156,20 @@ typedef struct {
   int       ret;
 } srsb200_tb_t;
 
+/*
+ * HARQ soft buffers (srsran_softbuffer_rx_t, lib/src/phy/fec/softbuffer.c:36-178). Default = host-coherent: every
+ * decode_tb call uploads buffer_f[r] of the code blocks it decodes and writes the combined LLRs back, so the caller's
+ * memory is always what the reference would hold. With srsb200_softbuffer_set_resident(e, 1) the engine keeps a device
+ * mirror keyed by the host pointer buffer_f[r] instead: no per-call copies; the caller must then forward the
+ * reference's reset points (srsran_softbuffer_rx_reset / _reset_tbs / _reset_cb, softbuffer.c:139-169) to
+ * srsb200_softbuffer_reset, may fetch the contents with srsb200_softbuffer_sync_to_host, and frees the mirror in
+ * srsran_softbuffer_rx_free via srsb200_softbuffer_release. A buffer first seen without a reset adopts the host content.
+ */
+int srsb200_softbuffer_set_resident(srsb200_engine_t* e, int resident);
+int srsb200_softbuffer_reset(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);
+int srsb200_softbuffer_sync_to_host(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);
+int srsb200_softbuffer_release(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);
+
 /* decode n transport blocks (possibly of different UEs/cells/subframes) as one batched submission */
 int srsb200_decode_tb_batch(srsb200_engine_t* e, srsb200_tb_t* tbs, uint32_t n, uint32_t max_iterations);
 /* single transport block = decode_tb (sch.c:509); returns tb->ret */

@@ -61,6 +61,9 @@ def lib():
         L.srsb200_rm_turbo_rx_lut.argtypes = [vp, vp, vp, u32, u32, u32]
         L.srsb200_rm_table.argtypes = [u32, u32, vp]
         L.srsb200_decode_tb_batch.argtypes = [vp, vp, u32, u32]
+        L.srsb200_softbuffer_set_resident.argtypes = [vp, i32]
+        for fn in (L.srsb200_softbuffer_reset, L.srsb200_softbuffer_sync_to_host, L.srsb200_softbuffer_release):
+            fn.argtypes = [vp, C.POINTER(C.c_void_p), u32]
         L.srsb200_decode_tb.argtypes = [vp, vp, u32]
         _LIB = L
     return _LIB
@@ -227,6 +230,23 @@ class Engine:
         e = np.ascontiguousarray(e, np.int16)
         assert buf.dtype == np.int16 and buf.flags.c_contiguous
         return self._L.srsb200_rm_turbo_rx_lut(self._h, _ptr(e), _ptr(buf), len(e), cb_idx, rv)
+
+    # ---- HARQ soft buffers: host-coherent (default) or device-resident mirror
+    def softbuffer_set_resident(self, on):
+        _check(self._L.srsb200_softbuffer_set_resident(self._h, int(on)), "srsb200_softbuffer_set_resident")
+
+    def softbuffer_reset(self, tb):
+        """srsran_softbuffer_rx_reset for a TransportBlock in resident mode (also clears its host-side flags)"""
+        tb.buffer_f[:] = 0
+        tb.cb_crc[:] = 0
+        tb.tb_crc[:] = 0
+        _check(self._L.srsb200_softbuffer_reset(self._h, tb._bf, tb.max_cb), "srsb200_softbuffer_reset")
+
+    def softbuffer_sync_to_host(self, tb):
+        _check(self._L.srsb200_softbuffer_sync_to_host(self._h, tb._bf, tb.max_cb), "srsb200_softbuffer_sync_to_host")
+
+    def softbuffer_release(self, tb):
+        _check(self._L.srsb200_softbuffer_release(self._h, tb._bf, tb.max_cb), "srsb200_softbuffer_release")
 
     # ---- transport blocks
     def decode_tb_batch(self, reqs, max_iterations):

@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace srsb200;
@@ -190,6 +191,18 @@ struct srsb200_engine {
   struct ProfEv { cudaEvent_t a, b; int kind; };
   std::vector<ProfEv> prof;
 
+  // device-resident HARQ soft buffers (srsb200_softbuffer_*): host buffer_f pointer -> device copy
+  bool softbuffer_resident = false;
+  std::unordered_map<const void*, int16_t*> softslots;
+  std::vector<int16_t*> softslot_free;
+  std::vector<void*>    softslot_chunks;
+
+  // last plan built by srsb200_decode_tb_batch and the shape it was built for
+  struct srsb200_plan* tb_plan = nullptr;
+  std::vector<uint32_t> tb_K, tb_olen;
+  std::vector<uint8_t>  tb_kind;
+  std::vector<uint64_t> tb_boff, tb_ooff;
+
   // last plan built by srsb200_tdec_batch, reused when the next submission has the same shape
   struct srsb200_plan* cached_plan = nullptr;
   std::vector<uint32_t> cached_K;
@@ -288,6 +301,83 @@ static int ensure_rm_table(srsb200_engine* e, uint32_t cb_idx, uint32_t rv)
   return 0;
 }
 
+// ------------------------------------------------------------------ device-resident soft buffers
+static const size_t SOFTSLOT_ELEMS = 18688;  // SOFTBUFFER_SIZE (18600) rounded up to a multiple of 64 int16
+static int softslot_get(srsb200_engine* e, const void* host, int16_t** out, bool upload_if_new)
+{
+  auto it = e->softslots.find(host);
+  if (it != e->softslots.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (e->softslot_free.empty()) {
+    const size_t per_chunk = 1024;
+    void* chunk = nullptr;
+    CUDA_TRY(cudaMalloc(&chunk, per_chunk * SOFTSLOT_ELEMS * sizeof(int16_t)));
+    e->softslot_chunks.push_back(chunk);
+    for (size_t i = 0; i < per_chunk; i++) e->softslot_free.push_back((int16_t*)chunk + (per_chunk - 1 - i) * SOFTSLOT_ELEMS);
+  }
+  int16_t* d = e->softslot_free.back();
+  e->softslot_free.pop_back();
+  e->softslots[host] = d;
+  // first touch of a soft buffer that was never reset through srsb200_softbuffer_reset: adopt the host content
+  if (upload_if_new) CUDA_TRY(cudaMemcpyAsync(d, host, SRSB200_SOFTBUFFER_SIZE * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
+  *out = d;
+  return 0;
+}
+
+extern "C" int srsb200_softbuffer_set_resident(srsb200_engine_t* e, int resident)
+{
+  if (!e) return SRSB200_ERROR_NO_DEVICE;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  e->softbuffer_resident = resident != 0;
+  return SRSB200_SUCCESS;
+}
+
+extern "C" int srsb200_softbuffer_reset(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb)
+{
+  if (!e) return SRSB200_ERROR_NO_DEVICE;
+  if (!buffer_f) return SRSB200_ERROR_INVALID_INPUTS;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  for (uint32_t i = 0; i < nof_cb; i++) {
+    int16_t* d = nullptr;
+    if (softslot_get(e, buffer_f[i], &d, false)) return SRSB200_ERROR;
+    CUDA_TRY(cudaMemsetAsync(d, 0, SOFTSLOT_ELEMS * sizeof(int16_t), e->stream));
+  }
+  return SRSB200_SUCCESS;
+}
+
+extern "C" int srsb200_softbuffer_sync_to_host(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb)
+{
+  if (!e) return SRSB200_ERROR_NO_DEVICE;
+  if (!buffer_f) return SRSB200_ERROR_INVALID_INPUTS;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  for (uint32_t i = 0; i < nof_cb; i++) {
+    auto it = e->softslots.find(buffer_f[i]);
+    if (it != e->softslots.end())
+      CUDA_TRY(cudaMemcpyAsync(buffer_f[i], it->second, SRSB200_SOFTBUFFER_SIZE * sizeof(int16_t), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return SRSB200_SUCCESS;
+}
+
+extern "C" int srsb200_softbuffer_release(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb)
+{
+  if (!e) return SRSB200_ERROR_NO_DEVICE;
+  if (!buffer_f) return SRSB200_ERROR_INVALID_INPUTS;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  for (uint32_t i = 0; i < nof_cb; i++) {
+    auto it = e->softslots.find(buffer_f[i]);
+    if (it != e->softslots.end()) {
+      e->softslot_free.push_back(it->second);
+      e->softslots.erase(it);
+    }
+  }
+  return SRSB200_SUCCESS;
+}
+
 static int ensure_tb_crc_words(srsb200_engine* e, uint32_t nbits)
 {
   if (e->tb_crc_words_n >= nbits) return 0;
@@ -363,6 +453,8 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   if (e->cached_plan) srsb200_plan_destroy(e->cached_plan);
+  if (e->tb_plan) srsb200_plan_destroy(e->tb_plan);
+  for (void* p : e->softslot_chunks) cudaFree(p);
   for (void* p : e->owned) cudaFree(p);
   for (int i = 0; i < 8; i++)
     if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);

@@ -230,3 +230,37 @@ def test_decode_tb_argument_errors(sb, eng):
     small = sb.TransportBlock(75376, max_cb=2)            # C = 13 > softbuffer->max_cb
     assert eng.decode_tb(small, 6, 0, np.zeros(86400, np.int16), 6) == -2
     assert eng.decode_tb(sb.TransportBlock(6128), 2, 0, np.zeros(14400, np.int16), 6) == -2   # filler bits (F != 0)
+
+
+def test_decode_tb_device_resident_softbuffers(sb, o):
+    """srsb200_softbuffer_set_resident(1): the HARQ buffers live on the device between transmissions; results and (after
+    sync_to_host) buffer contents must equal the host-coherent / oracle ones, including reset and first-touch adoption"""
+    eng = sb.Engine(0)
+    eng.softbuffer_set_resident(True)
+    for tbs, G, Qm, eb in ((6200, 9000, 4, 0.5), (36696, 43200, 6, 0.5)):
+        tb = sb.TransportBlock(tbs)
+        for round_ in range(2):  # second round re-uses the same soft buffer after a reset (new data indicator)
+            eng.softbuffer_reset(tb)
+            st = None
+            for tx, rv in enumerate((0, 2, 3, 1)):
+                _, e = vecgen.make_tb(tbs, G, Qm, rv, eb, 77 + round_, scale=100)
+                res_o = o.decode_tb(tbs, Qm, rv, e, 6, st)
+                st = res_o["state"]
+                tb.data[:] = 0
+                assert eng.decode_tb(tb, Qm, rv, e, 6) == res_o["ret"]
+                eng.softbuffer_sync_to_host(tb)
+                _check_tb(res_o, tb, st)
+        eng.softbuffer_release(tb)
+    # first touch without a reset adopts the host content
+    tbs, G, Qm = 6200, 9000, 4
+    tb = sb.TransportBlock(tbs)
+    rng = np.random.default_rng(5)
+    tb.buffer_f[:] = rng.integers(-50, 50, tb.buffer_f.shape).astype(np.int16)
+    st = ol.new_tb_state(2)
+    st["buffer_f"][:] = tb.buffer_f
+    _, e = vecgen.make_tb(tbs, G, Qm, 0, 1.5, 3)
+    res_o = o.decode_tb(tbs, Qm, 0, e, 6, st)
+    assert eng.decode_tb(tb, Qm, 0, e, 6) == res_o["ret"]
+    eng.softbuffer_sync_to_host(tb)
+    _check_tb(res_o, tb, res_o["state"])
+    eng.close()

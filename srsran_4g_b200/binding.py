@@ -237,8 +237,7 @@ class Engine:
 
     def softbuffer_reset(self, tb):
         """srsran_softbuffer_rx_reset for a TransportBlock in resident mode (also clears its host-side flags)"""
-        tb.buffer_f[:] = 0
-        tb.cb_crc[:] = 0
+        tb.cb_crc[:] = 0  # (the host buffer_f is not authoritative in resident mode and is left alone)
         tb.tb_crc[:] = 0
         _check(self._L.srsb200_softbuffer_reset(self._h, tb._bf, tb.max_cb), "srsb200_softbuffer_reset")
 

@@ -340,11 +340,17 @@ extern "C" int srsb200_softbuffer_reset(srsb200_engine_t* e, int16_t** buffer_f,
   if (!buffer_f) return SRSB200_ERROR_INVALID_INPUTS;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
-  for (uint32_t i = 0; i < nof_cb; i++) {
-    int16_t* d = nullptr;
-    if (softslot_get(e, buffer_f[i], &d, false)) return SRSB200_ERROR;
-    CUDA_TRY(cudaMemsetAsync(d, 0, SOFTSLOT_ELEMS * sizeof(int16_t), e->stream));
-  }
+  // one kernel zeroes every listed mirror (a cudaMemsetAsync per code block costs more host time than the decode)
+  std::vector<int16_t*> list(nof_cb);
+  for (uint32_t i = 0; i < nof_cb; i++)
+    if (softslot_get(e, buffer_f[i], &list[i], false)) return SRSB200_ERROR;
+  if (nof_cb == 0) return SRSB200_SUCCESS;
+  void* d_list;
+  if (ensure_scratch(e, 5, sizeof(int16_t*) * nof_cb, &d_list)) return SRSB200_ERROR;
+  CUDA_TRY(cudaMemcpyAsync(d_list, list.data(), sizeof(int16_t*) * nof_cb, cudaMemcpyHostToDevice, e->stream));
+  zero_slots_kernel<<<dim3((SOFTSLOT_ELEMS / 8 + 255) / 256, nof_cb), 256, 0, e->stream>>>((int16_t* const*)d_list, (uint32_t)(SOFTSLOT_ELEMS / 8));
+  e->launches++;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));  // `list` (pageable) must stay alive until the copy has been issued and consumed
   return SRSB200_SUCCESS;
 }
 

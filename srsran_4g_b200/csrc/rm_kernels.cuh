@@ -34,6 +34,13 @@ __global__ void __launch_bounds__(256) rm_rx_kernel(const RmJob* __restrict__ jo
   j.buf[t] = (int16_t)(uint16_t)((uint16_t)j.buf[t] + sum);
 }
 
+// zero a list of soft-buffer mirrors (srsran_softbuffer_rx_reset forwarded to the device): grid = (ceil(n16/256), n_slots)
+__global__ void __launch_bounds__(256) zero_slots_kernel(int16_t* const* __restrict__ slots, uint32_t n_uint4)
+{
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n_uint4) reinterpret_cast<uint4*>(slots[blockIdx.y])[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 /*
  * CRC of a byte string by linearity: crc = XOR over set bits of x^(nbits-1-pos+24) mod g. words[m] = x^(m+24) mod g.
  * One block per job; crc_out[job] must be zero on entry (atomicXor accumulation).

@@ -89,23 +89,58 @@ res["config3_pdsch_2cw_steady"] = {"ms_per_subframe_host_to_host": dt * 1e3, "in
 
 # ---- config 5: 64 cells x one 100-PRB PUSCH TB (13 CB, K=5824) per subframe on one GPU, one batched submission per subframe
 cells = 64
-tbl = [sb.TransportBlock(tbs) for _ in range(cells)]
-el = [vecgen.make_tb(tbs, G, Qm, 0, 4.0, 500 + c, scale=700)[1] for c in range(4)]
-def one_subframe():
-    rq = []
-    for c in range(cells):
-        tb = tbl[c]
-        tb.buffer_f[:] = 0; tb.cb_crc[:] = 0
-        rq.append((tb, Qm, 0, el[c % 4]))
-    eng.decode_tb_batch(rq, 8)
-    return rq
-rq = one_subframe()
+el = [vecgen.make_tb(tbs, G, Qm, 0, 6.0, 500 + c, scale=700)[1] for c in range(4)]
 r0 = o.decode_tb(tbs, Qm, 0, el[0], 8)
-assert tbl[0].ret == r0["ret"] and (tbl[0].cb_noi[:13] == r0["cb_noi"][:13]).all() and (tbl[0].data[:9425] == r0["data"][:9425]).all()
-dt = timeit(one_subframe, reps=5, warm=1)
-res["config5_64_cells_832_cb_per_subframe"] = {"ms_per_subframe_host_to_host": dt * 1e3, "info_Mbit_s": cells * tbs / dt / 1e6, "code_blocks": 13 * cells,
-                                                "all_tb_ok": bool(all(tb.ret == 0 for tb in tbl)),
-                                                "note": "round-1 path copies every soft buffer host->device->host per call (device-resident HARQ mirror = next); 1/2/4/8-GPU scaling shards cells per GPU with no collective"}
+
+
+def subframe_runner(engine, resident):
+    tbl = [sb.TransportBlock(tbs) for _ in range(cells)]
+    engine.softbuffer_set_resident(resident)
+
+    def one_subframe():
+        rq = []
+        for c in range(cells):
+            tb = tbl[c]
+            if resident:
+                engine.softbuffer_reset(tb)  # new-data indicator: srsran_softbuffer_rx_reset forwarded to the device mirror
+            else:
+                tb.buffer_f[:] = 0
+                tb.cb_crc[:] = 0
+            rq.append((tb, Qm, 0, el[c % 4]))
+        engine.decode_tb_batch(rq, 8)
+    return tbl, one_subframe
+
+
+for resident in (False, True):
+    tbl, one_subframe = subframe_runner(eng, resident)
+    one_subframe()
+    assert tbl[0].ret == r0["ret"] and (tbl[0].cb_noi[:13] == r0["cb_noi"][:13]).all() and (tbl[0].data[:9425] == r0["data"][:9425]).all()
+    dt = timeit(one_subframe, reps=5, warm=1)
+    res["config5_64_cells_832_cb_per_subframe_%s" % ("device_resident_softbuffers" if resident else "host_coherent_softbuffers")] = {
+        "ms_per_subframe_host_to_host": dt * 1e3, "info_Mbit_s": cells * tbs / dt / 1e6, "code_blocks": 13 * cells,
+        "tb_ok": int(sum(tb.ret == 0 for tb in tbl)), "parity": "cell 0 bit-exact vs oracle (ret, iteration counts, bytes)"}
+eng.softbuffer_set_resident(False)
+
+# several PHY worker threads, one engine each (the reference runs 3-4 workers): subframes of different workers overlap on the GPU
+import threading
+nthr = 4
+engs = [sb.Engine(0) for _ in range(nthr)]
+runners = [subframe_runner(engs[i], True)[1] for i in range(nthr)]
+for r in runners:
+    r()
+def worker(fn, n):
+    for _ in range(n):
+        fn()
+nsub = 6
+t0 = time.perf_counter()
+ths = [threading.Thread(target=worker, args=(runners[i], nsub)) for i in range(nthr)]
+[t.start() for t in ths]; [t.join() for t in ths]
+dt = time.perf_counter() - t0
+res["config5_4_worker_threads_device_resident"] = {"subframes": nthr * nsub, "ms_per_subframe_aggregate": dt / (nthr * nsub) * 1e3,
+                                                   "info_Mbit_s": nthr * nsub * cells * tbs / dt / 1e6,
+                                                   "note": "1/2/4/8-GPU scaling shards cells per GPU with no collective (one engine per worker thread per GPU)"}
+for e_ in engs:
+    e_.close()
 eng.close()
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 with open(os.path.join(ROOT, "profiles", "r01_configs.json"), "w") as f:

@@ -252,29 +252,54 @@ static int ensure_ktable(srsb200_engine* e, int kidx)
   qpp_tables(kidx, fwd, rev);
   KTable kt;
   memset(&kt, 0, sizeof(kt));
-  for (int kind = 0; kind < 3; kind++) {
-    std::vector<uint2> t1(R), t2(R);
-    for (uint32_t i = 0; i < R; i++) {
-      t1[i] = make_uint2(0, 0);
-      t2[i] = make_uint2(0, 0);
-    }
+  {
+    std::vector<uint32_t> r1(R, 0u), r2(R, 0u);
     for (uint32_t i = 0; i < K; i++) {
-      uint32_t w1 = kind ? e->crc_words[kind][K - 1 - i] : 0u;
-      uint32_t w2 = kind ? e->crc_words[kind][K - 1 - fwd[i]] : 0u;
-      t1[i]       = make_uint2(rev[i], w1);
-      t2[i]       = make_uint2(fwd[i], w2);
+      r1[i] = rev[i];
+      r2[i] = fwd[i];
     }
-    uint2 *d1, *d2;
-    CUDA_TRY(cudaMalloc(&d1, R * sizeof(uint2)));
-    CUDA_TRY(cudaMalloc(&d2, R * sizeof(uint2)));
+    uint32_t *d1, *d2;
+    CUDA_TRY(cudaMalloc(&d1, R * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&d2, R * sizeof(uint32_t)));
     e->owned.push_back(d1);
     e->owned.push_back(d2);
-    CUDA_TRY(cudaMemcpyAsync(d1, t1.data(), R * sizeof(uint2), cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(cudaMemcpyAsync(d2, t2.data(), R * sizeof(uint2), cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));  // the host vectors die at the end of this scope
-    kt.dec1[kind] = d1;
-    kt.dec2[kind] = d2;
+    CUDA_TRY(cudaMemcpyAsync(d1, r1.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(d2, r2.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    kt.row1 = d1;
+    kt.row2 = d2;
   }
+  for (int kind = 1; kind < 3; kind++) {
+    // nibble tables: contribution of every 4-bit group of decisions of a 16-step window to the CRC
+    const uint32_t nw = R / 16;
+    std::vector<uint32_t> n1((size_t)nw * 64, 0u), n2((size_t)nw * 64, 0u);
+    for (uint32_t w = 0; w < nw; w++)
+      for (uint32_t j = 0; j < 4; j++)
+        for (uint32_t v = 1; v < 16; v++) {
+          uint32_t x1 = 0, x2 = 0;
+          for (uint32_t b = 0; b < 4; b++) {
+            const uint32_t i = 16 * w + 4 * j + b;
+            if (((v >> b) & 1u) && i < K) {
+              x1 ^= e->crc_words[kind][K - 1 - i];
+              x2 ^= e->crc_words[kind][K - 1 - fwd[i]];
+            }
+          }
+          n1[((size_t)w * 4 + j) * 16 + v] = x1;
+          n2[((size_t)w * 4 + j) * 16 + v] = x2;
+        }
+    uint32_t *d1, *d2;
+    CUDA_TRY(cudaMalloc(&d1, n1.size() * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&d2, n2.size() * sizeof(uint32_t)));
+    e->owned.push_back(d1);
+    e->owned.push_back(d2);
+    CUDA_TRY(cudaMemcpyAsync(d1, n1.data(), n1.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(d2, n2.data(), n2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));  // the host vectors die at the end of this scope
+    kt.nib1[kind] = d1;
+    kt.nib2[kind] = d2;
+  }
+  kt.nib1[0] = kt.nib1[2];  // CRC_NONE: the result is ignored, any table will do
+  kt.nib2[0] = kt.nib2[2];
   uint16_t* drev;
   CUDA_TRY(cudaMalloc(&drev, K * sizeof(uint16_t)));
   e->owned.push_back(drev);
@@ -533,6 +558,7 @@ struct srsb200_plan {
   uint32_t* d_crc_acc = nullptr;  // [n_cb] running CRC of the current half-iteration
   uint8_t*  d_done = nullptr;     // [n_cb]
   uint8_t*  d_active = nullptr;   // [n_groups]
+  uint32_t* d_arrivals = nullptr; // [n_groups] job blocks of the group that have finished the current half-iteration
   bool      uniform = false;
   bool      contiguous = false;  // one (K, crc) bucket and code block i at llr offset i*(3K+12), output offset i*K/8
 };
@@ -595,7 +621,9 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
       (ce = cudaMalloc(&p->d_out_off, sizeof(uint64_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_crc_acc, sizeof(uint32_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_done, std::max<uint32_t>(1, n))) != cudaSuccess ||
-      (ce = cudaMalloc(&p->d_active, std::max<uint32_t>(1, p->n_groups))) != cudaSuccess) {
+      (ce = cudaMalloc(&p->d_active, std::max<uint32_t>(1, p->n_groups))) != cudaSuccess ||
+      (ce = cudaMalloc(&p->d_arrivals, sizeof(uint32_t) * std::max<uint32_t>(1, p->n_groups))) != cudaSuccess ||
+      (ce = cudaMemset(p->d_arrivals, 0, sizeof(uint32_t) * std::max<uint32_t>(1, p->n_groups))) != cudaSuccess) {
     cudaGetLastError();
     srsb200_plan_destroy(p);
     return fail(SRSB200_ERROR, "plan allocation failed: %s", cudaGetErrorString(ce));
@@ -632,6 +660,7 @@ extern "C" void srsb200_plan_destroy(srsb200_plan_t* p)
   cudaFree(p->d_crc_acc);
   cudaFree(p->d_done);
   cudaFree(p->d_active);
+  cudaFree(p->d_arrivals);
   delete p;
 }
 
@@ -650,7 +679,7 @@ struct RangeArgs {
   cudaStream_t   st;
 };
 
-// one launch of the decode chain of a group range; kind: 0 extract, 1 scan, 2 job, 3 status, 4 emit
+// one launch of the decode chain of a group range; kind: 0 extract, 1 scan, 2 job (+ per-block verdict), 4 emit
 static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, int kind, uint32_t n, const int16_t* d_llr, uint32_t max_iter,
                        uint32_t min_iter, int early_stop, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok)
 {
@@ -675,13 +704,12 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
     } break;
     case 2: {
       ProfScope ps(e, 6, st);
-      if (mode == 0) job_kernel<0><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc);
-      else if (mode == 1) job_kernel<1><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc);
-      else job_kernel<2><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc);
-    } break;
-    case 3: {
-      ProfScope ps(e, 7, st);
-      status_kernel<<<ng, 64, 0, st>>>(dg, p->d_crc_acc, d_noi, d_ok, p->d_done, da, n + 1, max_iter, min_iter, early_stop);
+      if (mode == 0) job_kernel<0><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, max_iter,
+                                                      min_iter, early_stop);
+      else if (mode == 1) job_kernel<1><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, max_iter,
+                                                      min_iter, early_stop);
+      else job_kernel<2><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, max_iter,
+                                                      min_iter, early_stop);
     } break;
     default: {
       ProfScope ps(e, 2, st);
@@ -739,7 +767,6 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     for (uint32_t n = start_iter; n < max_iter; n++) {
       launch_one(e, p, rg[s], 1, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
       launch_one(e, p, rg[s], 2, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
-      launch_one(e, p, rg[s], 3, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
     }
     launch_one(e, p, rg[s], 4, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
     if (io) {

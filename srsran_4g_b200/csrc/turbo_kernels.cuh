@@ -37,10 +37,14 @@ constexpr int NEG_INF2 = 0xD8F0D8F0;  // two int16 of -10000 (turbodecoder_gen.c
 
 // ---------------------------------------------------------------- device-side descriptors
 struct KTable {
-  // per code-block size: (row index to scatter to, CRC position word) per trellis step, padded to R rows
-  const uint2* dec1[3];  // [crc_kind] : .x = rev[i],  .y = R_kind[K-1-i]
-  const uint2* dec2[3];  // [crc_kind] : .x = fwd[i],  .y = R_kind[K-1-fwd[i]]
-  const uint16_t* rev;   // natural position j -> interleaved index i (for the final bit gather)
+  // per code-block size, padded to R rows:
+  const uint32_t* row1;     // DEC1 write-back row per trellis step i: rev[i]
+  const uint32_t* row2;     // DEC2 write-back row per trellis step i: fwd[i]
+  // CRC by linearity, one 4x16 nibble table per 16-step window: nib[w][j][v] = XOR over the set bits b of v of
+  // x^(K-1-pos(16w+4j+b)+24) mod g, pos(i) = i for DEC1 and fwd[i] for DEC2; [crc_kind] (kind 0 aliases kind 2)
+  const uint32_t* nib1[3];
+  const uint32_t* nib2[3];
+  const uint16_t* rev;      // natural position j -> interleaved index i (for the final bit gather)
 };
 
 struct Group {
@@ -119,10 +123,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
   asm volatile(
@@ -136,16 +136,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async()
-{
-  asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 // forward recursion step without LLR (alpha part of map_gen_alpha, turbodecoder_gen.c:148-191); same ordering rule
@@ -162,52 +152,6 @@ __device__ __forceinline__ void alpha_step(uint32_t (&a)[8], uint32_t x, uint32_
   const uint32_t n5 = paddmax(a[2], y, t5);
   const uint32_t n6 = paddmax(a[5], y, t6);
   a[0] = n0; a[1] = n1; a[2] = n2; a[3] = n3; a[4] = n4; a[5] = n5; a[6] = n6; a[7] = n7;
-}
-
-// one backward step of chain b and one forward step of chain a with their statements interleaved: two independent
-// dependency chains in one instruction stream (a lone in-order warp needs >= 5 cycles between dependent instructions)
-__device__ __forceinline__ void beta_alpha_step(uint32_t (&b)[8], uint32_t xb, uint32_t yb, uint32_t (&a)[8], uint32_t xa, uint32_t ya)
-{
-  const uint32_t xyb = padd(xb, yb);
-  const uint32_t xya = padd(xa, ya);
-  const uint32_t tb2 = padd(b[1], xb);
-  const uint32_t ta1 = padd(a[2], xa);
-  const uint32_t tb3 = padd(b[1], yb);
-  const uint32_t ta2 = padd(a[5], xa);
-  const uint32_t tb4 = padd(b[2], yb);
-  const uint32_t ta5 = padd(a[3], xa);
-  const uint32_t tb5 = padd(b[2], xb);
-  const uint32_t ta6 = padd(a[4], xa);
-  const uint32_t nb1 = paddmax(b[0], xyb, b[4]);
-  const uint32_t na0 = paddmax(a[1], xya, a[0]);
-  const uint32_t nb0 = paddmax(b[4], xyb, b[0]);
-  const uint32_t na3 = paddmax(a[6], xya, a[7]);
-  const uint32_t nb6 = paddmax(b[3], xyb, b[7]);
-  const uint32_t na4 = paddmax(a[0], xya, a[1]);
-  const uint32_t nb7 = paddmax(b[7], xyb, b[3]);
-  const uint32_t na7 = paddmax(a[7], xya, a[6]);
-  const uint32_t nb2 = paddmax(b[5], yb, tb2);
-  const uint32_t na1 = paddmax(a[3], ya, ta1);
-  const uint32_t nb3 = paddmax(b[5], xb, tb3);
-  const uint32_t na2 = paddmax(a[4], ya, ta2);
-  const uint32_t nb4 = paddmax(b[6], xb, tb4);
-  const uint32_t na5 = paddmax(a[2], ya, ta5);
-  const uint32_t nb5 = paddmax(b[6], yb, tb5);
-  const uint32_t na6 = paddmax(a[5], ya, ta6);
-  b[0] = nb0; b[1] = nb1; b[2] = nb2; b[3] = nb3; b[4] = nb4; b[5] = nb5; b[6] = nb6; b[7] = nb7;
-  a[0] = na0; a[1] = na1; a[2] = na2; a[3] = na3; a[4] = na4; a[5] = na5; a[6] = na6; a[7] = na7;
-}
-
-__device__ __forceinline__ void normalise2(uint32_t (&s)[8], uint32_t (&t)[8])
-{
-  const uint32_t ns = psub(0u, s[0]), nt = psub(0u, t[0]);
-#pragma unroll
-  for (int i = 1; i < 8; i++) {
-    s[i] = padd(s[i], ns);
-    t[i] = padd(t[i], nt);
-  }
-  s[0] = 0u;
-  t[0] = 0u;
 }
 
 // hard decision of both halves: bit 15 / bit 31 set iff the int16 is > 0  (tdec_gen_decision_byte: app > 0)
@@ -541,7 +485,8 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
 struct JobStage {
   uint32_t s[3][WC][LANES];     // input rows of the window
   uint32_t ck[2][LANES][8];     // un-normalised beta at the top of its two 8-step halves (checkpoints 2w+1, 2w+2)
-  uint2    tab[WC];             // (scatter row, CRC position word) per step
+  uint32_t row[WC];             // write-back row per step
+  uint32_t nib[4][16];          // CRC nibble table of this window
 };
 struct alignas(128) JobWarpSmem {
   JobStage st[2];
@@ -602,10 +547,12 @@ __device__ __forceinline__ uint32_t alpha_llr_step(uint32_t (&a)[8], const uint3
  */
 template <int MODE>
 __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws,
-                                            const uint8_t* __restrict__ group_active, const uint8_t* __restrict__ done,
-                                            uint32_t* __restrict__ crc_acc)
+                                            uint8_t* __restrict__ group_active, uint8_t* __restrict__ done, uint32_t* __restrict__ crc_acc,
+                                            uint32_t* __restrict__ arrivals, uint8_t* __restrict__ noi, uint8_t* __restrict__ ok, uint32_t cnt,
+                                            uint32_t max_iter, uint32_t min_iter, int early_stop)
 {
   if (!group_active[blockIdx.y]) return;
+  __shared__ uint32_t s_last;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int       wid  = threadIdx.x >> 5;
   const int       lane = threadIdx.x & 31;
@@ -614,7 +561,6 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   const uint32_t  K    = g.K;
   const int       nwin = (int)((K + WC - 1) / WC);
   const int       w0   = (int)(blockIdx.x * 4 + wid) * WPJ;
-  if (w0 >= nwin) return;
   const int       w1   = min(w0 + WPJ, nwin);
   const GroupPtrs gp   = group_ptrs(ws, g);
   const KTable&   kt   = ktabs[g.kidx];
@@ -622,7 +568,8 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   const uint32_t* in0  = (MODE == 2) ? gp.app2 : gp.syst;
   const uint32_t* in1  = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
   const uint32_t* in2  = (MODE == 1) ? gp.par0 : nullptr;
-  const uint2*    tab  = (MODE == 2) ? kt.dec2[g.crc_kind] : kt.dec1[g.crc_kind];
+  const uint32_t* rowt = (MODE == 2) ? kt.row2 : kt.row1;
+  const uint32_t* nibt = (MODE == 2) ? kt.nib2[g.crc_kind] : kt.nib1[g.crc_kind];
   uint32_t*       dst  = (MODE == 2) ? gp.app1p : gp.app2;
   uint32_t*       bits = (MODE == 2) ? gp.bits2 : gp.bits1;
 
@@ -639,9 +586,10 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
     const uint32_t     bar   = smem_u32(&sm->bar[w & 1]);
     const uint32_t     d0    = smem_u32(&st.s[0][0][0]);
     const size_t       off   = (size_t)w * WC * LANES;
-    constexpr uint32_t BYTES = WC * LANES * 4, CKBYTES = 2 * 8 * LANES * 4, TABBYTES = WC * 8;
+    constexpr uint32_t BYTES = WC * LANES * 4, CKBYTES = 2 * 8 * LANES * 4, TABBYTES = WC * 4 + 4 * 16 * 4;
     const uint32_t*    ck    = gp.ckB + (size_t)(2 * w + 1) * 8 * LANES;
-    const uint2*       tb    = tab + (size_t)w * WC;
+    const uint32_t*    rw    = rowt + (size_t)w * WC;
+    const uint32_t*    nb    = nibt + (size_t)w * 64;
     if (MODE == 1) {
       asm volatile(
           "{\n.reg .pred p;\n"
@@ -651,10 +599,11 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
           "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%6], %3, [%0];\n"
           "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%7], [%8], %3, [%0];\n"
           "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%9], [%10], %11, [%0];\n"
-          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%12], [%13], %14, [%0];\n}"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%12], [%13], 64, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%14], [%15], 256, [%0];\n}"
           ::"r"(bar), "r"(3u * BYTES + CKBYTES + TABBYTES), "r"(d0), "r"(BYTES), "r"(d0 + BYTES), "l"(in0 + off), "l"(in1 + off),
-            "r"(d0 + 2 * BYTES), "l"(in2 + off), "r"(smem_u32(&st.ck[0][0][0])), "l"(ck), "r"(CKBYTES), "r"(smem_u32(&st.tab[0])), "l"(tb),
-            "r"(TABBYTES)
+            "r"(d0 + 2 * BYTES), "l"(in2 + off), "r"(smem_u32(&st.ck[0][0][0])), "l"(ck), "r"(CKBYTES), "r"(smem_u32(&st.row[0])), "l"(rw),
+            "r"(smem_u32(&st.nib[0][0])), "l"(nb)
           : "memory");
     } else {
       asm volatile(
@@ -664,13 +613,14 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
           "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %3, [%0];\n"
           "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%6], %3, [%0];\n"
           "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%7], [%8], %9, [%0];\n"
-          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%10], [%11], %12, [%0];\n}"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%10], [%11], 64, [%0];\n"
+          "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%12], [%13], 256, [%0];\n}"
           ::"r"(bar), "r"(2u * BYTES + CKBYTES + TABBYTES), "r"(d0), "r"(BYTES), "r"(d0 + BYTES), "l"(in0 + off), "l"(in1 + off),
-            "r"(smem_u32(&st.ck[0][0][0])), "l"(ck), "r"(CKBYTES), "r"(smem_u32(&st.tab[0])), "l"(tb), "r"(TABBYTES)
+            "r"(smem_u32(&st.ck[0][0][0])), "l"(ck), "r"(CKBYTES), "r"(smem_u32(&st.row[0])), "l"(rw), "r"(smem_u32(&st.nib[0][0])), "l"(nb)
           : "memory");
     }
   };
-  issue(w0);
+  if (w0 < nwin) issue(w0);
 
   const int cb_lo = g.cb[lane], cb_hi = g.cb[32 + lane];
   uint32_t  keep  = 0;
@@ -680,7 +630,7 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   uint32_t ph0 = 0, ph1 = 0;
   // alpha state entering the first window (the windows of this warp are consecutive, so it simply carries on)
   uint32_t a[8];
-  {
+  if (w0 < nwin) {
     const uint4* ca = reinterpret_cast<const uint4*>(gp.ckA + ((size_t)(w0 / WPJ) * LANES + lane) * 8);
     const uint4  c0 = ca[0], c1 = ca[1];
     a[0] = c0.x; a[1] = c0.y; a[2] = c0.z; a[3] = c0.w;
@@ -744,49 +694,54 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
         uint32_t ap = (MODE == 1) ? st.s[1][r][lane] : (MODE == 2 ? st.s[0][r][lane] : 0u);
         uint32_t L  = alpha_llr_step(a, B[j], x, y);
         if (j == 3 || j == 7) normalise(a);
-        const uint2 t = st.tab[r];
-        dst[(size_t)t.x * LANES + lane] = (MODE == 0) ? L : psub(L, ap);
-        const uint32_t pos = positive_mask(L);
-        crc_lo ^= (pos & 0x8000u) ? t.y : 0u;
-        crc_hi ^= (pos & 0x80000000u) ? t.y : 0u;
-        bitacc = ((bitacc >> 1) & 0x7fff7fffu) | pos;
+        dst[(size_t)st.row[r] * LANES + lane] = (MODE == 0) ? L : psub(L, ap);
+        bitacc = ((bitacc >> 1) & 0x7fff7fffu) | positive_mask(L);
       }
     }
     if (nsub == 1) bitacc = (bitacc >> 8) & 0x00ff00ffu;  // K = 8 mod 16: the last word holds eight decisions
+    // CRC of the 16 decisions of this window by linearity: four nibble look-ups per code block (the per-bit form costs
+    // ~5 ALU-pipe instructions per step, and the ALU pipe is what bounds this kernel)
+    {
+      const uint32_t wl = bitacc & 0xffffu, wh = bitacc >> 16;
+      crc_lo ^= st.nib[0][wl & 15u] ^ st.nib[1][(wl >> 4) & 15u] ^ st.nib[2][(wl >> 8) & 15u] ^ st.nib[3][wl >> 12];
+      crc_hi ^= st.nib[0][wh & 15u] ^ st.nib[1][(wh >> 4) & 15u] ^ st.nib[2][(wh >> 8) & 15u] ^ st.nib[3][wh >> 12];
+    }
     uint32_t* bw = bits + (size_t)w * LANES + lane;
     if (keep) bitacc = (bitacc & ~keep) | (*bw & keep);  // finished code blocks keep their final decisions
     *bw = bitacc;
   }
   if (cb_lo >= 0 && !(keep & 0xffffu) && crc_lo) atomicXor(&crc_acc[cb_lo], crc_lo);
   if (cb_hi >= 0 && !(keep & 0xffff0000u) && crc_hi) atomicXor(&crc_acc[cb_hi], crc_hi);
-}
-#undef LOAD_XY
 
-/*
- * Per-code-block verdict after half-iteration number cnt (1-based): the loop condition of decode_tb_cb
- * (lib/src/phy/phch/sch.c:426-456). grid = n_groups, block = 64.
- */
-__global__ void __launch_bounds__(64) status_kernel(const Group* __restrict__ groups, uint32_t* __restrict__ crc_acc, uint8_t* __restrict__ noi,
-                                                    uint8_t* __restrict__ ok, uint8_t* __restrict__ done, uint8_t* __restrict__ group_active,
-                                                    uint32_t cnt, uint32_t max_iter, uint32_t min_iter, int early_stop)
-{
-  const Group& g = groups[blockIdx.x];
-  if (!group_active[blockIdx.x]) return;
-  const int cb     = g.cb[threadIdx.x];
-  int       active = 0;
-  if (cb >= 0) {
-    if (!done[cb]) {
-      const uint32_t okv = (g.crc_kind != 0 && crc_acc[cb] == 0u) ? 1u : 0u;
-      noi[cb] = (uint8_t)cnt;
-      ok[cb]  = (uint8_t)okv;
-      if ((early_stop && okv && cnt >= min_iter) || cnt >= max_iter) done[cb] = 1;
-      else active = 1;
+  // ---------------- per-code-block verdict, by the LAST block of the group to finish (sch.c:426-456):
+  // half-iteration count, CRC == 0 accepted from the min_iter-th on, done flags, group activity for the next launches
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&arrivals[blockIdx.y], 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  int active = 0;
+  if (threadIdx.x < 64) {
+    const int cb = g.cb[threadIdx.x];
+    if (cb >= 0) {
+      if (!done[cb]) {
+        const uint32_t okv = (g.crc_kind != 0 && __ldcg(&crc_acc[cb]) == 0u) ? 1u : 0u;
+        noi[cb] = (uint8_t)cnt;
+        ok[cb]  = (uint8_t)okv;
+        if ((early_stop && okv && cnt >= min_iter) || cnt >= max_iter) done[cb] = 1;
+        else active = 1;
+      }
+      crc_acc[cb] = 0u;
     }
-    crc_acc[cb] = 0u;
   }
   active = __syncthreads_or(active);
-  if (threadIdx.x == 0) group_active[blockIdx.x] = (uint8_t)(active ? 1 : 0);
+  if (threadIdx.x == 0) {
+    group_active[blockIdx.y] = (uint8_t)(active ? 1 : 0);
+    arrivals[blockIdx.y]     = 0u;
+  }
 }
+#undef LOAD_XY
 
 /*
  * De-multiplex natural-order LLRs (tdec_gen_extract_input, turbodecoder_gen.c:238-258) of up to 64 code blocks into the

@@ -328,7 +328,9 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "job_kernel (all half-iteration launches of one step, timed without sub-batch overlap)", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (%s)" % peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
-                     "note": "compulsory bytes of the whole decode (6.13 B/info bit) over the job kernels' time; see roofline_int for the integer-issue view"},
+                     "measured_dram_GBps": (traffic / (per_launch_ms * 1e-3) / 1e9) if traffic else None,
+                     "measured_dram_frac": (traffic / (per_launch_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic else None,
+                     "note": "achieved = compulsory bytes of the whole decode (6.13 B/info bit, SURVEY 8(d)) over the job kernels' time; traffic / measured_dram_* = what ncu saw the job kernels move (profiles/dram_traffic.json); roofline_int = the integer-issue view"},
         "roofline_int": {"bound": "int16x2 issue (VIADD/VIMNMX/VIADDMNMX .16x2, two pipes)", "kernel": "job_kernel", "achieved": int_achieved,
                          "peak": INT_PEAK_TOPS, "unit": "T packed-instr/s", "frac": int_achieved / INT_PEAK_TOPS,
                          "algorithmic_ops_per_launch": alg_ops, "executed_half_iterations_per_launch": half_iters,

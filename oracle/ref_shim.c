@@ -476,3 +476,69 @@ double ref_tdec_batch(int       impl,
   /* wall time from the first thread leaving the start barrier to the last thread finishing its share */
   return err ? -1.0 : t1 - t0;
 }
+
+/*
+ * The reference's encode_tb_off loop (lib/src/phy/phch/sch.c:240-358; static there and sch.c drags in the whole PHY, so
+ * the loop is restated here around the *reference's own* primitives): srsran_tcod_encode_lut (CRC attach + turbo
+ * encode on packed bytes) and srsran_rm_turbo_tx_lut (interleave into the circular buffer at rv 0, bit selection).
+ * Each CB's circular buffer is primed with an rv=0 call when rv != 0, as a HARQ process would have done.
+ * e_bits must hold (nof_e_bits+7)/8 + 8 bytes; it is zeroed first.
+ */
+int ref_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, const uint8_t* data, uint8_t* e_bits)
+{
+  ref_init();
+  if (!data || !e_bits) {
+    return -2;
+  }
+  srsran_cbsegm_t seg;
+  if (srsran_cbsegm(&seg, tbs)) {
+    return -1;
+  }
+  if (seg.F || Qm == 0 || rv >= 4) {
+    return -1;
+  }
+  static srsran_tcod_t enc;
+  static int           enc_ready = 0;
+  pthread_mutex_lock(&g_lock);
+  if (!enc_ready) {
+    srsran_tcod_init(&enc, MAX_K);
+    enc_ready = 1;
+  }
+  srsran_crc_t crc_tb, crc_cb;
+  srsran_crc_init(&crc_tb, CRC24A, 24);
+  srsran_crc_init(&crc_cb, CRC24B, 24);
+  uint8_t* cb_in  = calloc(MAX_K / 8 + 16, 1);
+  uint8_t* parity = calloc(3 * MAX_K / 8 + 16, 1);
+  uint8_t* w_buff = calloc(SOFTBUFFER_SIZE, 1);
+  uint8_t* scratch = calloc((nof_e_bits + 7) / 8 + 64, 1);
+  int      ret = 0;
+  memset(e_bits, 0, (nof_e_bits + 7) / 8);
+  uint32_t Gp = nof_e_bits / Qm, gamma = seg.C > 0 ? Gp % seg.C : Gp;
+  srsran_crc_set_init(&crc_tb, 0);
+  uint32_t wp = 0, rp = 0;
+  for (uint32_t i = 0; i < seg.C; i++) {
+    uint32_t cb_len = i < seg.C2 ? seg.K2 : seg.K1, cblen_idx = i < seg.C2 ? seg.K2_idx : seg.K1_idx;
+    uint32_t rlen   = seg.C > 1 ? cb_len - 24 : cb_len;
+    uint32_t n_e    = (i <= seg.C - gamma - 1) ? Qm * (Gp / seg.C) : Qm * ((uint32_t)ceilf((float)Gp / seg.C));
+    bool     last   = i == seg.C - 1;
+    memcpy(cb_in, &data[rp / 8], (last ? rlen - 24 : rlen) / 8);
+    srsran_tcod_encode_lut(&enc, &crc_tb, seg.C > 1 ? &crc_cb : NULL, cb_in, parity, cblen_idx, last);
+    /* the circular buffer (softbuffer->buffer_b[i]) is filled only at rv 0 (rm_turbo.c:358-366): prime it first */
+    if (rv != 0 && srsran_rm_turbo_tx_lut(w_buff, cb_in, parity, &scratch[wp / 8], cblen_idx, n_e, wp % 8, 0)) {
+      ret = -1;
+      break;
+    }
+    if (srsran_rm_turbo_tx_lut(w_buff, cb_in, parity, &e_bits[wp / 8], cblen_idx, n_e, wp % 8, rv)) {
+      ret = -1;
+      break;
+    }
+    rp += rlen;
+    wp += n_e;
+  }
+  pthread_mutex_unlock(&g_lock);
+  free(cb_in);
+  free(parity);
+  free(w_buff);
+  free(scratch);
+  return ret;
+}

@@ -678,3 +678,74 @@ int orc_decode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, c
   memset(cb_crc, 0, C);
   return -1;
 }
+
+/* ------------------------------------------------------------------ transport-block encode */
+/*
+ * encode_tb_off, lib/src/phy/phch/sch.c:240-358, at bit level: TB CRC24A over the payload (srsran_tcod_encode_lut feeds
+ * every payload byte of every CB to crc_tb, turbocoder.c:217-225), segmentation with the K2 (smaller) blocks FIRST
+ * (sch.c:287-293 - note the reference's decoder puts K1 first, sch.c:384-389; they agree only when C2 == 0, which is the
+ * case for every standard TBS), CRC24B per CB when C > 1, turbo encode, rate matching with the E rule of sch.c:299-303
+ * ("i <= C - gamma - 1" gets the floor), output packed at bit offset wp.
+ */
+int orc_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, const uint8_t* data, uint8_t* e_bits)
+{
+  if (!data || !e_bits) {
+    return -2;
+  }
+  uint32_t sg[12];
+  if (orc_cbsegm(tbs, sg)) {
+    return -1;
+  }
+  uint32_t F = sg[0], C = sg[1], K1 = sg[2], K2 = sg[3], C2 = sg[7];
+  if (F || Qm == 0 || rv >= 4) {
+    return -1;
+  }
+  memset(e_bits, 0, (nof_e_bits + 7) / 8);
+  if (C == 0) {
+    return 0;
+  }
+  uint32_t Gp = nof_e_bits / Qm, gamma = Gp % C;
+  /* payload + TB CRC as bits */
+  uint8_t* tb = malloc(tbs + 24);
+  for (uint32_t i = 0; i < tbs; i++) {
+    tb[i] = (data[i / 8] >> (7 - i % 8)) & 1;
+  }
+  uint32_t crc = orc_crc_bits(ORC_CRC24A, 24, tb, (int)tbs);
+  for (int i = 0; i < 24; i++) {
+    tb[tbs + i] = (crc >> (23 - i)) & 1;
+  }
+  uint8_t* cb    = malloc(ORC_MAX_K);
+  uint8_t* coded = malloc(3 * ORC_MAX_K + 12);
+  uint8_t* e     = malloc(nof_e_bits + 8 * Qm + 8);
+  uint32_t rp = 0, wp = 0;
+  int      ret = 0;
+  for (uint32_t i = 0; i < C && !ret; i++) {
+    uint32_t K    = i < C2 ? K2 : K1;
+    uint32_t rlen = C > 1 ? K - 24 : K;
+    uint32_t n_e  = (i <= C - gamma - 1) ? Qm * (Gp / C) : Qm * (uint32_t)ceilf((float)Gp / C);
+    memcpy(cb, &tb[rp], rlen);
+    if (C > 1) {
+      uint32_t c = orc_crc_bits(ORC_CRC24B, 24, cb, (int)rlen);
+      for (int b = 0; b < 24; b++) {
+        cb[rlen + b] = (c >> (23 - b)) & 1;
+      }
+    }
+    if (orc_tcod_encode(cb, coded, K) || orc_rm_tx(coded, K, e, n_e, rv)) {
+      ret = -1;
+      break;
+    }
+    for (uint32_t n = 0; n < n_e; n++) {
+      uint32_t pos = wp + n;
+      if (e[n]) {
+        e_bits[pos / 8] |= (uint8_t)(0x80 >> (pos % 8));
+      }
+    }
+    rp += rlen;
+    wp += n_e;
+  }
+  free(tb);
+  free(cb);
+  free(coded);
+  free(e);
+  return ret;
+}

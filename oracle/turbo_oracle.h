@@ -52,6 +52,11 @@ int orc_decode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, c
                   uint32_t max_iterations, int16_t* buffer_f, uint8_t* sb_data, uint8_t* cb_crc, uint8_t* tb_crc,
                   uint8_t* data, uint32_t* cb_noi, float* avg_iterations);
 
+/* transport-block encode (bit-level restatement of encode_tb_off, sch.c:240-358). data: tbs/8 packed bytes;
+ * e_bits: packed MSB-first, (nof_e_bits+7)/8 bytes, zero-filled then written up to Qm*(nof_e_bits/Qm) bits.
+ * Returns 0, -1 (filler bits / Qm == 0 / bad tbs) or -2 (null pointers). */
+int orc_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, const uint8_t* data, uint8_t* e_bits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,9 @@ class _Lib:
         self._dec_tb = f("decode_tb")
         self._dec_tb.argtypes = [C.c_uint32] * 4 + [i16p, C.c_uint32, i16p, u8p, u8p, u8p, u8p, u32p, C.POINTER(C.c_float)]
         self._dec_tb.restype = C.c_int
+        self._enc_tb = f("encode_tb")
+        self._enc_tb.argtypes = [C.c_uint32] * 4 + [u8p, u8p]
+        self._enc_tb.restype = C.c_int
         if p == "ref_":
             L.ref_init()
             self._trace = L.ref_tdec_trace; self._trace.argtypes = [C.c_int, C.c_uint32, i16p, C.c_uint32, u8p, C.c_void_p]
@@ -182,6 +185,13 @@ class _Lib:
         ret = self._dec_tb(tbs, Qm, rv, G, e_bits, max_iterations, state["buffer_f"], state["sb_data"], state["cb_crc"],
                            tb_crc, data, noi, C.byref(avg))
         return dict(ret=ret, data=data, cb_noi=noi, tb_crc=int(tb_crc[0]), avg_iterations=avg.value, state=state, seg=seg)
+
+    def encode_tb(self, tbs, Qm, rv, nof_e_bits, data):
+        """-> (ret, e_bits packed MSB-first, (nof_e_bits+7)//8 bytes)"""
+        data = np.ascontiguousarray(data, np.uint8)
+        e = np.zeros((nof_e_bits + 7) // 8 + 64, np.uint8)
+        ret = self._enc_tb(tbs, Qm, rv, nof_e_bits, data, e)
+        return ret, e[:(nof_e_bits + 7) // 8]
 
 
 def new_tb_state(Cn):

@@ -53,7 +53,7 @@ const char* srsb200_last_error(void);
 /* number of kernels launched by this engine since creation (bench.py's gpu_launches claim) */
 uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e);
 /* per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg). profile_read synchronises and
- * returns, per kernel kind (0 extract, 2 emit, 3 rate de-match, 4 TB CRC, 5 alpha/beta scan, 6 window jobs, 7 status), the
+ * returns, per kernel kind (0 extract, 2 emit, 3 rate de-match, 4 TB CRC, 5 alpha/beta scan, 6 window jobs, 7 transport-block encode), the
  * summed milliseconds and launch counts since the previous read. While profiling is enabled a decode runs as one chain
  * of launches (the sub-batch overlap of srsb200_engine_set_subbatches is off) so the durations are not inflated. */
 int srsb200_engine_profile(srsb200_engine_t* e, int enable);
@@ -174,6 +174,32 @@ int srsb200_softbuffer_release(srsb200_engine_t* e, int16_t** buffer_f, uint32_t
 int srsb200_decode_tb_batch(srsb200_engine_t* e, srsb200_tb_t* tbs, uint32_t n, uint32_t max_iterations);
 /* single transport block = decode_tb (sch.c:509); returns tb->ret */
 int srsb200_decode_tb(srsb200_engine_t* e, srsb200_tb_t* tb, uint32_t max_iterations);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Transport-block ENCODE (the transmit mirror of the path)
+ * replaces: static encode_tb_off / encode_tb, lib/src/phy/phch/sch.c:240-375 (hence srsran_dlsch_encode[2], sch.c:611-639,
+ *           and the data part of srsran_ulsch_encode), i.e. per code block
+ *           srsran_tcod_encode_lut  lib/src/phy/fec/turbo/turbocoder.c:186-360  (CRC24A/CRC24B attach + turbo encode)
+ *           srsran_rm_turbo_tx_lut  lib/src/phy/fec/turbo/rm_turbo.c:345-388    (circular buffer + bit selection)
+ * Semantics kept: K2 (smaller) code blocks first (sch.c:287-293), E = Qm*floor(G'/C) for r <= C-gamma-1 else
+ * Qm*ceil(G'/C) (sch.c:299-303), code block r packed MSB-first at bit offset sum(E_0..E_{r-1}); return codes: -2 for
+ * null pointers, -1 for filler bits / Qm == 0 / C > max_cb / rv > 3 / segmentation failure, 0 otherwise (tbs == 0 writes
+ * nothing). Differences: every call encodes from `data` (the reference re-reads its circular buffer softbuffer->buffer_b
+ * for rv != 0 and data == NULL is accepted there; here data == NULL is -2), and the (nof_e_bits+7)/8 output bytes are
+ * written whole (pad bits zero) instead of bit-spliced into the previous content.
+ */
+typedef struct {
+  uint32_t       tbs;        /* cb_segm->tbs */
+  uint32_t       Qm;
+  uint32_t       rv;
+  uint32_t       nof_e_bits; /* G */
+  uint32_t       max_cb;     /* softbuffer->max_cb */
+  const uint8_t* data;       /* tbs/8 payload bytes (host) */
+  uint8_t*       e_bits;     /* out (host): packed, (nof_e_bits+7)/8 bytes */
+  int32_t        ret;        /* out: per-TB return code */
+} srsb200_tb_tx_t;
+int srsb200_encode_tb_batch(srsb200_engine_t* e, srsb200_tb_tx_t* tbs, uint32_t n);
+int srsb200_encode_tb(srsb200_engine_t* e, srsb200_tb_tx_t* tb); /* returns tb->ret */
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,8 @@ def lib():
         for fn in (L.srsb200_softbuffer_reset, L.srsb200_softbuffer_sync_to_host, L.srsb200_softbuffer_release):
             fn.argtypes = [vp, C.POINTER(C.c_void_p), u32]
         L.srsb200_decode_tb.argtypes = [vp, vp, u32]
+        L.srsb200_encode_tb_batch.argtypes = [vp, vp, u32]
+        L.srsb200_encode_tb.argtypes = [vp, vp]
         _LIB = L
     return _LIB
 
@@ -104,6 +106,11 @@ class _TbStruct(C.Structure):
     _fields_ = [("tbs", C.c_uint32), ("Qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32), ("e_bits", C.c_void_p),
                 ("buffer_f", C.POINTER(C.c_void_p)), ("sb_data", C.POINTER(C.c_void_p)), ("cb_crc", C.c_void_p), ("tb_crc", C.c_void_p),
                 ("max_cb", C.c_uint32), ("data", C.c_void_p), ("cb_noi", C.c_void_p), ("avg_iterations", C.c_float), ("ret", C.c_int)]
+
+
+class _TbTxStruct(C.Structure):
+    _fields_ = [("tbs", C.c_uint32), ("Qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32), ("max_cb", C.c_uint32),
+                ("data", C.c_void_p), ("e_bits", C.c_void_p), ("ret", C.c_int32)]
 
 
 class TransportBlock:
@@ -180,7 +187,7 @@ class Engine:
         ms = (C.c_double * 8)()
         cnt = (C.c_uint64 * 8)()
         _check(self._L.srsb200_engine_profile_read(self._h, ms, cnt), "srsb200_engine_profile_read")
-        names = ["extract", "decode", "emit", "rm", "tbcrc", "scan", "job", "status"]
+        names = ["extract", "decode", "emit", "rm", "tbcrc", "scan", "job", "tbenc"]
         return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names)}
 
     # ---- batched decode, host buffers
@@ -257,6 +264,30 @@ class Engine:
         for s, (tb, _, _, _) in zip(arr, reqs):
             tb.ret, tb.avg_iterations = s.ret, s.avg_iterations
         return ret
+
+    def encode_tb_batch(self, reqs, max_cb=256):
+        """reqs: list of (tbs, Qm, rv, nof_e_bits, data bytes) -> (ret, [(tb_ret, e_bits packed uint8)])"""
+        arr = (_TbTxStruct * len(reqs))()
+        keep = []
+        for s, (tbs, Qm, rv, G, data) in zip(arr, reqs):
+            d = None if data is None else np.ascontiguousarray(data, np.uint8)
+            e = np.zeros((G + 7) // 8, np.uint8)
+            keep.append((d, e))
+            s.tbs, s.Qm, s.rv, s.nof_e_bits, s.max_cb = tbs, Qm, rv, G, max_cb
+            s.data = None if d is None else d.ctypes.data
+            s.e_bits = e.ctypes.data
+        ret = self._L.srsb200_encode_tb_batch(self._h, arr, len(reqs))
+        return ret, [(int(s.ret), k[1]) for s, k in zip(arr, keep)]
+
+    def encode_tb(self, tbs, Qm, rv, nof_e_bits, data, max_cb=256):
+        s = _TbTxStruct()
+        d = None if data is None else np.ascontiguousarray(data, np.uint8)
+        e = np.zeros((nof_e_bits + 7) // 8, np.uint8)
+        s.tbs, s.Qm, s.rv, s.nof_e_bits, s.max_cb = tbs, Qm, rv, nof_e_bits, max_cb
+        s.data = None if d is None else d.ctypes.data
+        s.e_bits = e.ctypes.data
+        ret = self._L.srsb200_encode_tb(self._h, C.byref(s))
+        return ret, e
 
     def decode_tb(self, tb, Qm, rv, e_bits, max_iterations, nof_e_bits=None):
         s = _TbStruct()

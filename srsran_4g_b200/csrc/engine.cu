@@ -7,6 +7,7 @@
 #include "../../include/lte_qpp_params.h"
 #include "turbo_kernels.cuh"
 #include "rm_kernels.cuh"
+#include "tx_kernels.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -176,8 +177,9 @@ struct srsb200_engine {
   uint16_t* d_rm[LTE_NOF_CB_SIZES][4];
 
   // scratch for the host-pointer APIs (grown on demand)
-  void*  d_scratch[8]   = {nullptr};
-  size_t scratch_cap[8] = {0};
+  void*  d_scratch[12]   = {nullptr};  // 0-7 receive side, 8-11 transmit side
+  size_t scratch_cap[12] = {0};
+  uint32_t* d_crc24b_words = nullptr;  // x^(m+24) mod g24B, m < 6144 (tx_cb_kernel)
 
   // sub-batch streams (see launch_plan)
   static const int MAX_SUB = 8;
@@ -487,7 +489,7 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
   if (e->tb_plan) srsb200_plan_destroy(e->tb_plan);
   for (void* p : e->softslot_chunks) cudaFree(p);
   for (void* p : e->owned) cudaFree(p);
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < 12; i++)
     if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);
   cudaFree(e->d_ktab);
   if (e->d_tb_crc_words) cudaFree(e->d_tb_crc_words);
@@ -506,7 +508,7 @@ extern "C" int srsb200_engine_profile(srsb200_engine_t* e, int enable)
   e->profiling = enable != 0;
   return SRSB200_SUCCESS;
 }
-// ms[kind] += elapsed, cnt[kind] += launches; kinds: 0 extract, 2 emit, 3 rate-dematch, 4 tb-crc, 5 scan, 6 job, 7 status.
+// ms[kind] += elapsed, cnt[kind] += launches; kinds: 0 extract, 2 emit, 3 rate-dematch, 4 tb-crc, 5 scan, 6 job, 7 tb-encode.
 // Synchronises. While profiling is on, decodes run as a single chain (no sub-batch overlap).
 extern "C" int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[8])
 {
@@ -720,7 +722,7 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
 }
 
 /*
- * A decode is a chain of dependent launches: extract, then per half-iteration {scan, job, status}, then emit. Every
+ * A decode is a chain of dependent launches: extract, then per half-iteration {scan, job}, then emit. Every
  * half-iteration up to max_iter is enqueued; groups whose code blocks are all done exit at once.
  *
  * Host-pointer submissions of a contiguous equal-size batch are cut into S ranges of groups, each with its own stream:
@@ -1007,3 +1009,4 @@ extern "C" int srsb200_rm_turbo_rx_lut(srsb200_engine_t* e, const int16_t* input
 
 // ------------------------------------------------------------------ transport blocks (decode_tb)
 #include "tb_decode.inc"
+#include "tb_encode.inc"

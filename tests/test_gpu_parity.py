@@ -264,3 +264,74 @@ def test_decode_tb_device_resident_softbuffers(sb, o):
     eng.softbuffer_sync_to_host(tb)
     _check_tb(res_o, tb, res_o["state"])
     eng.close()
+
+
+# ------------------------------------------------------------------ transport-block encode
+ENC_TBS = [16, 40, 104, 1000, 2984, 6120, 6200, 12216, 36696, 75376]
+
+
+@pytest.mark.parametrize("Qm,rv", [(2, 0), (4, 1), (6, 2), (2, 3)])
+def test_encode_tb_matches_oracle(eng, o, Qm, rv):
+    """every e-bit of srsb200_encode_tb equals the oracle's (itself pinned to the reference's LUT encoder / rate matcher)"""
+    for tbs in ENC_TBS:
+        ret, seg = o.cbsegm(tbs)
+        if ret or seg["F"]:
+            continue
+        rng = np.random.default_rng(tbs + 13 * Qm + rv)
+        data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        for G in (Qm * ((tbs * 2) // Qm), Qm * ((tbs * 4 + 12 * seg["C"]) // Qm) + 1, Qm * (tbs // Qm // 2 + 7)):
+            r0, e0 = o.encode_tb(tbs, Qm, rv, G, data)
+            r1, e1 = eng.encode_tb(tbs, Qm, rv, G, data)
+            assert r0 == r1 == 0
+            assert np.array_equal(e0, e1), f"tbs={tbs} G={G}: first differing byte {np.flatnonzero(e0 != e1)[:4]}"
+
+
+def test_encode_tb_c2_order(eng, o):
+    """a non-standard TBS with C2 > 0 and F == 0: the smaller code blocks go first (sch.c:287-293)"""
+    for tbs in range(6200, 30000, 8):
+        ret, seg = o.cbsegm(tbs)
+        if ret == 0 and seg["F"] == 0 and seg["C2"] > 0:
+            break
+    data = np.random.default_rng(tbs).integers(0, 256, tbs // 8, dtype=np.uint8)
+    for Qm, G in ((2, 6 * tbs), (6, 6 * (tbs // 4))):
+        r0, e0 = o.encode_tb(tbs, Qm, 0, G, data)
+        r1, e1 = eng.encode_tb(tbs, Qm, 0, G, data)
+        assert r0 == r1 == 0 and np.array_equal(e0, e1)
+
+
+def test_encode_tb_batch_mixed(eng, o):
+    """many transport blocks of different shapes in one submission"""
+    rng = np.random.default_rng(77)
+    reqs = []
+    for tbs, Qm, rv in [(75376, 6, 0), (16, 2, 1), (36696, 4, 2), (6120, 2, 3), (2984, 6, 0), (12216, 4, 0), (75376, 2, 1)] * 3:
+        G = Qm * int(rng.integers(tbs // Qm // 2 + 8, 3 * tbs // Qm + 40))
+        reqs.append((tbs, Qm, rv, G, rng.integers(0, 256, tbs // 8, dtype=np.uint8)))
+    ret, res = eng.encode_tb_batch(reqs)
+    assert ret == 0
+    for (tbs, Qm, rv, G, data), (r, e) in zip(reqs, res):
+        r0, e0 = o.encode_tb(tbs, Qm, rv, G, data)
+        assert r == r0 == 0 and np.array_equal(e, e0)
+
+
+def test_encode_tb_errors(eng):
+    d = np.zeros(2000, np.uint8)
+    assert eng.encode_tb(1000, 0, 0, 3000, d)[0] == -1            # Qm == 0
+    assert eng.encode_tb(6152, 2, 0, 30000, d)[0] == -1           # filler bits
+    assert eng.encode_tb(12216, 2, 0, 30000, d, max_cb=1)[0] == -1  # C > max_cb
+    assert eng.encode_tb(1000, 2, 4, 3000, d)[0] == -1            # rv > 3
+    assert eng.encode_tb(1000, 2, 0, 3000, None)[0] == -2         # no payload
+    r, e = eng.encode_tb(0, 2, 0, 64, d)
+    assert r == 0 and not e.any()                                 # tbs == 0: nothing written
+
+
+def test_encode_then_decode_round_trip(sb, eng):
+    """the engine's own encoder feeds its decoder: hard-decision LLRs of the e-bits decode back to the payload"""
+    tbs, Qm = 75376, 6
+    G = Qm * 20000
+    data = np.random.default_rng(5).integers(0, 256, tbs // 8, dtype=np.uint8)
+    r, e = eng.encode_tb(tbs, Qm, 0, G, data)
+    assert r == 0
+    llr = ((np.unpackbits(e)[:G].astype(np.int16) * 2 - 1) * 30).astype(np.int16)
+    tb = sb.TransportBlock(tbs=tbs)
+    assert eng.decode_tb(tb, Qm, 0, llr, 8) == 0
+    assert np.array_equal(tb.data[:tbs // 8], data)

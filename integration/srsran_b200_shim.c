@@ -7,7 +7,7 @@
  *   lib/src/phy/fec/turbo/turbodecoder.c      (srsran_tdec_*)
  *   the rx half of lib/src/phy/fec/turbo/rm_turbo.c (srsran_rm_turbo_rx_lut[_])
  * and provides srsran_b200_decode_tb(), which lib/src/phy/phch/sch.c:decode_tb calls instead of its serial
- * decode_tb_cb loop (two-line patch). Everything above decode_tb (srsran_dlsch_decode[2],
+ * decode_tb_cb loop (two-line patch), and srsran_b200_encode_tb() for sch.c:encode_tb_off likewise. Everything above decode_tb (srsran_dlsch_decode[2],
  * srsran_ulsch_decode with its UCI de-multiplexing) is untouched and funnels into it exactly as before.
  *
  * The device handle lives in fields the reference already has: h->dec16_hdlr[0] (srsb200_tdec_t*). One engine per
@@ -255,6 +255,77 @@ int srsran_b200_decode_tb_batch(srsran_sch_t**           q,
   return ret == SRSB200_SUCCESS ? SRSRAN_SUCCESS : SRSRAN_ERROR;
 }
 
+/* ------------------------------------------------------------------ transmit side: sch.c encode_tb_off */
+/* dst bits [off, off+n) <- src bits [0, n), MSB first; every other bit of dst is preserved (what srsran_bit_copy does) */
+static void splice_bits(uint8_t* dst, uint32_t off, const uint8_t* src, uint32_t n)
+{
+  if ((off & 7u) == 0) {
+    memcpy(&dst[off / 8], src, n / 8);
+    if (n & 7u) {
+      uint8_t mask = (uint8_t)(0xff00u >> (n & 7u));
+      dst[off / 8 + n / 8] = (uint8_t)((dst[off / 8 + n / 8] & ~mask) | (src[n / 8] & mask));
+    }
+    return;
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t p   = off + i;
+    uint8_t  bit = (src[i / 8] >> (7 - (i & 7u))) & 1u;
+    dst[p / 8]   = (uint8_t)((dst[p / 8] & ~(0x80u >> (p & 7u))) | (bit ? (0x80u >> (p & 7u)) : 0));
+  }
+}
+
+/*
+ * Drop-in body of sch.c's static encode_tb_off(): same arguments and return codes. CRC attach, turbo encoding and rate
+ * matching of all code blocks run on the device as one submission; the bits land at bit offset w_offset of e_bits and
+ * the rest of e_bits is preserved, as srsran_rm_turbo_tx_lut + srsran_bit_copy leave it. The transmit soft buffer
+ * (softbuffer->buffer_b, the per-block circular buffers) is not used: every redundancy version is produced from `data`.
+ */
+int srsran_b200_encode_tb(srsran_sch_t*           q,
+                          srsran_softbuffer_tx_t* softbuffer,
+                          srsran_cbsegm_t*        cb_segm,
+                          uint32_t                Qm,
+                          uint32_t                rv,
+                          uint32_t                nof_e_bits,
+                          uint8_t*                data,
+                          uint8_t*                e_bits,
+                          uint32_t                w_offset)
+{
+  if (q == NULL || e_bits == NULL || cb_segm == NULL || softbuffer == NULL) {
+    ERROR("Invalid parameters: e_bits=%d, cb_segm=%d, softbuffer=%d", e_bits != 0, cb_segm != 0, softbuffer != 0);
+    return SRSRAN_ERROR_INVALID_INPUTS;
+  }
+  if (data == NULL && cb_segm->C > 0 && !cb_segm->F && Qm) {
+    ERROR("srsran_b200: retransmission without payload is not offloaded (no device-side circular buffer)");
+    return SRSRAN_ERROR;
+  }
+  uint32_t nbytes = (nof_e_bits + 7) / 8;
+  uint8_t* tmp    = w_offset || (Qm && nof_e_bits % Qm) || (nof_e_bits & 7u) ? malloc(nbytes + 8) : e_bits;
+  if (!tmp) {
+    return SRSRAN_ERROR;
+  }
+  srsb200_tb_tx_t tb;
+  memset(&tb, 0, sizeof(tb));
+  tb.tbs        = cb_segm->tbs;
+  tb.Qm         = Qm;
+  tb.rv         = rv;
+  tb.nof_e_bits = nof_e_bits;
+  tb.max_cb     = softbuffer->max_cb;
+  tb.data       = data ? data : (const uint8_t*)"";
+  tb.e_bits     = tmp;
+  int ret = srsb200_encode_tb(engine(), &tb);
+  if (ret == SRSB200_ERROR_NO_DEVICE) {
+    ERROR("srsran_b200: %s", srsb200_last_error());
+    ret = SRSRAN_ERROR;
+  }
+  if (tmp != e_bits) {
+    if (ret == SRSRAN_SUCCESS && cb_segm->C > 0 && Qm) {
+      splice_bits(e_bits, w_offset, tmp, Qm * (nof_e_bits / Qm)); /* sum of the per-block E, sch.c:299-303 */
+    }
+    free(tmp);
+  }
+  return ret;
+}
+
 /* ------------------------------------------------------------------ self-test hook (tests/test_shim.py, ctypes) */
 /*
  * Runs srsran_b200_decode_tb through REAL reference structs (srsran_sch_t, srsran_softbuffer_rx_t, srsran_cbsegm_t built
@@ -304,4 +375,26 @@ int srsran_b200_selftest_decode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint3
 size_t srsran_b200_selftest_sizeof_tdec(void)
 {
   return sizeof(srsran_tdec_t);
+}
+
+/* srsran_b200_encode_tb through real srsran_sch_t / srsran_softbuffer_tx_t / srsran_cbsegm_t objects */
+int srsran_b200_selftest_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, uint8_t* data, uint8_t* e_bits, uint32_t w_offset,
+                                   uint32_t max_cb)
+{
+  srsran_sch_t* q = calloc(1, sizeof(srsran_sch_t));
+  if (!q) {
+    return SRSRAN_ERROR;
+  }
+  srsran_softbuffer_tx_t sb;
+  memset(&sb, 0, sizeof(sb));
+  sb.max_cb = max_cb;
+  uint32_t        sg[8];
+  srsran_cbsegm_t seg;
+  memset(&seg, 0, sizeof(seg));
+  srsb200_cbsegm(tbs, sg);
+  seg.F = sg[0]; seg.C = sg[1]; seg.K1 = sg[2]; seg.K2 = sg[3]; seg.K1_idx = sg[4]; seg.K2_idx = sg[5]; seg.C1 = sg[6]; seg.C2 = sg[7];
+  seg.tbs = tbs; seg.L_tb = 24; seg.L_cb = 24;
+  int ret = srsran_b200_encode_tb(q, &sb, &seg, Qm, rv, nof_e_bits, data, e_bits, w_offset);
+  free(q);
+  return ret;
 }

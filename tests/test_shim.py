@@ -21,7 +21,7 @@ def test_shim_builds_against_reference_headers():
     import __graft_entry__ as g
     g.build()
     out = subprocess.check_output(["make", "-s", "-C", os.path.join(ROOT, "integration"), "check"]).decode()
-    assert "exports all 14" in out
+    assert "exports all 15" in out
 
 
 @pytest.fixture(scope="module")
@@ -82,3 +82,26 @@ def test_shim_rm_and_decode_tb(shim):
         K1 = res["seg"]["K1"]
         nb = (K1 - 24) // 8 + K1 // 8
         assert (data[:nb] == res["data"][:nb]).all()
+
+
+@pytest.mark.gpu
+def test_shim_encode_tb(shim):
+    """srsran_b200_encode_tb through srsran_sch_t / srsran_softbuffer_tx_t / srsran_cbsegm_t: bits at w_offset equal the
+    oracle's, every other bit of e_bits is preserved (srsran_bit_copy semantics of encode_tb_off)"""
+    o = ol.oracle()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(9)
+    for tbs, Qm, rv, G, woff in [(12216, 6, 0, 19200, 0), (12216, 4, 2, 19202, 0), (2984, 2, 1, 4000, 12), (75376, 6, 3, 90000, 24), (40, 2, 0, 121, 3)]:
+        data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        r0, e0 = o.encode_tb(tbs, Qm, rv, G, data)
+        nb = Qm * (G // Qm)
+        e = rng.integers(0, 256, (G + woff + 7) // 8 + 8, dtype=np.uint8)
+        before = np.unpackbits(e)
+        ret = shim.srsran_b200_selftest_encode_tb(tbs, Qm, rv, G, p(data), p(e), woff, 64)
+        assert ret == r0 == 0
+        after = np.unpackbits(e)
+        assert np.array_equal(after[woff:woff + nb], np.unpackbits(e0)[:nb])
+        assert np.array_equal(after[:woff], before[:woff]) and np.array_equal(after[woff + nb:], before[woff + nb:])
+    d = np.zeros(2000, np.uint8); e = np.zeros(8000, np.uint8)
+    assert shim.srsran_b200_selftest_encode_tb(6152, 2, 0, 30000, p(d), p(e), 0, 64) == -1   # filler bits
+    assert shim.srsran_b200_selftest_encode_tb(12216, 2, 0, 30000, p(d), p(e), 0, 1) == -1   # C > max_cb

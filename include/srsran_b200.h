@@ -117,6 +117,9 @@ int  srsb200_tdec_get_nof_iterations(srsb200_tdec_t* h);              /* :107 */
 int  srsb200_tdec_iteration(srsb200_tdec_t* h, const int16_t* input, uint8_t* output); /* :113 one half-iteration + decision */
 int  srsb200_tdec_run_all(srsb200_tdec_t* h, const int16_t* input, uint8_t* output, uint32_t nof_iterations,
                           uint32_t long_cb);                          /* :115-116 */
+/* the hard decision of the latest half-iteration again (the static tdec_decision_byte wrapper, turbodecoder.c:370-378;
+ * the north-star's "get_hard_decision"); -1 before the first half-iteration */
+int  srsb200_tdec_get_hard_decision(srsb200_tdec_t* h, uint8_t* output);
 
 /* ------------------------------------------------------------------ rate de-matching: srsran_rm_turbo_rx_lut */
 /* replaces srsran_rm_turbo_gentables / srsran_rm_turbo_free_tables (rm_turbo.h:54,56); idempotent, thread-safe */

@@ -136,6 +136,15 @@ int srsran_tdec_run_all(srsran_tdec_t* h, int16_t* input, uint8_t* output, uint3
   return SRSRAN_SUCCESS;
 }
 
+/* Names the reference does not have but integrators ask for: thin aliases. */
+int srsran_tdec_get_hard_decision(srsran_tdec_t* h, uint8_t* output, uint32_t long_cb)
+{
+  if (h == NULL || output == NULL || long_cb != h->current_long_cb) {
+    return SRSRAN_ERROR_INVALID_INPUTS;
+  }
+  return srsb200_tdec_get_hard_decision((srsb200_tdec_t*)h->dec16_hdlr[0], output) == SRSB200_SUCCESS ? SRSRAN_SUCCESS : SRSRAN_ERROR;
+}
+
 /* ------------------------------------------------------------------ srsran_rm_turbo_rx_lut (rm_turbo.h:54-84), rx half */
 void srsran_b200_rm_turbo_gentables(void)
 {
@@ -201,6 +210,12 @@ int srsran_b200_decode_tb(srsran_sch_t*           q,
     q->avg_iterations  = tb.avg_iterations;
   }
   return ret;
+}
+
+int srsran_sch_decode(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer, srsran_cbsegm_t* cb_segm, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits,
+                      int16_t* e_bits, uint8_t* data)
+{
+  return srsran_b200_decode_tb(q, softbuffer, cb_segm, Qm, rv, nof_e_bits, e_bits, data);
 }
 
 /*

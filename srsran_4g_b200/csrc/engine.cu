@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -57,8 +58,13 @@ extern "C" int srsb200_cbindex(uint32_t long_cb)
 }
 static int cbindex_exact(uint32_t K)
 {
-  int i = srsb200_cbindex(K);
-  return (i >= 0 && lte_qpp_params[i].K == K) ? i : -1;
+  // direct K -> index table (a 16384-block submission validates every block: a linear search per block costs ~1 ms)
+  static const std::vector<int16_t> lut = [] {
+    std::vector<int16_t> t(SRSB200_MAX_K + 1, (int16_t)-1);
+    for (int i = 0; i < LTE_NOF_CB_SIZES; i++) t[lte_qpp_params[i].K] = (int16_t)i;
+    return t;
+  }();
+  return K <= SRSB200_MAX_K ? lut[K] : -1;
 }
 extern "C" uint32_t srsb200_tdec_autoimp_get_subblocks(uint32_t) { return 0; }
 
@@ -750,11 +756,25 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
   uint32_t S = 1;
   if (!e->profiling) S = std::max(1u, std::min((uint32_t)(io ? e->n_sub : e->n_sub_dev), p->n_groups / 16u));
   RangeArgs rg[srsb200_engine::MAX_SUB];
+  // Host-pointer submissions end with the decode of the LAST range after the last copy has landed, and a decode has a
+  // latency floor of ~1 ms however small it is (sequential recursions) - so the ranges shrink geometrically towards the
+  // end (weights ... 8 8 4 2 1): the tail is one small decode instead of 1/S of the batch.
+  uint32_t wsum = 0, wacc = 0, wgt[srsb200_engine::MAX_SUB];
   for (uint32_t s = 0; s < S; s++) {
-    rg[s].g0 = (uint32_t)((uint64_t)p->n_groups * s / S);
-    rg[s].g1 = (uint32_t)((uint64_t)p->n_groups * (s + 1) / S);
+    wgt[s] = io ? std::min(8u, 1u << (S - 1 - s)) : 1u;
+    wsum += wgt[s];
+  }
+  for (uint32_t s = 0; s < S; s++) {
+    rg[s].g0 = (uint32_t)((uint64_t)p->n_groups * wacc / wsum);
+    wacc += wgt[s];
+    rg[s].g1 = (uint32_t)((uint64_t)p->n_groups * wacc / wsum);
     rg[s].st = (S == 1) ? e->stream : e->sub[s];
   }
+  const auto t_host0 = std::chrono::steady_clock::now();
+  static const bool trace_env = getenv("SRSB200_TRACE") != nullptr;
+  const bool  trace = trace_env && io && S > 1;
+  cudaEvent_t tev[2 * srsb200_engine::MAX_SUB], tev0 = nullptr;
+  if (trace) { cudaEventCreate(&tev0); cudaEventRecord(tev0, e->stream); }
   if (S > 1) {
     CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
     for (uint32_t s = 0; s < S; s++) CUDA_TRY(cudaStreamWaitEvent(e->sub[s], e->ev_fork, 0));
@@ -762,9 +782,11 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
   for (uint32_t s = 0; s < S; s++) {
     // group g of a contiguous plan holds code blocks [64 g, 64 g + 64)
     const uint64_t c0 = 64ull * rg[s].g0, c1 = std::min<uint64_t>(64ull * rg[s].g1, p->n_cb);
-    if (io)
+    if (io) {
       CUDA_TRY(cudaMemcpyAsync(const_cast<int16_t*>(d_llr) + c0 * io->L, io->h_llr + c0 * io->L, (c1 - c0) * io->L * sizeof(int16_t),
                                cudaMemcpyHostToDevice, rg[s].st));
+      if (trace) { cudaEventCreate(&tev[2 * s]); cudaEventCreate(&tev[2 * s + 1]); cudaEventRecord(tev[2 * s], rg[s].st); }
+    }
     if (do_extract) launch_one(e, p, rg[s], 0, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
     for (uint32_t n = start_iter; n < max_iter; n++) {
       launch_one(e, p, rg[s], 1, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
@@ -775,6 +797,7 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
       CUDA_TRY(cudaMemcpyAsync(io->h_out + c0 * io->KB, d_out + c0 * io->KB, (c1 - c0) * io->KB, cudaMemcpyDeviceToHost, rg[s].st));
       CUDA_TRY(cudaMemcpyAsync(io->h_noi + c0, d_noi + c0, c1 - c0, cudaMemcpyDeviceToHost, rg[s].st));
       CUDA_TRY(cudaMemcpyAsync(io->h_ok + c0, d_ok + c0, c1 - c0, cudaMemcpyDeviceToHost, rg[s].st));
+      if (trace) cudaEventRecord(tev[2 * s + 1], rg[s].st);
     }
   }
   if (S > 1) {
@@ -782,6 +805,21 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
       CUDA_TRY(cudaEventRecord(e->ev_join[s], e->sub[s]));
       CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[s], 0));
     }
+  }
+  if (trace) {
+    // opt-in timeline of a host-pointer submission (SRSB200_TRACE=1): when each range's input landed / its results left
+    fprintf(stderr, "srsb200 trace: all launches enqueued after %.3f ms of host time\n",
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count());
+    cudaStreamSynchronize(e->stream);
+    for (uint32_t s = 0; s < S; s++) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, tev0, tev[2 * s]);
+      cudaEventElapsedTime(&b, tev0, tev[2 * s + 1]);
+      fprintf(stderr, "srsb200 trace: range %u groups [%u,%u) h2d done %.3f ms, results out %.3f ms\n", s, rg[s].g0, rg[s].g1, a, b);
+      cudaEventDestroy(tev[2 * s]);
+      cudaEventDestroy(tev[2 * s + 1]);
+    }
+    cudaEventDestroy(tev0);
   }
   CUDA_TRY(cudaGetLastError());
   return SRSB200_SUCCESS;
@@ -803,6 +841,10 @@ extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_
   if (!e) return fail(SRSB200_ERROR_NO_DEVICE, "no engine (no CUDA device?)");
   if (n == 0) return SRSB200_SUCCESS;
   if (!K || !llr || !llr_offset || !out_bytes || !out_offset || !noi || !crc_ok) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
+  static const bool trace = getenv("SRSB200_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_entry = trace ? now() : 0;
+  double t_plan = 0, t_enq = 0;
   for (uint32_t i = 0; i < n; i++) {
     if (cbindex_exact(K[i]) < 0) return fail(SRSB200_ERROR_INVALID_INPUTS, "code block %u: K=%u is not an LTE turbo block size", i, K[i]);
     if (llr_offset[i] + 3ull * K[i] + 12 > llr_len) return fail(SRSB200_ERROR_INVALID_INPUTS, "code block %u: LLR range exceeds llr_len", i);
@@ -840,6 +882,7 @@ extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_
     return SRSB200_ERROR;
   }
   cudaError_t ce = cudaSuccess;
+  if (trace) t_plan = now();
   if (p->contiguous && llr_len == (uint64_t)n * (3ull * K[0] + 12) && out_len == (uint64_t)n * (K[0] / 8)) {
     // chunked copies overlapped with the decode of the neighbouring ranges
     HostIO io;
@@ -854,7 +897,9 @@ extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_
     if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(noi, d_noi, n, cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(crc_ok, d_ok, n, cudaMemcpyDeviceToHost, e->stream);
   }
+  if (trace) t_enq = now();
   if (ce == cudaSuccess && r == 0) ce = cudaStreamSynchronize(e->stream);
+  if (trace) fprintf(stderr, "srsb200 trace: host: checks+plan %.3f ms, enqueue %.3f ms, wait %.3f ms\n", t_plan - t_entry, t_enq - t_plan, now() - t_enq);
   if (ce != cudaSuccess) {
     cudaGetLastError();
     return fail(SRSB200_ERROR, "batch decode failed: %s", cudaGetErrorString(ce));
@@ -966,6 +1011,19 @@ extern "C" int srsb200_tdec_run_all(srsb200_tdec_t* t, const int16_t* input, uin
   CUDA_TRY(cudaMemcpyAsync(output, t->d_out, long_cb / 8, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   t->n_iter = (int)iters;
+  return SRSB200_SUCCESS;
+}
+
+// hard decision of the latest half-iteration again (the static tdec_decision_byte wrapper, turbodecoder.c:370-378)
+extern "C" int srsb200_tdec_get_hard_decision(srsb200_tdec_t* t, uint8_t* output)
+{
+  if (!t || !output) return SRSB200_ERROR_INVALID_INPUTS;
+  if (t->current_cbidx < 0 || t->n_iter == 0) return fail(SRSB200_ERROR, "no half-iteration has run on this decoder yet");
+  srsb200_engine* e = t->e;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaMemcpyAsync(output, t->d_out, t->current_long_cb / 8, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
   return SRSB200_SUCCESS;
 }
 

@@ -21,7 +21,7 @@ def test_shim_builds_against_reference_headers():
     import __graft_entry__ as g
     g.build()
     out = subprocess.check_output(["make", "-s", "-C", os.path.join(ROOT, "integration"), "check"]).decode()
-    assert "exports all 15" in out
+    assert "exports all 17" in out
 
 
 @pytest.fixture(scope="module")
@@ -51,6 +51,10 @@ def test_shim_tdec_symbols(shim):
             assert shim.srsran_tdec_get_nof_iterations(h) == it + 1
         assert shim.srsran_tdec_run_all(h, llr.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 3, K) == 0
         assert (out == hard[2]).all()
+        again = np.zeros(K // 8, np.uint8)
+        assert shim.srsran_tdec_get_hard_decision(h, again.ctypes.data_as(C.c_void_p), K) == 0   # north-star alias
+        assert (again == hard[2]).all()
+        assert shim.srsran_tdec_get_hard_decision(h, again.ctypes.data_as(C.c_void_p), K + 8) == -2
     shim.srsran_tdec_free(h)
 
 

@@ -187,6 +187,10 @@ struct srsb200_engine {
   size_t scratch_cap[12] = {0};
   uint32_t* d_crc24b_words = nullptr;  // x^(m+24) mod g24B, m < 6144 (tx_cb_kernel)
 
+  // pinned staging arenas for pageable caller buffers (0: host->device, 1: device->host), see Stager
+  void*  h_stage[2]     = {nullptr, nullptr};
+  size_t h_stage_cap[2] = {0, 0};
+
   // sub-batch streams (see launch_plan)
   static const int MAX_SUB = 8;
   int          n_sub = 8;      // ranges of a host-pointer submission (copy/compute overlap)
@@ -250,6 +254,79 @@ static int ensure_scratch(srsb200_engine* e, int slot, size_t bytes, void** out)
   *out = e->d_scratch[slot];
   return 0;
 }
+
+/*
+ * Copies between caller memory and the device. cudaMemcpyAsync on PAGEABLE memory is synchronous and costs ~10-30 us per
+ * call (the driver stages it) - a transport-block submission makes hundreds of them (e-bits per TB, soft buffer per code
+ * block). The Stager sends pinned/registered caller buffers straight to the DMA engine and routes pageable ones through
+ * an engine-owned pinned arena: host memcpy of buffer i+1 overlaps the DMA of buffer i, and device->host results are
+ * copied out of the arena after the one final synchronise.
+ */
+struct Stager {
+  srsb200_engine* e;
+  size_t used[2] = {0, 0};
+  struct Out { void* dst; const void* src; size_t bytes; };
+  std::vector<Out> outs;
+  explicit Stager(srsb200_engine* e_) : e(e_) {}
+  // both arenas must be sized before the first copy (they cannot move while copies are in flight)
+  int reserve(size_t in_bytes, size_t out_bytes)
+  {
+    const size_t want[2] = {in_bytes, out_bytes};
+    for (int i = 0; i < 2; i++) {
+      if (e->h_stage_cap[i] >= want[i]) continue;
+      if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
+      e->h_stage[i]     = nullptr;
+      e->h_stage_cap[i] = 0;
+      const size_t cap = want[i] + want[i] / 4 + 65536;
+      CUDA_TRY(cudaHostAlloc(&e->h_stage[i], cap, cudaHostAllocDefault));
+      e->h_stage_cap[i] = cap;
+    }
+    return 0;
+  }
+  static bool pinned(const void* p)
+  {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+  }
+  cudaError_t h2d(void* dst, const void* src, size_t bytes, cudaStream_t st)
+  {
+    if (bytes == 0) return cudaSuccess;
+    if (!pinned(src)) {
+      const size_t off = (used[0] + 63) & ~(size_t)63;
+      if (off + bytes <= e->h_stage_cap[0]) {
+        void* s = (uint8_t*)e->h_stage[0] + off;
+        memcpy(s, src, bytes);
+        used[0] = off + bytes;
+        src     = s;
+      }
+    }
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  }
+  cudaError_t d2h(void* dst, const void* src, size_t bytes, cudaStream_t st)
+  {
+    if (bytes == 0) return cudaSuccess;
+    if (!pinned(dst)) {
+      const size_t off = (used[1] + 63) & ~(size_t)63;
+      if (off + bytes <= e->h_stage_cap[1]) {
+        void* s = (uint8_t*)e->h_stage[1] + off;
+        used[1] = off + bytes;
+        outs.push_back({dst, s, bytes});
+        dst = s;
+      }
+    }
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+  }
+  // after the stream has been synchronised
+  void finish()
+  {
+    for (auto& o : outs) memcpy(o.dst, o.src, o.bytes);
+    outs.clear();
+  }
+};
 
 static int ensure_ktable(srsb200_engine* e, int kidx)
 {
@@ -498,6 +575,8 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
   for (int i = 0; i < 12; i++)
     if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);
   cudaFree(e->d_ktab);
+  for (int i = 0; i < 2; i++)
+    if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
   if (e->d_tb_crc_words) cudaFree(e->d_tb_crc_words);
   for (int i = 0; i < srsb200_engine::MAX_SUB; i++) {
     if (e->sub[i]) cudaStreamDestroy(e->sub[i]);

@@ -245,8 +245,12 @@ def main():
         step()
     prof = eng.profile_read()
     eng.profile(False)
+    ms_per_rank = [ms / args.steps]
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        allms = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allms, t)
+        ms_per_rank = [float(x.item()) / args.steps for x in allms]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     bits_per_step = float(n_cb) * K * world
@@ -322,7 +326,7 @@ def main():
                    "l2": "inputs (%.0f MB LLRs + %.0f MB streams per step) exceed the 126 MB L2" % (n_cb * (3 * K + 12) * 2 / 1e6, n_cb * 5 * (K + 32) * 2 / 1e6)},
         "mean_half_iterations": float(noi.mean()), "crc_ok_fraction": float(ok.mean()),
         "noi_hist": {str(int(k)): int(v) for k, v in zip(*np.unique(noi, return_counts=True))},
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches), "ms_per_step_per_rank": ms_per_rank,
         "kernel_ms_per_step": {k: v[0] / psteps for k, v in prof.items() if v[1]},
         "kernel_launches_per_step": {k: v[1] // psteps for k, v in prof.items() if v[1]},
         "roofline": {"bound": "hbm", "kernel": "job_kernel (all half-iteration launches of one step, timed without sub-batch overlap)", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

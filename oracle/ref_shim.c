@@ -542,3 +542,154 @@ int ref_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, c
   free(scratch);
   return ret;
 }
+
+/* ------------------------------------------------------------------ the LITERAL sch.c entry points */
+#include "srsran/phy/phch/pdsch_cfg.h"
+#include "srsran/phy/phch/sch.h"
+
+static srsran_sch_t g_sch;
+static int          g_sch_ready = 0;
+static int          sch_ready(void)
+{
+  if (!g_sch_ready) {
+    if (srsran_sch_init(&g_sch)) {
+      return -1;
+    }
+    g_sch_ready = 1;
+  }
+  return 0;
+}
+static srsran_mod_t mod_of(uint32_t Qm)
+{
+  switch (Qm) {
+    case 1:
+      return SRSRAN_MOD_BPSK;
+    case 2:
+      return SRSRAN_MOD_QPSK;
+    case 4:
+      return SRSRAN_MOD_16QAM;
+    case 6:
+      return SRSRAN_MOD_64QAM;
+    default:
+      return SRSRAN_MOD_256QAM;
+  }
+}
+
+/*
+ * srsran_dlsch_encode2 itself (sch.c:618-650 -> static encode_tb -> encode_tb_off): the reference's own transport-block
+ * encoder, untouched. A fresh tx soft buffer per call; for rv != 0 the same buffer first sees the rv = 0 transmission,
+ * as a HARQ process does. e_bits must hold (nof_e_bits+7)/8 + 8 bytes.
+ */
+int ref_dlsch_encode(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, uint8_t* data, uint8_t* e_bits)
+{
+  ref_init();
+  pthread_mutex_lock(&g_lock);
+  int ret = -1;
+  if (sch_ready() == 0) {
+    srsran_softbuffer_tx_t sb;
+    if (srsran_softbuffer_tx_init(&sb, 110) == 0) {
+      srsran_pdsch_cfg_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.grant.nof_tb         = 1;
+      cfg.grant.tb[0].tbs      = (int)tbs;
+      cfg.grant.tb[0].mod      = mod_of(Qm);
+      cfg.grant.tb[0].nof_bits = nof_e_bits;
+      cfg.grant.tb[0].enabled  = true;
+      cfg.softbuffers.tx[0]    = &sb;
+      ret                      = 0;
+      if (rv != 0) {
+        uint8_t* scratch    = calloc((nof_e_bits + 7) / 8 + 64, 1);
+        cfg.grant.tb[0].rv  = 0;
+        ret                 = srsran_dlsch_encode2(&g_sch, &cfg, data, scratch, 0, 1);
+        free(scratch);
+      }
+      if (ret == 0) {
+        cfg.grant.tb[0].rv = (int)rv;
+        ret                = srsran_dlsch_encode2(&g_sch, &cfg, data, e_bits, 0, 1);
+      }
+      srsran_softbuffer_tx_free(&sb);
+    }
+  }
+  pthread_mutex_unlock(&g_lock);
+  return ret;
+}
+
+/*
+ * srsran_dlsch_decode2 itself (sch.c:580-609 -> static decode_tb -> decode_tb_cb) with the PRODUCTION decoder
+ * (srsran_tdec_init = AUTO = AVX2/SSE windowed, sub-block input layout). Its soft values and iteration counts are not
+ * the parity target, but everything the loop decides from CRCs is: return code, data bytes and their
+ * layout, cb_crc / tb_crc flags, cached code blocks across HARQ transmissions. Used to cross-check the restated loop.
+ * The soft buffer lives across calls in *handle (create with ref_dlsch_rx_new, free with ref_dlsch_rx_free).
+ */
+void* ref_dlsch_rx_new(void)
+{
+  srsran_softbuffer_rx_t* sb = calloc(1, sizeof(srsran_softbuffer_rx_t));
+  if (sb && srsran_softbuffer_rx_init(sb, 110)) {
+    free(sb);
+    sb = NULL;
+  }
+  return sb;
+}
+void ref_dlsch_rx_free(void* h)
+{
+  if (h) {
+    srsran_softbuffer_rx_free((srsran_softbuffer_rx_t*)h);
+    free(h);
+  }
+}
+void ref_dlsch_rx_reset(void* h, uint32_t tbs)
+{
+  srsran_softbuffer_rx_reset_tbs((srsran_softbuffer_rx_t*)h, tbs);
+}
+int ref_dlsch_decode(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, int16_t* e_bits, uint32_t max_iterations, uint8_t* data,
+                     uint8_t* cb_crc, uint8_t* tb_crc, float* avg_iterations)
+{
+  ref_init();
+  pthread_mutex_lock(&g_lock);
+  int ret = -1;
+  if (sch_ready() == 0) {
+    srsran_softbuffer_rx_t* sb = (srsran_softbuffer_rx_t*)h;
+    srsran_pdsch_cfg_t      cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.grant.nof_tb         = 1;
+    cfg.grant.tb[0].tbs      = (int)tbs;
+    cfg.grant.tb[0].mod      = mod_of(Qm);
+    cfg.grant.tb[0].rv       = (int)rv;
+    cfg.grant.tb[0].nof_bits = nof_e_bits;
+    cfg.grant.tb[0].enabled  = true;
+    cfg.softbuffers.rx[0]    = sb;
+    srsran_sch_set_max_noi(&g_sch, max_iterations);
+    ret = srsran_dlsch_decode2(&g_sch, &cfg, e_bits, data, 0, 1);
+    for (uint32_t i = 0; i < sb->max_cb; i++) {
+      cb_crc[i] = sb->cb_crc[i] ? 1 : 0;
+    }
+    *tb_crc         = sb->tb_crc ? 1 : 0;
+    *avg_iterations = srsran_sch_last_noi(&g_sch);
+  }
+  pthread_mutex_unlock(&g_lock);
+  return ret;
+}
+uint32_t ref_dlsch_rx_max_cb(void* h)
+{
+  return ((srsran_softbuffer_rx_t*)h)->max_cb;
+}
+
+/* ulsch_deinterleave itself (sch.c:994-1021; non-static, no header) */
+void ulsch_deinterleave(int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, int16_t* g_bits, srsran_uci_bit_t* ri_bits,
+                        uint32_t nof_ri_bits, uint8_t* ri_present, uint32_t* inteleaver_lut);
+int ref_ulsch_deinterleave(int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, int16_t* g_bits, const uint32_t* ri_positions,
+                           uint32_t nof_ri_bits)
+{
+  uint32_t          n   = H_prime_total * Qm;
+  srsran_uci_bit_t* ri  = calloc(nof_ri_bits + 1, sizeof(srsran_uci_bit_t));
+  uint8_t*          prs = calloc(n + 64, 1);
+  uint32_t*         lut = calloc(n + 64, sizeof(uint32_t));
+  for (uint32_t i = 0; i < nof_ri_bits; i++) {
+    ri[i].position = ri_positions[i];
+  }
+  ulsch_deinterleave(q_bits, Qm, H_prime_total, N_pusch_symbs, g_bits, ri, nof_ri_bits, prs, lut);
+  free(ri);
+  free(prs);
+  free(lut);
+  return 0;
+}

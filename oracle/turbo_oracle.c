@@ -28,6 +28,7 @@
 #include "../include/lte_qpp_params.h"
 
 #include <pthread.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -748,4 +749,37 @@ int orc_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, c
   free(coded);
   free(e);
   return ret;
+}
+
+/* ------------------------------------------------------------------ UL-SCH channel de-interleaver */
+int orc_ulsch_deinterleave(const int16_t* q, uint32_t Qm, uint32_t H, uint32_t nsymb, int16_t* g, const uint32_t* ri_pos, uint32_t nof_ri)
+{
+  if (!q || !g || Qm == 0 || nsymb == 0 || H < nsymb) {
+    return -2;
+  }
+  uint32_t n = H * Qm, rows = H / nsymb, cols = nsymb;
+  uint8_t*  is_ri = calloc(n + 1, 1);
+  uint32_t* lut   = calloc(n + 1, sizeof(uint32_t));
+  for (uint32_t i = 0; i < nof_ri; i++) {
+    if (ri_pos[i] < n) {
+      is_ri[ri_pos[i]] = 1;
+    }
+  }
+  uint32_t idx = 0;
+  for (uint32_t j = 0; j < rows; j++) {
+    for (uint32_t i = 0; i < cols; i++) {
+      for (uint32_t k = 0; k < Qm; k++) {
+        uint32_t p = j * Qm + i * rows * Qm + k;
+        lut[p]     = is_ri[p] ? 0 : idx++;
+      }
+    }
+  }
+  /* positions outside the rows x cols matrix (H not a multiple of nsymb) keep lut = 0, as the reference's calloc'd /
+   * reused table would - callers always pass H = rows * cols */
+  for (uint32_t p = 0; p < n; p++) {
+    g[lut[p]] = q[p];
+  }
+  free(is_ri);
+  free(lut);
+  return 0;
 }

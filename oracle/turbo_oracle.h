@@ -57,6 +57,13 @@ int orc_decode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, c
  * Returns 0, -1 (filler bits / Qm == 0 / bad tbs) or -2 (null pointers). */
 int orc_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, const uint8_t* data, uint8_t* e_bits);
 
+/* UL-SCH channel de-interleaver (36.212 5.2.2.8) as realised by ulsch_deinterleave + ulsch_interleave_gen +
+ * srsran_vec_lut_sis (sch.c:661-682,994-1021, vector.c:147-152): g[lut[p]] = q[p] for p ascending, lut[p] = running
+ * count of non-RI positions in row-major (row j, column i, bit k) order, position p = j*Qm + i*rows*Qm + k, and 0 for
+ * positions that carry RI (so g[0] ends up holding the LAST position that maps to 0). g must hold H_prime_total*Qm. */
+int orc_ulsch_deinterleave(const int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, int16_t* g_bits,
+                           const uint32_t* ri_positions, uint32_t nof_ri_bits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -800,7 +800,7 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
     } break;
     default: {
       ProfScope ps(e, 2, st);
-      emit_kernel<<<ng, 256, emit_smem_bytes(p->max_R, p->max_R), st>>>(dg, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off, p->d_out_len);
+      emit_kernel<<<dim3(ng, EMIT_SPLIT), 256, emit_smem_bytes(p->max_R, p->max_R), st>>>(dg, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off, p->d_out_len);
     } break;
   }
   e->launches++;

@@ -844,10 +844,12 @@ extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const
 /*
  * Final hard-decision bytes (tdec_gen_decision_byte, MSB first) of every code block of a group: the decisions of the
  * last half-iteration each block ran; after a DEC2 half-iteration they are gathered through the QPP permutation
- * (app1[fwd[i]] = ext2[i], decision on app1). grid = n_groups, block = 256, dynamic smem = emit_smem_bytes(R, K).
+ * (app1[fwd[i]] = ext2[i], decision on app1). grid = (n_groups, EMIT_SPLIT), block = 256, dynamic smem =
+ * emit_smem_bytes(R, K); the blocks of a group each transpose the (small) decision arrays and share the output words.
  * The group's two decision arrays are transposed into shared memory ([code block][16-bit piece]), then each warp
  * produces 32 consecutive output words of one code block (coalesced 128-byte stores).
  */
+static constexpr int EMIT_SPLIT = 4;
 __host__ __device__ inline size_t emit_smem_bytes(uint32_t R, uint32_t K)
 {
   const uint32_t P = R / 16 + 2;  // 16-bit pieces per code block, padded so that a row is an odd number of words
@@ -878,7 +880,7 @@ emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, 
   for (uint32_t i = tid; i < K; i += 256) srev[i] = rev[i];
   __syncthreads();
   const uint32_t nwords = (K + 31) / 32, nchunk = (nwords + 31) / 32;
-  for (uint32_t task = wid; task < 64 * nchunk; task += 8) {
+  for (uint32_t task = wid + 8 * blockIdx.y; task < 64 * nchunk; task += 8 * gridDim.y) {
     const uint32_t cbl = task / nchunk, word = (task % nchunk) * 32 + lane;
     const int      cb  = g.cb[cbl];
     if (cb < 0 || word >= nwords) continue;

@@ -101,6 +101,29 @@ def main():
             tb[p + "avg"] = np.float32(res["avg_iterations"])
     tb["cases"] = np.array(tb_cases, np.float64)
     np.savez_compressed(os.path.join(HERE, "tb_harq.npz"), **tb)
+    # ---- transmit side + UL-SCH de-interleaver, from the LITERAL sch.c (srsran_dlsch_encode2, ulsch_deinterleave)
+    tx = {}
+    enc_cases = [(40, 2, 0, 120), (6120, 4, 1, 4 * 2500), (12216, 6, 2, 19200), (36696, 2, 3, 2 * 30000), (75376, 6, 0, 86400)]
+    for n, (tbs, Qm, rv, Gb) in enumerate(enc_cases):
+        data = np.random.default_rng(4000 + n).integers(0, 256, tbs // 8, dtype=np.uint8)
+        ret, e = r.dlsch_encode(tbs, Qm, rv, Gb, data)
+        assert ret == 0
+        tx["enc%d_data" % n] = data
+        tx["enc%d_e" % n] = e
+    tx["enc_cases"] = np.array(enc_cases, np.uint32)
+    dei_cases = [(2, 12 * 12 * 6, 12, 0), (4, 12 * 12 * 25, 12, 8), (6, 12 * 11 * 100, 11, 24)]
+    for n, (Qm, H, nsymb, nri) in enumerate(dei_cases):
+        rows = H // nsymb
+        q = np.random.default_rng(5000 + n).integers(-30000, 30000, H * Qm).astype(np.int16)
+        ri = []
+        for m in range(nri // Qm if Qm else 0):
+            rr, cc = rows - 1 - m // 4, (1, 4, 7, 10)[m % 4]
+            ri += [rr * Qm + cc * rows * Qm + k for k in range(Qm)]
+        tx["dei%d_q" % n] = q
+        tx["dei%d_ri" % n] = np.array(ri, np.uint32)
+        tx["dei%d_g" % n] = r.ulsch_deinterleave(q, Qm, H, nsymb, ri)
+    tx["dei_cases"] = np.array(dei_cases, np.uint32)
+    np.savez_compressed(os.path.join(HERE, "tx.npz"), **tx)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

@@ -68,11 +68,22 @@ class _Lib:
             self._batch = L.ref_tdec_batch
             self._batch.argtypes = [C.c_int, C.c_uint32, i16p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, u8p, u8p, u8p]
             self._rm_rx_auto = L.ref_rm_rx_auto; self._rm_rx_auto.argtypes = [i16p, i16p, C.c_uint32, C.c_uint32, C.c_uint32]
+            # the literal sch.c entry points (srsran_dlsch_encode2 / srsran_dlsch_decode2 / ulsch_deinterleave)
+            L.ref_dlsch_encode.argtypes = [C.c_uint32] * 4 + [u8p, u8p]; L.ref_dlsch_encode.restype = C.c_int
+            L.ref_dlsch_rx_new.restype = C.c_void_p
+            L.ref_dlsch_rx_free.argtypes = [C.c_void_p]
+            L.ref_dlsch_rx_reset.argtypes = [C.c_void_p, C.c_uint32]
+            L.ref_dlsch_rx_max_cb.argtypes = [C.c_void_p]; L.ref_dlsch_rx_max_cb.restype = C.c_uint32
+            L.ref_dlsch_decode.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [i16p, C.c_uint32, u8p, u8p, u8p, C.POINTER(C.c_float)]
+            L.ref_dlsch_decode.restype = C.c_int
+            L.ref_ulsch_deinterleave.argtypes = [i16p, C.c_uint32, C.c_uint32, C.c_uint32, i16p, u32p, C.c_uint32]
         else:
             self._trace = L.orc_tdec_trace; self._trace.argtypes = [C.c_uint32, i16p, C.c_uint32, u8p, C.c_void_p]
             self._run_all = L.orc_tdec_run_all; self._run_all.argtypes = [C.c_uint32, i16p, C.c_uint32, u8p]
             self._batch = L.orc_tdec_batch
             self._batch.argtypes = [C.c_uint32, i16p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, u8p, u8p, u8p]
+            L.orc_ulsch_deinterleave.argtypes = [i16p, C.c_uint32, C.c_uint32, C.c_uint32, i16p, u32p, C.c_uint32]
+            L.orc_ulsch_deinterleave.restype = C.c_int
         self._trace.restype = C.c_int
         self._run_all.restype = C.c_int
         self._batch.restype = C.c_double
@@ -192,6 +203,35 @@ class _Lib:
         e = np.zeros((nof_e_bits + 7) // 8 + 64, np.uint8)
         ret = self._enc_tb(tbs, Qm, rv, nof_e_bits, data, e)
         return ret, e[:(nof_e_bits + 7) // 8]
+
+    # ---- literal sch.c functions (compiled reference only)
+    def dlsch_encode(self, tbs, Qm, rv, nof_e_bits, data):
+        data = np.ascontiguousarray(data, np.uint8).copy()
+        e = np.zeros((nof_e_bits + 7) // 8 + 64, np.uint8)
+        ret = self.lib.ref_dlsch_encode(tbs, Qm, rv, nof_e_bits, data, e)
+        return ret, e[:(nof_e_bits + 7) // 8]
+
+    def dlsch_rx_new(self):
+        return self.lib.ref_dlsch_rx_new()
+
+    def dlsch_rx_free(self, h):
+        self.lib.ref_dlsch_rx_free(h)
+
+    def dlsch_decode(self, h, tbs, Qm, rv, e_bits, max_iterations):
+        """srsran_dlsch_decode2 with the production (AUTO) decoder on the persistent soft buffer h"""
+        e_bits = np.ascontiguousarray(e_bits, np.int16)
+        ncb = self.lib.ref_dlsch_rx_max_cb(h)
+        data = np.zeros(ncb * 768 + 8, np.uint8)
+        cbc = np.zeros(ncb, np.uint8); tbc = np.zeros(1, np.uint8); avg = C.c_float(0)
+        ret = self.lib.ref_dlsch_decode(h, tbs, Qm, rv, len(e_bits), e_bits, max_iterations, data, cbc, tbc, C.byref(avg))
+        return dict(ret=ret, data=data, cb_crc=cbc, tb_crc=int(tbc[0]), avg_iterations=avg.value)
+
+    def ulsch_deinterleave(self, q_bits, Qm, H_prime_total, N_pusch_symbs, ri_positions=()):
+        q_bits = np.ascontiguousarray(q_bits, np.int16)
+        g = np.zeros(H_prime_total * Qm + 8, np.int16)
+        ri = np.ascontiguousarray(np.array(list(ri_positions) + [0], np.uint32))
+        getattr(self.lib, self.p + "ulsch_deinterleave")(q_bits, Qm, H_prime_total, N_pusch_symbs, g, ri, len(ri_positions))
+        return g[:H_prime_total * Qm]
 
 
 def new_tb_state(Cn):

@@ -88,3 +88,21 @@ def test_tb_harq(o):
             assert (st["cb_crc"] == t[p + "cb_crc"]).all()
             assert zlib.crc32(st["buffer_f"].tobytes()) == int(t[p + "buf_fp"])
             assert np.float32(res["avg_iterations"]) == t[p + "avg"]
+
+
+def test_encode_tb_golden(o):
+    """e-bits of srsran_dlsch_encode2 (the literal sch.c of the reference, run in the build container)"""
+    t = np.load(os.path.join(G, "tx.npz"))
+    for n, (tbs, Qm, rv, Gb) in enumerate(t["enc_cases"]):
+        ret, e = o.encode_tb(int(tbs), int(Qm), int(rv), int(Gb), t["enc%d_data" % n])
+        nb = int(Qm) * (int(Gb) // int(Qm))
+        assert ret == 0 and np.array_equal(np.unpackbits(e)[:nb], np.unpackbits(t["enc%d_e" % n])[:nb])
+
+
+def test_ulsch_deinterleave_golden(o):
+    t = np.load(os.path.join(G, "tx.npz"))
+    for n, (Qm, H, nsymb, nri) in enumerate(t["dei_cases"]):
+        ri = t["dei%d_ri" % n]
+        g = o.ulsch_deinterleave(t["dei%d_q" % n], int(Qm), int(H), int(nsymb), list(ri))
+        nd = int(H) * int(Qm) - len(ri)
+        assert np.array_equal(g[:nd], t["dei%d_g" % n][:nd])

@@ -1,0 +1,108 @@
+"""The oracle against the LITERAL lib/src/phy/phch/sch.c of the reference (compiled into oracle/_ref together with the
+UCI/CQI/convolutional code it links against): srsran_dlsch_encode2, srsran_dlsch_decode2, ulsch_deinterleave."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import vecgen
+
+ref = ol.ref()
+pytestmark = pytest.mark.skipif(ref is None, reason="oracle/_ref not built")
+
+
+@pytest.mark.parametrize("tbs", [40, 1000, 6120, 6200, 12216, 36696, 75376])
+@pytest.mark.parametrize("Qm,rv", [(2, 0), (4, 1), (6, 2), (2, 3), (6, 0)])
+def test_encode_tb_vs_srsran_dlsch_encode2(tbs, Qm, rv):
+    o = ol.oracle()
+    _, seg = o.cbsegm(tbs)
+    if seg["F"]:
+        pytest.skip("filler bits")
+    rng = np.random.default_rng(tbs + Qm + rv)
+    data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    for G in (Qm * ((tbs * 2) // Qm), Qm * ((tbs * 4 + 12 * seg["C"]) // Qm), Qm * (tbs // Qm // 2 + 7)):
+        r0, e0 = o.encode_tb(tbs, Qm, rv, G, data)
+        r1, e1 = ref.dlsch_encode(tbs, Qm, rv, G, data)
+        assert r0 == r1 == 0
+        assert np.array_equal(np.unpackbits(e0)[:G], np.unpackbits(e1)[:G])
+
+
+def test_dlsch_encode2_error_codes():
+    o = ol.oracle()
+    d = np.zeros(2000, np.uint8)
+    assert ref.dlsch_encode(6152, 2, 0, 30000, d)[0] == o.encode_tb(6152, 2, 0, 30000, d)[0] == -1   # filler bits
+
+
+def _harq_case(tbs, Qm, G, kill, seed):
+    """three transmissions (rv 0, 2, 0), high SNR; in the first one the LLRs of the code blocks in `kill` are replaced by noise so
+    they certainly fail while the others certainly pass - no dependence on which decoder flavour runs"""
+    o = ol.oracle()
+    _, seg = o.cbsegm(tbs)
+    Cn = seg["C"]
+    payload, e0 = vecgen.make_tb(tbs, G, Qm, 0, 12.0, seed, scale=40)
+    _, e2 = vecgen.make_tb(tbs, G, Qm, 2, 12.0, seed, scale=40, payload=np.unpackbits(payload)[:tbs])
+    Gp = G // Qm
+    gamma = Gp % Cn
+    n_e = Qm * (Gp // Cn)
+    e0 = e0.copy()
+    for r in kill:
+        E, rp = n_e, r * n_e
+        if r > Cn - gamma:
+            E = n_e + Qm
+            rp = (Cn - gamma) * n_e + (r - (Cn - gamma)) * E
+        e0[rp:rp + E] = np.random.default_rng(seed + r).integers(-40, 41, E)   # garbage (all-zero LLRs would decode to the all-zero codeword, CRC 0)
+    _, e0b = vecgen.make_tb(tbs, G, Qm, 0, 12.0, seed + 1, scale=40, payload=np.unpackbits(payload)[:tbs])
+    return payload, [(0, e0), (2, e2), (0, e0b)], seg
+
+
+@pytest.mark.parametrize("tbs,Qm,G,kill", [(12216, 4, 4 * 4500, [1]), (36696, 6, 6 * 8000, [0, 3]), (75376, 6, 86400, [5, 12]), (6120, 2, 2 * 5000, [0]),
+                                           (36696, 2, 2 * 30000, [])])
+def test_decode_tb_loop_vs_srsran_dlsch_decode2(tbs, Qm, G, kill):
+    """return code, data bytes, cb_crc / tb_crc flags of the restated decode_tb loop equal the literal srsran_dlsch_decode2
+    (production AUTO decoder) across a HARQ retransmission with cached code blocks"""
+    o = ol.oracle()
+    payload, txs, seg = _harq_case(tbs, Qm, G, kill, 77 + tbs)
+    h = ref.dlsch_rx_new()
+    st = None
+    decoded = False
+    try:
+        for rv, e in txs:
+            a = o.decode_tb(tbs, Qm, rv, e, 8, st)
+            st = a["state"]
+            b = ref.dlsch_decode(h, tbs, Qm, rv, e, 8)
+            assert a["ret"] == b["ret"]
+            assert a["tb_crc"] == b["tb_crc"]
+            assert np.array_equal(st["cb_crc"][:seg["C"]], b["cb_crc"][:seg["C"]])
+            assert np.array_equal(a["data"][:tbs // 8], b["data"][:tbs // 8]) or a["ret"] != 0
+            if a["ret"] == 0 and not decoded:
+                decoded = True
+                assert np.array_equal(a["data"][:tbs // 8], payload[:tbs // 8])
+            # (a transmission AFTER the TB has passed skips every code block and returns the never-filled cache:
+            #  sch.c:391-392,468-473 - the loop above still checks that both sides agree on that)
+        assert decoded
+    finally:
+        ref.dlsch_rx_free(h)
+
+
+@pytest.mark.parametrize("Qm", [2, 4, 6])
+@pytest.mark.parametrize("nprb,nsymb", [(1, 12), (6, 12), (25, 10), (100, 12), (100, 11)])
+def test_ulsch_deinterleave_vs_reference(Qm, nprb, nsymb):
+    o = ol.oracle()
+    H = nprb * 12 * nsymb
+    rows = H // nsymb
+    rng = np.random.default_rng(H + Qm)
+    q = rng.integers(-30000, 30000, H * Qm).astype(np.int16)
+    # no RI, then RI on the four RI columns (36.212 table 5.2.2.8-1 columns 1,4,7,10) of the last rows, then on position 0
+    cases = [[]]
+    ri_cols = [c for c in (1, 4, 7, 10) if c < nsymb]
+    pos = []
+    for n_ in range(min(8, rows)):
+        r = rows - 1 - n_ // 4
+        c = ri_cols[n_ % len(ri_cols)]
+        pos += [r * Qm + c * rows * Qm + k for k in range(Qm)]
+    cases.append(pos)
+    cases.append(pos + [0, 1])
+    for ri in cases:
+        g0 = o.ulsch_deinterleave(q, Qm, H, nsymb, ri)
+        g1 = ref.ulsch_deinterleave(q, Qm, H, nsymb, ri)
+        n_data = H * Qm - len(set(ri))
+        assert np.array_equal(g0[:n_data], g1[:n_data])

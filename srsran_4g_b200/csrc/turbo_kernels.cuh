@@ -845,52 +845,58 @@ extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const
  * Final hard-decision bytes (tdec_gen_decision_byte, MSB first) of every code block of a group: the decisions of the
  * last half-iteration each block ran; after a DEC2 half-iteration they are gathered through the QPP permutation
  * (app1[fwd[i]] = ext2[i], decision on app1). grid = (n_groups, EMIT_SPLIT), block = 256, dynamic smem =
- * emit_smem_bytes(R, K); the blocks of a group each transpose the (small) decision arrays and share the output words.
+ * emit_smem_bytes(R, K); block y of a group transposes and emits the code blocks held in lanes [8y, 8y+8).
  * The group's two decision arrays are transposed into shared memory ([code block][16-bit piece]), then each warp
  * produces 32 consecutive output words of one code block (coalesced 128-byte stores).
  */
-static constexpr int EMIT_SPLIT = 4;
+static constexpr int EMIT_SPLIT = 4;  // blocks per group: block y owns the code blocks in lanes [8y, 8y+8) (both halves)
 __host__ __device__ inline size_t emit_smem_bytes(uint32_t R, uint32_t K)
 {
   const uint32_t P = R / 16 + 2;  // 16-bit pieces per code block, padded so that a row is an odd number of words
-  return (size_t)2 * 64 * (P | 2u) * 2 + ((K + 63) & ~63u) * 2;
+  return (size_t)2 * (64 / EMIT_SPLIT) * (P | 2u) * 2 + ((K + 63) & ~63u) * 2;
 }
 __global__ void __launch_bounds__(256)
 emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws, const uint8_t* __restrict__ noi,
             uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_len)
 {
   extern __shared__ __align__(16) uint8_t esm[];
+  constexpr uint32_t NL = LANES / EMIT_SPLIT, NC = 2 * NL;  // lanes / code blocks of this block
   const Group&    g    = groups[blockIdx.x];
   const GroupPtrs gp   = group_ptrs(ws, g);
   const uint32_t  K    = g.K;
   const uint32_t  NP   = (K + 15) / 16;             // pieces actually used
   const uint32_t  P    = (g.R / 16 + 2) | 2u;       // row pitch in int16; P/2 is odd => conflict-free transposed stores
+  const uint32_t  L0   = NL * blockIdx.y;
   uint16_t*       T1   = reinterpret_cast<uint16_t*>(esm);
-  uint16_t*       T2   = T1 + 64 * P;
-  uint16_t*       srev = T2 + 64 * P;
+  uint16_t*       T2   = T1 + NC * P;
+  uint16_t*       srev = T2 + NC * P;
   const int       tid  = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  for (uint32_t p = wid; p < NP; p += 8) {
-    const uint32_t w1 = gp.bits1[(size_t)p * LANES + lane], w2 = gp.bits2[(size_t)p * LANES + lane];
-    T1[lane * P + p]        = (uint16_t)w1;
-    T1[(32 + lane) * P + p] = (uint16_t)(w1 >> 16);
-    T2[lane * P + p]        = (uint16_t)w2;
-    T2[(32 + lane) * P + p] = (uint16_t)(w2 >> 16);
+  bool any = false;
+  for (uint32_t c = 0; c < NC; c++) any |= g.cb[(c / NL) * 32 + L0 + (c % NL)] >= 0;
+  if (!any) return;
+  for (uint32_t idx = tid; idx < NP * NL; idx += 256) {
+    const uint32_t p = idx / NL, l = idx % NL;
+    const uint32_t w1 = gp.bits1[(size_t)p * LANES + L0 + l], w2 = gp.bits2[(size_t)p * LANES + L0 + l];
+    T1[l * P + p]        = (uint16_t)w1;
+    T1[(NL + l) * P + p] = (uint16_t)(w1 >> 16);
+    T2[l * P + p]        = (uint16_t)w2;
+    T2[(NL + l) * P + p] = (uint16_t)(w2 >> 16);
   }
   const uint16_t* rev = ktabs[g.kidx].rev;
   for (uint32_t i = tid; i < K; i += 256) srev[i] = rev[i];
   __syncthreads();
   const uint32_t nwords = (K + 31) / 32, nchunk = (nwords + 31) / 32;
-  for (uint32_t task = wid + 8 * blockIdx.y; task < 64 * nchunk; task += 8 * gridDim.y) {
-    const uint32_t cbl = task / nchunk, word = (task % nchunk) * 32 + lane;
-    const int      cb  = g.cb[cbl];
+  for (uint32_t task = wid; task < NC * nchunk; task += 8) {
+    const uint32_t c = task / nchunk, word = (task % nchunk) * 32 + lane;
+    const int      cb = g.cb[(c / NL) * 32 + L0 + (c % NL)];
     if (cb < 0 || word >= nwords) continue;
     const uint32_t nt = min(32u, K - word * 32);  // K is a multiple of 8 but not always of 32
     uint32_t       v  = 0;
     if (noi[cb] & 1u) {
       // last half-iteration was a DEC1: natural order, two 16-bit pieces
-      v = (uint32_t)T1[cbl * P + 2 * word] | (nt > 16 ? ((uint32_t)T1[cbl * P + 2 * word + 1] << 16) : 0u);
+      v = (uint32_t)T1[c * P + 2 * word] | (nt > 16 ? ((uint32_t)T1[c * P + 2 * word + 1] << 16) : 0u);
     } else {
-      const uint16_t* t2 = T2 + cbl * P;
+      const uint16_t* t2 = T2 + c * P;
 #pragma unroll 8
       for (uint32_t t = 0; t < 32; t++) {
         const uint32_t tt = (t + lane) & 31u;  // rotate so that the lanes of a warp hit different banks

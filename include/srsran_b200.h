@@ -157,6 +157,19 @@ typedef struct {
   uint32_t* cb_noi;      /* may be NULL */
   float     avg_iterations;
   int       ret;
+  /* Optional UL-SCH source (the step right before decode_tb on the eNB path, srsran_ulsch_decode sch.c:1122-1193).
+   * When q_bits != NULL, e_bits is ignored: the channel de-interleaver (ulsch_deinterleave sch.c:994-1021 =
+   * ulsch_interleave_gen :661-682 + srsran_vec_lut_sis vector.c:147-152) runs on the device,
+   *     g[lut[p]] = q[p],  p ascending,  lut[p] = rank of p among the non-RI positions in (row, column, bit) order, 0 for RI,
+   * and the transport block is decoded from g + e_offset without leaving the device. */
+  const int16_t*  q_bits;        /* H_prime_total*Qm interleaved LLRs (host) */
+  uint32_t        H_prime_total; /* nb_q / Qm; must be a multiple of N_pusch_symbs */
+  uint32_t        N_pusch_symbs;
+  const uint32_t* ri_positions;  /* srsran_uci_bit_t.position of the RI bits (q->ack_ri_bits), may be NULL */
+  uint32_t        nof_ri_bits;   /* Q'_ri * Qm */
+  uint32_t        e_offset;      /* Q'_cqi * Qm: first g-bit of the UL-SCH data */
+  int16_t*        g_bits;        /* optional out (host): first nof_g_out de-interleaved values (CQI decoding reads them) */
+  uint32_t        nof_g_out;
 } srsb200_tb_t;
 
 /*
@@ -172,6 +185,11 @@ int srsb200_softbuffer_set_resident(srsb200_engine_t* e, int resident);
 int srsb200_softbuffer_reset(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);
 int srsb200_softbuffer_sync_to_host(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);
 int srsb200_softbuffer_release(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);
+
+/* UL-SCH channel de-interleaver alone (host in, host out): g_bits receives H_prime_total*Qm values, of which the first
+ * H_prime_total*Qm - nof_ri_bits are defined (as in the reference) */
+int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs,
+                               int16_t* g_bits, const uint32_t* ri_positions, uint32_t nof_ri_bits);
 
 /* decode n transport blocks (possibly of different UEs/cells/subframes) as one batched submission */
 int srsb200_decode_tb_batch(srsb200_engine_t* e, srsb200_tb_t* tbs, uint32_t n, uint32_t max_iterations);

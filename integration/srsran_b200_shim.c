@@ -27,6 +27,7 @@
 #include "srsran/phy/fec/turbo/rm_turbo.h"
 #include "srsran/phy/fec/turbo/turbodecoder.h"
 #include "srsran/phy/phch/sch.h"
+#include "srsran/phy/phch/uci_cfg.h"
 #include "srsran/phy/utils/debug.h"
 
 #include "srsran_b200.h"
@@ -270,6 +271,83 @@ int srsran_b200_decode_tb_batch(srsran_sch_t**           q,
   return ret == SRSB200_SUCCESS ? SRSRAN_SUCCESS : SRSRAN_ERROR;
 }
 
+/* ------------------------------------------------------------------ eNB uplink: srsran_ulsch_decode's data path */
+/*
+ * ulsch_deinterleave (sch.c:994-1021) + decode_tb (sch.c:509-573) of srsran_ulsch_decode (sch.c:1122-1193) in one device
+ * submission: the interleaved LLRs q_bits go to the device once, are de-interleaved there (RI positions skipped) and the
+ * transport block is decoded from g + e_offset. If g_bits != NULL its first nof_g_out values are returned (the CQI
+ * decoder reads the front of the de-interleaved stream). ri_bits / nof_ri_bits are q->ack_ri_bits / Q'_ri * Qm.
+ */
+int srsran_b200_ulsch_decode_tb(srsran_sch_t*           q,
+                                srsran_softbuffer_rx_t* softbuffer,
+                                srsran_cbsegm_t*        cb_segm,
+                                uint32_t                Qm,
+                                uint32_t                rv,
+                                int16_t*                q_bits,
+                                uint32_t                H_prime_total,
+                                uint32_t                N_pusch_symbs,
+                                srsran_uci_bit_t*       ri_bits,
+                                uint32_t                nof_ri_bits,
+                                uint32_t                e_offset,
+                                uint32_t                nof_e_bits,
+                                int16_t*                g_bits,
+                                uint32_t                nof_g_out,
+                                uint8_t*                data)
+{
+  if (q == NULL || data == NULL || softbuffer == NULL || q_bits == NULL || cb_segm == NULL || Qm == 0 || (nof_ri_bits && ri_bits == NULL)) {
+    return SRSRAN_ERROR_INVALID_INPUTS;
+  }
+  uint32_t* ri = nof_ri_bits ? malloc(nof_ri_bits * sizeof(uint32_t)) : NULL;
+  for (uint32_t i = 0; i < nof_ri_bits; i++) {
+    ri[i] = ri_bits[i].position;
+  }
+  uint8_t      tb_crc = 0;
+  srsb200_tb_t tb;
+  memset(&tb, 0, sizeof(tb));
+  tb.tbs           = cb_segm->tbs;
+  tb.Qm            = Qm;
+  tb.rv            = rv;
+  tb.nof_e_bits    = nof_e_bits;
+  tb.buffer_f      = softbuffer->buffer_f;
+  tb.sb_data       = softbuffer->data;
+  tb.cb_crc        = (uint8_t*)softbuffer->cb_crc;
+  tb.tb_crc        = &tb_crc;
+  tb.max_cb        = softbuffer->max_cb;
+  tb.data          = data;
+  tb.q_bits        = q_bits;
+  tb.H_prime_total = H_prime_total;
+  tb.N_pusch_symbs = N_pusch_symbs;
+  tb.ri_positions  = ri;
+  tb.nof_ri_bits   = nof_ri_bits;
+  tb.e_offset      = e_offset;
+  tb.g_bits        = g_bits;
+  tb.nof_g_out     = g_bits ? nof_g_out : 0;
+  int ret = srsb200_decode_tb(engine(), &tb, q->max_iterations);
+  free(ri);
+  if (ret == SRSB200_ERROR_NO_DEVICE) {
+    ERROR("srsran_b200: %s", srsb200_last_error());
+    return SRSRAN_ERROR;
+  }
+  if (cb_segm->tbs != 0 && cb_segm->C != 0 && ret != SRSRAN_ERROR_INVALID_INPUTS) {
+    softbuffer->tb_crc = tb_crc != 0;
+    q->avg_iterations  = tb.avg_iterations;
+  }
+  return ret;
+}
+
+/* ulsch_deinterleave alone (for grants that carry CQI: the CQI decoder needs g_bits on the host before decode_tb) */
+int srsran_b200_ulsch_deinterleave(int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, int16_t* g_bits,
+                                   srsran_uci_bit_t* ri_bits, uint32_t nof_ri_bits)
+{
+  uint32_t* ri = nof_ri_bits ? malloc(nof_ri_bits * sizeof(uint32_t)) : NULL;
+  for (uint32_t i = 0; i < nof_ri_bits; i++) {
+    ri[i] = ri_bits[i].position;
+  }
+  int ret = srsb200_ulsch_deinterleave(engine(), q_bits, Qm, H_prime_total, N_pusch_symbs, g_bits, ri, nof_ri_bits);
+  free(ri);
+  return ret == SRSB200_SUCCESS ? SRSRAN_SUCCESS : (ret == SRSB200_ERROR_INVALID_INPUTS ? SRSRAN_ERROR_INVALID_INPUTS : SRSRAN_ERROR);
+}
+
 /* ------------------------------------------------------------------ transmit side: sch.c encode_tb_off */
 /* dst bits [off, off+n) <- src bits [0, n), MSB first; every other bit of dst is preserved (what srsran_bit_copy does) */
 static void splice_bits(uint8_t* dst, uint32_t off, const uint8_t* src, uint32_t n)
@@ -410,6 +488,53 @@ int srsran_b200_selftest_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint3
   seg.F = sg[0]; seg.C = sg[1]; seg.K1 = sg[2]; seg.K2 = sg[3]; seg.K1_idx = sg[4]; seg.K2_idx = sg[5]; seg.C1 = sg[6]; seg.C2 = sg[7];
   seg.tbs = tbs; seg.L_tb = 24; seg.L_cb = 24;
   int ret = srsran_b200_encode_tb(q, &sb, &seg, Qm, rv, nof_e_bits, data, e_bits, w_offset);
+  free(q);
+  return ret;
+}
+
+/* srsran_b200_ulsch_decode_tb through real reference structs; RI positions are given as plain indices */
+int srsran_b200_selftest_ulsch_decode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, int16_t* q_bits, uint32_t H_prime_total, uint32_t N_pusch_symbs,
+                                         const uint32_t* ri_positions, uint32_t nof_ri_bits, uint32_t e_offset, uint32_t nof_e_bits, int16_t* g_bits,
+                                         uint32_t nof_g_out, uint32_t max_iterations, uint32_t max_cb, int16_t* buffer_f, uint8_t* sb_data,
+                                         uint8_t* cb_crc, uint8_t* tb_crc, uint8_t* data)
+{
+  srsran_sch_t* q = calloc(1, sizeof(srsran_sch_t));
+  if (!q) {
+    return SRSRAN_ERROR;
+  }
+  q->max_iterations = max_iterations ? max_iterations : 10;
+  srsran_softbuffer_rx_t sb;
+  memset(&sb, 0, sizeof(sb));
+  sb.max_cb      = max_cb;
+  sb.max_cb_size = SOFTBUFFER_SIZE;
+  sb.buffer_f    = calloc(max_cb, sizeof(int16_t*));
+  sb.data        = calloc(max_cb, sizeof(uint8_t*));
+  sb.cb_crc      = calloc(max_cb, sizeof(bool));
+  for (uint32_t i = 0; i < max_cb; i++) {
+    sb.buffer_f[i] = &buffer_f[(size_t)i * SOFTBUFFER_SIZE];
+    sb.data[i]     = &sb_data[(size_t)i * (SOFTBUFFER_SIZE / 8)];
+    sb.cb_crc[i]   = cb_crc[i] != 0;
+  }
+  srsran_uci_bit_t* ri = calloc(nof_ri_bits + 1, sizeof(srsran_uci_bit_t));
+  for (uint32_t i = 0; i < nof_ri_bits; i++) {
+    ri[i].position = ri_positions[i];
+  }
+  uint32_t        sg[8];
+  srsran_cbsegm_t seg;
+  memset(&seg, 0, sizeof(seg));
+  srsb200_cbsegm(tbs, sg);
+  seg.F = sg[0]; seg.C = sg[1]; seg.K1 = sg[2]; seg.K2 = sg[3]; seg.K1_idx = sg[4]; seg.K2_idx = sg[5]; seg.C1 = sg[6]; seg.C2 = sg[7];
+  seg.tbs = tbs; seg.L_tb = 24; seg.L_cb = 24;
+  int ret = srsran_b200_ulsch_decode_tb(q, &sb, &seg, Qm, rv, q_bits, H_prime_total, N_pusch_symbs, ri, nof_ri_bits, e_offset, nof_e_bits, g_bits, nof_g_out,
+                                        data);
+  for (uint32_t i = 0; i < max_cb; i++) {
+    cb_crc[i] = sb.cb_crc[i] ? 1 : 0;
+  }
+  *tb_crc = sb.tb_crc ? 1 : 0;
+  free(ri);
+  free(sb.buffer_f);
+  free(sb.data);
+  free(sb.cb_crc);
   free(q);
   return ret;
 }

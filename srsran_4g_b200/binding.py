@@ -66,6 +66,7 @@ def lib():
             fn.argtypes = [vp, C.POINTER(C.c_void_p), u32]
         L.srsb200_decode_tb.argtypes = [vp, vp, u32]
         L.srsb200_encode_tb_batch.argtypes = [vp, vp, u32]
+        L.srsb200_ulsch_deinterleave.argtypes = [vp, vp, u32, u32, u32, vp, vp, u32]
         L.srsb200_encode_tb.argtypes = [vp, vp]
         _LIB = L
     return _LIB
@@ -105,7 +106,9 @@ def rm_table(cb_idx, rv):
 class _TbStruct(C.Structure):
     _fields_ = [("tbs", C.c_uint32), ("Qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32), ("e_bits", C.c_void_p),
                 ("buffer_f", C.POINTER(C.c_void_p)), ("sb_data", C.POINTER(C.c_void_p)), ("cb_crc", C.c_void_p), ("tb_crc", C.c_void_p),
-                ("max_cb", C.c_uint32), ("data", C.c_void_p), ("cb_noi", C.c_void_p), ("avg_iterations", C.c_float), ("ret", C.c_int)]
+                ("max_cb", C.c_uint32), ("data", C.c_void_p), ("cb_noi", C.c_void_p), ("avg_iterations", C.c_float), ("ret", C.c_int),
+                ("q_bits", C.c_void_p), ("H_prime_total", C.c_uint32), ("N_pusch_symbs", C.c_uint32), ("ri_positions", C.c_void_p),
+                ("nof_ri_bits", C.c_uint32), ("e_offset", C.c_uint32), ("g_bits", C.c_void_p), ("nof_g_out", C.c_uint32)]
 
 
 class _TbTxStruct(C.Structure):
@@ -140,6 +143,18 @@ class TransportBlock:
         s.cb_crc, s.tb_crc = self.cb_crc.ctypes.data, self.tb_crc.ctypes.data
         s.max_cb = self.max_cb
         s.data, s.cb_noi = self.data.ctypes.data, self.cb_noi.ctypes.data
+
+    def fill_ul(self, s, Qm, rv, q_bits, H_prime_total, N_pusch_symbs, nof_e_bits, ri_positions=(), e_offset=0, nof_g_out=0):
+        """UL-SCH source: the e-bits are produced on the device by the channel de-interleaver from q_bits"""
+        self.fill(s, Qm, rv, np.zeros(0, np.int16), nof_e_bits)
+        s.e_bits = None
+        self._q = np.ascontiguousarray(q_bits, np.int16)
+        self._ri = np.ascontiguousarray(np.array(list(ri_positions), np.uint32))
+        self.g_bits = np.zeros(max(nof_g_out, 1), np.int16)
+        s.q_bits, s.H_prime_total, s.N_pusch_symbs = self._q.ctypes.data, H_prime_total, N_pusch_symbs
+        s.ri_positions = self._ri.ctypes.data if len(self._ri) else None
+        s.nof_ri_bits, s.e_offset = len(self._ri), e_offset
+        s.g_bits, s.nof_g_out = self.g_bits.ctypes.data, nof_g_out
 
 
 class Engine:
@@ -288,6 +303,23 @@ class Engine:
         s.e_bits = e.ctypes.data
         ret = self._L.srsb200_encode_tb(self._h, C.byref(s))
         return ret, e
+
+    def ulsch_deinterleave(self, q_bits, Qm, H_prime_total, N_pusch_symbs, ri_positions=()):
+        q = np.ascontiguousarray(q_bits, np.int16)
+        g = np.zeros(H_prime_total * Qm, np.int16)
+        ri = np.ascontiguousarray(np.array(list(ri_positions), np.uint32))
+        ret = self._L.srsb200_ulsch_deinterleave(self._h, _ptr(q), Qm, H_prime_total, N_pusch_symbs, _ptr(g), _ptr(ri) if len(ri) else None, len(ri))
+        return ret, g
+
+    def ulsch_decode_batch(self, reqs, max_iterations):
+        """reqs: list of (TransportBlock, Qm, rv, q_bits, H_prime_total, N_pusch_symbs, nof_e_bits, ri_positions, e_offset, nof_g_out)"""
+        arr = (_TbStruct * len(reqs))()
+        for s, r in zip(arr, reqs):
+            r[0].fill_ul(s, *r[1:])
+        ret = self._L.srsb200_decode_tb_batch(self._h, arr, len(reqs), max_iterations)
+        for s, r in zip(arr, reqs):
+            r[0].ret, r[0].avg_iterations = s.ret, s.avg_iterations
+        return ret
 
     def decode_tb(self, tb, Qm, rv, e_bits, max_iterations, nof_e_bits=None):
         s = _TbStruct()

@@ -183,8 +183,8 @@ struct srsb200_engine {
   uint16_t* d_rm[LTE_NOF_CB_SIZES][4];
 
   // scratch for the host-pointer APIs (grown on demand)
-  void*  d_scratch[12]   = {nullptr};  // 0-7 receive side, 8-11 transmit side
-  size_t scratch_cap[12] = {0};
+  void*  d_scratch[16]   = {nullptr};  // 0-7 receive side, 8-11 transmit side, 12-13 UL-SCH de-interleaver
+  size_t scratch_cap[16] = {0};
   uint32_t* d_crc24b_words = nullptr;  // x^(m+24) mod g24B, m < 6144 (tx_cb_kernel)
 
   // pinned staging arenas for pageable caller buffers (0: host->device, 1: device->host), see Stager
@@ -572,7 +572,7 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
   if (e->tb_plan) srsb200_plan_destroy(e->tb_plan);
   for (void* p : e->softslot_chunks) cudaFree(p);
   for (void* p : e->owned) cudaFree(p);
-  for (int i = 0; i < 12; i++)
+  for (int i = 0; i < 16; i++)
     if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);
   cudaFree(e->d_ktab);
   for (int i = 0; i < 2; i++)
@@ -1145,5 +1145,69 @@ extern "C" int srsb200_rm_turbo_rx_lut(srsb200_engine_t* e, const int16_t* input
 }
 
 // ------------------------------------------------------------------ transport blocks (decode_tb)
+// ------------------------------------------------------------------ UL-SCH channel de-interleaver
+// geometry + RI bookkeeping of one de-interleave (the q / g / ri_scan pointers are set by the caller)
+static void deint_job_fill(DeintJob& j, std::vector<uint32_t>& sc, uint32_t Qm, uint32_t H, uint32_t nsymb, const uint32_t* ri_positions, uint32_t nof_ri)
+{
+  j.Qm = Qm; j.cols = nsymb; j.rows = H / nsymb;
+  const uint32_t ng = H * Qm;
+  // RI positions -> sorted, de-duplicated scan-order indices (row, column, bit)
+  uint32_t max_ri_pos = 0;
+  sc.clear();
+  for (uint32_t i = 0; i < nof_ri; i++) {
+    const uint32_t p = ri_positions[i];
+    if (p >= ng) continue;
+    const uint32_t col = p / (j.rows * j.Qm), r2 = p % (j.rows * j.Qm), row = r2 / j.Qm, bit = r2 % j.Qm;
+    sc.push_back((row * j.cols + col) * j.Qm + bit);
+    max_ri_pos = std::max(max_ri_pos, p);
+  }
+  std::sort(sc.begin(), sc.end());
+  sc.erase(std::unique(sc.begin(), sc.end()), sc.end());
+  // first non-RI element in scan order (it has rank 0) and the last position the reference's loop writes to g[0]
+  uint32_t s0 = 0;
+  while (s0 < sc.size() && sc[s0] == s0) s0++;
+  const uint32_t row0 = s0 / (j.cols * j.Qm), rem0 = s0 % (j.cols * j.Qm), col0 = rem0 / j.Qm, bit0 = rem0 % j.Qm;
+  const uint32_t p0 = row0 * j.Qm + col0 * j.rows * j.Qm + bit0;
+  j.p_star = sc.empty() ? p0 : std::max(p0, max_ri_pos);
+  j.nri    = (uint32_t)sc.size();
+}
+
+extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs,
+                                          int16_t* g_bits, const uint32_t* ri_positions, uint32_t nof_ri_bits)
+{
+  if (!e) return fail(SRSB200_ERROR_NO_DEVICE, "no engine (no CUDA device?)");
+  if (!q_bits || !g_bits || Qm == 0 || N_pusch_symbs == 0 || H_prime_total == 0 || H_prime_total % N_pusch_symbs || (nof_ri_bits && !ri_positions))
+    return SRSB200_ERROR_INVALID_INPUTS;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t ng = (size_t)H_prime_total * Qm;
+  DeintJob j;
+  std::vector<uint32_t> sc;
+  deint_job_fill(j, sc, Qm, H_prime_total, N_pusch_symbs, ri_positions, nof_ri_bits);
+  void *d_q, *d_g, *d_dj;
+  const size_t dj_bytes = (sizeof(DeintJob) + 15) & ~(size_t)15;
+  if (ensure_scratch(e, 12, ng * sizeof(int16_t), &d_q) || ensure_scratch(e, 4, ng * sizeof(int16_t), &d_g) ||
+      ensure_scratch(e, 13, dj_bytes + sc.size() * 4 + 16, &d_dj))
+    return SRSB200_ERROR;
+  j.q       = (const int16_t*)d_q;
+  j.g       = (int16_t*)d_g;
+  j.ri_scan = reinterpret_cast<const uint32_t*>((uint8_t*)d_dj + dj_bytes);
+  Stager stg(e);
+  if (stg.reserve(ng * sizeof(int16_t) + dj_bytes + sc.size() * 4 + 4096, ng * sizeof(int16_t) + 4096)) return SRSB200_ERROR;
+  CUDA_TRY(stg.h2d(d_q, q_bits, ng * sizeof(int16_t), e->stream));
+  CUDA_TRY(stg.h2d(d_dj, &j, sizeof(DeintJob), e->stream));
+  if (!sc.empty()) CUDA_TRY(stg.h2d((uint8_t*)d_dj + dj_bytes, sc.data(), sc.size() * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(d_g, 0, ng * sizeof(int16_t), e->stream));  // the nof_ri_bits values past the data are left stale by the reference
+  {
+    ProfScope ps(e, 3);
+    ulsch_deint_kernel<<<dim3(std::min<uint32_t>(64u, (uint32_t)(ng + 255) / 256), 1), 256, 0, e->stream>>>((const DeintJob*)d_dj);
+    e->launches++;
+  }
+  CUDA_TRY(stg.d2h(g_bits, d_g, ng * sizeof(int16_t), e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  stg.finish();
+  return SRSB200_SUCCESS;
+}
+
 #include "tb_decode.inc"
 #include "tb_encode.inc"

@@ -66,4 +66,37 @@ __global__ void __launch_bounds__(256) crc_bytes_kernel(const CrcJob* __restrict
   if ((threadIdx.x & 31) == 0 && acc) atomicXor(&crc_out[blockIdx.y], acc);
 }
 
+/*
+ * UL-SCH channel de-interleaver (36.212 5.2.2.8; ulsch_deinterleave, lib/src/phy/phch/sch.c:994-1021). The reference
+ * builds lut[] with a running counter over the rows x cols x Qm matrix in (row, column, bit) order - position
+ * p = row*Qm + col*rows*Qm + bit - skipping the positions that carry RI (lut = 0 there), then scatters g[lut[p]] = q[p]
+ * for ascending p. Here thread s owns the s-th matrix element in that order: its rank is s minus the number of RI elements
+ * before it (binary search in the job's sorted list), so writes are coalesced and no table is built. g[0] receives
+ * q[p_star], the last position the sequential loop would have written there (an RI position when there is one).
+ */
+struct DeintJob {
+  const int16_t*  q;
+  int16_t*        g;
+  const uint32_t* ri_scan;  // sorted scan-order indices of the RI positions
+  uint32_t        nri, rows, cols, Qm, p_star;
+};
+__global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __restrict__ jobs)
+{
+  const DeintJob j = jobs[blockIdx.y];
+  const uint32_t n = j.rows * j.cols * j.Qm;
+  for (uint32_t s = blockIdx.x * 256 + threadIdx.x; s < n; s += gridDim.x * 256) {
+    // number of RI scan indices < s, and whether s itself is one
+    uint32_t lo = 0, hi = j.nri;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (j.ri_scan[mid] < s) lo = mid + 1; else hi = mid;
+    }
+    if (lo < j.nri && j.ri_scan[lo] == s) continue;
+    const uint32_t rank = s - lo;
+    const uint32_t row = s / (j.cols * j.Qm), rem = s - row * j.cols * j.Qm, col = rem / j.Qm, bit = rem - col * j.Qm;
+    const uint32_t p = row * j.Qm + col * j.rows * j.Qm + bit;
+    j.g[rank] = j.q[rank == 0 ? j.p_star : p];
+  }
+}
+
 }  // namespace srsb200

@@ -335,3 +335,85 @@ def test_encode_then_decode_round_trip(sb, eng):
     tb = sb.TransportBlock(tbs=tbs)
     assert eng.decode_tb(tb, Qm, 0, llr, 8) == 0
     assert np.array_equal(tb.data[:tbs // 8], data)
+
+
+# ------------------------------------------------------------------ UL-SCH channel de-interleaver
+def _ri_positions(Qm, rows, nsymb, nbits):
+    """RI lands on columns 1,4,7,10 from the last row upwards (36.212 table 5.2.2.8-1), Qm bits per symbol"""
+    cols = [c for c in (1, 4, 7, 10) if c < nsymb]
+    pos = []
+    for m in range(nbits // Qm):
+        r, c = rows - 1 - m // len(cols), cols[m % len(cols)]
+        pos += [r * Qm + c * rows * Qm + k for k in range(Qm)]
+    return pos
+
+
+@pytest.mark.parametrize("Qm", [2, 4, 6])
+def test_ulsch_deinterleave_matches_oracle(eng, o, Qm):
+    for nprb, nsymb in [(1, 12), (6, 12), (25, 10), (100, 12), (100, 11)]:
+        H = nprb * 12 * nsymb
+        rows = H // nsymb
+        q = np.random.default_rng(H * 7 + Qm).integers(-30000, 30000, H * Qm).astype(np.int16)
+        for ri in ([], _ri_positions(Qm, rows, nsymb, 8 * Qm), _ri_positions(Qm, rows, nsymb, 4 * Qm) + [0, 1], list(range(Qm))):
+            ret, g = eng.ulsch_deinterleave(q, Qm, H, nsymb, ri)
+            assert ret == 0
+            g0 = o.ulsch_deinterleave(q, Qm, H, nsymb, ri)
+            nd = H * Qm - len(set(ri))
+            assert np.array_equal(g[:nd], g0[:nd]), (nprb, nsymb, len(ri))
+    assert eng.ulsch_deinterleave(q, Qm, 145, 12, [])[0] == -2   # H' not a multiple of the symbol count
+
+
+def test_ulsch_deinterleave_golden(eng):
+    t = np.load(os.path.join(G, "tx.npz"))
+    for n, (Qm, H, nsymb, nri) in enumerate(t["dei_cases"]):
+        ri = list(t["dei%d_ri" % n])
+        ret, g = eng.ulsch_deinterleave(t["dei%d_q" % n], int(Qm), int(H), int(nsymb), ri)
+        nd = int(H) * int(Qm) - len(ri)
+        assert ret == 0 and np.array_equal(g[:nd], t["dei%d_g" % n][:nd])
+
+
+def test_ulsch_decode_from_interleaved_llrs(sb, eng, o):
+    """srsran_ulsch_decode's data path on the device: q_bits -> de-interleave -> (skip RI and CQI) -> decode_tb, against the
+    oracle's de-interleaver followed by the oracle's decode_tb; two HARQ transmissions, several TBs in one submission"""
+    cases = [(12216, 4, 25, 12, 8, 0), (75376, 6, 100, 12, 24, 36), (2984, 2, 15, 11, 0, 0), (36696, 6, 50, 12, 12, 0)]
+    tbl = [sb.TransportBlock(c[0]) for c in cases]
+    st = [None] * len(cases)
+    for rv in (0, 2):
+        reqs, exp = [], []
+        for n, (tbs, Qm, nprb, nsymb, nri_sym, ncqi_sym) in enumerate(cases):
+            H = nprb * 12 * nsymb
+            rows = H // nsymb
+            ri = _ri_positions(Qm, rows, nsymb, nri_sym * Qm)
+            e_off = ncqi_sym * Qm
+            Gbits = H * Qm - len(ri) - e_off
+            _, e = vecgen.make_tb(tbs, Gbits, Qm, rv, 3.0, 300 + n, scale=100)
+            rng = np.random.default_rng(40 + n + rv)
+            g = np.concatenate([rng.integers(-500, 500, e_off).astype(np.int16), e])
+            # interleave: inverse of the reference's de-interleaver on the non-RI positions, noise on the RI positions
+            q = rng.integers(-500, 500, H * Qm).astype(np.int16)
+            # build the permutation explicitly (positions in (row, col, bit) scan order, RI skipped)
+            is_ri = np.zeros(H * Qm, bool); is_ri[ri] = True
+            j, i, k = np.meshgrid(np.arange(rows), np.arange(nsymb), np.arange(Qm), indexing="ij")
+            p = (j * Qm + i * rows * Qm + k).reshape(-1)
+            p = p[~is_ri[p]]
+            q[p] = g[:len(p)]
+            g_ref = o.ulsch_deinterleave(q, Qm, H, nsymb, ri)
+            res = o.decode_tb(tbs, Qm, rv, g_ref[e_off:e_off + Gbits], 8, st[n])
+            st[n] = res["state"]
+            exp.append((res, g_ref, e_off))
+            reqs.append((tbl[n], Qm, rv, q, H, nsymb, Gbits, ri, e_off, e_off))
+        for tb in tbl:
+            tb.data[:] = 0
+        assert eng.ulsch_decode_batch(reqs, 8) == 0
+        for n, (res, g_ref, e_off) in enumerate(exp):
+            tb = tbl[n]
+            Cn = res["seg"]["C"]
+            assert tb.ret == res["ret"]
+            assert np.array_equal(tb.cb_noi[:Cn], res["cb_noi"][:Cn])
+            assert np.array_equal(tb.cb_crc[:Cn], res["state"]["cb_crc"][:Cn])
+            assert np.array_equal(tb.buffer_f[:Cn], res["state"]["buffer_f"][:Cn])
+            if res["ret"] == 0:
+                assert np.array_equal(tb.data[:cases[n][0] // 8], res["data"][:cases[n][0] // 8])
+            if e_off:
+                assert np.array_equal(tb.g_bits[:e_off], g_ref[:e_off])
+    assert all(tb.ret == 0 for tb in tbl)

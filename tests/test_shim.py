@@ -21,7 +21,7 @@ def test_shim_builds_against_reference_headers():
     import __graft_entry__ as g
     g.build()
     out = subprocess.check_output(["make", "-s", "-C", os.path.join(ROOT, "integration"), "check"]).decode()
-    assert "exports all 17" in out
+    assert "exports all 19" in out
 
 
 @pytest.fixture(scope="module")
@@ -109,3 +109,44 @@ def test_shim_encode_tb(shim):
     d = np.zeros(2000, np.uint8); e = np.zeros(8000, np.uint8)
     assert shim.srsran_b200_selftest_encode_tb(6152, 2, 0, 30000, p(d), p(e), 0, 64) == -1   # filler bits
     assert shim.srsran_b200_selftest_encode_tb(12216, 2, 0, 30000, p(d), p(e), 0, 1) == -1   # C > max_cb
+
+
+@pytest.mark.gpu
+def test_shim_ulsch_decode_tb(shim):
+    """srsran_b200_ulsch_decode_tb (de-interleave + decode_tb in one device submission) on real reference structs against
+    oracle de-interleaver + oracle decode_tb"""
+    o = ol.oracle()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    tbs, Qm, nprb, nsymb = 12216, 4, 25, 12
+    H = nprb * 12 * nsymb
+    rows = H // nsymb
+    ri = []
+    for m in range(8):
+        r, c = rows - 1 - m // 4, (1, 4, 7, 10)[m % 4]
+        ri += [r * Qm + c * rows * Qm + k for k in range(Qm)]
+    ri = np.array(ri, np.uint32)
+    Gb = H * Qm - len(ri)
+    Cn = 2
+    buf = np.zeros((Cn, ol.SOFTBUFFER_SIZE), np.int16); sbd = np.zeros((Cn, ol.SOFTBUFFER_SIZE // 8), np.uint8)
+    cbc = np.zeros(Cn, np.uint8); tbc = np.zeros(1, np.uint8)
+    st = None
+    for rv in (0, 2):
+        _, e = vecgen.make_tb(tbs, Gb, Qm, rv, 1.0, 91, scale=100)
+        rng = np.random.default_rng(rv)
+        q = rng.integers(-500, 500, H * Qm).astype(np.int16)
+        is_ri = np.zeros(H * Qm, bool); is_ri[ri] = True
+        j, i, k = np.meshgrid(np.arange(rows), np.arange(nsymb), np.arange(Qm), indexing="ij")
+        pos = (j * Qm + i * rows * Qm + k).reshape(-1)
+        pos = pos[~is_ri[pos]]
+        q[pos] = e
+        g_ref = o.ulsch_deinterleave(q, Qm, H, nsymb, list(ri))
+        res = o.decode_tb(tbs, Qm, rv, g_ref[:Gb], 6, st); st = res["state"]
+        data = np.zeros(Cn * 768 + 8, np.uint8)
+        g = np.zeros(16, np.int16)
+        ret = shim.srsran_b200_selftest_ulsch_decode_tb(tbs, Qm, rv, p(q), H, nsymb, p(ri), len(ri), 0, Gb, p(g), 16, 6, Cn, p(buf), p(sbd), p(cbc), p(tbc),
+                                                        p(data))
+        assert ret == res["ret"] and int(tbc[0]) == res["tb_crc"] and (cbc == st["cb_crc"]).all()
+        assert (buf == st["buffer_f"]).all() and (g == g_ref[:16]).all()
+        if ret == 0:
+            assert (data[:tbs // 8] == res["data"][:tbs // 8]).all()
+    assert ret == 0

@@ -101,6 +101,13 @@ int  srsb200_tdec_plan_uniform(srsb200_engine_t* e, uint32_t n, uint32_t K, int 
 void srsb200_plan_destroy(srsb200_plan_t* plan);
 int  srsb200_tdec_run_plan_dev(srsb200_engine_t* e, srsb200_plan_t* plan, const int16_t* d_llr, uint32_t max_iter,
                                uint32_t min_iter, int early_stop, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_crc_ok);
+/* Device-resident submissions are asynchronous AND pipelined: every plan is bound to one of two lanes of streams, a
+ * submission waits for the work already queued on the engine stream and for the previous submission of the SAME plan,
+ * and submissions of different plans overlap on the GPU (the latency-bound last half-iterations of one batch hide under
+ * the bandwidth-bound first ones of the next). Results are complete after srsb200_engine_sync(); to order other work on
+ * srsb200_engine_stream() after them without blocking the host call srsb200_engine_flush() first. Submissions of two
+ * plans in flight at once must not share output buffers. */
+int  srsb200_engine_flush(srsb200_engine_t* e);
 int  srsb200_engine_sync(srsb200_engine_t* e);
 
 /* ------------------------------------------------------------------ per-object decoder: srsran_tdec_* */

@@ -37,6 +37,7 @@ def lib():
         L.srsb200_engine_stream.argtypes = [vp]
         L.srsb200_engine_stream.restype = vp
         L.srsb200_engine_sync.argtypes = [vp]
+        L.srsb200_engine_flush.argtypes = [vp]
         L.srsb200_engine_profile.argtypes = [vp, i32]
         L.srsb200_engine_set_subbatches.argtypes = [vp, i32]
         L.srsb200_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
@@ -190,6 +191,10 @@ class Engine:
 
     def sync(self):
         _check(self._L.srsb200_engine_sync(self._h), "srsb200_engine_sync")
+
+    def flush(self):
+        """order the engine stream after every device-resident submission still in flight (does not block the host)"""
+        _check(self._L.srsb200_engine_flush(self._h), "srsb200_engine_flush")
 
     def set_subbatches(self, n):
         _check(self._L.srsb200_engine_set_subbatches(self._h, n), "srsb200_engine_set_subbatches")

@@ -195,6 +195,12 @@ struct srsb200_engine {
   static const int MAX_SUB = 8;
   int          n_sub = 8;      // ranges of a host-pointer submission (copy/compute overlap)
   int          n_sub_dev = 4;  // ranges of a device-resident submission (their launch chains overlap a little: +3-4 %)
+  // Device-resident submissions run on one of two LANES (sub[0..3] / sub[4..7]; a plan is bound to a lane when it is built)
+  // and are joined back into `stream` lazily (join_pending): the latency-bound last half-iterations of one submission
+  // then overlap the bandwidth-bound first ones of the next submission of ANOTHER plan (+11 % on the bench workload).
+  static const int N_LANES = 2;
+  int          next_lane = 0;
+  bool         pending[MAX_SUB] = {false};
   cudaStream_t sub[MAX_SUB] = {nullptr};
   cudaEvent_t  ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
 
@@ -221,6 +227,8 @@ struct srsb200_engine {
   std::vector<uint8_t>  cached_kind;
   std::vector<uint64_t> cached_loff, cached_ooff;
 };
+
+static int join_pending(srsb200_engine* e);
 
 struct ProfScope {
   srsb200_engine* e; int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
@@ -450,6 +458,7 @@ extern "C" int srsb200_softbuffer_reset(srsb200_engine_t* e, int16_t** buffer_f,
   if (!buffer_f) return SRSB200_ERROR_INVALID_INPUTS;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   // one kernel zeroes every listed mirror (a cudaMemsetAsync per code block costs more host time than the decode)
   std::vector<int16_t*> list(nof_cb);
   for (uint32_t i = 0; i < nof_cb; i++)
@@ -470,6 +479,7 @@ extern "C" int srsb200_softbuffer_sync_to_host(srsb200_engine_t* e, int16_t** bu
   if (!buffer_f) return SRSB200_ERROR_INVALID_INPUTS;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   for (uint32_t i = 0; i < nof_cb; i++) {
     auto it = e->softslots.find(buffer_f[i]);
     if (it != e->softslots.end())
@@ -567,6 +577,7 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
 {
   if (!e) return;
   cudaSetDevice(e->device);
+  join_pending(e);
   cudaStreamSynchronize(e->stream);
   if (e->cached_plan) srsb200_plan_destroy(e->cached_plan);
   if (e->tb_plan) srsb200_plan_destroy(e->tb_plan);
@@ -598,7 +609,9 @@ extern "C" int srsb200_engine_profile(srsb200_engine_t* e, int enable)
 extern "C" int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[8])
 {
   if (!e) return SRSB200_ERROR_INVALID_INPUTS;
+  std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   for (int i = 0; i < 8; i++) { ms[i] = 0; cnt[i] = 0; }
   for (auto& p : e->prof) {
@@ -622,10 +635,19 @@ extern "C" int srsb200_engine_set_subbatches(srsb200_engine_t* e, int n)
 
 extern "C" uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e) { return e ? e->launches : 0; }
 extern "C" void*    srsb200_engine_stream(const srsb200_engine_t* e) { return e ? (void*)e->stream : nullptr; }
+extern "C" int      srsb200_engine_flush(srsb200_engine_t* e)
+{
+  if (!e) return SRSB200_ERROR_INVALID_INPUTS;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  return join_pending(e) ? SRSB200_ERROR : SRSB200_SUCCESS;
+}
 extern "C" int      srsb200_engine_sync(srsb200_engine_t* e)
 {
   if (!e) return SRSB200_ERROR_INVALID_INPUTS;
+  std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   return SRSB200_SUCCESS;
 }
@@ -647,6 +669,7 @@ struct srsb200_plan {
   uint8_t*  d_active = nullptr;   // [n_groups]
   uint32_t* d_arrivals = nullptr; // [n_groups] job blocks of the group that have finished the current half-iteration
   bool      uniform = false;
+  int       lane = 0;            // which pair of sub-stream sets runs its device-resident submissions
   bool      contiguous = false;  // one (K, crc) bucket and code block i at llr offset i*(3K+12), output offset i*K/8
 };
 
@@ -664,6 +687,8 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
   }
   srsb200_plan* p = new srsb200_plan();
   p->e            = e;
+  p->lane         = e->next_lane;
+  e->next_lane    = (e->next_lane + 1) % srsb200_engine::N_LANES;
   p->n_cb         = n;
   uint64_t off    = 0;
   for (auto& kv : buckets) {
@@ -756,6 +781,7 @@ extern "C" int srsb200_tdec_plan_uniform(srsb200_engine_t* e, uint32_t n, uint32
   if (!e || !plan) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   int r = build_plan(e, n, nullptr, nullptr, K, crc_kind, nullptr, nullptr, plan);
   if (r == SRSB200_SUCCESS) (*plan)->uniform = true;
   return r;
@@ -767,6 +793,17 @@ struct RangeArgs {
 };
 
 // one launch of the decode chain of a group range; kind: 0 extract, 1 scan, 2 job (+ per-block verdict), 4 emit
+// make the engine stream wait for every lazily joined device-resident submission (stream-ordered, does not block the host)
+static int join_pending(srsb200_engine* e)
+{
+  for (int s = 0; s < srsb200_engine::MAX_SUB; s++) {
+    if (!e->pending[s]) continue;
+    e->pending[s] = false;
+    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[s], 0));
+  }
+  return 0;
+}
+
 static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, int kind, uint32_t n, const int16_t* d_llr, uint32_t max_iter,
                        uint32_t min_iter, int early_stop, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok)
 {
@@ -781,7 +818,7 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
   switch (kind) {
     case 0: {
       ProfScope ps(e, 0, st);
-      extract_kernel<<<dim3(p->max_R / XT, ng), 256, 0, st>>>(dg, p->d_ws, d_llr, p->d_llr_off);
+      extract_kernel<<<dim3(p->max_R / XT, ng), 256, 0, st>>>(dg, p->d_ws, d_llr, p->d_llr_off, da, p->d_done, p->d_crc_acc);
     } break;
     case 1: {
       ProfScope ps(e, 5, st);
@@ -823,17 +860,17 @@ struct HostIO {
 };
 
 static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr, uint32_t max_iter, uint32_t min_iter, int early_stop,
-                       uint32_t start_iter, bool do_extract, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok, const HostIO* io = nullptr)
+                       uint32_t start_iter, bool do_extract, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok, const HostIO* io = nullptr, bool lazy = false)
 {
   if (p->n_groups == 0) return SRSB200_SUCCESS;
   if (max_iter == 0) max_iter = 1;  // run_all is a do-while (turbodecoder.c:542-546)
-  if (start_iter == 0) {
-    CUDA_TRY(cudaMemsetAsync(p->d_crc_acc, 0, sizeof(uint32_t) * p->n_cb, e->stream));
-    CUDA_TRY(cudaMemsetAsync(p->d_done, 0, p->n_cb, e->stream));
-    CUDA_TRY(cudaMemsetAsync(p->d_active, 1, p->n_groups, e->stream));
-  }
+  // (extract_kernel re-arms the per-block CRC / done flags and the group's active flag: no memsets here, so that a
+  //  lazily joined submission never touches state of a plan that is still running on the other lane)
   uint32_t S = 1;
   if (!e->profiling) S = std::max(1u, std::min((uint32_t)(io ? e->n_sub : e->n_sub_dev), p->n_groups / 16u));
+  if (e->profiling) lazy = false;
+  const uint32_t sbase = lazy ? (uint32_t)p->lane * (srsb200_engine::MAX_SUB / srsb200_engine::N_LANES) : 0u;
+  if (lazy) S = std::min(S, (uint32_t)(srsb200_engine::MAX_SUB / srsb200_engine::N_LANES));
   RangeArgs rg[srsb200_engine::MAX_SUB];
   // Host-pointer submissions end with the decode of the LAST range after the last copy has landed, and a decode has a
   // latency floor of ~1 ms however small it is (sequential recursions) - so the ranges shrink geometrically towards the
@@ -847,16 +884,16 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     rg[s].g0 = (uint32_t)((uint64_t)p->n_groups * wacc / wsum);
     wacc += wgt[s];
     rg[s].g1 = (uint32_t)((uint64_t)p->n_groups * wacc / wsum);
-    rg[s].st = (S == 1) ? e->stream : e->sub[s];
+    rg[s].st = (S == 1 && !lazy) ? e->stream : e->sub[sbase + s];
   }
   const auto t_host0 = std::chrono::steady_clock::now();
   static const bool trace_env = getenv("SRSB200_TRACE") != nullptr;
   const bool  trace = trace_env && io && S > 1;
   cudaEvent_t tev[2 * srsb200_engine::MAX_SUB], tev0 = nullptr;
   if (trace) { cudaEventCreate(&tev0); cudaEventRecord(tev0, e->stream); }
-  if (S > 1) {
+  if (S > 1 || lazy) {
     CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
-    for (uint32_t s = 0; s < S; s++) CUDA_TRY(cudaStreamWaitEvent(e->sub[s], e->ev_fork, 0));
+    for (uint32_t s = 0; s < S; s++) CUDA_TRY(cudaStreamWaitEvent(e->sub[sbase + s], e->ev_fork, 0));
   }
   for (uint32_t s = 0; s < S; s++) {
     // group g of a contiguous plan holds code blocks [64 g, 64 g + 64)
@@ -879,10 +916,11 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
       if (trace) cudaEventRecord(tev[2 * s + 1], rg[s].st);
     }
   }
-  if (S > 1) {
+  if (S > 1 || lazy) {
     for (uint32_t s = 0; s < S; s++) {
-      CUDA_TRY(cudaEventRecord(e->ev_join[s], e->sub[s]));
-      CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[s], 0));
+      CUDA_TRY(cudaEventRecord(e->ev_join[sbase + s], e->sub[sbase + s]));
+      if (lazy) e->pending[sbase + s] = true;
+      else CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[sbase + s], 0));
     }
   }
   if (trace) {
@@ -910,7 +948,7 @@ extern "C" int srsb200_tdec_run_plan_dev(srsb200_engine_t* e, srsb200_plan_t* pl
   if (!e || !plan || !d_llr || !d_out || !d_noi || !d_crc_ok) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
-  return launch_plan(e, plan, d_llr, max_iter, min_iter, early_stop, 0, true, d_out, d_noi, d_crc_ok);
+  return launch_plan(e, plan, d_llr, max_iter, min_iter, early_stop, 0, true, d_out, d_noi, d_crc_ok, nullptr, true);
 }
 
 extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_t* K, const uint8_t* crc_kind, const int16_t* llr,
@@ -931,6 +969,7 @@ extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_
   }
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   srsb200_plan* p = nullptr;
   int r = 0;
   {
@@ -1060,6 +1099,7 @@ extern "C" int srsb200_tdec_iteration(srsb200_tdec_t* t, const int16_t* input, u
   srsb200_engine* e = t->e;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   const uint32_t K = t->current_long_cb;
   bool first = t->n_iter == 0;
   if (first) CUDA_TRY(cudaMemcpyAsync(t->d_in, input, (3 * K + 12) * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
@@ -1083,6 +1123,7 @@ extern "C" int srsb200_tdec_run_all(srsb200_tdec_t* t, const int16_t* input, uin
   srsb200_engine* e = t->e;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   CUDA_TRY(cudaMemcpyAsync(t->d_in, input, (3 * long_cb + 12) * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
   uint32_t iters = nof_iterations ? nof_iterations : 1;  // do-while: at least one (turbodecoder.c:542-546)
   int r = launch_plan(e, t->plan, t->d_in, iters, 1, 0, 0, true, t->d_out, t->d_noi, t->d_ok);
@@ -1101,6 +1142,7 @@ extern "C" int srsb200_tdec_get_hard_decision(srsb200_tdec_t* t, uint8_t* output
   srsb200_engine* e = t->e;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   CUDA_TRY(cudaMemcpyAsync(output, t->d_out, t->current_long_cb / 8, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   return SRSB200_SUCCESS;
@@ -1125,6 +1167,7 @@ extern "C" int srsb200_rm_turbo_rx_lut(srsb200_engine_t* e, const int16_t* input
   if (in_len == 0) return SRSB200_SUCCESS;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   if (ensure_rm_table(e, cb_idx, rv_idx)) return SRSB200_ERROR;
   const uint32_t L = 3 * lte_qpp_params[cb_idx].K + 12;
   void *d_e, *d_buf;
@@ -1180,6 +1223,7 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
     return SRSB200_ERROR_INVALID_INPUTS;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
   const size_t ng = (size_t)H_prime_total * Qm;
   DeintJob j;
   std::vector<uint32_t> sc;

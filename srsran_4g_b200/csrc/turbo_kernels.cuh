@@ -752,13 +752,22 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
  */
 constexpr int XT = 32;  // rows per tile
 __global__ void __launch_bounds__(256)
-extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const int16_t* __restrict__ llr, const uint64_t* __restrict__ llr_off)
+extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const int16_t* __restrict__ llr, const uint64_t* __restrict__ llr_off,
+               uint8_t* __restrict__ active, uint8_t* __restrict__ done, uint32_t* __restrict__ crc_acc)
 {
   constexpr int ROWW = 3 * XT / 2 + 1;      // words per tile row: 96 int16 + pad (odd => conflict-free column reads)
   __shared__ uint32_t tile[64][ROWW];
   const Group&    g  = groups[blockIdx.y];
   const uint32_t  K  = g.K;
   const uint32_t  k0 = blockIdx.x * XT;  // first row of this tile
+  if (blockIdx.x == 0) {
+    // a new decode starts here: re-arm the group and its code blocks (stream-ordered before the first scan)
+    if (threadIdx.x < 64 && g.cb[threadIdx.x] >= 0) {
+      done[g.cb[threadIdx.x]]    = 0;
+      crc_acc[g.cb[threadIdx.x]] = 0;
+    }
+    if (threadIdx.x == 0) active[blockIdx.y] = 1;
+  }
   if (k0 >= g.R) return;
   const GroupPtrs gp   = group_ptrs(ws, g);
   const int       tid  = threadIdx.x, wid = tid >> 5, lane = tid & 31;

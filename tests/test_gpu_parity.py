@@ -417,3 +417,33 @@ def test_ulsch_decode_from_interleaved_llrs(sb, eng, o):
             if e_off:
                 assert np.array_equal(tb.g_bits[:e_off], g_ref[:e_off])
     assert all(tb.ret == 0 for tb in tbl)
+
+
+# ------------------------------------------------------------------ device-resident, pipelined submissions (bench.py's path)
+def test_device_resident_plans_pipelined(sb, eng, o):
+    """srsb200_tdec_plan_uniform + srsb200_tdec_run_plan_dev: two plans used alternately (their submissions overlap on the
+    GPU), the same plan re-submitted back to back (serialised), results after srsb200_engine_sync / _flush bit-exact"""
+    import torch
+    K, n = 1024, 2112   # 33 groups: the submission is split over sub-streams and joined lazily
+    dev = torch.device("cuda", 0)
+    sets = []
+    for seed in (1, 2, 3):
+        _, l48 = vecgen.make_cb_batch(K, 48, 1.0, 700 + seed)
+        _, out, noi, ok = o.tdec_batch(K, l48, 8, True, nthreads=4)
+        reps = -(-n // 48)
+        llr = np.tile(l48, (reps, 1))[:n].copy()
+        sets.append((torch.from_numpy(llr).to(dev), np.tile(out, (reps, 1))[:n], np.tile(noi, reps)[:n], np.tile(ok, reps)[:n]))
+    plans = [eng.plan_uniform(n, K, sb.CRC_24B) for _ in range(2)]
+    bufs = [(torch.zeros((n, K // 8), dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev),
+             torch.zeros(n, dtype=torch.uint8, device=dev)) for _ in range(6)]
+    order = [(0, 0), (1, 1), (0, 2), (1, 0), (1, 1), (0, 2)]   # (plan, input set); submissions 3 and 4 reuse plan 1 back to back
+    for b, (pi, si) in zip(bufs, order):
+        eng.run_plan_dev(plans[pi], sets[si][0].data_ptr(), 8, 2, True, b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr())
+    eng.flush()
+    eng.sync()
+    for b, (pi, si) in zip(bufs, order):
+        assert np.array_equal(b[1].cpu().numpy(), sets[si][2])
+        assert np.array_equal(b[2].cpu().numpy(), sets[si][3])
+        assert np.array_equal(b[0].cpu().numpy(), sets[si][1])
+    for p in plans:
+        eng.plan_destroy(p)

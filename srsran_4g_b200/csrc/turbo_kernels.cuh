@@ -57,14 +57,14 @@ struct Group {
 };
 
 // workspace layout of one group (all uint32 [rows][32]):
-//   syst[R] par0[R] par1[R] app1p[R] app2[R] ckA[(R/(WC*WPJ)+1)*8] ckB[(R/CKB+1)*8] bits1[R/16] bits2[R/16]
+//   syst[R] par0[R] par1[R] xa1[R] app2[R] systp[R] ckA[(R/(WC*WPJ)+1)*8] ckB[(R/CKB+1)*8] bits1[R/16] bits2[R/16]
 __host__ __device__ inline uint64_t group_ws_words(uint32_t R)
 {
-  return (uint64_t)LANES * (5ull * R + (R / (WC * WPJ) + 1) * 8ull + (R / CKB + 1) * 8ull + 2ull * (R / 16));
+  return (uint64_t)LANES * (6ull * R + (R / (WC * WPJ) + 1) * 8ull + (R / CKB + 1) * 8ull + 2ull * (R / 16));
 }
 
 struct GroupPtrs {
-  uint32_t *syst, *par0, *par1, *app1p, *app2, *ckA, *ckB, *bits1, *bits2;
+  uint32_t *syst, *par0, *par1, *xa1, *app2, *systp, *ckA, *ckB, *bits1, *bits2;
 };
 __host__ __device__ inline GroupPtrs group_ptrs(uint8_t* ws, const Group& g)
 {
@@ -74,9 +74,10 @@ __host__ __device__ inline GroupPtrs group_ptrs(uint8_t* ws, const Group& g)
   p.syst      = b;
   p.par0      = b + s;
   p.par1      = b + 2 * s;
-  p.app1p     = b + 3 * s;
+  p.xa1       = b + 3 * s;  // DEC1 input with a-priori, pre-added: syst + app1 (rows >= K: syst, the termination steps)
   p.app2      = b + 4 * s;
-  p.ckA       = b + 5 * s;
+  p.systp     = b + 5 * s;  // syst in interleaved order (systp[j] = syst[fwd[j]]), written once by the first DEC1 job
+  p.ckA       = b + 6 * s;
   p.ckB       = p.ckA + (uint64_t)(g.R / (WC * WPJ) + 1) * 8 * LANES;
   p.bits1     = p.ckB + (uint64_t)(g.R / CKB + 1) * 8 * LANES;
   p.bits2     = p.bits1 + (uint64_t)(g.R / 16) * LANES;
@@ -165,10 +166,10 @@ __device__ __forceinline__ uint32_t positive_mask(uint32_t v)
 __device__ long long g_probe_cycles[1024];
 #endif
 // staged chunks in flight per scan warp (bulk copies run NS-1 chunks ahead of the recursion), sized so that the four
-// warps of a block fit in one SM's shared memory: 2 streams x 3 stages or 3 streams x 2 stages of 8 KB each = 48 KB
+// warps of a block fit in one SM's shared memory: 2 streams x 3 stages of 8 KB each = 48 KB
 template <int MODE> struct ScanCfg {
-  static constexpr int NSTR = (MODE == 1) ? 3 : 2;
-  static constexpr int NS   = (MODE == 1) ? 2 : 3;
+  static constexpr int NSTR = 2;  // every mode reads x and y: DEC1 with a-priori reads the pre-added stream xa1
+  static constexpr int NS   = 3;
 };
 template <int MODE> struct ScanStageT {
   uint32_t s[ScanCfg<MODE>::NSTR][W][LANES];
@@ -198,15 +199,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-#define LOAD_XY(st, r)                                                   \
-  uint32_t x = (st).s[0][(r)][lane];                                     \
-  uint32_t y;                                                            \
-  if (MODE == 1) {                                                       \
-    x = padd(x, (st).s[1][(r)][lane]);                                   \
-    y = (st).s[2][(r)][lane];                                            \
-  } else {                                                               \
-    y = (st).s[1][(r)][lane];                                            \
-  }
+// scans: stream 0 = x, stream 1 = y in every mode
+#define LOAD_XY(st, r)                   \
+  uint32_t x = (st).s[0][(r)][lane];     \
+  uint32_t y = (st).s[1][(r)][lane];
+// jobs: MODE 0 {syst, par0}, MODE 1 {syst, xa1, par0} (x = xa1), MODE 2 {app2, par1, systp}
+#define JLOAD_XY(st, r)                                                  \
+  uint32_t x = (st).s[(MODE == 1) ? 1 : 0][(r)][lane];                   \
+  uint32_t y = (st).s[(MODE == 1) ? 2 : 1][(r)][lane];
 
 // A lone warp issues roughly one instruction every two cycles (tools/microbench/lone_warp_step.cu: 22.7 cycles per
 // 13-instruction step), so the scans are written to execute as few instructions per trellis step as possible:
@@ -268,7 +268,7 @@ __device__ __forceinline__ void alpha_block(const ScanStageT<MODE>& st, int r0, 
 
 /*
  * MODE 0: DEC1 on the first half-iteration (no a-priori)   x = syst,          y = par0
- * MODE 1: DEC1 with a-priori                                x = syst + app1p,  y = par0
+ * MODE 1: DEC1 with a-priori                                x = xa1 (= syst + app1, pre-added by the DEC2 job),  y = par0
  * MODE 2: DEC2                                              x = app2,          y = par1
  * grid = ceil(n_groups / 2), block = 160 = five warps: warps 0-3 are the backward (beta) and forward (alpha) recursions of
  * two groups, warp 4 is the PRODUCER that issues every bulk copy (HBM -> shared memory) for them.
@@ -311,9 +311,9 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
       if (gi < n_groups && group_active[gi]) {
         const Group&    g  = groups[gi];
         const GroupPtrs gp = group_ptrs(ws, g);
-        src[w][0] = (MODE == 2) ? gp.app2 : gp.syst;
-        src[w][1] = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
-        src[w][2] = (MODE == 1) ? gp.par0 : nullptr;
+        src[w][0] = (MODE == 2) ? gp.app2 : (MODE == 1 ? gp.xa1 : gp.syst);
+        src[w][1] = (MODE == 2) ? gp.par1 : gp.par0;
+        src[w][2] = nullptr;
         cK4[w]    = (int)g.K / W;
         nchunk[w] = (w & 1) ? ((int)g.K + W - 1) / W : cK4[w] + 1;
       }
@@ -334,18 +334,7 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
         if (lane == 0) mbar_arrive(&sm->full[w][s]);
         continue;
 #endif
-        if (MODE == 1) {
-          asm volatile(
-              "{\n.reg .pred p;\n"
-              "elect.sync _|p, 0xffffffff;\n"
-              "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
-              "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%5], %4, [%0];\n"
-              "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%6], %4, [%0];\n"
-              "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%8], [%7], %4, [%0];\n}"
-              ::"r"(bar), "r"(3u * BYTES), "r"(d0), "r"(d0 + BYTES), "r"(BYTES), "l"(src[w][0] + off), "l"(src[w][1] + off),
-                "l"(src[w][2] + off), "r"(d0 + 2 * BYTES)
-              : "memory");
-        } else {
+        {
           asm volatile(
               "{\n.reg .pred p;\n"
               "elect.sync _|p, 0xffffffff;\n"
@@ -415,7 +404,7 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
       __syncwarp();
       int nslot = W / CKB;
       if (c == cK) {
-        // termination steps k = K+2, K+1, K (no a-priori there: app1p rows >= K stay zero); no normalisation at k = K
+        // termination steps k = K+2, K+1, K (no a-priori there: xa1 rows >= K hold the bare systematic values); no normalisation at k = K
 #pragma unroll
         for (int r = 2; r >= 0; r--) {
           LOAD_XY(st, (K - cK * W) + r);
@@ -541,7 +530,7 @@ __device__ __forceinline__ uint32_t alpha_llr_step(uint32_t (&a)[8], const uint3
 /*
  * grid = (ceil(nwin_max / (4*WPJ)), n_groups), block = 128 (4 warps). Warp j of block bx handles windows
  * [(4*bx + j)*WPJ, +WPJ) of its group. Write-back (turbodecoder_iter.h:104-128 with the vec_sub / vec_lut glue folded in):
- *   MODE 0: app2[rev[i]]  = L            MODE 1: app2[rev[i]] = L - app1p[i]          MODE 2: app1p[fwd[i]] = L - app2[i]
+ *   MODE 0: app2[rev[i]]  = L            MODE 1: app2[rev[i]] = L - app1[i]           MODE 2: xa1[fwd[i]] = syst[fwd[i]] + L - app2[i]
  * Everything a window needs - its input rows, its two beta checkpoints, its step table - arrives in shared memory through
  * one group of bulk asynchronous copies issued one window ahead; the loop itself performs no global loads.
  */
@@ -566,11 +555,11 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   const KTable&   kt   = ktabs[g.kidx];
 
   const uint32_t* in0  = (MODE == 2) ? gp.app2 : gp.syst;
-  const uint32_t* in1  = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.app1p : gp.par0);
-  const uint32_t* in2  = (MODE == 1) ? gp.par0 : nullptr;
+  const uint32_t* in1  = (MODE == 2) ? gp.par1 : (MODE == 1 ? gp.xa1 : gp.par0);
+  const uint32_t* in2  = (MODE == 2) ? gp.systp : (MODE == 1 ? gp.par0 : nullptr);
   const uint32_t* rowt = (MODE == 2) ? kt.row2 : kt.row1;
   const uint32_t* nibt = (MODE == 2) ? kt.nib2[g.crc_kind] : kt.nib1[g.crc_kind];
-  uint32_t*       dst  = (MODE == 2) ? gp.app1p : gp.app2;
+  uint32_t*       dst  = (MODE == 2) ? gp.xa1 : gp.app2;
   uint32_t*       bits = (MODE == 2) ? gp.bits2 : gp.bits1;
 
   if (lane == 0) {
@@ -590,7 +579,7 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
     const uint32_t*    ck    = gp.ckB + (size_t)(2 * w + 1) * 8 * LANES;
     const uint32_t*    rw    = rowt + (size_t)w * WC;
     const uint32_t*    nb    = nibt + (size_t)w * 64;
-    if (MODE == 1) {
+    if (MODE != 0) {
       asm volatile(
           "{\n.reg .pred p;\n"
           "elect.sync _|p, 0xffffffff;\n"
@@ -667,34 +656,46 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
           for (int i = 0; i < 8; i++) t[i] = B[7][i];
         }
         {
-          LOAD_XY(st, 8 * s + 7);
+          JLOAD_XY(st, 8 * s + 7);
           beta_step_to(B[6], t, x, y);
         }
       }
 #pragma unroll
       for (int j = 5; j >= 3; j--) {
-        LOAD_XY(st, 8 * s + 1 + j);
+        JLOAD_XY(st, 8 * s + 1 + j);
         beta_step_to(B[j], B[j + 1], x, y);
       }
       {
         uint32_t t[8];
         normalise_to(t, B[3]);  // k = lo + 8s + 4
-        LOAD_XY(st, 8 * s + 3);
+        JLOAD_XY(st, 8 * s + 3);
         beta_step_to(B[2], t, x, y);
       }
 #pragma unroll
       for (int j = 1; j >= 0; j--) {
-        LOAD_XY(st, 8 * s + 1 + j);
+        JLOAD_XY(st, 8 * s + 1 + j);
         beta_step_to(B[j], B[j + 1], x, y);
       }
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const int r = 8 * s + j;
-        LOAD_XY(st, r);
-        uint32_t ap = (MODE == 1) ? st.s[1][r][lane] : (MODE == 2 ? st.s[0][r][lane] : 0u);
-        uint32_t L  = alpha_llr_step(a, B[j], x, y);
+        JLOAD_XY(st, r);
+        uint32_t L = alpha_llr_step(a, B[j], x, y);
         if (j == 3 || j == 7) normalise(a);
-        dst[(size_t)st.row[r] * LANES + lane] = (MODE == 0) ? L : psub(L, ap);
+        // what the next half-iteration reads (turbodecoder_iter.h:104-128 with the vec_sub / vec_lut glue folded in; all
+        // wrapping int16, so re-association is exact):
+        //   MODE 0: app2[rev[i]] = L                        and, once, systp[rev[i]] = syst[i]
+        //   MODE 1: app2[rev[i]] = L - app1[i] = (L + syst[i]) - xa1[i]
+        //   MODE 2: xa1[fwd[i]]  = syst[fwd[i]] + (L - app2[i]) = systp[i] + (L - app2[i])
+        const size_t o = (size_t)st.row[r] * LANES + lane;
+        if (MODE == 0) {
+          dst[o]      = L;
+          gp.systp[o] = x;
+        } else if (MODE == 1) {
+          dst[o] = psub(padd(L, st.s[0][r][lane]), x);
+        } else {
+          dst[o] = padd(st.s[2][r][lane], psub(L, x));
+        }
         bitacc = ((bitacc >> 1) & 0x7fff7fffu) | positive_mask(L);
       }
     }
@@ -747,7 +748,7 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
  * De-multiplex natural-order LLRs (tdec_gen_extract_input, turbodecoder_gen.c:238-258) of up to 64 code blocks into the
  * group's packed [row][lane] streams. grid = (R / XT, n_groups), block = 256. HBM-bound: every LLR is read once
  * (coalesced 192-byte runs per code block) and written once (coalesced 128-byte rows); only the three channel streams are
- * written (app1p / app2 rows < K are produced by the decoder before they are read).
+ * written, plus the termination rows of xa1 (xa1 / app2 / systp rows < K are produced by the decoder before they are read).
  * llr_off[cb] = element offset of the code block's 3K+12 int16 in llr.
  */
 constexpr int XT = 32;  // rows per tile
@@ -845,7 +846,8 @@ extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const
     gp.syst[o]  = sv;
     gp.par0[o]  = p0;
     gp.par1[o]  = p1;
-    gp.app1p[o] = 0;   // rows >= K must stay zero (no a-priori on the termination steps)
+    gp.xa1[o]   = sv;  // rows >= K keep the bare systematic value (no a-priori on the termination steps); rows < K are
+                       // overwritten by the first DEC2 job before any DEC1 reads them
     gp.app2[o]  = a2;  // second encoder's termination systematic values
   }
 }

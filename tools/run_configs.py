@@ -54,6 +54,33 @@ for i in range(0, len(Ks), 37):
     _, oo, on, ook = o.tdec_batch(int(Ks[i]), llrs[i][None, :], 8, True)
     assert on[0] == noi[i] and ook[0] == ok[i] and (oo[0] == outs[i]).all()
 dt = timeit(lambda: eng.tdec_batch(Ks, llrs, 8, early_stop=True), reps=3, warm=1)
+# the same submission through the C ABI with flat, caller-prepared arrays (what a C caller pays), 8 and 64 blocks per size
+import ctypes as C
+Lc = sb.lib()
+for per in (8, 64):
+    Kf, lf = [], []
+    for idx in range(188):
+        k = o.cbsize(idx)
+        _, l = synth.make_llr_batch(k, per, 2.0 if k < 512 else 1.5, 100 + idx, n_distinct=min(per, 8))
+        for i in range(per):
+            Kf.append(k); lf.append(l[i])
+    Kf = np.array(Kf, np.uint32)
+    flat = np.concatenate(lf).astype(np.int16)
+    loff = np.concatenate([[0], np.cumsum(3 * Kf.astype(np.uint64) + 12)[:-1]]).astype(np.uint64)
+    ooff = np.concatenate([[0], np.cumsum(Kf.astype(np.uint64) // 8)[:-1]]).astype(np.uint64)
+    fo = np.zeros(int((Kf // 8).sum()), np.uint8); fn = np.zeros(len(Kf), np.uint8); fk = np.zeros(len(Kf), np.uint8)
+    kinds = np.full(len(Kf), sb.CRC_24B, np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    def call():
+        assert Lc.srsb200_tdec_batch(eng.handle, len(Kf), vp(Kf), vp(kinds), vp(flat), vp(loff), len(flat), 8, 2, 1, vp(fo), vp(ooff), len(fo), vp(fn), vp(fk)) == 0
+    dtf = timeit(call, reps=5, warm=2)
+    eng.profile(True); eng.profile_read(); call(); prof = eng.profile_read(); eng.profile(False)
+    res["config4_mixed_188_sizes_x%d_c_abi" % per] = {"code_blocks": int(len(Kf)), "info_bits": int(Kf.sum()), "ms_host_to_host": dtf * 1e3,
+                                                      "info_Mbit_s_host_to_host": float(Kf.sum()) / dtf / 1e6,
+                                                      "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+                                                      "info_Mbit_s_kernels": float(Kf.sum()) / (sum(v[0] for v in prof.values()) * 1e-3) / 1e6,
+                                                      "note": "pageable numpy buffers (the H2D of the LLRs dominates the 64-per-size case)"}
+
 res["config4_mixed_188_sizes_x8"] = {"code_blocks": int(len(Ks)), "info_bits": int(Ks.sum()), "ms_host_to_host": dt * 1e3, "info_Mbit_s_host_to_host": float(Ks.sum()) / dt / 1e6,
                                      "crc_ok_fraction": float(ok.mean()), "parity": "sampled blocks bit-exact vs oracle",
                                      "note": "includes python-side concatenation of the ragged inputs and plan building for 188 buckets"}
@@ -143,6 +170,8 @@ for e_ in engs:
     e_.close()
 eng.close()
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-with open(os.path.join(ROOT, "profiles", "r01_configs.json"), "w") as f:
-    json.dump(res, f, indent=1)
+for d_ in ("profiles", "gpurun_out"):
+    os.makedirs(os.path.join(ROOT, d_), exist_ok=True)
+    with open(os.path.join(ROOT, d_, "r01_configs.json"), "w") as f:
+        json.dump(res, f, indent=1)
 print(json.dumps(res, indent=1))

@@ -693,3 +693,81 @@ int ref_ulsch_deinterleave(int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total,
   free(lut);
   return 0;
 }
+
+/* ------------------------------------------------------------------ srsran_ulsch_encode / srsran_ulsch_decode themselves */
+#include "srsran/phy/phch/pusch_cfg.h"
+static void pusch_cfg_fill(srsran_pusch_cfg_t* cfg, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_symb, uint32_t L_prb, uint32_t ri_len)
+{
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->grant.L_prb         = L_prb;
+  cfg->grant.nof_symb      = nof_symb;
+  cfg->grant.nof_re        = L_prb * 12 * nof_symb;
+  cfg->grant.tb.tbs        = (int)tbs;
+  cfg->grant.tb.mod        = mod_of(Qm);
+  cfg->grant.tb.rv         = (int)rv;
+  cfg->grant.tb.nof_bits   = cfg->grant.nof_re * Qm;
+  cfg->grant.tb.enabled    = true;
+  cfg->grant.last_tb       = cfg->grant.tb;
+  cfg->uci_cfg.cqi.ri_len  = ri_len; /* 1-bit RI multiplexed on the PUSCH (no CQI, no ACK) */
+  cfg->uci_offset.I_offset_ri  = 5;
+  cfg->uci_offset.I_offset_cqi = 6;
+  cfg->uci_offset.I_offset_ack = 5;
+}
+
+/* q_bits: packed interleaved bits, L_prb*12*nof_symb*Qm/8 bytes (+8 spare) */
+int ref_ulsch_encode(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_symb, uint32_t L_prb, uint32_t ri_len, uint32_t ri_value, uint8_t* data,
+                     uint8_t* q_bits)
+{
+  ref_init();
+  pthread_mutex_lock(&g_lock);
+  int ret = -1;
+  if (sch_ready() == 0) {
+    srsran_softbuffer_tx_t sb;
+    if (srsran_softbuffer_tx_init(&sb, 110) == 0) {
+      srsran_pusch_cfg_t cfg;
+      pusch_cfg_fill(&cfg, tbs, Qm, rv, nof_symb, L_prb, ri_len);
+      cfg.softbuffers.tx = &sb;
+      srsran_uci_value_t uci;
+      memset(&uci, 0, sizeof(uci));
+      uci.ri          = (uint8_t)ri_value;
+      uint8_t* g_bits = calloc(cfg.grant.tb.nof_bits / 8 + 64, 1);
+      ret             = srsran_ulsch_encode(&g_sch, &cfg, data, &uci, g_bits, q_bits);
+      free(g_bits);
+      srsran_softbuffer_tx_free(&sb);
+    }
+  }
+  pthread_mutex_unlock(&g_lock);
+  return ret;
+}
+
+/* q_llr: L_prb*12*nof_symb*Qm interleaved LLRs (unscrambled); soft buffer handle as for ref_dlsch_decode */
+int ref_ulsch_decode(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_symb, uint32_t L_prb, uint32_t ri_len, int16_t* q_llr,
+                     uint32_t max_iterations, uint8_t* data, uint8_t* cb_crc, uint8_t* tb_crc, float* avg_iterations, uint8_t* ri_out)
+{
+  ref_init();
+  pthread_mutex_lock(&g_lock);
+  int ret = -1;
+  if (sch_ready() == 0) {
+    srsran_softbuffer_rx_t* sb = (srsran_softbuffer_rx_t*)h;
+    srsran_pusch_cfg_t      cfg;
+    pusch_cfg_fill(&cfg, tbs, Qm, rv, nof_symb, L_prb, ri_len);
+    cfg.softbuffers.rx = sb;
+    srsran_uci_value_t uci;
+    memset(&uci, 0, sizeof(uci));
+    uint32_t nb    = cfg.grant.tb.nof_bits;
+    int16_t* g     = calloc(nb + 64, sizeof(int16_t));
+    uint8_t* c_seq = calloc(nb + 64, 1);
+    srsran_sch_set_max_noi(&g_sch, max_iterations);
+    ret = srsran_ulsch_decode(&g_sch, &cfg, q_llr, g, c_seq, data, &uci);
+    for (uint32_t i = 0; i < sb->max_cb; i++) {
+      cb_crc[i] = sb->cb_crc[i] ? 1 : 0;
+    }
+    *tb_crc         = sb->tb_crc ? 1 : 0;
+    *avg_iterations = srsran_sch_last_noi(&g_sch);
+    *ri_out         = uci.ri;
+    free(g);
+    free(c_seq);
+  }
+  pthread_mutex_unlock(&g_lock);
+  return ret;
+}

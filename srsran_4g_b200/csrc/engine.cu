@@ -948,6 +948,8 @@ extern "C" int srsb200_tdec_run_plan_dev(srsb200_engine_t* e, srsb200_plan_t* pl
   if (!e || !plan || !d_llr || !d_out || !d_noi || !d_crc_ok) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
+  // (profiling runs the submission on the engine stream itself: order it after whatever is still in flight on the lanes)
+  if (e->profiling && join_pending(e)) return SRSB200_ERROR;
   return launch_plan(e, plan, d_llr, max_iter, min_iter, early_stop, 0, true, d_out, d_noi, d_crc_ok, nullptr, true);
 }
 

@@ -77,6 +77,9 @@ class _Lib:
             L.ref_dlsch_decode.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [i16p, C.c_uint32, u8p, u8p, u8p, C.POINTER(C.c_float)]
             L.ref_dlsch_decode.restype = C.c_int
             L.ref_ulsch_deinterleave.argtypes = [i16p, C.c_uint32, C.c_uint32, C.c_uint32, i16p, u32p, C.c_uint32]
+            L.ref_ulsch_encode.argtypes = [C.c_uint32] * 7 + [u8p, u8p]; L.ref_ulsch_encode.restype = C.c_int
+            L.ref_ulsch_decode.argtypes = [C.c_void_p] + [C.c_uint32] * 6 + [i16p, C.c_uint32, u8p, u8p, u8p, C.POINTER(C.c_float), u8p]
+            L.ref_ulsch_decode.restype = C.c_int
         else:
             self._trace = L.orc_tdec_trace; self._trace.argtypes = [C.c_uint32, i16p, C.c_uint32, u8p, C.c_void_p]
             self._run_all = L.orc_tdec_run_all; self._run_all.argtypes = [C.c_uint32, i16p, C.c_uint32, u8p]
@@ -226,6 +229,22 @@ class _Lib:
         ret = self.lib.ref_dlsch_decode(h, tbs, Qm, rv, len(e_bits), e_bits, max_iterations, data, cbc, tbc, C.byref(avg))
         return dict(ret=ret, data=data, cb_crc=cbc, tb_crc=int(tbc[0]), avg_iterations=avg.value)
 
+    def ulsch_encode(self, tbs, Qm, rv, nof_symb, L_prb, data, ri_len=0, ri_value=0):
+        """srsran_ulsch_encode -> (ret, interleaved hard bits q[L_prb*12*nof_symb*Qm])"""
+        nb = L_prb * 12 * nof_symb * Qm
+        q = np.zeros(nb // 8 + 64, np.uint8)
+        ret = self.lib.ref_ulsch_encode(tbs, Qm, rv, nof_symb, L_prb, ri_len, ri_value, np.ascontiguousarray(data, np.uint8).copy(), q)
+        return ret, np.unpackbits(q)[:nb]
+
+    def ulsch_decode(self, h, tbs, Qm, rv, nof_symb, L_prb, q_llr, max_iterations, ri_len=0):
+        """srsran_ulsch_decode on the persistent soft buffer h"""
+        q_llr = np.ascontiguousarray(q_llr, np.int16)
+        ncb = self.lib.ref_dlsch_rx_max_cb(h)
+        data = np.zeros(ncb * 768 + 8, np.uint8)
+        cbc = np.zeros(ncb, np.uint8); tbc = np.zeros(1, np.uint8); ri = np.zeros(1, np.uint8); avg = C.c_float(0)
+        ret = self.lib.ref_ulsch_decode(h, tbs, Qm, rv, nof_symb, L_prb, ri_len, q_llr, max_iterations, data, cbc, tbc, C.byref(avg), ri)
+        return dict(ret=ret, data=data, cb_crc=cbc, tb_crc=int(tbc[0]), avg_iterations=avg.value, ri=int(ri[0]))
+
     def ulsch_deinterleave(self, q_bits, Qm, H_prime_total, N_pusch_symbs, ri_positions=()):
         q_bits = np.ascontiguousarray(q_bits, np.int16)
         g = np.zeros(H_prime_total * Qm + 8, np.int16)
@@ -248,6 +267,19 @@ def oracle():
     if _oracle is None:
         _oracle = _Lib(build_oracle(), "orc_")
     return _oracle
+
+
+PHY_B200_SO = os.path.join(ROOT, "integration", "_build", "libsrsran_phy_b200.so")
+_phy = None
+
+
+def phy_b200():
+    """The reference's own sch.c with the SRSRAN_B200 hooks applied, linked against the shim + libsrsran_b200.so
+    (integration/Makefile `phy`); same flat entry points as ref(). Needs a GPU. None when it has not been built."""
+    global _phy
+    if _phy is None and os.path.exists(PHY_B200_SO):
+        _phy = _Lib(PHY_B200_SO, "ref_")
+    return _phy
 
 
 def ref():

@@ -1,0 +1,90 @@
+"""The drop-in shown end to end: the reference's OWN lib/src/phy/phch/sch.c, with the three SRSRAN_B200 hooks of
+INTEGRATION.md applied at build time (integration/apply_b200_patch.py), linked against the shim and libsrsran_b200.so.
+srsran_dlsch_decode2 / srsran_dlsch_encode2 / srsran_ulsch_decode / srsran_ulsch_encode of that library run on the GPU
+engine and must give what the oracle (= the reference's generic int16 decoder) gives, bit for bit."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import vecgen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def phy():
+    p = ol.phy_b200()
+    if p is None:
+        pytest.skip("integration/_build/libsrsran_phy_b200.so not built (needs /root/reference at build time)")
+    return p
+
+
+def test_dlsch_decode2_on_the_engine(phy):
+    """srsran_dlsch_decode2 -> decode_tb -> srsran_b200_decode_tb: return code, bytes, flags AND average half-iterations
+    equal the oracle's over a HARQ sequence (the production SIMD decoder would differ in the iteration counts)"""
+    o = ol.oracle()
+    for tbs, Qm, G, eb in [(12216, 4, 4 * 4500, 1.0), (75376, 6, 86400, 4.5), (6120, 2, 2 * 5000, 0.5), (36696, 6, 6 * 8000, 3.0)]:
+        h = phy.dlsch_rx_new()
+        st = None
+        try:
+            for rv in (0, 2, 3, 1):
+                _, e = vecgen.make_tb(tbs, G, Qm, rv, eb, 11 + tbs, scale=100)
+                a = o.decode_tb(tbs, Qm, rv, e, 8, st)
+                st = a["state"]
+                b = phy.dlsch_decode(h, tbs, Qm, rv, e, 8)
+                Cn = a["seg"]["C"]
+                assert a["ret"] == b["ret"] and a["tb_crc"] == b["tb_crc"]
+                assert np.array_equal(st["cb_crc"][:Cn], b["cb_crc"][:Cn])
+                assert np.float32(a["avg_iterations"]) == np.float32(b["avg_iterations"])
+                nb = (Cn - 1) * ((a["seg"]["K1"] - 24) // 8) + a["seg"]["K1"] // 8 if Cn > 1 else tbs // 8 + 3
+                assert np.array_equal(a["data"][:nb], b["data"][:nb])
+        finally:
+            phy.dlsch_rx_free(h)
+
+
+def test_dlsch_encode2_on_the_engine(phy):
+    o = ol.oracle()
+    for tbs, Qm, rv, G in [(40, 2, 0, 120), (12216, 6, 2, 19200), (75376, 6, 0, 86400), (36696, 4, 3, 4 * 12000), (6120, 2, 1, 9000)]:
+        data = np.random.default_rng(tbs + rv).integers(0, 256, tbs // 8, dtype=np.uint8)
+        r0, e0 = o.encode_tb(tbs, Qm, rv, G, data)
+        r1, e1 = phy.dlsch_encode(tbs, Qm, rv, G, data)
+        nb = Qm * (G // Qm)
+        assert r0 == r1 == 0 and np.array_equal(np.unpackbits(e0)[:nb], np.unpackbits(e1)[:nb])
+
+
+@pytest.mark.parametrize("tbs,Qm,nprb,nsymb,ri_len", [(2984, 2, 15, 12, 0), (12216, 4, 25, 12, 1), (36696, 6, 50, 12, 1), (75376, 6, 100, 12, 0)])
+def test_ulsch_decode_on_the_engine(phy, tbs, Qm, nprb, nsymb, ri_len):
+    """srsran_ulsch_decode with the de-interleaver + decode fused on the device (grants with and without RI)"""
+    o = ol.oracle()
+    ref = ol.ref()
+    rng = np.random.default_rng(tbs + ri_len)
+    data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    ret, qb = phy.ulsch_encode(tbs, Qm, 0, nsymb, nprb, data, ri_len, 1)    # encode side also runs on the engine
+    assert ret >= 0   # the number of RI/ACK bits placed
+    if ref is not None:
+        ret_c, qb_c = ref.ulsch_encode(tbs, Qm, 0, nsymb, nprb, data, ri_len, 1)
+        assert ret_c == ret and np.array_equal(qb, qb_c)
+    H = nprb * 12 * nsymb
+    noise = rng.normal(0, 45 if ri_len == 0 else 25, H * Qm)
+    llr = np.clip((qb.astype(np.float64) * 2 - 1) * 60 + noise, -2000, 2000).astype(np.int16)
+    h = phy.dlsch_rx_new()
+    try:
+        b = phy.ulsch_decode(h, tbs, Qm, 0, nsymb, nprb, llr, 8, ri_len)
+    finally:
+        phy.dlsch_rx_free(h)
+    if ri_len == 0:
+        g = o.ulsch_deinterleave(llr, Qm, H, nsymb, [])
+        a = o.decode_tb(tbs, Qm, 0, g, 8)
+        assert a["ret"] == b["ret"] and a["tb_crc"] == b["tb_crc"]
+        assert np.float32(a["avg_iterations"]) == np.float32(b["avg_iterations"])
+        if a["ret"] == 0:
+            assert np.array_equal(a["data"][:tbs // 8], b["data"][:tbs // 8])
+    else:
+        assert b["ret"] == 0 and np.array_equal(b["data"][:tbs // 8], data)
+        if ref is not None:
+            hc = ref.dlsch_rx_new()
+            try:
+                c = ref.ulsch_decode(hc, tbs, Qm, 0, nsymb, nprb, llr, 8, ri_len)
+            finally:
+                ref.dlsch_rx_free(hc)
+            assert c["ret"] == b["ret"] and c["ri"] == b["ri"] and np.array_equal(c["data"][:tbs // 8], b["data"][:tbs // 8])

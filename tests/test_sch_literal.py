@@ -106,3 +106,26 @@ def test_ulsch_deinterleave_vs_reference(Qm, nprb, nsymb):
         g1 = ref.ulsch_deinterleave(q, Qm, H, nsymb, ri)
         n_data = H * Qm - len(set(ri))
         assert np.array_equal(g0[:n_data], g1[:n_data])
+
+
+@pytest.mark.parametrize("tbs,Qm,nprb,nsymb,ri_len", [(2984, 2, 15, 12, 0), (12216, 4, 25, 12, 1), (36696, 6, 50, 12, 1), (6120, 2, 30, 11, 0)])
+def test_ulsch_chain_literal(tbs, Qm, nprb, nsymb, ri_len):
+    """srsran_ulsch_encode -> LLRs -> srsran_ulsch_decode (both literal) returns the payload; without RI the oracle chain
+    (de-interleaver + decode_tb) agrees with it on the bytes"""
+    o = ol.oracle()
+    rng = np.random.default_rng(tbs)
+    data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    ret, qb = ref.ulsch_encode(tbs, Qm, 0, nsymb, nprb, data, ri_len, 1)
+    assert ret >= 0   # srsran_ulsch_encode returns the number of RI/ACK bits it placed
+    llr = ((qb.astype(np.int16) * 2 - 1) * 60).astype(np.int16)
+    h = ref.dlsch_rx_new()
+    try:
+        r = ref.ulsch_decode(h, tbs, Qm, 0, nsymb, nprb, llr, 8, ri_len)
+    finally:
+        ref.dlsch_rx_free(h)
+    assert r["ret"] == 0 and np.array_equal(r["data"][:tbs // 8], data)
+    if not ri_len:   # (the RI value itself is UCI control decoding with the scrambling sequence: not this path)
+        H = nprb * 12 * nsymb
+        g = o.ulsch_deinterleave(llr, Qm, H, nsymb, [])
+        a = o.decode_tb(tbs, Qm, 0, g, 8)
+        assert a["ret"] == 0 and np.array_equal(a["data"][:tbs // 8], data)

@@ -9,16 +9,20 @@
  *     one warp = a "group" of up to 64 code blocks of equal K in lock-step.
  *   - all soft streams of a group live in HBM as [row k][32 lanes] packed words, so every access of a warp is one
  *     coalesced 128-byte row and the QPP (de)interleaver is a *row* move with a warp-uniform row index.
- *   - a half-iteration (one constituent MAP decode + glue) is three launches:
+ *   - a half-iteration (one constituent MAP decode + glue) is two launches:
  *       scan_kernel   : the two inherently sequential recursions, alpha forward and beta backward, one warp each per
- *                       group, storing only the state every WC steps (checkpoints). Exact by construction.
- *       job_kernel    : window-parallel. A warp takes a window of WC steps, its alpha checkpoint at the start and its
- *                       beta checkpoint at the end, recomputes beta of the window into REGISTERS (8 steps at a time),
+ *                       group (fed by a producer warp), storing only checkpoints: beta every CKB steps, alpha every
+ *                       WC*WPJ steps. Exact by construction.
+ *       job_kernel    : window-parallel. A warp takes WPJ consecutive windows of WC steps, the alpha checkpoint at the
+ *                       start and the beta checkpoints inside, recomputes beta into REGISTERS (8 steps at a time),
  *                       runs alpha + LLR + extrinsic/QPP write-back + hard decision + CRC (by linearity) over it.
  *                       Bit-identical because the recursions are deterministic from the checkpointed states. This
- *                       is where ~75% of the instructions are, spread over K/WC x more warps than code-block groups.
- *       status_kernel : per-code-block CRC verdict, half-iteration count and early-stop flag; groups whose blocks
+ *                       is where ~70% of the instructions are, spread over K/(WC*WPJ) x more warps than groups.
+ *                       The last block of a group to finish applies the per-code-block verdict (CRC == 0 from the
+ *                       min_iter-th half-iteration on, half-iteration count, early-stop flag); groups whose blocks
  *                       are all done make the later launches exit immediately.
+ *     extract_kernel before (de-multiplex the 3K+12 LLRs into the lane-packed streams) and emit_kernel after (hard
+ *     bits back to bytes, through the QPP permutation when the last half-iteration was a DEC2).
  *   - input windows are staged HBM -> shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier, SASS
  *     UBLKCP), double-buffered per warp, so warps spend no issue slots on loads.
  */

@@ -447,3 +447,58 @@ def test_device_resident_plans_pipelined(sb, eng, o):
         assert np.array_equal(b[0].cpu().numpy(), sets[si][1])
     for p in plans:
         eng.plan_destroy(p)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_submissions(sb, eng):
+    """n == 0 everywhere: success, nothing launched, nothing written"""
+    import ctypes as C
+    L = sb.lib()
+    n0 = eng.launch_count
+    assert L.srsb200_tdec_batch(eng.handle, 0, None, None, None, None, 0, 8, 2, 1, None, None, 0, None, None) == 0
+    assert L.srsb200_decode_tb_batch(eng.handle, None, 0, 8) == 0
+    assert L.srsb200_encode_tb_batch(eng.handle, None, 0) == 0
+    assert eng.launch_count == n0
+    out, noi, ok = eng.tdec_batch(np.zeros(0, np.uint32), [], 8)
+    assert len(noi) == 0
+
+
+def test_largest_transport_block(sb, eng, o):
+    """2-layer 100-PRB TBS 149776: C = 25 code blocks of K = 6016, decode over two HARQ transmissions and
+    encode, against the oracle"""
+    tbs, Qm = 149776, 6
+    G = Qm * 28800
+    _, seg = o.cbsegm(tbs)
+    assert seg["C"] == 25 and seg["K1"] == 6016 and seg["F"] == 0
+    tb = sb.TransportBlock(tbs)
+    st = None
+    for rv in (0, 2):
+        _, e = vecgen.make_tb(tbs, G, Qm, rv, 3.5, 123, scale=700)
+        res = o.decode_tb(tbs, Qm, rv, e, 8, st)
+        st = res["state"]
+        tb.data[:] = 0
+        assert eng.decode_tb(tb, Qm, rv, e, 8) == res["ret"]
+        assert np.array_equal(tb.cb_noi[:25], res["cb_noi"][:25]) and np.array_equal(tb.cb_crc[:25], st["cb_crc"][:25])
+        assert np.array_equal(tb.buffer_f[:25], st["buffer_f"][:25])
+        if res["ret"] == 0:
+            assert np.array_equal(tb.data[:tbs // 8], res["data"][:tbs // 8])
+    assert res["ret"] == 0
+    data = np.random.default_rng(0).integers(0, 256, tbs // 8, dtype=np.uint8)
+    r0, e0 = o.encode_tb(tbs, Qm, 1, G, data)
+    r1, e1 = eng.encode_tb(tbs, Qm, 1, G, data)
+    assert r0 == r1 == 0 and np.array_equal(e0, e1)
+
+
+def test_every_block_size_one_submission(sb, eng, o):
+    """all 188 LTE sizes, three blocks each (two clean, one hopeless), one mixed submission: bits, counts, verdicts"""
+    Ks, llrs = [], []
+    for idx in range(188):
+        K = o.cbsize(idx)
+        for j in range(3):
+            _, l = vecgen.make_cb(K, 2.5 if j < 2 else -6.0, 9000 + 3 * idx + j)
+            Ks.append(K)
+            llrs.append(l)
+    out, noi, ok = eng.tdec_batch(np.array(Ks, np.uint32), llrs, 6, early_stop=True)
+    for i, K in enumerate(Ks):
+        _, oo, on, ook = o.tdec_batch(K, llrs[i][None, :], 6, True)
+        assert on[0] == noi[i] and ook[0] == ok[i] and np.array_equal(oo[0], out[i]), (K, i % 3)

@@ -150,24 +150,24 @@ eng.softbuffer_set_resident(False)
 
 # several PHY worker threads, one engine each (the reference runs 3-4 workers): subframes of different workers overlap on the GPU
 import threading
-nthr = 4
-engs = [sb.Engine(0) for _ in range(nthr)]
-runners = [subframe_runner(engs[i], True)[1] for i in range(nthr)]
-for r in runners:
-    r()
 def worker(fn, n):
     for _ in range(n):
         fn()
-nsub = 6
-t0 = time.perf_counter()
-ths = [threading.Thread(target=worker, args=(runners[i], nsub)) for i in range(nthr)]
-[t.start() for t in ths]; [t.join() for t in ths]
-dt = time.perf_counter() - t0
-res["config5_4_worker_threads_device_resident"] = {"subframes": nthr * nsub, "ms_per_subframe_aggregate": dt / (nthr * nsub) * 1e3,
-                                                   "info_Mbit_s": nthr * nsub * cells * tbs / dt / 1e6,
-                                                   "note": "1/2/4/8-GPU scaling shards cells per GPU with no collective (one engine per worker thread per GPU)"}
-for e_ in engs:
-    e_.close()
+for nthr in (4, 8):
+    engs = [sb.Engine(0) for _ in range(nthr)]
+    runners = [subframe_runner(engs[i], True)[1] for i in range(nthr)]
+    for r in runners:
+        r()
+    nsub = 6
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=worker, args=(runners[i], nsub)) for i in range(nthr)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    dt = time.perf_counter() - t0
+    res["config5_%d_worker_threads_device_resident" % nthr] = {"subframes": nthr * nsub, "ms_per_subframe_aggregate": dt / (nthr * nsub) * 1e3,
+                                                       "info_Mbit_s": nthr * nsub * cells * tbs / dt / 1e6,
+                                                       "note": "1/2/4/8-GPU scaling shards cells per GPU with no collective (one engine per worker thread per GPU)"}
+    for e_ in engs:
+        e_.close()
 eng.close()
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 for d_ in ("profiles", "gpurun_out"):

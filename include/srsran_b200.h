@@ -21,6 +21,7 @@
 #ifndef SRSRAN_B200_H
 #define SRSRAN_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -107,6 +108,13 @@ int  srsb200_tdec_run_plan_dev(srsb200_engine_t* e, srsb200_plan_t* plan, const 
  * the bandwidth-bound first ones of the next). Results are complete after srsb200_engine_sync(); to order other work on
  * srsb200_engine_stream() after them without blocking the host call srsb200_engine_flush() first. Submissions of two
  * plans in flight at once must not share output buffers. */
+/* Page-locked host memory for callers that do not link the CUDA runtime themselves: buffers obtained here (or registered
+ * with srsb200_host_register) go straight to the copy engines; pageable ones are staged through an engine-owned pinned
+ * arena with one extra host memcpy. */
+void* srsb200_host_alloc(size_t bytes);
+void  srsb200_host_free(void* p);
+int   srsb200_host_register(void* p, size_t bytes);   /* cudaHostRegister on an existing allocation */
+int   srsb200_host_unregister(void* p);
 int  srsb200_engine_flush(srsb200_engine_t* e);
 int  srsb200_engine_sync(srsb200_engine_t* e);
 

@@ -274,12 +274,14 @@ struct Stager {
   srsb200_engine* e;
   size_t used[2] = {0, 0};
   struct Out { void* dst; const void* src; size_t bytes; };
-  std::vector<Out> outs;
+  std::vector<Out>     outs;
+  std::vector<CopyJob> q;  // transfers queued since the last flush (device-visible addresses on both sides)
   explicit Stager(srsb200_engine* e_) : e(e_) {}
-  // both arenas must be sized before the first copy (they cannot move while copies are in flight)
-  int reserve(size_t in_bytes, size_t out_bytes)
+  // both arenas must be sized before the first copy (they cannot move while copies are in flight); max_jobs = upper bound
+  // of the transfers this call will queue (their job lists live in the host->device arena)
+  int reserve(size_t in_bytes, size_t out_bytes, size_t max_jobs = 64)
   {
-    const size_t want[2] = {in_bytes, out_bytes};
+    const size_t want[2] = {in_bytes + (max_jobs + 64) * sizeof(CopyJob) + 4096, out_bytes};
     for (int i = 0; i < 2; i++) {
       if (e->h_stage_cap[i] >= want[i]) continue;
       if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
@@ -291,43 +293,90 @@ struct Stager {
     }
     return 0;
   }
-  static bool pinned(const void* p)
+  // page-locked (cudaHostAlloc / cudaHostRegister) memory -> the address the GPU uses for it, else nullptr
+  static void* device_view(const void* p)
   {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
       cudaGetLastError();
-      return false;
+      return nullptr;
     }
-    return a.type == cudaMemoryTypeHost;
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+  }
+  void* arena_take(int which, size_t bytes)
+  {
+    const size_t off = (used[which] + 63) & ~(size_t)63;
+    if (off + bytes > e->h_stage_cap[which]) return nullptr;
+    used[which] = off + bytes;
+    return (uint8_t*)e->h_stage[which] + off;
   }
   cudaError_t h2d(void* dst, const void* src, size_t bytes, cudaStream_t st)
   {
     if (bytes == 0) return cudaSuccess;
-    if (!pinned(src)) {
-      const size_t off = (used[0] + 63) & ~(size_t)63;
-      if (off + bytes <= e->h_stage_cap[0]) {
-        void* s = (uint8_t*)e->h_stage[0] + off;
-        memcpy(s, src, bytes);
-        used[0] = off + bytes;
-        src     = s;
-      }
+    const void* dv = device_view(src);
+    if (!dv) {
+      void* s = arena_take(0, bytes);
+      if (!s) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);  // arena exhausted: the slow way
+      memcpy(s, src, bytes);
+      dv = s;  // cudaHostAlloc memory: same address on the device (unified virtual addressing)
     }
-    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    q.push_back({dv, dst, bytes});
+    return cudaSuccess;
   }
   cudaError_t d2h(void* dst, const void* src, size_t bytes, cudaStream_t st)
   {
     if (bytes == 0) return cudaSuccess;
-    if (!pinned(dst)) {
-      const size_t off = (used[1] + 63) & ~(size_t)63;
-      if (off + bytes <= e->h_stage_cap[1]) {
-        void* s = (uint8_t*)e->h_stage[1] + off;
-        used[1] = off + bytes;
-        outs.push_back({dst, s, bytes});
-        dst = s;
+    void* dv = device_view(dst);
+    if (!dv) {
+      void* s = arena_take(1, bytes);
+      if (!s) {
+        cudaError_t ce = flush(st);
+        return ce != cudaSuccess ? ce : cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+      }
+      outs.push_back({dst, s, bytes});
+      dv = s;
+    }
+    q.push_back({src, dv, bytes});
+    return cudaSuccess;
+  }
+  // issue everything queued so far, in stream order: call before a kernel that consumes uploaded data / before the final
+  // synchronise. Neighbouring transfers that are contiguous on both sides are merged (buffers staged through the arena
+  // always are); what is then still large goes to the copy engines (a kernel pulling megabytes across PCIe would hold
+  // SM slots for the whole transfer), the many small ones - job lists, decoded bytes, flags - become ONE
+  // gather_copy_kernel launch instead of one driver call each.
+  cudaError_t flush(cudaStream_t st)
+  {
+    if (q.empty()) return cudaSuccess;
+    std::vector<CopyJob> m;
+    for (auto& j : q) {
+      if (!m.empty() && (const uint8_t*)m.back().src + m.back().bytes == (const uint8_t*)j.src && (uint8_t*)m.back().dst + m.back().bytes == (uint8_t*)j.dst)
+        m.back().bytes += j.bytes;
+      else
+        m.push_back(j);
+    }
+    q.clear();
+    cudaError_t ce = cudaSuccess;
+    size_t      nsmall = 0;
+    for (auto& j : m) nsmall += j.bytes < BIG;
+    CopyJob* list = nsmall > 2 ? (CopyJob*)arena_take(0, nsmall * sizeof(CopyJob)) : nullptr;
+    size_t   k    = 0;
+    uint64_t maxb = 0;
+    for (auto& j : m) {
+      if (j.bytes >= BIG || !list) {
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDefault, st);
+      } else {
+        list[k++] = j;
+        maxb      = std::max<uint64_t>(maxb, j.bytes);
       }
     }
-    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+    if (k && ce == cudaSuccess) {
+      gather_copy_kernel<<<dim3((unsigned)((maxb + 16383) / 16384), (unsigned)k), 256, 0, st>>>(list);
+      e->launches++;
+      ce = cudaGetLastError();
+    }
+    return ce;
   }
+  static constexpr uint64_t BIG = 32768;
   // after the stream has been synchronised
   void finish()
   {
@@ -635,6 +684,37 @@ extern "C" int srsb200_engine_set_subbatches(srsb200_engine_t* e, int n)
 
 extern "C" uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e) { return e ? e->launches : 0; }
 extern "C" void*    srsb200_engine_stream(const srsb200_engine_t* e) { return e ? (void*)e->stream : nullptr; }
+extern "C" void* srsb200_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void srsb200_host_free(void* p)
+{
+  if (p) cudaFreeHost(p);
+}
+extern "C" int srsb200_host_register(void* p, size_t bytes)
+{
+  if (!p || !bytes) return SRSB200_ERROR_INVALID_INPUTS;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return SRSB200_ERROR;
+  }
+  return SRSB200_SUCCESS;
+}
+extern "C" int srsb200_host_unregister(void* p)
+{
+  if (!p) return SRSB200_ERROR_INVALID_INPUTS;
+  if (cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return SRSB200_ERROR;
+  }
+  return SRSB200_SUCCESS;
+}
 extern "C" int      srsb200_engine_flush(srsb200_engine_t* e)
 {
   if (!e) return SRSB200_ERROR_INVALID_INPUTS;
@@ -1243,6 +1323,7 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
   CUDA_TRY(stg.h2d(d_q, q_bits, ng * sizeof(int16_t), e->stream));
   CUDA_TRY(stg.h2d(d_dj, &j, sizeof(DeintJob), e->stream));
   if (!sc.empty()) CUDA_TRY(stg.h2d((uint8_t*)d_dj + dj_bytes, sc.data(), sc.size() * 4, e->stream));
+  CUDA_TRY(stg.flush(e->stream));
   CUDA_TRY(cudaMemsetAsync(d_g, 0, ng * sizeof(int16_t), e->stream));  // the nof_ri_bits values past the data are left stale by the reference
   {
     ProfScope ps(e, 3);
@@ -1250,6 +1331,7 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
     e->launches++;
   }
   CUDA_TRY(stg.d2h(g_bits, d_g, ng * sizeof(int16_t), e->stream));
+  CUDA_TRY(stg.flush(e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   stg.finish();
   return SRSB200_SUCCESS;

@@ -99,4 +99,35 @@ __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __rest
   }
 }
 
+/*
+ * Many small host<->device transfers as ONE launch: the job list and the host buffers are page-locked memory that the
+ * GPU addresses directly (unified virtual addressing), so block (x, j) simply copies its share of job j. A transport-block
+ * submission moves one buffer per TB (e-bits in, bytes out) and, without device-resident soft buffers, two per code
+ * block; as cudaMemcpyAsync calls those serialise on the driver (~4 us each, process-wide lock) and bound the
+ * multi-threaded uplink case, as one kernel they cost one launch.
+ */
+struct CopyJob {
+  const void* src;
+  void*       dst;
+  uint64_t    bytes;
+};
+__global__ void __launch_bounds__(256) gather_copy_kernel(const CopyJob* __restrict__ jobs)
+{
+  const CopyJob  j   = jobs[blockIdx.y];
+  const uint64_t tid = (uint64_t)blockIdx.x * 256 + threadIdx.x, nth = (uint64_t)gridDim.x * 256;
+  const uint8_t* s   = static_cast<const uint8_t*>(j.src);
+  uint8_t*       d   = static_cast<uint8_t*>(j.dst);
+  if ((((uintptr_t)s | (uintptr_t)d) & 15u) == 0) {
+    const uint64_t n16 = j.bytes / 16;
+    for (uint64_t i = tid; i < n16; i += nth) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+    for (uint64_t i = n16 * 16 + tid; i < j.bytes; i += nth) d[i] = s[i];
+  } else if ((((uintptr_t)s | (uintptr_t)d) & 3u) == 0) {
+    const uint64_t n4 = j.bytes / 4;
+    for (uint64_t i = tid; i < n4; i += nth) reinterpret_cast<uint32_t*>(d)[i] = reinterpret_cast<const uint32_t*>(s)[i];
+    for (uint64_t i = n4 * 4 + tid; i < j.bytes; i += nth) d[i] = s[i];
+  } else {
+    for (uint64_t i = tid; i < j.bytes; i += nth) d[i] = s[i];
+  }
+}
+
 }  // namespace srsb200

@@ -750,6 +750,19 @@ struct srsb200_plan {
   uint32_t* d_arrivals = nullptr; // [n_groups] job blocks of the group that have finished the current half-iteration
   bool      uniform = false;
   int       lane = 0;            // which pair of sub-stream sets runs its device-resident submissions
+  // the launch chain of a small (single-range) decode as an instantiated CUDA graph, valid for exactly these arguments
+  cudaGraphExec_t graph = nullptr;
+  struct GraphKey {
+    const void *llr, *out, *noi, *ok;
+    uint32_t max_iter, min_iter, start_iter;
+    int early_stop, do_extract;
+    bool operator==(const GraphKey& o) const
+    {
+      return llr == o.llr && out == o.out && noi == o.noi && ok == o.ok && max_iter == o.max_iter && min_iter == o.min_iter &&
+             start_iter == o.start_iter && early_stop == o.early_stop && do_extract == o.do_extract;
+    }
+  } graph_key{};
+  uint32_t graph_launches = 0;
   bool      contiguous = false;  // one (K, crc) bucket and code block i at llr offset i*(3K+12), output offset i*K/8
 };
 
@@ -844,6 +857,7 @@ extern "C" void srsb200_plan_destroy(srsb200_plan_t* p)
 {
   if (!p) return;
   if (p->e) cudaSetDevice(p->e->device);
+  if (p->graph) cudaGraphExecDestroy(p->graph);
   cudaFree(p->d_groups);
   cudaFree(p->d_ws);
   cudaFree(p->d_llr_off);
@@ -965,6 +979,41 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     wacc += wgt[s];
     rg[s].g1 = (uint32_t)((uint64_t)p->n_groups * wacc / wsum);
     rg[s].st = (S == 1 && !lazy) ? e->stream : e->sub[sbase + s];
+  }
+  // Small decodes (one range on the engine stream: a transport block, a single code block) are launch-bound: extract +
+  // 2 x max_iter + emit kernels of tens of microseconds each, and in a multi-threaded PHY every launch takes the
+  // process-wide driver lock. Their chain is captured once per (plan, arguments) into a CUDA graph and replayed.
+  static const bool use_graphs = getenv("SRSB200_NO_GRAPHS") == nullptr;
+  if (use_graphs && S == 1 && !lazy && !io && !e->profiling && start_iter == 0 && do_extract) {
+    const srsb200_plan::GraphKey key{d_llr, d_out, d_noi, d_ok, max_iter, min_iter, start_iter, early_stop, do_extract ? 1 : 0};
+    if (!p->graph || !(p->graph_key == key)) {
+      if (p->graph) cudaGraphExecDestroy(p->graph);
+      p->graph = nullptr;
+      cudaGraph_t g = nullptr;
+      const uint64_t l0 = e->launches;
+      if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        if (do_extract) launch_one(e, p, rg[0], 0, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+        for (uint32_t n = start_iter; n < max_iter; n++) {
+          launch_one(e, p, rg[0], 1, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+          launch_one(e, p, rg[0], 2, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+        }
+        launch_one(e, p, rg[0], 4, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+        if (cudaStreamEndCapture(e->stream, &g) == cudaSuccess && g && cudaGraphInstantiate(&p->graph, g, 0) == cudaSuccess) {
+          p->graph_key      = key;
+          p->graph_launches = (uint32_t)(e->launches - l0);
+        } else {
+          p->graph = nullptr;
+        }
+        if (g) cudaGraphDestroy(g);
+      }
+      e->launches = l0;
+      cudaGetLastError();
+    }
+    if (p->graph) {
+      CUDA_TRY(cudaGraphLaunch(p->graph, e->stream));
+      e->launches += p->graph_launches;
+      return SRSB200_SUCCESS;
+    }
   }
   const auto t_host0 = std::chrono::steady_clock::now();
   static const bool trace_env = getenv("SRSB200_TRACE") != nullptr;

@@ -38,6 +38,11 @@ def lib():
         L.srsb200_engine_stream.restype = vp
         L.srsb200_engine_sync.argtypes = [vp]
         L.srsb200_engine_flush.argtypes = [vp]
+        L.srsb200_host_alloc.argtypes = [C.c_size_t]
+        L.srsb200_host_alloc.restype = vp
+        L.srsb200_host_free.argtypes = [vp]
+        L.srsb200_host_register.argtypes = [vp, C.c_size_t]
+        L.srsb200_host_unregister.argtypes = [vp]
         L.srsb200_engine_profile.argtypes = [vp, i32]
         L.srsb200_engine_set_subbatches.argtypes = [vp, i32]
         L.srsb200_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]

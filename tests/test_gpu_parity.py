@@ -502,3 +502,42 @@ def test_every_block_size_one_submission(sb, eng, o):
     for i, K in enumerate(Ks):
         _, oo, on, ook = o.tdec_batch(K, llrs[i][None, :], 6, True)
         assert on[0] == noi[i] and ook[0] == ok[i] and np.array_equal(oo[0], out[i]), (K, i % 3)
+
+
+def test_page_locked_caller_buffers(sb, eng, o):
+    """e-bits and decoded bytes in page-locked memory from srsb200_host_alloc (contiguous, so the uploads merge into one DMA
+    and the small read-backs ride the gather-copy kernel) give the same results as pageable numpy buffers"""
+    import ctypes as C
+    L = sb.lib()
+    L.srsb200_host_alloc.restype = C.c_void_p
+    L.srsb200_host_alloc.argtypes = [C.c_size_t]
+    L.srsb200_host_free.argtypes = [C.c_void_p]
+    cases = [(12216, 19200, 6), (6200, 9000, 4), (75376, 86400, 6), (2984, 4000, 2)]
+    tot = sum(c[1] for c in cases)
+    p_e = L.srsb200_host_alloc(tot * 2)
+    p_d = L.srsb200_host_alloc(len(cases) * (13 * 768 + 8))
+    assert p_e and p_d
+    try:
+        e_all = np.ctypeslib.as_array((C.c_int16 * tot).from_address(p_e))
+        d_all = np.ctypeslib.as_array((C.c_uint8 * (len(cases) * (13 * 768 + 8))).from_address(p_d))
+        reqs, exp, off = [], [], 0
+        for n, (tbs, Gb, Qm) in enumerate(cases):
+            _, e = vecgen.make_tb(tbs, Gb, Qm, 0, 3.0, 600 + n)
+            e_all[off:off + Gb] = e
+            tb = sb.TransportBlock(tbs)
+            tb.data = d_all[n * (13 * 768 + 8):(n + 1) * (13 * 768 + 8)]
+            tb.data[:] = 0
+            reqs.append((tb, Qm, 0, e_all[off:off + Gb]))
+            exp.append(o.decode_tb(tbs, Qm, 0, e, 8))
+            off += Gb
+        assert eng.decode_tb_batch(reqs, 8) == 0
+        for (tb, _, _, _), r, (tbs, _, _) in zip(reqs, exp, cases):
+            Cn = r["seg"]["C"]
+            assert tb.ret == r["ret"] and np.array_equal(tb.cb_noi[:Cn], r["cb_noi"][:Cn])
+            assert np.array_equal(tb.buffer_f[:Cn], r["state"]["buffer_f"][:Cn])
+            if r["ret"] == 0:
+                assert np.array_equal(tb.data[:tbs // 8], r["data"][:tbs // 8])
+    finally:
+        L.srsb200_host_free(p_e)
+        L.srsb200_host_free(p_d)
+    assert L.srsb200_host_register(None, 16) == -2

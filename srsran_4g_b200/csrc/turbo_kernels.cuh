@@ -755,7 +755,7 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
  * written, plus the termination rows of xa1 (xa1 / app2 / systp rows < K are produced by the decoder before they are read).
  * llr_off[cb] = element offset of the code block's 3K+12 int16 in llr.
  */
-constexpr int XT = 32;  // rows per tile
+constexpr int XT = 64;  // rows per tile
 __global__ void __launch_bounds__(256)
 extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const int16_t* __restrict__ llr, const uint64_t* __restrict__ llr_off,
                uint8_t* __restrict__ active, uint8_t* __restrict__ done, uint32_t* __restrict__ crc_acc)

@@ -34,7 +34,7 @@ namespace srsb200 {
 
 constexpr int W        = 64;  // rows per staged chunk of the scan kernels; streams are padded to a multiple of W rows
 constexpr int WC       = 16;  // checkpoint spacing = window of one job = one hard-bit word
-constexpr int WPJ      = 8;   // windows per job warp
+constexpr int WPJ      = 16;  // windows per job warp (swept 8 / 12 / 16 / 32 on the bench workload: 41.6 / 42.0 / 42.6 / 42.0 Gbit/s)
 constexpr int CKB      = 8;   // spacing of the beta checkpoints (one per 8-step register window of the job kernel)
 constexpr int LANES    = 32;
 constexpr int NEG_INF2 = 0xD8F0D8F0;  // two int16 of -10000 (turbodecoder_gen.c:37)

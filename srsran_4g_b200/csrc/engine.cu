@@ -180,7 +180,8 @@ struct srsb200_engine {
   uint32_t  tb_crc_words_n = 0;
 
   // rate-matching tables [cb_idx][rv] (device, uint16[3K+12]) built lazily
-  uint16_t* d_rm[LTE_NOF_CB_SIZES][4];
+  uint16_t* d_rm[LTE_NOF_CB_SIZES][4];      // T    (transmit side: e[n] = coded[T[n mod L]])
+  uint16_t* d_rm_inv[LTE_NOF_CB_SIZES][4];  // Tinv (receive side: soft-buffer position p collects e[Tinv[p] + kL])
 
   // scratch for the host-pointer APIs (grown on demand)
   void*  d_scratch[16]   = {nullptr};  // 0-7 receive side, 8-11 transmit side, 12-13 UL-SCH de-interleaver
@@ -459,12 +460,18 @@ static int ensure_rm_table(srsb200_engine* e, uint32_t cb_idx, uint32_t rv)
   if (e->d_rm[cb_idx][rv]) return 0;
   std::vector<uint16_t> T;
   rm_table_host(cb_idx, rv, T);
+  std::vector<uint16_t> both(2 * T.size());
+  for (size_t n = 0; n < T.size(); n++) {
+    both[n]                   = T[n];
+    both[T.size() + T[n]]     = (uint16_t)n;  // inverse permutation
+  }
   uint16_t* d;
-  CUDA_TRY(cudaMalloc(&d, T.size() * sizeof(uint16_t)));
+  CUDA_TRY(cudaMalloc(&d, both.size() * sizeof(uint16_t)));
   e->owned.push_back(d);
-  CUDA_TRY(cudaMemcpyAsync(d, T.data(), T.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(d, both.data(), both.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
-  e->d_rm[cb_idx][rv] = d;
+  e->d_rm[cb_idx][rv]     = d;
+  e->d_rm_inv[cb_idx][rv] = d + T.size();  // L = 3K+12 is even: the inverse table starts 4-byte aligned
   return 0;
 }
 
@@ -597,6 +604,7 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   e->device         = device;
   memset(e->have_k, 0, sizeof(e->have_k));
   memset(e->d_rm, 0, sizeof(e->d_rm));
+  memset(e->d_rm_inv, 0, sizeof(e->d_rm_inv));
   memset(e->h_ktab, 0, sizeof(e->h_ktab));
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   if (const char* env = getenv("SRSB200_SUBBATCHES")) e->n_sub = std::max(1, std::min((int)srsb200_engine::MAX_SUB, atoi(env)));
@@ -1306,11 +1314,11 @@ extern "C" int srsb200_rm_turbo_rx_lut(srsb200_engine_t* e, const int16_t* input
   CUDA_TRY(cudaMemcpyAsync(d_e, input, (size_t)in_len * 2, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaMemcpyAsync(d_buf, output, (size_t)L * 2, cudaMemcpyHostToDevice, e->stream));
   RmJob job;
-  job.e = (const int16_t*)d_e; job.buf = (int16_t*)d_buf; job.table = e->d_rm[cb_idx][rv_idx]; job.E = in_len; job.L = L;
+  job.e = (const int16_t*)d_e; job.buf = (int16_t*)d_buf; job.table = e->d_rm_inv[cb_idx][rv_idx]; job.E = in_len; job.L = L;
   void* d_job;
   if (ensure_scratch(e, 6, sizeof(RmJob), &d_job)) return SRSB200_ERROR;
   CUDA_TRY(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, e->stream));
-  rm_rx_kernel<<<dim3((L + 255) / 256, 1), 256, 0, e->stream>>>((const RmJob*)d_job);
+  rm_rx_kernel<<<1, RM_THREADS, std::min(in_len, RM_SMEM_ELEMS) * sizeof(int16_t), e->stream>>>((const RmJob*)d_job);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(output, d_buf, (size_t)L * 2, cudaMemcpyDeviceToHost, e->stream));

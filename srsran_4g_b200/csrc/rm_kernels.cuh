@@ -1,12 +1,16 @@
 /*
- * rm_kernels.cuh - rate de-matching + HARQ soft combining (srsran_rm_turbo_rx_lut, lib/src/phy/fec/turbo/rm_turbo.c:390-445)
- * and transport-block CRC24A (decode_tb, lib/src/phy/phch/sch.c:563) as sm_100a kernels.
+ * rm_kernels.cuh - rate de-matching + HARQ soft combining (srsran_rm_turbo_rx_lut, lib/src/phy/fec/turbo/rm_turbo.c:390-445),
+ * transport-block CRC24A (decode_tb, lib/src/phy/phch/sch.c:563), the UL-SCH channel de-interleaver and the gather copy as
+ * sm_100a kernels.
  *
  * The reference computes  output[T[i mod L]] += input[i]  for i < E  (L = 3K+12, int16 wrap). T is a permutation of
- * 0..L-1, so thread n < L owns every received LLR that lands on soft-buffer position T[n]:
- *     sum_n = e[n] + e[n+L] + e[n+2L] + ...   (repetition when E > L),   buf[T[n]] += sum_n
- * Loads of e are coalesced, the read-modify-write of the soft buffer is conflict-free without atomics, and the result is
- * the reference's bit for bit because 16-bit wrapping addition is associative.
+ * 0..L-1, so soft-buffer position p receives exactly the received LLRs  e[n], e[n+L], e[n+2L], ...  with n = Tinv[p]
+ * (repetition when E > L). The kernel runs in that GATHER form: a block owns a code block, stages its e-bits in shared
+ * memory (13 KB at the 100-PRB 64QAM operating point) and walks the soft buffer in order - the read-modify-write of the
+ * 35 KB soft buffer is coalesced, the permuted reads hit shared memory. (The first version scattered: thread n did
+ * buf[T[n]] += e[n]; the sub-block interleaver puts consecutive n 192 bytes apart, so every 2-byte read-modify-write
+ * cost two 32-byte sectors - 338 GB/s, 5 % of the HBM peak, measured on 6656 code blocks.) Bit-identical to the
+ * reference because 16-bit wrapping addition is associative and commutative.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -16,22 +20,35 @@ namespace srsb200 {
 
 struct RmJob {
   const int16_t*  e;      // first received LLR of this code block (device)
-  int16_t*        buf;    // soft buffer of this code block, natural layout (device)
-  const uint16_t* table;  // T[0..L)
+  int16_t*        buf;    // soft buffer of this code block, natural layout (device, 4-byte aligned)
+  const uint16_t* table;  // Tinv[0..L): position in the transmitted (circular-buffer) order of soft-buffer element p
   uint32_t        E;
   uint32_t        L;
 };
 
-// grid = (ceil(maxL/256), n_jobs), block = 256
-__global__ void __launch_bounds__(256) rm_rx_kernel(const RmJob* __restrict__ jobs)
+constexpr uint32_t RM_SMEM_ELEMS = 24576;  // e-bits staged per block (48 KB); the rest of a longer e is read from global
+constexpr int      RM_THREADS    = 512;
+
+// grid = n_jobs, block = RM_THREADS, dynamic shared memory = min(max E, RM_SMEM_ELEMS) * 2 bytes
+__global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restrict__ jobs)
 {
-  const RmJob    j = jobs[blockIdx.y];
-  const uint32_t n = blockIdx.x * 256 + threadIdx.x;
-  if (n >= j.L || n >= j.E) return;
-  uint32_t sum = 0;
-  for (uint32_t i = n; i < j.E; i += j.L) sum += (uint16_t)j.e[i];
-  const uint32_t t = j.table[n];
-  j.buf[t] = (int16_t)(uint16_t)((uint16_t)j.buf[t] + sum);
+  extern __shared__ __align__(16) int16_t se[];
+  const RmJob    j  = jobs[blockIdx.x];
+  const uint32_t ns = min(j.E, RM_SMEM_ELEMS);
+  for (uint32_t i = threadIdx.x; i < ns; i += RM_THREADS) se[i] = j.e[i];
+  __syncthreads();
+  // two soft-buffer elements per thread (L is even, buf is 4-byte aligned): 128-byte accesses per warp
+  uint32_t* buf2 = reinterpret_cast<uint32_t*>(j.buf);
+  for (uint32_t p2 = threadIdx.x; p2 < j.L / 2; p2 += RM_THREADS) {
+    const uint32_t tt = reinterpret_cast<const uint32_t*>(j.table)[p2];
+    uint32_t       n0 = tt & 0xffffu, n1 = tt >> 16;
+    if (n0 >= j.E && n1 >= j.E) continue;  // nothing received for these two positions
+    uint32_t s0 = 0, s1 = 0;
+    for (uint32_t i = n0; i < j.E; i += j.L) s0 += (uint16_t)(i < ns ? se[i] : j.e[i]);
+    for (uint32_t i = n1; i < j.E; i += j.L) s1 += (uint16_t)(i < ns ? se[i] : j.e[i]);
+    const uint32_t old = buf2[p2];
+    buf2[p2] = ((old + s0) & 0xffffu) | ((((old >> 16) + s1) & 0xffffu) << 16);
+  }
 }
 
 // zero a list of soft-buffer mirrors (srsran_softbuffer_rx_reset forwarded to the device): grid = (ceil(n16/256), n_slots)

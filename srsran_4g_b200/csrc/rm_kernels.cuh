@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(256) crc_bytes_kernel(const CrcJob* __restrict
  * UL-SCH channel de-interleaver (36.212 5.2.2.8; ulsch_deinterleave, lib/src/phy/phch/sch.c:994-1021). The reference
  * builds lut[] with a running counter over the rows x cols x Qm matrix in (row, column, bit) order - position
  * p = row*Qm + col*rows*Qm + bit - skipping the positions that carry RI (lut = 0 there), then scatters g[lut[p]] = q[p]
- * for ascending p. Here thread s owns the s-th matrix element in that order: its rank is s minus the number of RI elements
- * before it (binary search in the job's sorted list), so writes are coalesced and no table is built. g[0] receives
+ * for ascending p. Here a thread owns one (row, column) pair, i.e. Qm consecutive matrix elements in that order: the rank
+ * of an element is its scan index minus the number of RI elements before it (one binary search per pair in the job's
+ * sorted list), so writes are coalesced, reads are Qm-value runs, and no table is built. g[0] receives
  * q[p_star], the last position the sequential loop would have written there (an RI position when there is one).
  */
 struct DeintJob {
@@ -99,20 +100,27 @@ struct DeintJob {
 };
 __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __restrict__ jobs)
 {
-  const DeintJob j = jobs[blockIdx.y];
-  const uint32_t n = j.rows * j.cols * j.Qm;
-  for (uint32_t s = blockIdx.x * 256 + threadIdx.x; s < n; s += gridDim.x * 256) {
-    // number of RI scan indices < s, and whether s itself is one
+  const DeintJob j  = jobs[blockIdx.y];
+  const uint32_t np = j.rows * j.cols;  // (row, column) pairs = modulation symbols; a thread moves the Qm values of one
+  for (uint32_t sp = blockIdx.x * 256 + threadIdx.x; sp < np; sp += gridDim.x * 256) {
+    const uint32_t row = sp / j.cols, col = sp - row * j.cols;
+    const uint32_t s0  = sp * j.Qm;                                   // scan index of its first value
+    const int16_t* src = j.q + (size_t)row * j.Qm + (size_t)col * j.rows * j.Qm;
+    // number of RI scan indices < s0 (binary search), then walk the list together with the Qm values
     uint32_t lo = 0, hi = j.nri;
     while (lo < hi) {
       const uint32_t mid = (lo + hi) >> 1;
-      if (j.ri_scan[mid] < s) lo = mid + 1; else hi = mid;
+      if (j.ri_scan[mid] < s0) lo = mid + 1; else hi = mid;
     }
-    if (lo < j.nri && j.ri_scan[lo] == s) continue;
-    const uint32_t rank = s - lo;
-    const uint32_t row = s / (j.cols * j.Qm), rem = s - row * j.cols * j.Qm, col = rem / j.Qm, bit = rem - col * j.Qm;
-    const uint32_t p = row * j.Qm + col * j.rows * j.Qm + bit;
-    j.g[rank] = j.q[rank == 0 ? j.p_star : p];
+    for (uint32_t bit = 0; bit < j.Qm; bit++) {
+      const uint32_t s = s0 + bit;
+      if (lo < j.nri && j.ri_scan[lo] == s) {
+        lo++;
+        continue;
+      }
+      const uint32_t rank = s - lo;
+      j.g[rank] = rank == 0 ? j.q[j.p_star] : src[bit];
+    }
   }
 }
 

@@ -623,9 +623,12 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<2>)));
   CUDA_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)emit_smem_bytes(((SRSB200_MAX_K + 3 + W - 1) / W) * W, SRSB200_MAX_K + 64)));
-  CUDA_TRY(cudaFuncSetAttribute(job_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
-  CUDA_TRY(cudaFuncSetAttribute(job_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
-  CUDA_TRY(cudaFuncSetAttribute(job_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
   *out = e;
   return SRSB200_SUCCESS;
 }
@@ -758,6 +761,7 @@ struct srsb200_plan {
   uint32_t* d_arrivals = nullptr; // [n_groups] job blocks of the group that have finished the current half-iteration
   bool      uniform = false;
   int       lane = 0;            // which pair of sub-stream sets runs its device-resident submissions
+  uint32_t  wpj = WPJ;           // windows per job warp: 16 for machine-filling batches (throughput), 8 otherwise (latency)
   // the launch chain of a small (single-range) decode as an instantiated CUDA graph, valid for exactly these arguments
   cudaGraphExec_t graph = nullptr;
   struct GraphKey {
@@ -804,7 +808,7 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
     const std::vector<int32_t>& ids = kv.second;
     for (size_t s = 0; s < ids.size(); s += 64) {
       Group g;
-      g.K = k; g.R = R; g.kidx = (uint32_t)kidx; g.crc_kind = kind; g.ws_off = off;
+      g.K = k; g.R = R; g.kidx = (uint32_t)kidx; g.crc_kind = kind; g.ws_off = off; g.wpj = WPJ; g.pad_ = 0;
       size_t cnt = std::min<size_t>(64, ids.size() - s);
       // fill low halves first so that a half-empty group still uses all lanes
       for (int j = 0; j < 64; j++) g.cb[j] = -1;
@@ -821,6 +825,10 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
     }
   }
   p->n_groups = (uint32_t)p->h_groups.size();
+  // 128+ groups fill the machine with job warps even at 16 windows per warp; below that shorter runs cut the latency of the
+  // job kernel (a warp walks its run sequentially: 256 steps x ~144 cycles at 16 windows)
+  p->wpj = p->n_groups >= 128 ? 16u : (uint32_t)WPJ;
+  for (auto& g : p->h_groups) g.wpj = p->wpj;
   p->ws_bytes = off;
   p->contiguous = buckets.size() == 1;
   for (uint32_t i = 0; i < n && p->contiguous; i++) {
@@ -915,7 +923,7 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
   cudaStream_t   st = r.st;
   const int      mode = (n == 0) ? 0 : ((n & 1u) ? 2 : 1);
   const uint32_t nwin_max = (p->max_R + WC - 1) / WC;
-  const dim3     sgrid((ng + 1) / 2), jgrid((nwin_max + 4 * WPJ - 1) / (4 * WPJ), ng);
+  const dim3     sgrid((ng + 1) / 2), jgrid((nwin_max + 4 * p->wpj - 1) / (4 * p->wpj), ng);
   const size_t   jsm = 4 * sizeof(JobWarpSmem);
   switch (kind) {
     case 0: {
@@ -930,12 +938,15 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
     } break;
     case 2: {
       ProfScope ps(e, 6, st);
-      if (mode == 0) job_kernel<0><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, max_iter,
-                                                      min_iter, early_stop);
-      else if (mode == 1) job_kernel<1><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, max_iter,
-                                                      min_iter, early_stop);
-      else job_kernel<2><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, max_iter,
-                                                      min_iter, early_stop);
+#define SRSB200_JOB(M, WP)                                                                                                                    \
+  job_kernel<M, WP><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, \
+                                             max_iter, min_iter, early_stop)
+      if (p->wpj == 16) {
+        if (mode == 0) SRSB200_JOB(0, 16); else if (mode == 1) SRSB200_JOB(1, 16); else SRSB200_JOB(2, 16);
+      } else {
+        if (mode == 0) SRSB200_JOB(0, 8); else if (mode == 1) SRSB200_JOB(1, 8); else SRSB200_JOB(2, 8);
+      }
+#undef SRSB200_JOB
     } break;
     default: {
       ProfScope ps(e, 2, st);

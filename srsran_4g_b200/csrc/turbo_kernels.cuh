@@ -34,7 +34,9 @@ namespace srsb200 {
 
 constexpr int W        = 64;  // rows per staged chunk of the scan kernels; streams are padded to a multiple of W rows
 constexpr int WC       = 16;  // checkpoint spacing = window of one job = one hard-bit word
-constexpr int WPJ      = 16;  // windows per job warp (swept 8 / 12 / 16 / 32 on the bench workload: 41.6 / 42.0 / 42.6 / 42.0 Gbit/s)
+constexpr int WPJ      = 8;   // smallest number of windows per job warp (sizes the alpha checkpoint array). The number in use
+                              // is per plan (Group::wpj): 16 for big batches (swept 8 / 12 / 16 / 32 on the bench workload: 41.6 /
+                              // 42.0 / 42.6 / 42.0 Gbit/s), 8 for small ones, where a job warp's sequential run is latency
 constexpr int CKB      = 8;   // spacing of the beta checkpoints (one per 8-step register window of the job kernel)
 constexpr int LANES    = 32;
 constexpr int NEG_INF2 = 0xD8F0D8F0;  // two int16 of -10000 (turbodecoder_gen.c:37)
@@ -56,6 +58,8 @@ struct Group {
   uint32_t R;          // rows per stream = ceil((K+3)/W)*W
   uint32_t kidx;       // index into the KTable array
   uint32_t crc_kind;   // 0 none, 1 CRC24A, 2 CRC24B
+  uint32_t wpj;        // windows per job warp = alpha checkpoint spacing / WC (8 or 16)
+  uint32_t pad_;
   uint64_t ws_off;     // byte offset of this group's workspace
   int32_t  cb[64];     // code-block ids: lane l holds cb[l] (low half) and cb[32+l] (high half); -1 = empty
 };
@@ -247,7 +251,7 @@ __device__ __forceinline__ void beta_block(const ScanStageT<MODE>& st, int r0, u
 }
 
 template <int MODE, int N>
-__device__ __forceinline__ void alpha_block(const ScanStageT<MODE>& st, int r0, int k0, uint32_t (&a)[8], uint32_t* ckA, int lane)
+__device__ __forceinline__ void alpha_block(const ScanStageT<MODE>& st, int r0, int k0, uint32_t (&a)[8], uint32_t* ckA, int lane, int run_shift)
 {
   // steps k = k0+1 .. k0+N (rows r0 .. r0+N-1); k0 is a multiple of 8
   uint32_t xs[N], ys[N];
@@ -258,8 +262,8 @@ __device__ __forceinline__ void alpha_block(const ScanStageT<MODE>& st, int r0, 
     ys[j] = y;
   }
   // a job warp only needs the alpha state at its first window: one checkpoint per WPJ windows
-  if ((k0 % (WC * WPJ)) == 0) {
-    uint4* ck = reinterpret_cast<uint4*>(ckA + ((size_t)(k0 / (WC * WPJ)) * LANES + lane) * 8);
+  if ((k0 & ((1 << run_shift) - 1)) == 0) {  // run = WC * wpj steps (a power of two)
+    uint4* ck = reinterpret_cast<uint4*>(ckA + ((size_t)(k0 >> run_shift) * LANES + lane) * 8);
     ck[0]     = make_uint4(a[0], a[1], a[2], a[3]);
     ck[1]     = make_uint4(a[4], a[5], a[6], a[7]);
   }
@@ -452,7 +456,8 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ---------------- forward recursion (alpha part of map_gen_alpha): chunks 0, 1, ...
-    uint32_t a[8];
+    uint32_t  a[8];
+    const int run_shift = 31 - __clz(WC * (int)g.wpj);  // log2 of the alpha checkpoint spacing of this plan
     a[0] = 0u;
 #pragma unroll
     for (int i = 1; i < 8; i++) a[i] = NEG_INF2;
@@ -460,8 +465,8 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
       const ScanStageT<MODE>& st  = acquire(c);
       const int               end = min(K, (c + 1) * W);
       int                     k0  = c * W;
-      for (; k0 + 16 <= end; k0 += 16) alpha_block<MODE, 16>(st, k0 - c * W, k0, a, gp.ckA, lane);
-      if (k0 < end) alpha_block<MODE, 8>(st, k0 - c * W, k0, a, gp.ckA, lane);
+      for (; k0 + 16 <= end; k0 += 16) alpha_block<MODE, 16>(st, k0 - c * W, k0, a, gp.ckA, lane, run_shift);
+      if (k0 < end) alpha_block<MODE, 8>(st, k0 - c * W, k0, a, gp.ckA, lane, run_shift);
       release(c);
     }
   }
@@ -538,7 +543,7 @@ __device__ __forceinline__ uint32_t alpha_llr_step(uint32_t (&a)[8], const uint3
  * Everything a window needs - its input rows, its two beta checkpoints, its step table - arrives in shared memory through
  * one group of bulk asynchronous copies issued one window ahead; the loop itself performs no global loads.
  */
-template <int MODE>
+template <int MODE, int WPJ_T>
 __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws,
                                             uint8_t* __restrict__ group_active, uint8_t* __restrict__ done, uint32_t* __restrict__ crc_acc,
                                             uint32_t* __restrict__ arrivals, uint8_t* __restrict__ noi, uint8_t* __restrict__ ok, uint32_t cnt,
@@ -553,8 +558,9 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   const Group&    g    = groups[blockIdx.y];
   const uint32_t  K    = g.K;
   const int       nwin = (int)((K + WC - 1) / WC);
-  const int       w0   = (int)(blockIdx.x * 4 + wid) * WPJ;
-  const int       w1   = min(w0 + WPJ, nwin);
+  constexpr int   wpj  = WPJ_T;  // == g.wpj (the host picks the instantiation)
+  const int       w0   = (int)(blockIdx.x * 4 + wid) * wpj;
+  const int       w1   = min(w0 + wpj, nwin);
   const GroupPtrs gp   = group_ptrs(ws, g);
   const KTable&   kt   = ktabs[g.kidx];
 
@@ -624,7 +630,7 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   // alpha state entering the first window (the windows of this warp are consecutive, so it simply carries on)
   uint32_t a[8];
   if (w0 < nwin) {
-    const uint4* ca = reinterpret_cast<const uint4*>(gp.ckA + ((size_t)(w0 / WPJ) * LANES + lane) * 8);
+    const uint4* ca = reinterpret_cast<const uint4*>(gp.ckA + ((size_t)(w0 / wpj) * LANES + lane) * 8);
     const uint4  c0 = ca[0], c1 = ca[1];
     a[0] = c0.x; a[1] = c0.y; a[2] = c0.z; a[3] = c0.w;
     a[4] = c1.x; a[5] = c1.y; a[6] = c1.z; a[7] = c1.w;

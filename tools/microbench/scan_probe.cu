@@ -12,7 +12,7 @@ int main()
   size_t wsg = ((group_ws_words(R) * 4 + 255) / 256) * 256;
   uint8_t* ws; cudaMalloc(&ws, wsg * maxg); cudaMemset(ws, 1, wsg * maxg);
   std::vector<Group> hg(maxg);
-  for (int g = 0; g < maxg; g++) { hg[g].K = K; hg[g].R = R; hg[g].kidx = 187; hg[g].crc_kind = 2; hg[g].ws_off = wsg * g; for (int i = 0; i < 64; i++) hg[g].cb[i] = g * 64 + i; }
+  for (int g = 0; g < maxg; g++) { hg[g].K = K; hg[g].R = R; hg[g].kidx = 187; hg[g].crc_kind = 2; hg[g].wpj = WPJ; hg[g].ws_off = wsg * g; for (int i = 0; i < 64; i++) hg[g].cb[i] = g * 64 + i; }
   Group* dg; cudaMalloc(&dg, sizeof(Group) * maxg); cudaMemcpy(dg, hg.data(), sizeof(Group) * maxg, cudaMemcpyHostToDevice);
   uint8_t* act; cudaMalloc(&act, maxg); cudaMemset(act, 1, maxg);
   cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ScanSmemT<2>)));

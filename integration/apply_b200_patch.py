@@ -41,7 +41,7 @@ def main():
     last_inc = [m for m in re.finditer(r'^#include .*$', src, re.M)][-1]
     src = src[:last_inc.end()] + "\n" + PROTOS + src[last_inc.end():]
     src = insert_after_open_brace(src, r'static int decode_tb\(srsran_sch_t\*\s+q,[^)]*\)',
-                                  "#ifdef SRSRAN_B200\n  return srsran_b200_decode_tb(q, softbuffer, cb_segm, Qm, rv, nof_e_bits, e_bits, data);\n#endif\n")
+                                  "#ifdef SRSRAN_B200\n  if (q != NULL && !q->llr_is_8bit) {\n    return srsran_b200_decode_tb(q, softbuffer, cb_segm, Qm, rv, nof_e_bits, e_bits, data);\n  }\n#endif\n")
     src = insert_after_open_brace(src, r'static int encode_tb_off\(srsran_sch_t\*\s+q,[^)]*\)',
                                   "#ifdef SRSRAN_B200\n  return srsran_b200_encode_tb(q, softbuffer, cb_segm, Qm, rv, nof_e_bits, data, e_bits, w_offset);\n#endif\n")
     # srsran_ulsch_decode: right after Q_prime_ri is known
@@ -51,7 +51,7 @@ def main():
     a = src.index("uint32_t Q_prime_ri = (uint32_t)ret;", m.end())
     a = src.index("\n", a) + 1
     hook = '''#ifdef SRSRAN_B200
-  if (!cfg->uci_cfg.cqi.data_enable) { /* no CQI in this grant: de-interleave + decode in one device submission */
+  if (!cfg->uci_cfg.cqi.data_enable && !q->llr_is_8bit) { /* no CQI in this grant: de-interleave + decode in one device submission */
     if (cb_segm.tbs == 0) {
       return ret; /* what the reference returns here: the value left by uci_decode_ri_ack */
     }

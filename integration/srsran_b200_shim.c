@@ -137,6 +137,46 @@ int srsran_tdec_run_all(srsran_tdec_t* h, int16_t* input, uint8_t* output, uint3
   return SRSRAN_SUCCESS;
 }
 
+/*
+ * 8-bit LLR entry points (turbodecoder.h:118-121), so that the shim replaces turbodecoder.c completely at link time. The
+ * reference's 8-bit decoders are saturating SIMD variants with their own numerics (not the parity target); here the LLRs
+ * are widened to int16 and decoded by the exact int16 engine - same API, results of the generic decoder on those values.
+ * (sch.c reaches these only when q->llr_is_8bit; its own per-code-block loop then runs unchanged, see INTEGRATION.md.)
+ */
+static int16_t* widen_llr8(const int8_t* input, uint32_t long_cb)
+{
+  uint32_t n   = 3 * long_cb + 12;
+  int16_t* tmp = malloc(n * sizeof(int16_t));
+  if (tmp) {
+    for (uint32_t i = 0; i < n; i++) {
+      tmp[i] = input[i];
+    }
+  }
+  return tmp;
+}
+void srsran_tdec_iteration_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output)
+{
+  if (h->current_cbidx < 0) {
+    ERROR("Error CB index not set (call srsran_tdec_new_cb() first");
+    return;
+  }
+  int16_t* tmp = widen_llr8(input, h->current_long_cb);
+  if (tmp) {
+    srsran_tdec_iteration(h, tmp, output);
+    free(tmp);
+  }
+}
+int srsran_tdec_run_all_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb)
+{
+  int16_t* tmp = widen_llr8(input, long_cb);
+  if (!tmp) {
+    return SRSRAN_ERROR;
+  }
+  int ret = srsran_tdec_run_all(h, tmp, output, nof_iterations, long_cb);
+  free(tmp);
+  return ret;
+}
+
 /* Names the reference does not have but integrators ask for: thin aliases. */
 int srsran_tdec_get_hard_decision(srsran_tdec_t* h, uint8_t* output, uint32_t long_cb)
 {
@@ -183,7 +223,8 @@ int srsran_b200_decode_tb(srsran_sch_t*           q,
     return SRSRAN_ERROR_INVALID_INPUTS;
   }
   if (q->llr_is_8bit) {
-    ERROR("srsran_b200: 8-bit LLR mode is not offloaded (int16 path only)");
+    /* the sch.c hook only comes here for int16 LLRs (the 8-bit mode keeps the reference's per-code-block loop) */
+    ERROR("srsran_b200: 8-bit LLR mode does not use the batched entry point");
     return SRSRAN_ERROR_INVALID_INPUTS;
   }
   uint8_t      tb_crc = 0;

@@ -771,3 +771,34 @@ int ref_ulsch_decode(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t n
   pthread_mutex_unlock(&g_lock);
   return ret;
 }
+
+/* srsran_dlsch_decode2 in 8-bit LLR mode (q->llr_is_8bit: rate de-matching and turbo decoding on int8 values) */
+int ref_dlsch_decode8(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, int8_t* e_bits, uint32_t max_iterations, uint8_t* data,
+                      uint8_t* cb_crc, uint8_t* tb_crc)
+{
+  ref_init();
+  pthread_mutex_lock(&g_lock);
+  int ret = -1;
+  if (sch_ready() == 0) {
+    srsran_softbuffer_rx_t* sb = (srsran_softbuffer_rx_t*)h;
+    srsran_pdsch_cfg_t      cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.grant.nof_tb         = 1;
+    cfg.grant.tb[0].tbs      = (int)tbs;
+    cfg.grant.tb[0].mod      = mod_of(Qm);
+    cfg.grant.tb[0].rv       = (int)rv;
+    cfg.grant.tb[0].nof_bits = nof_e_bits;
+    cfg.grant.tb[0].enabled  = true;
+    cfg.softbuffers.rx[0]    = sb;
+    srsran_sch_set_max_noi(&g_sch, max_iterations);
+    g_sch.llr_is_8bit = true;
+    ret               = srsran_dlsch_decode2(&g_sch, &cfg, (int16_t*)e_bits, data, 0, 1);
+    g_sch.llr_is_8bit = false;
+    for (uint32_t i = 0; i < sb->max_cb; i++) {
+      cb_crc[i] = sb->cb_crc[i] ? 1 : 0;
+    }
+    *tb_crc = sb->tb_crc ? 1 : 0;
+  }
+  pthread_mutex_unlock(&g_lock);
+  return ret;
+}

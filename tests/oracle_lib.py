@@ -77,6 +77,9 @@ class _Lib:
             L.ref_dlsch_decode.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [i16p, C.c_uint32, u8p, u8p, u8p, C.POINTER(C.c_float)]
             L.ref_dlsch_decode.restype = C.c_int
             L.ref_ulsch_deinterleave.argtypes = [i16p, C.c_uint32, C.c_uint32, C.c_uint32, i16p, u32p, C.c_uint32]
+            i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
+            L.ref_dlsch_decode8.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [i8p, C.c_uint32, u8p, u8p, u8p]
+            L.ref_dlsch_decode8.restype = C.c_int
             L.ref_ulsch_encode.argtypes = [C.c_uint32] * 7 + [u8p, u8p]; L.ref_ulsch_encode.restype = C.c_int
             L.ref_ulsch_decode.argtypes = [C.c_void_p] + [C.c_uint32] * 6 + [i16p, C.c_uint32, u8p, u8p, u8p, C.POINTER(C.c_float), u8p]
             L.ref_ulsch_decode.restype = C.c_int
@@ -228,6 +231,15 @@ class _Lib:
         cbc = np.zeros(ncb, np.uint8); tbc = np.zeros(1, np.uint8); avg = C.c_float(0)
         ret = self.lib.ref_dlsch_decode(h, tbs, Qm, rv, len(e_bits), e_bits, max_iterations, data, cbc, tbc, C.byref(avg))
         return dict(ret=ret, data=data, cb_crc=cbc, tb_crc=int(tbc[0]), avg_iterations=avg.value)
+
+    def dlsch_decode8(self, h, tbs, Qm, rv, e_bits8, max_iterations):
+        """srsran_dlsch_decode2 with q->llr_is_8bit set (int8 LLRs) on the persistent soft buffer h"""
+        e = np.ascontiguousarray(e_bits8, np.int8)
+        ncb = self.lib.ref_dlsch_rx_max_cb(h)
+        data = np.zeros(ncb * 768 + 8, np.uint8)
+        cbc = np.zeros(ncb, np.uint8); tbc = np.zeros(1, np.uint8)
+        ret = self.lib.ref_dlsch_decode8(h, tbs, Qm, rv, len(e), e, max_iterations, data, cbc, tbc)
+        return dict(ret=ret, data=data, cb_crc=cbc, tb_crc=int(tbc[0]))
 
     def ulsch_encode(self, tbs, Qm, rv, nof_symb, L_prb, data, ri_len=0, ri_value=0):
         """srsran_ulsch_encode -> (ret, interleaved hard bits q[L_prb*12*nof_symb*Qm])"""

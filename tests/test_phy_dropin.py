@@ -88,3 +88,26 @@ def test_ulsch_decode_on_the_engine(phy, tbs, Qm, nprb, nsymb, ri_len):
             finally:
                 ref.dlsch_rx_free(hc)
             assert c["ret"] == b["ret"] and c["ri"] == b["ri"] and np.array_equal(c["data"][:tbs // 8], b["data"][:tbs // 8])
+
+
+def test_dlsch_decode2_8bit_mode_on_the_engine(phy):
+    """q->llr_is_8bit: the hooks leave sch.c's own per-code-block loop in place; it calls the reference's 8-bit rate
+    de-matcher and the shim's srsran_tdec_iteration_8bit (LLRs widened into the exact int16 engine). The reference's 8-bit
+    SIMD decoder has different numerics, so the comparison is on what a clean channel pins: return code, flags, bytes."""
+    ref = ol.ref()
+    for tbs, Qm, G in [(12216, 4, 4 * 4500), (36696, 6, 6 * 8000), (6120, 2, 2 * 5000)]:
+        payload, e = vecgen.make_tb(tbs, G, Qm, 0, 9.0, 21 + tbs, scale=20)
+        e8 = np.clip(e, -127, 127).astype(np.int8)
+        h = phy.dlsch_rx_new()
+        try:
+            b = phy.dlsch_decode8(h, tbs, Qm, 0, e8, 8)
+        finally:
+            phy.dlsch_rx_free(h)
+        assert b["ret"] == 0 and b["tb_crc"] == 1 and np.array_equal(b["data"][:tbs // 8], payload[:tbs // 8])
+        if ref is not None:
+            hc = ref.dlsch_rx_new()
+            try:
+                c = ref.dlsch_decode8(hc, tbs, Qm, 0, e8, 8)
+            finally:
+                ref.dlsch_rx_free(hc)
+            assert c["ret"] == b["ret"] and c["tb_crc"] == b["tb_crc"] and np.array_equal(c["data"][:tbs // 8], b["data"][:tbs // 8])

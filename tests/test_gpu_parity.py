@@ -541,3 +541,40 @@ def test_page_locked_caller_buffers(sb, eng, o):
         L.srsb200_host_free(p_e)
         L.srsb200_host_free(p_d)
     assert L.srsb200_host_register(None, 16) == -2
+
+
+def test_randomized_submissions(sb, eng, o):
+    """seeded sweep over submission shapes: random sets of block sizes and counts (partial groups, one block, > 64 equal
+    blocks), CRC kind per block, early stop on / off, 1..10 half-iterations, good and hopeless channels"""
+    rng = np.random.default_rng(20240)
+    sizes = [o.cbsize(i) for i in range(188)]
+    small = [k for k in sizes if k <= 1024]
+    for case in range(24):
+        nk = int(rng.integers(1, 5))
+        Ks, llrs, kinds = [], [], []
+        for _ in range(nk):
+            K = int(rng.choice(small if rng.random() < 0.8 else sizes))
+            cnt = int(rng.choice([1, 2, 3, 31, 33, 64, 65, 70])) if K <= 256 else int(rng.integers(1, 6))
+            eb = float(rng.choice([-3.0, 0.5, 1.5, 4.0]))
+            kind = int(rng.integers(0, 3))
+            for j in range(cnt):
+                _, l = vecgen.make_cb(K, eb, int(rng.integers(1 << 30)), scale=int(rng.choice([30, 100, 400])), with_crc=(kind != 0))
+                Ks.append(K); llrs.append(l); kinds.append(kind)
+        max_iter = int(rng.integers(1, 11))
+        early = bool(rng.integers(0, 2))
+        out, noi, ok = eng.tdec_batch(np.array(Ks, np.uint32), llrs, max_iter, early_stop=early, crc_kind=np.array(kinds, np.uint8))
+        for i in rng.permutation(len(Ks))[:12]:
+            K = Ks[i]
+            ref_out = o.tdec_run_all(K, llrs[i], max_iter) if not early or kinds[i] == 0 else None
+            if ref_out is not None:
+                # no early stop (or no CRC to stop on): all max_iter half-iterations run
+                assert noi[i] == max_iter and np.array_equal(out[i], ref_out), (case, K, max_iter, early, kinds[i])
+            else:
+                hard = o.tdec_trace(K, llrs[i], max_iter)
+                poly = ol.CRC24A if kinds[i] == 1 else ol.CRC24B
+                stop = max_iter
+                for it in range(1, max_iter + 1):
+                    if it >= 2 and o.crc_bytes(poly, hard[it - 1], K) == 0:
+                        stop = it
+                        break
+                assert noi[i] == stop and np.array_equal(out[i], hard[stop - 1]), (case, K, max_iter, kinds[i], noi[i], stop)

@@ -578,3 +578,37 @@ def test_randomized_submissions(sb, eng, o):
                         stop = it
                         break
                 assert noi[i] == stop and np.array_equal(out[i], hard[stop - 1]), (case, K, max_iter, kinds[i], noi[i], stop)
+
+
+def test_randomized_transport_block_batches(sb, eng, o):
+    """seeded sweep over transport-block submissions: random TBS / Qm / G / channel per block, 1-6 blocks per submission,
+    HARQ state carried over three transmissions (rv 0, 2, 1) so that cached, failing and passing code blocks mix"""
+    rng = np.random.default_rng(777)
+    pool = [16, 40, 1000, 2984, 6120, 6200, 12216, 36696, 75376]
+    for rnd in range(6):
+        n = int(rng.integers(1, 7))
+        specs = []
+        for i in range(n):
+            tbs = int(rng.choice(pool))
+            Qm = int(rng.choice([2, 4, 6]))
+            G = Qm * int(rng.integers(max(tbs // Qm // 2, 24), 2 * tbs // Qm + 60))
+            specs.append((tbs, Qm, G, float(rng.choice([-1.0, 0.5, 2.0, 5.0])), int(rng.integers(1 << 30))))
+        tbl = [sb.TransportBlock(s[0]) for s in specs]
+        st = [None] * n
+        for rv in (0, 2, 1):
+            reqs, exp = [], []
+            for i, (tbs, Qm, G, eb, seed) in enumerate(specs):
+                _, e = vecgen.make_tb(tbs, G, Qm, rv, eb, seed, scale=100 if Qm < 6 else 400)
+                res = o.decode_tb(tbs, Qm, rv, e, 7, st[i])
+                st[i] = res["state"]
+                exp.append(res)
+                tbl[i].data[:] = 0
+                reqs.append((tbl[i], Qm, rv, e))
+            assert eng.decode_tb_batch(reqs, 7) == 0
+            for tb, res in zip(tbl, exp):
+                assert tb.ret == res["ret"] and int(tb.tb_crc[0]) == res["tb_crc"]
+                C = res["seg"]["C"]
+                assert np.array_equal(tb.cb_noi[:C], res["cb_noi"][:C]) and np.array_equal(tb.cb_crc[:C], res["state"]["cb_crc"][:C])
+                assert np.array_equal(tb.buffer_f[:C], res["state"]["buffer_f"][:C]) and np.array_equal(tb.sb_data[:C], res["state"]["sb_data"][:C])
+                if res["ret"] == 0:
+                    assert np.array_equal(tb.data[:tb.tbs // 8], res["data"][:tb.tbs // 8])

@@ -546,7 +546,7 @@ def test_page_locked_caller_buffers(sb, eng, o):
 def test_randomized_submissions(sb, eng, o):
     """seeded sweep over submission shapes: random sets of block sizes and counts (partial groups, one block, > 64 equal
     blocks), CRC kind per block, early stop on / off, 1..10 half-iterations, good and hopeless channels"""
-    rng = np.random.default_rng(20240)
+    rng = np.random.default_rng(20240 + int(os.environ.get("SRSB200_FUZZ_SEED", "0")))   # more seeds: tools/fuzz.sh
     sizes = [o.cbsize(i) for i in range(188)]
     small = [k for k in sizes if k <= 1024]
     for case in range(24):
@@ -583,7 +583,7 @@ def test_randomized_submissions(sb, eng, o):
 def test_randomized_transport_block_batches(sb, eng, o):
     """seeded sweep over transport-block submissions: random TBS / Qm / G / channel per block, 1-6 blocks per submission,
     HARQ state carried over three transmissions (rv 0, 2, 1) so that cached, failing and passing code blocks mix"""
-    rng = np.random.default_rng(777)
+    rng = np.random.default_rng(777 + int(os.environ.get("SRSB200_FUZZ_SEED", "0")))
     pool = [16, 40, 1000, 2984, 6120, 6200, 12216, 36696, 75376]
     for rnd in range(6):
         n = int(rng.integers(1, 7))

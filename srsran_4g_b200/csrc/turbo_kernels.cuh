@@ -866,11 +866,11 @@ extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const
  * Final hard-decision bytes (tdec_gen_decision_byte, MSB first) of every code block of a group: the decisions of the
  * last half-iteration each block ran; after a DEC2 half-iteration they are gathered through the QPP permutation
  * (app1[fwd[i]] = ext2[i], decision on app1). grid = (n_groups, EMIT_SPLIT), block = 256, dynamic smem =
- * emit_smem_bytes(R, K); block y of a group transposes and emits the code blocks held in lanes [8y, 8y+8).
+ * emit_smem_bytes(R, K); block y of a group transposes and emits the code blocks held in lanes [4y, 4y+4).
  * The group's two decision arrays are transposed into shared memory ([code block][16-bit piece]), then each warp
  * produces 32 consecutive output words of one code block (coalesced 128-byte stores).
  */
-static constexpr int EMIT_SPLIT = 4;  // blocks per group: block y owns the code blocks in lanes [8y, 8y+8) (both halves)
+static constexpr int EMIT_SPLIT = 8;  // blocks per group: block y owns the code blocks in lanes [4y, 4y+4) (both halves)
 __host__ __device__ inline size_t emit_smem_bytes(uint32_t R, uint32_t K)
 {
   const uint32_t P = R / 16 + 2;  // 16-bit pieces per code block, padded so that a row is an odd number of words

@@ -70,13 +70,20 @@ __global__ void __launch_bounds__(256) crc_bytes_kernel(const CrcJob* __restrict
 {
   const CrcJob j   = jobs[blockIdx.y];
   uint32_t     acc = 0;
-  for (uint32_t byte = blockIdx.x * 256 + threadIdx.x; byte < j.nbits / 8; byte += gridDim.x * 256) {
-    uint32_t v = j.data[byte];
-    while (v) {
-      int      b   = 31 - __clz(v);        // bit b of the byte (b = 7 is the earliest bit)
-      uint32_t pos = byte * 8 + (7 - b);   // position in the message
-      acc ^= words[j.nbits - 1 - pos];
-      v &= ~(1u << b);
+  // the eight bits of a byte use eight CONSECUTIVE table entries (bit 7 - the earliest - the highest index): two 128-bit
+  // loads and eight masked XORs per byte, no data-dependent loop (nbits is a multiple of 8, so the entries are 32-byte aligned)
+  const uint32_t nbytes = j.nbits / 8;
+  for (uint32_t b0 = (blockIdx.x * 256 + threadIdx.x) * 4; b0 < nbytes; b0 += gridDim.x * 1024) {  // four bytes per thread and trip
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+      const uint32_t byte = b0 + k;
+      if (byte >= nbytes) break;
+      const uint32_t v = j.data[byte];
+      if (v == 0) continue;
+      const uint4* w  = reinterpret_cast<const uint4*>(words + (j.nbits - 8 - byte * 8));  // entries for bits 0..7 of the byte
+      const uint4  lo = __ldg(w), hi = __ldg(w + 1);
+      acc ^= (lo.x & (0u - (v & 1u))) ^ (lo.y & (0u - ((v >> 1) & 1u))) ^ (lo.z & (0u - ((v >> 2) & 1u))) ^ (lo.w & (0u - ((v >> 3) & 1u)));
+      acc ^= (hi.x & (0u - ((v >> 4) & 1u))) ^ (hi.y & (0u - ((v >> 5) & 1u))) ^ (hi.z & (0u - ((v >> 6) & 1u))) ^ (hi.w & (0u - (v >> 7)));
     }
   }
   acc = __reduce_xor_sync(0xffffffffu, acc);

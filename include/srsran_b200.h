@@ -185,6 +185,13 @@ typedef struct {
   uint32_t        e_offset;      /* Q'_cqi * Qm: first g-bit of the UL-SCH data */
   int16_t*        g_bits;        /* optional out (host): first nof_g_out de-interleaved values (CQI decoding reads them) */
   uint32_t        nof_g_out;
+  /* Optional descrambling on the device (36.211 6.3.1 / 7.2; srsran_sequence_pdsch_apply_s -> srsran_sequence_apply_s,
+   * lib/src/phy/common/sequence.c:507-561): with descramble != 0 the e_bits are the demodulator's output as it is,
+   * e_bits[i] is negated where the Gold sequence of seed c_init has c(i) = 1 (int16 wrap), fused into the rate de-matcher.
+   * c_init = rnti*2^14 + q*2^13 + floor(ns/2)*2^9 + cell_id for the PDSCH. Not combined with the q_bits source (on the
+   * uplink the host-side RI/ACK decoding needs the descrambled values first). */
+  uint32_t        descramble;
+  uint32_t        c_init;
 } srsb200_tb_t;
 
 /*

@@ -209,6 +209,9 @@ int srsran_rm_turbo_rx_lut(int16_t* input, int16_t* output, uint32_t in_len, uin
  * inputs), same side effects on the soft buffer (buffer_f accumulation, cb_crc / tb_crc, cached bytes) and on
  * q->avg_iterations. All code blocks of the transport block go to the device as one batched submission.
  */
+static int decode_tb_common(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer, srsran_cbsegm_t* cb_segm, uint32_t Qm, uint32_t rv,
+                            uint32_t nof_e_bits, int16_t* e_bits, uint8_t* data, int descramble, uint32_t c_init);
+
 int srsran_b200_decode_tb(srsran_sch_t*           q,
                           srsran_softbuffer_rx_t* softbuffer,
                           srsran_cbsegm_t*        cb_segm,
@@ -217,6 +220,31 @@ int srsran_b200_decode_tb(srsran_sch_t*           q,
                           uint32_t                nof_e_bits,
                           int16_t*                e_bits,
                           uint8_t*                data)
+{
+  return decode_tb_common(q, softbuffer, cb_segm, Qm, rv, nof_e_bits, e_bits, data, 0, 0);
+}
+
+/*
+ * The same with the descrambling of srsran_pdsch_decode (pdsch.c:726-732, srsran_sequence_pdsch_apply_s) moved onto the
+ * device: e_bits is the soft demodulator's output as it is, c_init the scrambling seed of the codeword
+ * (rnti << 14 | codeword << 13 | (nslot / 2) << 9 | cell id, 36.211 6.3.1). A caller in pdsch.c skips its own
+ * srsran_sequence_pdsch_apply_s and hands the seed down instead.
+ */
+int srsran_b200_decode_tb_scrambled(srsran_sch_t*           q,
+                                    srsran_softbuffer_rx_t* softbuffer,
+                                    srsran_cbsegm_t*        cb_segm,
+                                    uint32_t                Qm,
+                                    uint32_t                rv,
+                                    uint32_t                nof_e_bits,
+                                    int16_t*                e_bits,
+                                    uint8_t*                data,
+                                    uint32_t                c_init)
+{
+  return decode_tb_common(q, softbuffer, cb_segm, Qm, rv, nof_e_bits, e_bits, data, 1, c_init);
+}
+
+static int decode_tb_common(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer, srsran_cbsegm_t* cb_segm, uint32_t Qm, uint32_t rv,
+                            uint32_t nof_e_bits, int16_t* e_bits, uint8_t* data, int descramble, uint32_t c_init)
 {
   if (q == NULL || data == NULL || softbuffer == NULL || e_bits == NULL || cb_segm == NULL || Qm == 0) {
     ERROR("Missing inputs: data=%d, softbuffer=%d, e_bits=%d, cb_segm=%d Qm=%d", data != 0, softbuffer != 0, e_bits != 0, cb_segm != 0, Qm);
@@ -242,6 +270,8 @@ int srsran_b200_decode_tb(srsran_sch_t*           q,
   tb.max_cb     = softbuffer->max_cb;
   tb.data       = data;
   tb.cb_noi     = NULL;
+  tb.descramble = descramble ? 1u : 0u;
+  tb.c_init     = c_init;
   int ret = srsb200_decode_tb(engine(), &tb, q->max_iterations);
   if (ret == SRSB200_ERROR_NO_DEVICE) {
     ERROR("srsran_b200: %s", srsb200_last_error());

@@ -802,3 +802,10 @@ int ref_dlsch_decode8(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t 
   pthread_mutex_unlock(&g_lock);
   return ret;
 }
+
+/* srsran_sequence_apply_s itself (lib/src/phy/common/sequence.c:507-561) */
+#include "srsran/phy/common/sequence.h"
+void ref_sequence_apply_s(const int16_t* in, int16_t* out, uint32_t len, uint32_t c_init)
+{
+  srsran_sequence_apply_s(in, out, len, c_init);
+}

@@ -783,3 +783,30 @@ int orc_ulsch_deinterleave(const int16_t* q, uint32_t Qm, uint32_t H, uint32_t n
   free(lut);
   return 0;
 }
+
+/* ------------------------------------------------------------------ scrambling sequence */
+void orc_sequence_bits(uint32_t c_init, uint8_t* c, uint32_t len)
+{
+  /* x1(n+31) = x1(n+3) + x1(n), x1(0) = 1; x2(n+31) = x2(n+3) + x2(n+2) + x2(n+1) + x2(n), x2(0..30) = bits of c_init;
+   * c(n) = x1(n + 1600) + x2(n + 1600), all mod 2. 31-bit windows: bit j of a register = x(n + j). */
+  uint32_t x1 = 1, x2 = c_init & 0x7fffffffu;
+  for (uint32_t n = 0; n < 1600 + len; n++) {
+    if (n >= 1600) {
+      c[n - 1600] = (uint8_t)((x1 ^ x2) & 1u);
+    }
+    uint32_t f1 = (x1 ^ (x1 >> 3)) & 1u;
+    uint32_t f2 = (x2 ^ (x2 >> 1) ^ (x2 >> 2) ^ (x2 >> 3)) & 1u;
+    x1          = (x1 >> 1) | (f1 << 30);
+    x2          = (x2 >> 1) | (f2 << 30);
+  }
+}
+
+void orc_sequence_apply_s(const int16_t* in, int16_t* out, uint32_t len, uint32_t c_init)
+{
+  uint8_t* c = malloc(len ? len : 1);
+  orc_sequence_bits(c_init, c, len);
+  for (uint32_t i = 0; i < len; i++) {
+    out[i] = c[i] ? (int16_t)(uint16_t)(0u - (uint16_t)in[i]) : in[i];
+  }
+  free(c);
+}

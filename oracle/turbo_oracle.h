@@ -64,6 +64,12 @@ int orc_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, c
 int orc_ulsch_deinterleave(const int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, int16_t* g_bits,
                            const uint32_t* ri_positions, uint32_t nof_ri_bits);
 
+/* LTE scrambling sequence (36.211 7.2: Gold sequence of two length-31 LFSRs, Nc = 1600) applied as a sign to int16 LLRs:
+ * out[i] = c(i) ? -in[i] : in[i] (int16 wrap), what srsran_sequence_apply_s does (lib/src/phy/common/sequence.c:507-561);
+ * orc_sequence_bits writes c(0..len-1) as 0/1 bytes. */
+void orc_sequence_bits(uint32_t c_init, uint8_t* c, uint32_t len);
+void orc_sequence_apply_s(const int16_t* in, int16_t* out, uint32_t len, uint32_t c_init);
+
 #ifdef __cplusplus
 }
 #endif

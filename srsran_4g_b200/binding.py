@@ -114,7 +114,8 @@ class _TbStruct(C.Structure):
                 ("buffer_f", C.POINTER(C.c_void_p)), ("sb_data", C.POINTER(C.c_void_p)), ("cb_crc", C.c_void_p), ("tb_crc", C.c_void_p),
                 ("max_cb", C.c_uint32), ("data", C.c_void_p), ("cb_noi", C.c_void_p), ("avg_iterations", C.c_float), ("ret", C.c_int),
                 ("q_bits", C.c_void_p), ("H_prime_total", C.c_uint32), ("N_pusch_symbs", C.c_uint32), ("ri_positions", C.c_void_p),
-                ("nof_ri_bits", C.c_uint32), ("e_offset", C.c_uint32), ("g_bits", C.c_void_p), ("nof_g_out", C.c_uint32)]
+                ("nof_ri_bits", C.c_uint32), ("e_offset", C.c_uint32), ("g_bits", C.c_void_p), ("nof_g_out", C.c_uint32),
+                ("descramble", C.c_uint32), ("c_init", C.c_uint32)]
 
 
 class _TbTxStruct(C.Structure):
@@ -331,9 +332,12 @@ class Engine:
             r[0].ret, r[0].avg_iterations = s.ret, s.avg_iterations
         return ret
 
-    def decode_tb(self, tb, Qm, rv, e_bits, max_iterations, nof_e_bits=None):
+    def decode_tb(self, tb, Qm, rv, e_bits, max_iterations, nof_e_bits=None, c_init=None):
+        """c_init: the e_bits are still scrambled; descramble them on the device with the Gold sequence of that seed"""
         s = _TbStruct()
         tb.fill(s, Qm, rv, e_bits, nof_e_bits)
+        if c_init is not None:
+            s.descramble, s.c_init = 1, c_init
         ret = self._L.srsb200_decode_tb(self._h, C.byref(s), max_iterations)
         tb.ret, tb.avg_iterations = s.ret, s.avg_iterations
         return ret

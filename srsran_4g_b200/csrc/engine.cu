@@ -187,6 +187,8 @@ struct srsb200_engine {
   void*  d_scratch[16]   = {nullptr};  // 0-7 receive side, 8-11 transmit side, 12-13 UL-SCH de-interleaver
   size_t scratch_cap[16] = {0};
   uint32_t* d_crc24b_words = nullptr;  // x^(m+24) mod g24B, m < 6144 (tx_cb_kernel)
+  uint32_t* d_gold = nullptr;          // jump matrices of the scrambling LFSRs [2][GOLD_POWERS][32] (rm_rx_kernel)
+  uint32_t  h_gold[2][GOLD_POWERS][32];
 
   // pinned staging arenas for pageable caller buffers (0: host->device, 1: device->host), see Stager
   void*  h_stage[2]     = {nullptr, nullptr};
@@ -586,6 +588,40 @@ static int ensure_tb_crc_words(srsb200_engine* e, uint32_t nbits)
   return 0;
 }
 
+// ------------------------------------------------------------------ scrambling sequence (36.211 7.2), GF(2) jump-ahead
+// An LFSR window w (bit b = x(n + b), 31 bits) advances by one position as w' = (w >> 1) | (parity(w & taps) << 30). That map
+// is linear, so advancing by any offset is a product of the matrices A^(2^k); a matrix is kept as 31 row masks.
+static uint32_t gold_matvec_h(const uint32_t* rows, uint32_t x)
+{
+  uint32_t y = 0;
+  for (int r = 0; r < 31; r++) y |= (uint32_t)(__builtin_popcount(rows[r] & x) & 1) << r;
+  return y;
+}
+static uint32_t gold_jump_h(const uint32_t (*jump)[32], uint32_t x, uint32_t off)
+{
+  for (int k = 0; off; k++, off >>= 1)
+    if (off & 1u) x = gold_matvec_h(jump[k], x);
+  return x;
+}
+static void gold_build(uint32_t h[2][GOLD_POWERS][32])
+{
+  const uint32_t taps[2] = {0x9u, 0xFu};  // x1: x(n) + x(n+3); x2: x(n) + x(n+1) + x(n+2) + x(n+3)
+  for (int q = 0; q < 2; q++) {
+    for (int r = 0; r < 30; r++) h[q][0][r] = 1u << (r + 1);
+    h[q][0][30] = taps[q];
+    h[q][0][31] = 0;
+    for (int k = 1; k < GOLD_POWERS; k++) {
+      for (int r = 0; r < 31; r++) {  // row r of A^(2^k) = row r of A^(2^(k-1)) times A^(2^(k-1))
+        uint32_t acc = 0, m = h[q][k - 1][r];
+        for (int j = 0; j < 31; j++)
+          if ((m >> j) & 1u) acc ^= h[q][k - 1][j];
+        h[q][k][r] = acc;
+      }
+      h[q][k][31] = 0;
+    }
+  }
+}
+
 extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
 {
   if (!out) return fail(SRSB200_ERROR_INVALID_INPUTS, "null engine pointer");
@@ -621,6 +657,11 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   CUDA_TRY(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<0>)));
   CUDA_TRY(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<1>)));
   CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<2>)));
+  CUDA_TRY(cudaFuncSetAttribute(rm_rx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RM_SMEM_ELEMS * sizeof(int16_t))));
+  CUDA_TRY(cudaFuncSetAttribute(rm_rx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RM_SMEM_ELEMS * sizeof(int16_t))));
+  gold_build(e->h_gold);
+  CUDA_TRY(cudaMalloc(&e->d_gold, sizeof(e->h_gold)));
+  CUDA_TRY(cudaMemcpy(e->d_gold, e->h_gold, sizeof(e->h_gold), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)emit_smem_bytes(((SRSB200_MAX_K + 3 + W - 1) / W) * W, SRSB200_MAX_K + 64)));
   CUDA_TRY(cudaFuncSetAttribute(job_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
@@ -646,6 +687,7 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
   for (int i = 0; i < 16; i++)
     if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);
   cudaFree(e->d_ktab);
+  cudaFree(e->d_gold);
   for (int i = 0; i < 2; i++)
     if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
   if (e->d_tb_crc_words) cudaFree(e->d_tb_crc_words);
@@ -1326,10 +1368,11 @@ extern "C" int srsb200_rm_turbo_rx_lut(srsb200_engine_t* e, const int16_t* input
   CUDA_TRY(cudaMemcpyAsync(d_buf, output, (size_t)L * 2, cudaMemcpyHostToDevice, e->stream));
   RmJob job;
   job.e = (const int16_t*)d_e; job.buf = (int16_t*)d_buf; job.table = e->d_rm_inv[cb_idx][rv_idx]; job.E = in_len; job.L = L;
+  job.scramble = 0; job.c_off = 0; job.x1 = 0; job.x2 = 0;
   void* d_job;
   if (ensure_scratch(e, 6, sizeof(RmJob), &d_job)) return SRSB200_ERROR;
   CUDA_TRY(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, e->stream));
-  rm_rx_kernel<<<1, RM_THREADS, std::min(in_len, RM_SMEM_ELEMS) * sizeof(int16_t), e->stream>>>((const RmJob*)d_job);
+  rm_rx_kernel<false><<<1, RM_THREADS, std::min(in_len, RM_SMEM_ELEMS) * sizeof(int16_t), e->stream>>>((const RmJob*)d_job, e->d_gold);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(output, d_buf, (size_t)L * 2, cudaMemcpyDeviceToHost, e->stream));

@@ -24,19 +24,66 @@ struct RmJob {
   const uint16_t* table;  // Tinv[0..L): position in the transmitted (circular-buffer) order of soft-buffer element p
   uint32_t        E;
   uint32_t        L;
+  // optional descrambling (36.211 7.2) fused into the gather: the LLRs are still scrambled, e[i] belongs to position
+  // c_off + i of the codeword's scrambling sequence; x1 / x2 = LFSR windows at sequence position 0 (i.e. after Nc = 1600)
+  uint32_t        scramble, c_off, x1, x2;
 };
 
 constexpr uint32_t RM_SMEM_ELEMS = 24576;  // e-bits staged per block (48 KB); the rest of a longer e is read from global
 constexpr int      RM_THREADS    = 512;
+constexpr uint32_t RM_SC_WORDS   = 1024;   // scrambling bits held per block (32768 = more than any code block receives unrepeated)
+constexpr int      GOLD_POWERS   = 20;     // jump matrices A^(2^k), k < 20: offsets up to 2^20 sequence positions
 
-// grid = n_jobs, block = RM_THREADS, dynamic shared memory = min(max E, RM_SMEM_ELEMS) * 2 bytes
-__global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restrict__ jobs)
+// y = M x over GF(2) for a 31-bit LFSR window; M as 31 row masks (32 words, the last unused)
+__device__ __forceinline__ uint32_t gold_matvec(const uint32_t* __restrict__ rows, uint32_t x)
+{
+  uint32_t y = 0;
+#pragma unroll
+  for (int r = 0; r < 31; r++) y |= (uint32_t)(__popc(__ldg(rows + r) & x) & 1) << r;
+  return y;
+}
+// window of an LFSR `off` positions later: jump[k] = A^(2^k) (32 words each)
+__device__ __forceinline__ uint32_t gold_jump(const uint32_t* __restrict__ jump, uint32_t x, uint32_t off)
+{
+  for (int k = 0; off; k++, off >>= 1)
+    if (off & 1u) x = gold_matvec(jump + 32 * k, x);
+  return x;
+}
+
+// grid = n_jobs, block = RM_THREADS, dynamic shared memory = min(max E, RM_SMEM_ELEMS) * 2 bytes.
+// gold = jump matrices of the two LFSRs ([2][GOLD_POWERS][32] words), only read by jobs with scramble != 0
+// SCR = false: no job of the launch descrambles (the sequence staging and the sign test are compiled out)
+template <bool SCR>
+__global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restrict__ jobs, const uint32_t* __restrict__ gold)
 {
   extern __shared__ __align__(16) int16_t se[];
+  __shared__ uint32_t sc[SCR ? RM_SC_WORDS : 1];
   const RmJob    j  = jobs[blockIdx.x];
   const uint32_t ns = min(j.E, RM_SMEM_ELEMS);
   for (uint32_t i = threadIdx.x; i < ns; i += RM_THREADS) se[i] = j.e[i];
+  if (SCR && j.scramble) {
+    // 32 sequence bits per thread: jump both LFSR windows to position c_off + 32 w, 31 bits come straight out of the
+    // windows (bit b of a window = x(n + b)), the 32nd is the feedback bit
+    for (uint32_t w = threadIdx.x; w < (j.E + 31) / 32 && w < RM_SC_WORDS; w += RM_THREADS) {
+      const uint32_t a = gold_jump(gold, j.x1, j.c_off + 32 * w), b = gold_jump(gold + 32 * GOLD_POWERS, j.x2, j.c_off + 32 * w);
+      const uint32_t f = ((a ^ (a >> 3)) ^ (b ^ (b >> 1) ^ (b >> 2) ^ (b >> 3))) & 1u;
+      sc[w] = ((a ^ b) & 0x7fffffffu) | (f << 31);
+    }
+  }
   __syncthreads();
+  auto llr = [&](uint32_t i) -> uint32_t {
+    uint32_t v = (uint16_t)(i < ns ? se[i] : j.e[i]);
+    if (SCR && j.scramble) {
+      uint32_t c;
+      if ((i >> 5) < RM_SC_WORDS) {
+        c = (sc[i >> 5] >> (i & 31u)) & 1u;
+      } else {  // beyond the staged part (heavy repetition): one jump per element, rare
+        c = (gold_jump(gold, j.x1, j.c_off + i) ^ gold_jump(gold + 32 * GOLD_POWERS, j.x2, j.c_off + i)) & 1u;
+      }
+      if (c) v = 0u - v;  // int16 wrap: -(-32768) stays -32768 (sequence.c:545)
+    }
+    return v;
+  };
   // two soft-buffer elements per thread (L is even, buf is 4-byte aligned): 128-byte accesses per warp
   uint32_t* buf2 = reinterpret_cast<uint32_t*>(j.buf);
   for (uint32_t p2 = threadIdx.x; p2 < j.L / 2; p2 += RM_THREADS) {
@@ -44,8 +91,8 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
     uint32_t       n0 = tt & 0xffffu, n1 = tt >> 16;
     if (n0 >= j.E && n1 >= j.E) continue;  // nothing received for these two positions
     uint32_t s0 = 0, s1 = 0;
-    for (uint32_t i = n0; i < j.E; i += j.L) s0 += (uint16_t)(i < ns ? se[i] : j.e[i]);
-    for (uint32_t i = n1; i < j.E; i += j.L) s1 += (uint16_t)(i < ns ? se[i] : j.e[i]);
+    for (uint32_t i = n0; i < j.E; i += j.L) s0 += llr(i);
+    for (uint32_t i = n1; i < j.E; i += j.L) s1 += llr(i);
     const uint32_t old = buf2[p2];
     buf2[p2] = ((old + s0) & 0xffffu) | ((((old >> 16) + s1) & 0xffffu) << 16);
   }

@@ -58,6 +58,7 @@ class _Lib:
         self._dec_tb = f("decode_tb")
         self._dec_tb.argtypes = [C.c_uint32] * 4 + [i16p, C.c_uint32, i16p, u8p, u8p, u8p, u8p, u32p, C.POINTER(C.c_float)]
         self._dec_tb.restype = C.c_int
+        self._seq = f("sequence_apply_s"); self._seq.argtypes = [i16p, i16p, C.c_uint32, C.c_uint32]; self._seq.restype = None
         self._enc_tb = f("encode_tb")
         self._enc_tb.argtypes = [C.c_uint32] * 4 + [u8p, u8p]
         self._enc_tb.restype = C.c_int
@@ -202,6 +203,13 @@ class _Lib:
         ret = self._dec_tb(tbs, Qm, rv, G, e_bits, max_iterations, state["buffer_f"], state["sb_data"], state["cb_crc"],
                            tb_crc, data, noi, C.byref(avg))
         return dict(ret=ret, data=data, cb_noi=noi, tb_crc=int(tb_crc[0]), avg_iterations=avg.value, state=state, seg=seg)
+
+    def sequence_apply_s(self, llr, c_init):
+        """(de)scrambling of int16 LLRs with the LTE Gold sequence of seed c_init"""
+        llr = np.ascontiguousarray(llr, np.int16)
+        out = np.zeros_like(llr)
+        self._seq(llr, out, len(llr), c_init)
+        return out
 
     def encode_tb(self, tbs, Qm, rv, nof_e_bits, data):
         """-> (ret, e_bits packed MSB-first, (nof_e_bits+7)//8 bytes)"""

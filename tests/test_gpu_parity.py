@@ -612,3 +612,22 @@ def test_randomized_transport_block_batches(sb, eng, o):
                 assert np.array_equal(tb.buffer_f[:C], res["state"]["buffer_f"][:C]) and np.array_equal(tb.sb_data[:C], res["state"]["sb_data"][:C])
                 if res["ret"] == 0:
                     assert np.array_equal(tb.data[:tb.tbs // 8], res["data"][:tb.tbs // 8])
+
+
+@pytest.mark.parametrize("tbs,G,Qm", [(12216, 19200, 6), (75376, 86400, 6), (6120, 14400, 2), (40, 300, 2), (40, 72000, 2)])
+def test_decode_tb_with_device_descrambling(sb, eng, o, tbs, G, Qm):
+    """scrambled e-bits + c_init in, descrambling fused into the rate de-matcher (Gold sequence by GF(2) jump-ahead):
+    identical to descrambling with the oracle's srsran_sequence_apply_s restatement first; (40, 72000) exercises repetition
+    far beyond the staged part of the sequence"""
+    c_init = (0x4321 << 14) + (1 << 13) + (6 << 9) + 77
+    st = None
+    tb = sb.TransportBlock(tbs)
+    for rv in (0, 2):
+        _, e = vecgen.make_tb(tbs, G, Qm, rv, 1.5, 910 + tbs, scale=100)
+        e[0] = -32768                                     # its negation wraps
+        scr = o.sequence_apply_s(e, c_init)              # what the demodulator hands over (scrambling is an involution)
+        res = o.decode_tb(tbs, Qm, rv, o.sequence_apply_s(scr, c_init), 8, st)
+        st = res["state"]
+        tb.data[:] = 0
+        assert eng.decode_tb(tb, Qm, rv, scr, 8, c_init=c_init) == res["ret"]
+        _check_tb(res, tb, st)

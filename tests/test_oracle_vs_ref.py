@@ -151,3 +151,15 @@ def test_decode_tb_with_harq(libs, tbs, G, Qm):
         assert (ro["data"] == rr["data"]).all()
         for k in ("buffer_f", "sb_data", "cb_crc"):
             assert (so[k] == sr[k]).all(), k
+
+
+@pytest.mark.parametrize("c_init", [0, 1, 0x7FFFFFFF, (0x1234 << 14) + (1 << 13) + (7 << 9) + 301, (0xFFFF << 14) + (9 << 9) + 503, 123456789])
+def test_scrambling_sequence_vs_reference(libs, c_init):
+    """orc_sequence_apply_s against srsran_sequence_apply_s (the SSE / 24-bit-parallel generator of sequence.c), lengths
+    around its block sizes, values including -32768 (whose negation wraps)"""
+    o, r = libs
+    rng = np.random.default_rng(c_init % 1000)
+    for n in (1, 7, 23, 24, 25, 48, 1000, 86400):
+        x = rng.integers(-32768, 32768, n).astype(np.int16)
+        x[0] = -32768
+        assert np.array_equal(o.sequence_apply_s(x, c_init), r.sequence_apply_s(x, c_init)), n

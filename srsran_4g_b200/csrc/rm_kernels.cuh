@@ -50,6 +50,19 @@ __device__ __forceinline__ uint32_t gold_jump(const uint32_t* __restrict__ jump,
   return x;
 }
 
+// the same products with the 31 rows spread over the lanes of a warp (x and off are warp-uniform)
+__device__ __forceinline__ uint32_t warp_gold_matvec(const uint32_t* __restrict__ rows, uint32_t x, int lane)
+{
+  const uint32_t bit = lane < 31 ? (uint32_t)(__popc(__ldg(rows + lane) & x) & 1) : 0u;
+  return __ballot_sync(0xffffffffu, bit);
+}
+__device__ __forceinline__ uint32_t warp_gold_jump(const uint32_t* __restrict__ jump, uint32_t x, uint32_t off, int lane)
+{
+  for (int k = 0; off; k++, off >>= 1)
+    if (off & 1u) x = warp_gold_matvec(jump + 32 * k, x, lane);
+  return x;
+}
+
 // grid = n_jobs, block = RM_THREADS, dynamic shared memory = min(max E, RM_SMEM_ELEMS) * 2 bytes.
 // gold = jump matrices of the two LFSRs ([2][GOLD_POWERS][32] words), only read by jobs with scramble != 0
 // SCR = false: no job of the launch descrambles (the sequence staging and the sign test are compiled out)
@@ -62,12 +75,21 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
   const uint32_t ns = min(j.E, RM_SMEM_ELEMS);
   for (uint32_t i = threadIdx.x; i < ns; i += RM_THREADS) se[i] = j.e[i];
   if (SCR && j.scramble) {
-    // 32 sequence bits per thread: jump both LFSR windows to position c_off + 32 w, 31 bits come straight out of the
-    // windows (bit b of a window = x(n + b)), the 32nd is the feedback bit
-    for (uint32_t w = threadIdx.x; w < (j.E + 31) / 32 && w < RM_SC_WORDS; w += RM_THREADS) {
-      const uint32_t a = gold_jump(gold, j.x1, j.c_off + 32 * w), b = gold_jump(gold + 32 * GOLD_POWERS, j.x2, j.c_off + 32 * w);
-      const uint32_t f = ((a ^ (a >> 3)) ^ (b ^ (b >> 1) ^ (b >> 2) ^ (b >> 3))) & 1u;
-      sc[w] = ((a ^ b) & 0x7fffffffu) | (f << 31);
+    // The block's part of the scrambling sequence, 32 bits per word. A matrix-vector product over GF(2) is one popc per row:
+    // the 32 lanes of a warp take one row each and a ballot collects the new window, so a warp jumps both LFSR windows to
+    // its first word (offset c_off + 32 * first word, by powers A^(2^k)) and then walks word by word with A^32. 31 bits of a
+    // word come straight out of the windows (bit b = x(n + b)), the 32nd is the feedback bit.
+    const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t nw   = min((j.E + 31) / 32, RM_SC_WORDS), per = (nw + RM_THREADS / 32 - 1) / (RM_THREADS / 32);
+    const uint32_t w0 = wid * per, w1 = min(w0 + per, nw);
+    if (w0 < w1) {
+      uint32_t a = warp_gold_jump(gold, j.x1, j.c_off + 32 * w0, lane), b = warp_gold_jump(gold + 32 * GOLD_POWERS, j.x2, j.c_off + 32 * w0, lane);
+      for (uint32_t w = w0; w < w1; w++) {
+        const uint32_t f = ((a ^ (a >> 3)) ^ (b ^ (b >> 1) ^ (b >> 2) ^ (b >> 3))) & 1u;
+        if (lane == 0) sc[w] = ((a ^ b) & 0x7fffffffu) | (f << 31);
+        a = warp_gold_matvec(gold + 32 * 5, a, lane);                      // A^32
+        b = warp_gold_matvec(gold + 32 * GOLD_POWERS + 32 * 5, b, lane);
+      }
     }
   }
   __syncthreads();

@@ -43,4 +43,17 @@ for ul in (False, True):
         rm_ms = out["rm_rx_kernel"]["ms"]
         de_ms = p["rm"][0] - rm_ms                                # kind 3 = rate de-matching + de-interleaver launches
         out["ulsch_deint_kernel"] = {"ms": de_ms, "algorithmic_MB": de_bytes / 1e6, "GBps": de_bytes / max(de_ms, 1e-6) / 1e6, "frac_of_hbm_peak": de_bytes / max(de_ms, 1e-6) / 1e6 / 6542.1}
+# descrambling fused into the rate de-matcher: same submission with descramble / c_init set on every TB
+import ctypes as C
+from srsran_4g_b200.binding import _TbStruct
+def run_scr():
+    arr = (_TbStruct * n_tb)()
+    for c, (s, tb) in enumerate(zip(arr, tbl)):
+        eng.softbuffer_reset(tb)
+        tb.fill(s, Qm, 0, els[c % 4])
+        s.descramble, s.c_init = 1, 12345 + c
+    return sb.lib().srsb200_decode_tb_batch(eng.handle, arr, n_tb, 2)
+run_scr(); run_scr()
+eng.profile(True); eng.profile_read(); run_scr(); p = eng.profile_read(); eng.profile(False)
+out["rm_rx_kernel_with_descrambling"] = {"ms": p["rm"][0], "GBps": out["rm_rx_kernel"]["algorithmic_MB"] / p["rm"][0] / 1e3}
 print(json.dumps(out))

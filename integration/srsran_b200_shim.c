@@ -11,8 +11,8 @@
  * srsran_ulsch_decode with its UCI de-multiplexing) is untouched and funnels into it exactly as before.
  *
  * The device handle lives in fields the reference already has: h->dec16_hdlr[0] (srsb200_tdec_t*). One engine per
- * process, created on first use (device = $SRSRAN_B200_DEVICE or 0); the C ABI serialises calls per engine, so any
- * number of PHY worker threads may call concurrently, like the lock-free reference objects.
+ * calling thread, created on first use (device = $SRSRAN_B200_DEVICE or 0); the C ABI serialises calls per engine, so any
+ * number of PHY worker threads may call concurrently, like the lock-free reference objects, and their submissions overlap.
  *
  * Layout contract: srsran_tdec_autoimp_get_subblocks() returns 0 for every size, which makes srsran_rm_turbo_rx_lut and
  * the decoder agree on the natural (generic decoder) input order - SURVEY.md section 8(b).
@@ -32,21 +32,24 @@
 
 #include "srsran_b200.h"
 
-static pthread_once_t    g_once   = PTHREAD_ONCE_INIT;
-static srsb200_engine_t* g_engine = NULL;
+/*
+ * One engine per calling thread, created on first use: srsRAN runs one srsran_sch_t per PHY worker thread (x carrier), with
+ * no locks between them, and a decode is latency-bound (sequential recursions), so the submissions of different workers must
+ * be able to overlap on the GPU - which they do on separate engines (own streams and workspaces; examples/multicell_uplink.c
+ * measures it). Decoder objects remember the engine that created them and stay usable from any thread.
+ */
+static __thread srsb200_engine_t* t_engine = NULL;
 
-static void engine_create_once(void)
-{
-  const char* dev = getenv("SRSRAN_B200_DEVICE");
-  if (srsb200_engine_create(&g_engine, dev ? atoi(dev) : 0) != SRSB200_SUCCESS) {
-    ERROR("srsran_b200: %s", srsb200_last_error());
-    g_engine = NULL;
-  }
-}
 static srsb200_engine_t* engine(void)
 {
-  pthread_once(&g_once, engine_create_once);
-  return g_engine;
+  if (t_engine == NULL) {
+    const char* dev = getenv("SRSRAN_B200_DEVICE");
+    if (srsb200_engine_create(&t_engine, dev ? atoi(dev) : 0) != SRSB200_SUCCESS) {
+      ERROR("srsran_b200: %s", srsb200_last_error());
+      t_engine = NULL;
+    }
+  }
+  return t_engine;
 }
 
 /* ------------------------------------------------------------------ srsran_tdec_* (turbodecoder.h:97-116) */

@@ -111,3 +111,31 @@ def test_dlsch_decode2_8bit_mode_on_the_engine(phy):
             finally:
                 ref.dlsch_rx_free(hc)
             assert c["ret"] == b["ret"] and c["tb_crc"] == b["tb_crc"] and np.array_equal(c["data"][:tbs // 8], b["data"][:tbs // 8])
+
+
+def test_calls_from_several_threads(phy):
+    """the shim keeps one engine per calling thread: PHY workers decode through their own engines, objects created on one
+    thread (the srsran_sch_t's decoder) stay usable from the others"""
+    import threading
+    o = ol.oracle()
+    tbs, Qm, G = 12216, 4, 4 * 4500
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            _, e = vecgen.make_tb(tbs, G, Qm, 0, 2.0, 50 + i, scale=100)
+            h = phy.dlsch_rx_new()
+            try:
+                results[i] = (phy.dlsch_decode(h, tbs, Qm, 0, e, 8), o.decode_tb(tbs, Qm, 0, e, 8))
+            finally:
+                phy.dlsch_rx_free(h)
+        except BaseException as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errors, errors
+    for i, (b, a) in results.items():
+        assert a["ret"] == b["ret"] and np.float32(a["avg_iterations"]) == np.float32(b["avg_iterations"])
+        assert np.array_equal(a["data"][:tbs // 8], b["data"][:tbs // 8])

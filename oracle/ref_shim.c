@@ -378,6 +378,7 @@ typedef struct {
   double    t_start, t_end;
   int       err;
   pthread_barrier_t* barrier;
+  int       sb_layout; /* 1: decode from the sub-block soft-buffer layout prepared outside the timed region (production path) */
 } job_t;
 
 static double now_s(void)
@@ -387,6 +388,7 @@ static double now_s(void)
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+#define SB_STRIDE 18624 /* SOFTBUFFER_SIZE rounded up to a multiple of 32 int16 (64 bytes) */
 static void* job_run(void* arg)
 {
   job_t* j = (job_t*)arg;
@@ -400,17 +402,49 @@ static void* job_run(void* arg)
   srsran_crc_t  crc;
   srsran_crc_init(&crc, CRC24B, 24);
   /* decoder construction (interleaver tables for all sizes) is set-up cost, kept outside the timed region */
-  if (srsran_tdec_init_manual(&h, j->K, impl_of(j->impl))) {
+  /* (the sub-block input layout is only read in AUTO mode, where current_dec > 0: turbodecoder.c:486-493, turbodecoder_iter.h:90;
+   *  for K > 800 and K % 16 == 0 AUTO selects the same AVX2 windowed decoder as impl 5) */
+  if (srsran_tdec_init_manual(&h, j->K, j->sb_layout ? SRSRAN_TDEC_AUTO : impl_of(j->impl))) {
     j->err = -1;
     pthread_barrier_wait(j->barrier);
     return NULL;
   }
-  srsran_tdec_force_not_sb(&h);
   uint32_t L = 3 * j->K + 12;
+  int16_t* sb = NULL;
+  if (j->sb_layout) {
+    /* production input (sch.c:415-433): the rate de-matcher writes the soft buffer in the decoder's sub-block layout
+     * (srsran_tdec_autoimp_get_subblocks, rm_turbo.c:413) and srsran_tdec_iteration reads it as it is - no re-layout inside
+     * the decoder. Built here, OUTSIDE the timed region: e-bits of a full rv-0 transmission that
+     * de-rate-match to exactly the given natural-order LLRs (e[i] = d[T[i]], T the reference's own table). */
+    int       cb_idx = srsran_cbsegm_cbindex(j->K);
+    uint16_t* T      = calloc(L, sizeof(uint16_t));
+    int16_t*  e      = calloc(L + 64, sizeof(int16_t));
+    /* (the SIMD decoder does aligned loads from the soft buffer: the reference allocates it with srsran_vec_i16_malloc) */
+    if (posix_memalign((void**)&sb, 64, ((size_t)(j->last - j->first) * SB_STRIDE + 64) * sizeof(int16_t))) {
+      sb = NULL;
+    } else {
+      memset(sb, 0, ((size_t)(j->last - j->first) * SB_STRIDE + 64) * sizeof(int16_t));
+    }
+    if (!T || !e || !sb || cb_idx < 0 || ref_rm_table((uint32_t)cb_idx, 0, T)) {
+      j->err = -1;
+    } else {
+      for (uint32_t n = j->first; n < j->last; n++) {
+        const int16_t* d = &j->in[(size_t)n * L];
+        for (uint32_t i = 0; i < L; i++) {
+          e[i] = d[T[i]];
+        }
+        srsran_rm_turbo_rx_lut(e, &sb[(size_t)(n - j->first) * SB_STRIDE], L, (uint32_t)cb_idx, 0);
+      }
+    }
+    free(T);
+    free(e);
+  } else {
+    srsran_tdec_force_not_sb(&h);
+  }
   pthread_barrier_wait(j->barrier);
   j->t_start = now_s();
-  for (uint32_t n = j->first; n < j->last; n++) {
-    int16_t* in  = &j->in[(size_t)n * L];
+  for (uint32_t n = j->first; n < j->last && !j->err; n++) {
+    int16_t* in  = sb ? &sb[(size_t)(n - j->first) * SB_STRIDE] : &j->in[(size_t)n * L];
     uint8_t* out = &j->out[(size_t)n * (j->K / 8)];
     srsran_tdec_new_cb(&h, j->K);
     uint32_t noi = 0;
@@ -433,10 +467,12 @@ static void* job_run(void* arg)
   }
   j->t_end = now_s();
   srsran_tdec_free(&h);
+  free(sb);
   return NULL;
 }
 
-/* returns wall seconds for decoding n code blocks with nthreads pthreads (pinned to cores 0..nthreads-1 if pin) */
+/* returns wall seconds for decoding n code blocks with nthreads pthreads; pin: bit 0 = pin thread t to core t, bit 1 = feed the
+ * decoder the production sub-block layout (see job_run) instead of natural-order input with srsran_tdec_force_not_sb */
 double ref_tdec_batch(int       impl,
                       uint32_t  K,
                       int16_t*  in,
@@ -459,7 +495,7 @@ double ref_tdec_batch(int       impl,
   pthread_barrier_init(&barrier, NULL, nthreads);
   for (int t = 0; t < nthreads; t++) {
     jobs[t] = (job_t){impl, K, in, out, noi, crc_ok, (uint32_t)((uint64_t)n * t / nthreads),
-                      (uint32_t)((uint64_t)n * (t + 1) / nthreads), max_iter, early_stop, pin ? t : -1, 0, 0, 0, &barrier};
+                      (uint32_t)((uint64_t)n * (t + 1) / nthreads), max_iter, early_stop, (pin & 1) ? t : -1, 0, 0, 0, &barrier, (pin & 2) ? 1 : 0};
     pthread_create(&th[t], NULL, job_run, &jobs[t]);
   }
   int    err = 0;
@@ -630,6 +666,17 @@ void* ref_dlsch_rx_new(void)
   }
   return sb;
 }
+/* a soft buffer with room for max_cb code blocks (srsran_softbuffer_rx_init_guru, softbuffer.c:48): the 110-PRB one above holds 16,
+ * a two-layer transport block of 100 PRB has 25 */
+void* ref_dlsch_rx_new_guru(uint32_t max_cb)
+{
+  srsran_softbuffer_rx_t* sb = calloc(1, sizeof(srsran_softbuffer_rx_t));
+  if (sb && srsran_softbuffer_rx_init_guru(sb, max_cb, SOFTBUFFER_SIZE)) {
+    free(sb);
+    sb = NULL;
+  }
+  return sb;
+}
 void ref_dlsch_rx_free(void* h)
 {
   if (h) {
@@ -669,6 +716,82 @@ int ref_dlsch_decode(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t n
   pthread_mutex_unlock(&g_lock);
   return ret;
 }
+/*
+ * The multi-codeword / multi-layer forms of the two calls above (sch.c:580-609, 618-650): grant with nof_tb transport blocks,
+ * the call addresses codeword tb_idx and passes nof_layers; Nl = 2 whenever nof_layers != nof_tb, and decode_tb / encode_tb
+ * then see Qm * Nl (BASELINE config 3: 64QAM on 2 layers => 12). The other codeword of a 2-TB grant is filled with a
+ * different TBS / modulation on purpose: the call must not look at it.
+ */
+static void cw_cfg_fill(srsran_pdsch_cfg_t* cfg, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, uint32_t tb_idx, uint32_t nof_tb)
+{
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->grant.nof_tb = nof_tb;
+  for (uint32_t t = 0; t < nof_tb && t < SRSRAN_MAX_CODEWORDS; t++) {
+    cfg->grant.tb[t].tbs      = (t == tb_idx) ? (int)tbs : 1000;
+    cfg->grant.tb[t].mod      = (t == tb_idx) ? mod_of(Qm) : SRSRAN_MOD_QPSK;
+    cfg->grant.tb[t].rv       = (t == tb_idx) ? (int)rv : 1;
+    cfg->grant.tb[t].nof_bits = (t == tb_idx) ? nof_e_bits : 2400;
+    cfg->grant.tb[t].enabled  = true;
+  }
+}
+int ref_dlsch_decode_cw(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, int16_t* e_bits, uint32_t max_iterations,
+                        uint8_t* data, uint8_t* cb_crc, uint8_t* tb_crc, float* avg_iterations, uint32_t tb_idx, uint32_t nof_layers,
+                        uint32_t nof_tb)
+{
+  ref_init();
+  if (tb_idx >= SRSRAN_MAX_CODEWORDS || tb_idx >= nof_tb) {
+    return -2;
+  }
+  pthread_mutex_lock(&g_lock);
+  int ret = -1;
+  if (sch_ready() == 0) {
+    srsran_softbuffer_rx_t* sb = (srsran_softbuffer_rx_t*)h;
+    srsran_pdsch_cfg_t      cfg;
+    cw_cfg_fill(&cfg, tbs, Qm, rv, nof_e_bits, tb_idx, nof_tb);
+    cfg.softbuffers.rx[tb_idx] = sb;
+    srsran_sch_set_max_noi(&g_sch, max_iterations);
+    ret = srsran_dlsch_decode2(&g_sch, &cfg, e_bits, data, (int)tb_idx, nof_layers);
+    for (uint32_t i = 0; i < sb->max_cb; i++) {
+      cb_crc[i] = sb->cb_crc[i] ? 1 : 0;
+    }
+    *tb_crc         = sb->tb_crc ? 1 : 0;
+    *avg_iterations = srsran_sch_last_noi(&g_sch);
+  }
+  pthread_mutex_unlock(&g_lock);
+  return ret;
+}
+int ref_dlsch_encode_cw(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, uint8_t* data, uint8_t* e_bits, uint32_t tb_idx,
+                        uint32_t nof_layers, uint32_t nof_tb)
+{
+  ref_init();
+  if (tb_idx >= SRSRAN_MAX_CODEWORDS || tb_idx >= nof_tb) {
+    return -2;
+  }
+  pthread_mutex_lock(&g_lock);
+  int ret = -1;
+  if (sch_ready() == 0) {
+    srsran_softbuffer_tx_t sb;
+    if (srsran_softbuffer_tx_init_guru(&sb, 32, SOFTBUFFER_SIZE) == 0) {  /* room for the 25 code blocks of a two-layer TB */
+      srsran_pdsch_cfg_t cfg;
+      cw_cfg_fill(&cfg, tbs, Qm, 0, nof_e_bits, tb_idx, nof_tb);
+      cfg.softbuffers.tx[tb_idx] = &sb;
+      ret                        = 0;
+      if (rv != 0) {
+        uint8_t* scratch = calloc((nof_e_bits + 7) / 8 + 64, 1);
+        ret              = srsran_dlsch_encode2(&g_sch, &cfg, data, scratch, (int)tb_idx, nof_layers);
+        free(scratch);
+      }
+      if (ret == 0) {
+        cfg.grant.tb[tb_idx].rv = (int)rv;
+        ret                     = srsran_dlsch_encode2(&g_sch, &cfg, data, e_bits, (int)tb_idx, nof_layers);
+      }
+      srsran_softbuffer_tx_free(&sb);
+    }
+  }
+  pthread_mutex_unlock(&g_lock);
+  return ret;
+}
+
 uint32_t ref_dlsch_rx_max_cb(void* h)
 {
   return ((srsran_softbuffer_rx_t*)h)->max_cb;

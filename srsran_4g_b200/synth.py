@@ -4,8 +4,7 @@ has one). This is the encode direction of the path used only 
 srsran_tcod_encode (lib/src/phy/fec/turbo/turbocoder.c:77-185) output order: s0 p0 p'0 s1 ... then 12 tail values."""
 import numpy as np
 
-from .binding import cbindex, cbsize, lib
-import ctypes as C
+# (pure numpy / torch: this module must not load libsrsran_b200.so - bench.py's reference arm generates its inputs here)
 
 CRC24B_POLY = 0x1800063
 CRC24A_POLY = 0x1864CFB
@@ -13,8 +12,7 @@ CRC24A_POLY = 0x1864CFB
 
 def qpp(K):
     """pi(i) = (f1 i + f2 i^2) mod K with the 36.212 Table 5.1.3-3 parameters held by the library's host tables"""
-    idx = cbindex(K)
-    assert idx >= 0 and cbsize(idx) == K
+    assert K in _qpp_params(), "K=%d is not an LTE turbo block size" % K
     # recover f1, f2 through the published table in include/lte_qpp_params.h (parsed once)
     f1, f2 = _qpp_params()[K]
     i = np.arange(K, dtype=np.uint64)

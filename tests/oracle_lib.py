@@ -72,11 +72,15 @@ class _Lib:
             # the literal sch.c entry points (srsran_dlsch_encode2 / srsran_dlsch_decode2 / ulsch_deinterleave)
             L.ref_dlsch_encode.argtypes = [C.c_uint32] * 4 + [u8p, u8p]; L.ref_dlsch_encode.restype = C.c_int
             L.ref_dlsch_rx_new.restype = C.c_void_p
+            L.ref_dlsch_rx_new_guru.argtypes = [C.c_uint32]; L.ref_dlsch_rx_new_guru.restype = C.c_void_p
             L.ref_dlsch_rx_free.argtypes = [C.c_void_p]
             L.ref_dlsch_rx_reset.argtypes = [C.c_void_p, C.c_uint32]
             L.ref_dlsch_rx_max_cb.argtypes = [C.c_void_p]; L.ref_dlsch_rx_max_cb.restype = C.c_uint32
             L.ref_dlsch_decode.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [i16p, C.c_uint32, u8p, u8p, u8p, C.POINTER(C.c_float)]
             L.ref_dlsch_decode.restype = C.c_int
+            L.ref_dlsch_decode_cw.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [i16p, C.c_uint32, u8p, u8p, u8p, C.POINTER(C.c_float)] + [C.c_uint32] * 3
+            L.ref_dlsch_decode_cw.restype = C.c_int
+            L.ref_dlsch_encode_cw.argtypes = [C.c_uint32] * 4 + [u8p, u8p] + [C.c_uint32] * 3; L.ref_dlsch_encode_cw.restype = C.c_int
             L.ref_ulsch_deinterleave.argtypes = [i16p, C.c_uint32, C.c_uint32, C.c_uint32, i16p, u32p, C.c_uint32]
             i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
             L.ref_dlsch_decode8.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [i8p, C.c_uint32, u8p, u8p, u8p]
@@ -228,6 +232,9 @@ class _Lib:
     def dlsch_rx_new(self):
         return self.lib.ref_dlsch_rx_new()
 
+    def dlsch_rx_new_guru(self, max_cb):
+        return self.lib.ref_dlsch_rx_new_guru(max_cb)
+
     def dlsch_rx_free(self, h):
         self.lib.ref_dlsch_rx_free(h)
 
@@ -239,6 +246,22 @@ class _Lib:
         cbc = np.zeros(ncb, np.uint8); tbc = np.zeros(1, np.uint8); avg = C.c_float(0)
         ret = self.lib.ref_dlsch_decode(h, tbs, Qm, rv, len(e_bits), e_bits, max_iterations, data, cbc, tbc, C.byref(avg))
         return dict(ret=ret, data=data, cb_crc=cbc, tb_crc=int(tbc[0]), avg_iterations=avg.value)
+
+    def dlsch_decode_cw(self, h, tbs, Qm, rv, e_bits, max_iterations, tb_idx, nof_layers, nof_tb):
+        """srsran_dlsch_decode2(q, cfg, e_bits, data, tb_idx, nof_layers) on a grant with nof_tb codewords; Qm = bits per symbol of the
+        modulation (decode_tb sees Qm * Nl, Nl = 2 when nof_layers != nof_tb: sch.c:587-604)"""
+        e_bits = np.ascontiguousarray(e_bits, np.int16)
+        ncb = self.lib.ref_dlsch_rx_max_cb(h)
+        data = np.zeros(ncb * 768 + 8, np.uint8)
+        cbc = np.zeros(ncb, np.uint8); tbc = np.zeros(1, np.uint8); avg = C.c_float(0)
+        ret = self.lib.ref_dlsch_decode_cw(h, tbs, Qm, rv, len(e_bits), e_bits, max_iterations, data, cbc, tbc, C.byref(avg), tb_idx, nof_layers, nof_tb)
+        return dict(ret=ret, data=data, cb_crc=cbc, tb_crc=int(tbc[0]), avg_iterations=avg.value)
+
+    def dlsch_encode_cw(self, tbs, Qm, rv, nof_e_bits, data, tb_idx, nof_layers, nof_tb):
+        data = np.ascontiguousarray(data, np.uint8).copy()
+        e = np.zeros((nof_e_bits + 7) // 8 + 64, np.uint8)
+        ret = self.lib.ref_dlsch_encode_cw(tbs, Qm, rv, nof_e_bits, data, e, tb_idx, nof_layers, nof_tb)
+        return ret, e[:(nof_e_bits + 7) // 8]
 
     def dlsch_decode8(self, h, tbs, Qm, rv, e_bits8, max_iterations):
         """srsran_dlsch_decode2 with q->llr_is_8bit set (int8 LLRs) on the persistent soft buffer h"""
@@ -308,3 +331,32 @@ def ref():
     if _ref is None and os.path.exists(REF_SO):
         _ref = _Lib(REF_SO, "ref_")
     return _ref
+
+
+REF_NATIVE_SO = os.path.join(ORACLE_DIR, "_ref", "libsrsran_ref_native.so")
+_ref_native = None
+
+
+def ref_for_timing():
+    """-> (library, build description) for the CPU speed baseline: the reference compiled with its full release flags
+    including -march=native (oracle/Makefile) when THIS host has every ISA extension of the build host, else the portable
+    AVX2 + FMA build. Parity tests never use this one."""
+    global _ref_native
+    flags_file = os.path.join(ORACLE_DIR, "_ref", "native_cpu_flags.txt")
+    if os.path.exists(REF_NATIVE_SO) and os.path.exists(flags_file):
+        need = set(open(flags_file).read().split())
+        have = set()
+        try:
+            for line in open("/proc/cpuinfo"):
+                if line.startswith("flags"):
+                    have = set(line.split(":", 1)[1].split())
+                    break
+        except OSError:
+            pass
+        if need and need <= have:
+            if _ref_native is None:
+                _ref_native = _Lib(REF_NATIVE_SO, "ref_")
+            return _ref_native, "-O3 -Ofast -funroll-loops -march=native (reference release flags)"
+    r = ref()
+    return r, "-O3 -Ofast -funroll-loops -mavx2 -mfma (host lacks ISA extensions of the build host: no -march=native)"
+

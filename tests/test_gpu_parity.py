@@ -184,6 +184,31 @@ def test_decode_tb_harq_vs_oracle(sb, eng, o, tbs, G, Qm, eb):
         _check_tb(res_o, tb, st)
 
 
+@pytest.mark.parametrize("tbs,G,Qe,eb", [(149776, 12 * 14400, 12, 5.5),   # BASELINE config 3: 64QAM x 2 layers, C = 25, K = 6016
+                                          (75376, 8 * 11000, 8, 4.5),       # 256QAM
+                                          (97896, 16 * 7200, 16, 4.0),      # 256QAM x 2 layers
+                                          (36696, 8 * 5500, 8, 3.0)])       # 16QAM x 2 layers
+def test_decode_tb_layers_codewords(sb, eng, o, tbs, G, Qe, eb):
+    """decode_tb with Qm * Nl as srsran_dlsch_decode2 passes it for two layers / 256QAM (sch.c:587-604): rv 0,2,3,1 against the
+    oracle, whose loop is pinned to the literal srsran_dlsch_decode2 for these very cases (tests/test_sch_literal.py)"""
+    tb = sb.TransportBlock(tbs)
+    st = None
+    rets = []
+    for tx, rv in enumerate((0, 2, 3, 1)):
+        _, e = vecgen.make_tb(tbs, G, Qe, rv, eb, 177 + Qe, scale=100)
+        res_o = o.decode_tb(tbs, Qe, rv, e, 8, st)
+        st = res_o["state"]
+        tb.data[:] = 0
+        assert eng.decode_tb(tb, Qe, rv, e, 8) == res_o["ret"]
+        rets.append(res_o["ret"])
+        _check_tb(res_o, tb, st)
+    assert 0 in rets
+    if tb.seg["C"] > 16:
+        # the stock 110-PRB soft buffer (max_cb = 16) cannot take this transport block: -2 like decode_tb (sch.c:541-545)
+        small = sb.TransportBlock(tbs, max_cb=16)
+        assert eng.decode_tb(small, Qe, 0, np.zeros(G, np.int16), 8) == -2
+
+
 def test_decode_tb_golden_fixtures(sb, eng):
     """against outputs of the compiled reference (tests/golden/tb_harq.npz)"""
     t = np.load(os.path.join(G, "tb_harq.npz"))
@@ -631,3 +656,45 @@ def test_decode_tb_with_device_descrambling(sb, eng, o, tbs, G, Qm):
         tb.data[:] = 0
         assert eng.decode_tb(tb, Qm, rv, scr, 8, c_init=c_init) == res["ret"]
         _check_tb(res, tb, st)
+
+
+def test_bench_path_vs_oracle(sb, o):
+    """The path bench.py times: device-resident LLRs, srsb200_tdec_plan_uniform(8192+ blocks of K=6144) - i.e. 128+ full
+    groups, the big-batch kernel instantiations - two plans used alternately so that consecutive submissions are pipelined
+    on the engine's two lanes. Every block of 5 whole groups (320 blocks, one per range of the submission plus the last)
+    is compared with the oracle: hard bytes, half-iteration counts, CRC verdicts."""
+    import torch
+    K, n = 6144, 8192 + 64 * 3 + 17  # a partial last group as well
+    dev = torch.device("cuda", 0)
+    e = sb.Engine(0)
+    try:
+        bits, llr16 = vecgen.make_cb_batch(K, 16, 1.5, 4242)
+        coded = np.stack([o.encode(b) for b in bits])
+        rng = np.random.default_rng(99)
+        s = 2.0 * np.tile(coded, (n // 16 + 1, 1))[:n].astype(np.float64) - 1.0
+        big = vecgen.quantise(s + vecgen.sigma_for(1.5) * rng.standard_normal(s.shape), 100)
+        d_llr = torch.from_numpy(big).to(dev)
+        plans = [e.plan_uniform(n, K, sb.CRC_24B) for _ in range(2)]
+        outs = [(torch.zeros((n, K // 8), dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev),
+                 torch.zeros(n, dtype=torch.uint8, device=dev)) for _ in range(2)]
+        for step in range(6):
+            i = step % 2
+            e.run_plan_dev(plans[i], d_llr.data_ptr(), 8, 2, True, outs[i][0].data_ptr(), outs[i][1].data_ptr(), outs[i][2].data_ptr())
+        e.sync()
+        torch.cuda.synchronize()
+        for a, b in zip(outs[0], outs[1]):
+            assert torch.equal(a, b)
+        out, noi, ok = (t.cpu().numpy() for t in outs[0])
+        ngroups = (n + 63) // 64
+        sample = []
+        for g in (0, ngroups // 4 + 1, ngroups // 2 + 2, 3 * ngroups // 4 + 3, ngroups - 2, ngroups - 1):
+            sample += list(range(64 * g, min(n, 64 * g + 64)))
+        sample = np.array(sample)
+        assert len(sample) >= 320
+        _, oo, on, ook = o.tdec_batch(K, big[sample], 8, True, nthreads=os.cpu_count() or 4)
+        assert (on == noi[sample]).all() and (ook == ok[sample]).all() and (oo == out[sample]).all()
+        assert ok.mean() > 0.97 and noi.min() >= 2
+        for p in plans:
+            e.plan_destroy(p)
+    finally:
+        e.close()

@@ -42,6 +42,38 @@ def test_dlsch_decode2_on_the_engine(phy):
             phy.dlsch_rx_free(h)
 
 
+@pytest.mark.parametrize("tbs,Qm,G,eb,tb_idx,nof_layers,nof_tb", [
+    (149776, 6, 12 * 14400, 5.5, 0, 2, 1),   # BASELINE config 3: two layers, one TB -> decode_tb sees Qm * Nl = 12
+    (75376, 6, 86400, 4.5, 1, 2, 2),         # second codeword of a two-codeword grant
+    (75376, 8, 8 * 11000, 4.5, 0, 1, 1),     # 256QAM
+    (97896, 8, 16 * 7200, 4.0, 1, 4, 2)])    # 256QAM, second codeword, two layers each
+def test_dlsch_decode2_layers_codewords_on_the_engine(phy, tbs, Qm, G, eb, tb_idx, nof_layers, nof_tb):
+    """srsran_dlsch_decode2(q, cfg, e, data, tb_idx, nof_layers) of the patched sch.c on the GPU engine == oracle over rv 0,2,3,1"""
+    o = ol.oracle()
+    Qe = Qm * (2 if nof_layers != nof_tb else 1)
+    h = phy.dlsch_rx_new_guru(32)
+    st = None
+    try:
+        for rv in (0, 2, 3, 1):
+            _, e = vecgen.make_tb(tbs, G, Qe, rv, eb, 19 + tbs + tb_idx, scale=100)
+            a = o.decode_tb(tbs, Qe, rv, e, 8, st)
+            st = a["state"]
+            b = phy.dlsch_decode_cw(h, tbs, Qm, rv, e, 8, tb_idx, nof_layers, nof_tb)
+            Cn = a["seg"]["C"]
+            assert a["ret"] == b["ret"] and a["tb_crc"] == b["tb_crc"]
+            assert np.array_equal(st["cb_crc"][:Cn], b["cb_crc"][:Cn])
+            assert np.float32(a["avg_iterations"]) == np.float32(b["avg_iterations"])
+            nb = (Cn - 1) * ((a["seg"]["K1"] - 24) // 8) + a["seg"]["K1"] // 8
+            assert np.array_equal(a["data"][:nb], b["data"][:nb])
+    finally:
+        phy.dlsch_rx_free(h)
+    # the transmit side of the same grant
+    data = np.random.default_rng(tbs).integers(0, 256, tbs // 8, dtype=np.uint8)
+    r0, e0 = o.encode_tb(tbs, Qe, 0, G, data)
+    r1, e1 = phy.dlsch_encode_cw(tbs, Qm, 0, G, data, tb_idx, nof_layers, nof_tb)
+    assert r0 == r1 == 0 and np.array_equal(np.unpackbits(e0)[:G], np.unpackbits(e1)[:G])
+
+
 def test_dlsch_encode2_on_the_engine(phy):
     o = ol.oracle()
     for tbs, Qm, rv, G in [(40, 2, 0, 120), (12216, 6, 2, 19200), (75376, 6, 0, 86400), (36696, 4, 3, 4 * 12000), (6120, 2, 1, 9000)]:

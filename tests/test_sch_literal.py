@@ -129,3 +129,57 @@ def test_ulsch_chain_literal(tbs, Qm, nprb, nsymb, ri_len):
         g = o.ulsch_deinterleave(llr, Qm, H, nsymb, [])
         a = o.decode_tb(tbs, Qm, 0, g, 8)
         assert a["ret"] == 0 and np.array_equal(a["data"][:tbs // 8], data)
+
+
+# ---------------------------------------------------------------- 2 layers, second codeword, 256QAM (sch.c:580-609)
+# (tbs, Qm of the modulation, G, kill, tb_idx, nof_layers, nof_tb): Nl = 2 whenever nof_layers != nof_tb
+CW_CASES = [
+    (149776, 6, 12 * 14400, [3, 24], 0, 2, 1),   # BASELINE config 3: 100 PRB 64QAM on two layers, one TB -> Qm * Nl = 12, C = 25, K = 6016
+    (75376, 6, 86400, [12], 1, 2, 2),            # second codeword of a two-codeword grant (Nl = 1)
+    (75376, 8, 8 * 11000, [0, 7], 0, 1, 1),      # 256QAM
+    (97896, 8, 16 * 7200, [15], 1, 4, 2),        # 256QAM, four layers on two codewords -> Qm * Nl = 16, second codeword
+    (36696, 4, 8 * 5500, [], 0, 2, 1),           # 16QAM on two layers -> 8
+]
+
+
+@pytest.mark.parametrize("tbs,Qm,G,kill,tb_idx,nof_layers,nof_tb", CW_CASES)
+def test_decode_tb_layers_codewords_vs_srsran_dlsch_decode2(tbs, Qm, G, kill, tb_idx, nof_layers, nof_tb):
+    o = ol.oracle()
+    Qe = Qm * (2 if nof_layers != nof_tb else 1)
+    payload, txs, seg = _harq_case(tbs, Qe, G, kill, 91 + tbs + tb_idx)
+    if seg["C"] > 16:
+        # the stock 110-PRB soft buffer holds 16 code blocks: decode_tb refuses (sch.c:541-545; the product mirrors it through
+        # srsb200_tb_t.max_cb, tests/test_gpu_parity.py::test_decode_tb_layers_codewords)
+        h = ref.dlsch_rx_new()
+        try:
+            assert ref.dlsch_decode_cw(h, tbs, Qm, 0, txs[0][1], 8, tb_idx, nof_layers, nof_tb)["ret"] == -2
+        finally:
+            ref.dlsch_rx_free(h)
+    h = ref.dlsch_rx_new_guru(max(seg["C"], 16))
+    st, decoded = None, False
+    try:
+        for rv, e in txs:
+            a = o.decode_tb(tbs, Qe, rv, e, 8, st)
+            st = a["state"]
+            b = ref.dlsch_decode_cw(h, tbs, Qm, rv, e, 8, tb_idx, nof_layers, nof_tb)
+            assert a["ret"] == b["ret"] and a["tb_crc"] == b["tb_crc"]
+            assert np.array_equal(st["cb_crc"][:seg["C"]], b["cb_crc"][:seg["C"]])
+            assert np.array_equal(a["data"][:tbs // 8], b["data"][:tbs // 8]) or a["ret"] != 0
+            if a["ret"] == 0 and not decoded:
+                decoded = True
+                assert np.array_equal(a["data"][:tbs // 8], payload[:tbs // 8])
+        assert decoded
+    finally:
+        ref.dlsch_rx_free(h)
+
+
+@pytest.mark.parametrize("tbs,Qm,G,kill,tb_idx,nof_layers,nof_tb", CW_CASES)
+@pytest.mark.parametrize("rv", [0, 2])
+def test_encode_tb_layers_codewords_vs_srsran_dlsch_encode2(tbs, Qm, G, kill, tb_idx, nof_layers, nof_tb, rv):
+    o = ol.oracle()
+    Qe = Qm * (2 if nof_layers != nof_tb else 1)
+    data = np.random.default_rng(tbs + rv).integers(0, 256, tbs // 8, dtype=np.uint8)
+    r0, e0 = o.encode_tb(tbs, Qe, rv, G, data)
+    r1, e1 = ref.dlsch_encode_cw(tbs, Qm, rv, G, data, tb_idx, nof_layers, nof_tb)
+    assert r0 == r1 == 0
+    assert np.array_equal(np.unpackbits(e0)[:G], np.unpackbits(e1)[:G])

@@ -98,38 +98,75 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def kernel_source_sha():
+    """fingerprint of the CUDA sources: ncu-derived figures (profiles/dram_traffic.json) are only printed for the kernels they
+    were captured on"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "srsran_4g_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def cpu_decoder():
-    """(library wrapper, kind, impl id): oracle/_ref (the compiled reference, AVX2 windowed decoder) when it travelled
-    with the repo, else the clean-room port."""
+    """(library wrapper, kind, impl id, build description): oracle/_ref (the compiled reference, AVX2 windowed decoder, built
+    with the reference's release flags) when it travelled with the repo, else the clean-room port. Loaded through
+    tests/oracle_lib.py only - nothing of srsran_4g_b200's native code is touched on this leg."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
-    r = ol.ref()
+    r, build = ol.ref_for_timing()
     if r is not None:
-        return r, "reference", 5  # SRSRAN_TDEC_AVX_WINDOW
-    return ol.oracle(), "port", 1
+        return r, "reference", 5, build  # SRSRAN_TDEC_AVX_WINDOW / AUTO for K = 6144
+    return ol.oracle(), "port", 1, "gcc -O2 (clean-room generic int16 port)"
 
 
-def run_cpu(sample_cbs, min_seconds, seed):
-    """times the CPU decoder on a bounded sample with all host threads; returns dict for cpu_baseline"""
-    from srsran_4g_b200 import synth
-    lib, kind, impl = cpu_decoder()
-    cores = len(os.sched_getaffinity(0))
-    n = max(sample_cbs, cores * 8)
-    _, llr = synth.make_llr_batch(K, n, EBN0_DB, seed, LLR_SCALE, n_distinct=64)
-    lib.tdec_batch(K, llr[: cores * 2], MAX_ITER, True, nthreads=cores, impl=impl)  # warm-up (tables, page-in)
-    total_bits, total_s, reps, noi_all = 0, 0.0, 0, None
-    while total_s < min_seconds or reps < 2:
-        secs, _, noi, ok = lib.tdec_batch(K, llr, MAX_ITER, True, nthreads=cores, impl=impl, pin=1) if kind == "reference" else \
-            lib.tdec_batch(K, llr, MAX_ITER, True, nthreads=cores)
-        total_s += secs
-        total_bits += n * K
+CPU_CBS_PER_THREAD = 256
+
+
+class CpuArm:
+    """The reference's CPU implementation of the path on a bounded sample of the workload, all host threads, pinned. One
+    'step' = cores x 64 code blocks; the decoder objects and the production sub-block input layout (what srsran_rm_turbo_rx_lut
+    leaves in the soft buffer, sch.c:415) are prepared by every thread BEFORE its start barrier, as BASELINE.md section 3 says.
+    Used by BOTH CPU legs (cpu_baseline of the b200 arm and --impl reference), so their figures are the same measurement."""
+
+    def __init__(self, max_iter, seed):
+        from srsran_4g_b200 import synth  # pure numpy on this path (no native library)
+        self.lib, self.kind, self.impl, self.build = cpu_decoder()
+        self.cores = len(os.sched_getaffinity(0))
+        self.n = self.cores * CPU_CBS_PER_THREAD
+        self.max_iter = max_iter
+        _, self.llr = synth.make_llr_batch(K, self.n, EBN0_DB, seed, LLR_SCALE, n_distinct=64)
+        self.noi = None
+
+    def step(self):
+        """-> seconds inside the library between the start barrier and the last thread finishing"""
+        if self.kind == "reference":
+            secs, _, self.noi, _ = self.lib.tdec_batch(K, self.llr, self.max_iter, True, nthreads=self.cores, impl=self.impl, pin=3)
+        else:
+            secs, _, self.noi, _ = self.lib.tdec_batch(K, self.llr, self.max_iter, True, nthreads=self.cores)
+        return secs
+
+    def describe(self, steps, total_s):
+        name = ("srsRAN AVX2 windowed int16 decoder (turbodecoder_win.h, selected by srsran_tdec_init for K=6144) compiled from the "
+                "reference tree with %s, input in the rate de-matcher's sub-block layout" % self.build) if self.kind == "reference" \
+            else "clean-room generic int16 port (oracle/turbo_oracle.c)"
+        return "%d code blocks (%d per thread) of the same workload per step x %d steps (%.1f s), %s, %d pthreads pinned" % (
+            self.n, CPU_CBS_PER_THREAD, steps, total_s, name, self.cores)
+
+
+def run_cpu(max_iter, min_seconds, seed, warmup=2):
+    arm = CpuArm(max_iter, seed)
+    for _ in range(warmup):
+        arm.step()
+    total_s, reps = 0.0, 0
+    while total_s < min_seconds or reps < 3:
+        total_s += arm.step()
         reps += 1
-        noi_all = noi
-    name = "srsRAN AVX2 windowed int16 decoder (SRSRAN_TDEC_AVX_WINDOW, turbodecoder_win.h) compiled from the reference tree" \
-        if kind == "reference" else "clean-room generic int16 port (oracle/turbo_oracle.c)"
-    return {"value": total_bits / total_s / 1e6, "unit": "Mbit/s", "cores": cores, "kind": kind,
-            "sample": "%d code blocks of the same workload x %d passes (%.1f s), %s, %d pthreads pinned" % (n, reps, total_s, name, cores),
-            "mean_half_iterations": float(np.mean(noi_all))}, n, reps, total_s
+    return {"value": arm.n * K * reps / total_s / 1e6, "unit": "Mbit/s", "cores": arm.cores, "kind": arm.kind,
+            "sample": arm.describe(reps, total_s), "mean_half_iterations": float(np.mean(arm.noi))}
 
 
 def main():
@@ -155,28 +192,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = len(os.sched_getaffinity(0))
-        from srsran_4g_b200 import synth
-        lib, kind, impl = cpu_decoder()
-        per_thread = 64
-        n = cores * per_thread
-        _, llr = synth.make_llr_batch(K, n, EBN0_DB, 1234, LLR_SCALE, n_distinct=64)
-        run = (lambda: lib.tdec_batch(K, llr, args.max_iter, True, nthreads=cores, impl=impl, pin=1)) if kind == "reference" else \
-            (lambda: lib.tdec_batch(K, llr, args.max_iter, True, nthreads=cores))
-        for _ in range(args.warmup):
-            run()
+        arm = CpuArm(args.max_iter, 4321)
+        for _ in range(max(args.warmup, 3)):  # clocks and caches of 16 freshly woken cores need a few passes
+            arm.step()
         dt = 0.0
         for _ in range(args.steps):
-            dt += run()[0]  # decode time inside the library: decoder objects are built before its start barrier
-        val = n * K * args.steps / dt / 1e6
-        sample = "each step = %d code blocks (%d per thread) of the workload, %d pthreads pinned" % (n, per_thread, cores)
+            dt += arm.step()
+        val = arm.n * K * args.steps / dt / 1e6
+        sample = arm.describe(args.steps, dt)
         print(json.dumps({
             "impl": "reference", "metric": "turbo-decoded info Mbit/s (K=6144, 4 iter)", "value": val, "unit": "Mbit/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "decoder": "AVX2 windowed int16 (reference production decoder for K=6144)" if kind == "reference"
-                       else "generic int16 port", "bounded_sample": sample},
-            "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": cores, "kind": kind, "sample": sample},
+            "config": {"workload": WORKLOAD},
+            "note": "CPU arm: each step decodes a bounded sample of the workload (%d code blocks), not the 16384 of the GPU arm; "
+                    "throughput in Mbit/s is size-independent for independent code blocks" % arm.n,
+            "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -224,6 +255,15 @@ def main():
     good = ok == 1
     if not (got[good] == tx[idx[good]]).all():
         raise SystemExit("decoded bits differ from the transmitted payload on CRC-passing blocks")
+    # ... and a sample of this very batch against the oracle (the reference's generic int16 algorithm): bytes, half-iteration
+    # counts and CRC verdicts of 64 blocks spread over the batch. The checker only - never timed, never on the product path.
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    samp = np.unique(np.linspace(0, n_cb - 1, 64).astype(np.int64))
+    _, o_out, o_noi, o_ok = ol.oracle().tdec_batch(K, llr[torch.from_numpy(samp).to(dev)].cpu().numpy(), args.max_iter, True,
+                                                   nthreads=max(1, len(os.sched_getaffinity(0))))
+    if not ((o_out == got[samp]).all() and (o_noi == noi[samp]).all() and (o_ok == ok[samp]).all()):
+        raise SystemExit("bench batch: GPU results differ from the oracle on the sampled code blocks")
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -356,12 +396,20 @@ def main():
     hbm_achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
     alg_ops = ALG_OPS_PER_BIT_HALFITER * K * half_iters
     int_achieved = alg_ops / (per_launch_ms * 1e-3) / 1e12
-    traffic = None
+    # ncu-measured DRAM bytes: only for the kernel sources they were captured on (stale numbers are not printed)
+    traffic, traffic_total, traffic_note = None, None, "no ncu capture of these kernel sources under profiles/dram_traffic.json"
     try:
         with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
-            traffic = json.load(f).get("job_kernel_bytes_per_step")
+            tj = json.load(f)
+        if tj.get("kernel_source_sha") == kernel_source_sha():
+            traffic, traffic_total = tj.get("job_kernel_bytes_per_step"), tj.get("total_bytes_per_step")
+            traffic_note = tj.get("source")
+        else:
+            traffic_note = "profiles/dram_traffic.json was captured on other kernel sources (sha %s, now %s): not printed" % (
+                tj.get("kernel_source_sha"), kernel_source_sha())
     except Exception:
         pass
+    step_ms = ms / args.steps
     out = {
         "metric": "turbo-decoded info Mbit/s (K=6144, 4 iter)", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -380,17 +428,27 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
                      "measured_dram_GBps": (traffic / (per_launch_ms * 1e-3) / 1e9) if traffic else None,
                      "measured_dram_frac": (traffic / (per_launch_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic else None,
+                     "traffic_source": traffic_note,
                      "note": "achieved = compulsory bytes of the whole decode (6.13 B/info bit, SURVEY 8(d)) over the job kernels' time; traffic / measured_dram_* = what ncu saw the job kernels move (profiles/dram_traffic.json); roofline_int = the integer-issue view"},
         "roofline_int": {"bound": "int16x2 issue (VIADD/VIMNMX/VIADDMNMX .16x2, two pipes)", "kernel": "job_kernel", "achieved": int_achieved,
                          "peak": INT_PEAK_TOPS, "unit": "T packed-instr/s", "frac": int_achieved / INT_PEAK_TOPS,
                          "algorithmic_ops_per_launch": alg_ops, "executed_half_iterations_per_launch": half_iters,
                          "peak_source": "tools/microbench/int16x2_issue.cu on this pool (profiles/r01_int16x2_issue.txt)"},
     }
+    # the same two denominators over the WHOLE step as the driver times it (every kernel of the decode, pipelined), so that
+    # work a kernel split moves into another kernel cannot hide
+    out["roofline_step"] = {
+        "int": {"achieved": alg_ops / (step_ms * 1e-3) / 1e12, "peak": INT_PEAK_TOPS, "unit": "T packed-instr/s",
+                "frac": alg_ops / (step_ms * 1e-3) / 1e12 / INT_PEAK_TOPS},
+        "hbm": {"achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        "measured_dram_bytes_per_step": traffic_total,
+        "measured_dram_frac": (traffic_total / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if traffic_total else None,
+        "ms_per_step": step_ms}
     if e2e is not None:
         out["e2e"] = e2e
     if world == 1 and not args.no_cpu:
-        cb, _, _, _ = run_cpu(0, 10.0, 4321)
-        out["cpu_baseline"] = cb
+        out["cpu_baseline"] = run_cpu(args.max_iter, 10.0, 4321)
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -62,6 +62,10 @@ int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[
 /* host-pointer submissions of a contiguous equal-size batch are cut into this many ranges whose H2D / decode / D2H
  * overlap on separate streams (default 8, env SRSB200_SUBBATCHES; 1 = off) */
 int srsb200_engine_set_subbatches(srsb200_engine_t* e, int n);
+/* test hook for the error paths: the nth scratch-buffer request from now on fails (0 = off; env SRSB200_FAIL_ALLOC at
+ * engine creation). A failed submission returns SRSB200_ERROR with every queued transport block's ret = SRSB200_ERROR,
+ * nothing in flight, and the engine stays usable. */
+int srsb200_engine_inject_alloc_failure(srsb200_engine_t* e, int nth);
 /* stream the engine launches on (cudaStream_t), so callers can time with events on the same stream */
 void* srsb200_engine_stream(const srsb200_engine_t* e);
 
@@ -192,6 +196,9 @@ typedef struct {
    * uplink the host-side RI/ACK decoding needs the descrambled values first). */
   uint32_t        descramble;
   uint32_t        c_init;
+  /* Half-iteration limit of THIS transport block (q->max_iterations of its srsran_sch_t, sch.c:223-230); 0 = the
+   * max_iterations argument of the call. Blocks of one submission may differ. */
+  uint32_t        max_iterations;
 } srsb200_tb_t;
 
 /*
@@ -243,6 +250,28 @@ typedef struct {
 } srsb200_tb_tx_t;
 int srsb200_encode_tb_batch(srsb200_engine_t* e, srsb200_tb_tx_t* tbs, uint32_t n);
 int srsb200_encode_tb(srsb200_engine_t* e, srsb200_tb_tx_t* tb); /* returns tb->ret */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Several GPUs in one process: independent units, no exchange step, hence no collective - the dispatcher is
+ * host-side. One engine + one host thread per device; a submission is split by owner and the parts run concurrently.
+ * Reference analogue: one srsran_sch_t per PHY worker thread and carrier (srsenb/src/phy/lte/worker_pool.cc:32-58,
+ * cc_worker.cc:345). `owner[i]` = any id that is stable per HARQ entity (cell id, cell * nof_ue + ue, ...): the transport
+ * block goes to device owner[i] mod nof_devices, every time - soft-buffer mirrors stay where they are. owner == NULL: the
+ * soft buffer's address is the key.
+ */
+typedef struct srsb200_multi srsb200_multi_t;
+int  srsb200_device_count(void);
+/* devices == NULL / n == 0: every CUDA device of the process */
+int  srsb200_multi_create(srsb200_multi_t** m, const int* devices, int n);
+void srsb200_multi_destroy(srsb200_multi_t* m);
+int  srsb200_multi_nof_devices(const srsb200_multi_t* m);
+srsb200_engine_t* srsb200_multi_engine(srsb200_multi_t* m, int i);           /* e.g. for srsb200_softbuffer_set_resident per device */
+int  srsb200_multi_device_of(const srsb200_multi_t* m, uint64_t owner);      /* index into the device list */
+int  srsb200_multi_decode_tb_batch(srsb200_multi_t* m, srsb200_tb_t* tbs, uint32_t n, const uint64_t* owner, uint32_t max_iterations);
+/* flat code-block batch (srsb200_tdec_batch's arguments): contiguous ranges balanced by sum(K), one per device */
+int  srsb200_multi_tdec_batch(srsb200_multi_t* m, uint32_t n, const uint32_t* K, const uint8_t* crc_kind, const int16_t* llr,
+                              const uint64_t* llr_offset, uint64_t llr_len, uint32_t max_iter, uint32_t min_iter, int early_stop,
+                              uint8_t* out_bytes, const uint64_t* out_offset, uint64_t out_len, uint8_t* noi, uint8_t* crc_ok);
 
 #ifdef __cplusplus
 }

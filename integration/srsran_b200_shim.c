@@ -11,8 +11,9 @@
  * srsran_ulsch_decode with its UCI de-multiplexing) is untouched and funnels into it exactly as before.
  *
  * The device handle lives in fields the reference already has: h->dec16_hdlr[0] (srsb200_tdec_t*). One engine per
- * calling thread, created on first use (device = $SRSRAN_B200_DEVICE or 0); the C ABI serialises calls per engine, so any
- * number of PHY worker threads may call concurrently, like the lock-free reference objects, and their submissions overlap.
+ * calling thread and device, created on first use, destroyed at thread exit (devices: $SRSRAN_B200_DEVICES / $SRSRAN_B200_DEVICE,
+ * below); the C ABI serialises calls per engine, so any number of PHY worker threads may call concurrently, like the lock-free
+ * reference objects, and their submissions overlap.
  *
  * Layout contract: srsran_tdec_autoimp_get_subblocks() returns 0 for every size, which makes srsran_rm_turbo_rx_lut and
  * the decoder agree on the natural (generic decoder) input order - SURVEY.md section 8(b).
@@ -33,23 +34,120 @@
 #include "srsran_b200.h"
 
 /*
- * One engine per calling thread, created on first use: srsRAN runs one srsran_sch_t per PHY worker thread (x carrier), with
- * no locks between them, and a decode is latency-bound (sequential recursions), so the submissions of different workers must
- * be able to overlap on the GPU - which they do on separate engines (own streams and workspaces; examples/multicell_uplink.c
- * measures it). Decoder objects remember the engine that created them and stay usable from any thread.
+ * Engines: one per (calling thread, device), created on first use and destroyed when the thread exits (pthread key destructor).
+ * srsRAN runs one srsran_sch_t per PHY worker thread (x carrier) with no locks between them, and a decode is latency-bound
+ * (sequential recursions), so the submissions of different workers must be able to overlap on the GPU - which they do on
+ * separate engines (own streams and workspaces; examples/multicell_uplink.c measures it). Decoder objects remember the engine
+ * that created them and stay usable from any thread.
+ *
+ * Devices: SRSRAN_B200_DEVICES = "all" or a comma-separated list ("0,1,2,3") turns the shim into a multi-GPU dispatcher for a
+ * multi-cell eNB process (reference analogue: srsenb/src/phy/lte/worker_pool.cc:32-58 - one srsran_sch_t per worker and
+ * carrier); otherwise the single device SRSRAN_B200_DEVICE (default 0). Placement is by OWNER KEY modulo the device count: the
+ * soft buffer's address for transport blocks (a HARQ process always lands on the same GPU: SURVEY.md 8(e) "HARQ state is
+ * sticky"), the decoder object's address for srsran_tdec_*. No data crosses between devices - code blocks are independent.
  */
-static __thread srsb200_engine_t* t_engine = NULL;
+#define SHIM_MAX_DEV 16
+typedef struct {
+  srsb200_engine_t* eng[SHIM_MAX_DEV];
+} thread_engines_t;
+
+static pthread_key_t  g_key;
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+static int            g_ndev = 1;
+static int            g_dev[SHIM_MAX_DEV];
+
+static void thread_engines_free(void* p)
+{
+  thread_engines_t* te = (thread_engines_t*)p;
+  if (te) {
+    for (int i = 0; i < SHIM_MAX_DEV; i++) {
+      if (te->eng[i]) {
+        srsb200_engine_destroy(te->eng[i]); /* streams, pinned arenas, device tables and scratch of this thread */
+      }
+    }
+    free(te);
+  }
+}
+
+static void shim_init(void)
+{
+  pthread_key_create(&g_key, thread_engines_free);
+  const char* list = getenv("SRSRAN_B200_DEVICES");
+  const char* one  = getenv("SRSRAN_B200_DEVICE");
+  g_ndev   = 1;
+  g_dev[0] = one ? atoi(one) : 0;
+  if (list && *list) {
+    int n = 0;
+    if (!strcasecmp(list, "all")) {
+      int total = srsb200_device_count();
+      for (int d = 0; d < total && n < SHIM_MAX_DEV; d++) {
+        g_dev[n++] = d;
+      }
+    } else {
+      for (const char* p = list; *p && n < SHIM_MAX_DEV;) {
+        g_dev[n++] = atoi(p);
+        while (*p && *p != ',') {
+          p++;
+        }
+        if (*p == ',') {
+          p++;
+        }
+      }
+    }
+    if (n > 0) {
+      g_ndev = n;
+    }
+  }
+}
+
+static srsb200_engine_t* engine_slot(int slot)
+{
+  pthread_once(&g_once, shim_init);
+  thread_engines_t* te = (thread_engines_t*)pthread_getspecific(g_key);
+  if (te == NULL) {
+    te = calloc(1, sizeof(thread_engines_t));
+    if (te == NULL || pthread_setspecific(g_key, te)) {
+      free(te);
+      return NULL;
+    }
+  }
+  if (te->eng[slot] == NULL) {
+    if (srsb200_engine_create(&te->eng[slot], g_dev[slot]) != SRSB200_SUCCESS) {
+      ERROR("srsran_b200: %s", srsb200_last_error());
+      te->eng[slot] = NULL;
+    }
+  }
+  return te->eng[slot];
+}
+
+/* the calling thread's engine on the device that owns `key` */
+static srsb200_engine_t* engine_for(const void* key)
+{
+  pthread_once(&g_once, shim_init);
+  uint64_t k = (uint64_t)(uintptr_t)key;
+  k ^= k >> 17; /* allocator addresses share their low and high bits: mix before the modulo */
+  k *= 0x9E3779B97F4A7C15ull;
+  return engine_slot((int)((k >> 32) % (uint64_t)g_ndev));
+}
 
 static srsb200_engine_t* engine(void)
 {
-  if (t_engine == NULL) {
-    const char* dev = getenv("SRSRAN_B200_DEVICE");
-    if (srsb200_engine_create(&t_engine, dev ? atoi(dev) : 0) != SRSB200_SUCCESS) {
-      ERROR("srsran_b200: %s", srsb200_last_error());
-      t_engine = NULL;
-    }
-  }
-  return t_engine;
+  return engine_slot(0);
+}
+
+/* which device (index into the list) serves this soft buffer / decoder object - for tests and operators */
+int srsran_b200_device_of(const void* key)
+{
+  pthread_once(&g_once, shim_init);
+  uint64_t k = (uint64_t)(uintptr_t)key;
+  k ^= k >> 17;
+  k *= 0x9E3779B97F4A7C15ull;
+  return g_dev[(k >> 32) % (uint64_t)g_ndev];
+}
+int srsran_b200_nof_devices(void)
+{
+  pthread_once(&g_once, shim_init);
+  return g_ndev;
 }
 
 /* ------------------------------------------------------------------ srsran_tdec_* (turbodecoder.h:97-116) */
@@ -64,7 +162,7 @@ int srsran_tdec_init_manual(srsran_tdec_t* h, uint32_t max_long_cb, srsran_tdec_
   h->dec_type    = dec_type; /* every implementation type maps to the one bit-exact device decoder */
   h->max_long_cb = max_long_cb;
   srsb200_tdec_t* d = NULL;
-  if (srsb200_tdec_init(&d, engine(), max_long_cb) != SRSB200_SUCCESS) {
+  if (srsb200_tdec_init(&d, engine_for(h), max_long_cb) != SRSB200_SUCCESS) {
     ERROR("srsran_b200: %s", srsb200_last_error());
     return SRSRAN_ERROR;
   }
@@ -275,7 +373,7 @@ static int decode_tb_common(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer,
   tb.cb_noi     = NULL;
   tb.descramble = descramble ? 1u : 0u;
   tb.c_init     = c_init;
-  int ret = srsb200_decode_tb(engine(), &tb, q->max_iterations);
+  int ret = srsb200_decode_tb(engine_for(softbuffer), &tb, q->max_iterations);
   if (ret == SRSB200_ERROR_NO_DEVICE) {
     ERROR("srsran_b200: %s", srsb200_last_error());
     return SRSRAN_ERROR;
@@ -308,40 +406,68 @@ int srsran_b200_decode_tb_batch(srsran_sch_t**           q,
                                 uint32_t                 n,
                                 int*                     results)
 {
-  srsb200_tb_t* tb     = calloc(n, sizeof(srsb200_tb_t));
-  uint8_t*      tb_crc = calloc(n, 1);
-  if (!tb || !tb_crc) {
+  srsb200_tb_t* tb     = calloc(n ? n : 1, sizeof(srsb200_tb_t));
+  uint8_t*      tb_crc = calloc(n ? n : 1, 1);
+  uint32_t*     order  = calloc(n ? n : 1, sizeof(uint32_t));
+  if (!tb || !tb_crc || !order) {
     free(tb);
     free(tb_crc);
+    free(order);
+    for (uint32_t i = 0; i < n; i++) {
+      results[i] = SRSRAN_ERROR;
+    }
     return SRSRAN_ERROR;
   }
-  uint32_t max_it = 0;
-  for (uint32_t i = 0; i < n; i++) {
-    tb[i].tbs        = cb_segm[i].tbs;
-    tb[i].Qm         = Qm[i];
-    tb[i].rv         = rv[i];
-    tb[i].nof_e_bits = nof_e_bits[i];
-    tb[i].e_bits     = e_bits[i];
-    tb[i].buffer_f   = softbuffer[i]->buffer_f;
-    tb[i].sb_data    = softbuffer[i]->data;
-    tb[i].cb_crc     = (uint8_t*)softbuffer[i]->cb_crc;
-    tb[i].tb_crc     = &tb_crc[i];
-    tb[i].max_cb     = softbuffer[i]->max_cb;
-    tb[i].data       = data[i];
-    if (q[i]->max_iterations > max_it) {
-      max_it = q[i]->max_iterations;
+  /* group the transport blocks by owning device (stable within a device), one submission per device */
+  uint32_t m = 0;
+  int      ret = SRSB200_SUCCESS;
+  for (int d = 0; d < srsran_b200_nof_devices(); d++) {
+    uint32_t first = m;
+    srsb200_engine_t* e = NULL;
+    for (uint32_t i = 0; i < n; i++) {
+      srsb200_engine_t* ei = engine_for(softbuffer[i]);
+      if (srsran_b200_device_of(softbuffer[i]) != g_dev[d]) {
+        continue;
+      }
+      e                     = ei;
+      order[m]              = i;
+      tb[m].tbs             = cb_segm[i].tbs;
+      tb[m].Qm              = Qm[i];
+      tb[m].rv              = rv[i];
+      tb[m].nof_e_bits      = nof_e_bits[i];
+      tb[m].e_bits          = e_bits[i];
+      tb[m].buffer_f        = softbuffer[i]->buffer_f;
+      tb[m].sb_data         = softbuffer[i]->data;
+      tb[m].cb_crc          = (uint8_t*)softbuffer[i]->cb_crc;
+      tb[m].tb_crc          = &tb_crc[i];
+      tb[m].max_cb          = softbuffer[i]->max_cb;
+      tb[m].data            = data[i];
+      tb[m].max_iterations  = q[i]->max_iterations; /* every transport block stops at the limit of ITS srsran_sch_t */
+      m++;
+    }
+    if (m > first) {
+      /* (devices are served one after the other from this thread; callers that want the devices to overlap submit from one
+       *  thread per cell, as srsENB's worker pool does, or use srsb200_multi_decode_tb_batch) */
+      int r = srsb200_decode_tb_batch(e, &tb[first], m - first, 0);
+      if (r != SRSB200_SUCCESS) {
+        ret = r;
+        for (uint32_t j = first; j < m; j++) {
+          tb[j].ret = SRSB200_ERROR;
+        }
+      }
     }
   }
-  int ret = srsb200_decode_tb_batch(engine(), tb, n, max_it);
-  for (uint32_t i = 0; i < n && ret == SRSB200_SUCCESS; i++) {
-    results[i] = tb[i].ret;
-    if (cb_segm[i].tbs != 0 && cb_segm[i].C != 0 && tb[i].ret != SRSRAN_ERROR_INVALID_INPUTS) {
+  for (uint32_t j = 0; j < m; j++) {
+    uint32_t i = order[j];
+    results[i] = tb[j].ret;
+    if (cb_segm[i].tbs != 0 && cb_segm[i].C != 0 && tb[j].ret != SRSRAN_ERROR_INVALID_INPUTS && tb[j].ret != SRSB200_ERROR_NO_DEVICE) {
       softbuffer[i]->tb_crc = tb_crc[i] != 0;
-      q[i]->avg_iterations  = tb[i].avg_iterations;
+      q[i]->avg_iterations  = tb[j].avg_iterations;
     }
   }
   free(tb);
   free(tb_crc);
+  free(order);
   return ret == SRSB200_SUCCESS ? SRSRAN_SUCCESS : SRSRAN_ERROR;
 }
 
@@ -396,7 +522,7 @@ int srsran_b200_ulsch_decode_tb(srsran_sch_t*           q,
   tb.e_offset      = e_offset;
   tb.g_bits        = g_bits;
   tb.nof_g_out     = g_bits ? nof_g_out : 0;
-  int ret = srsb200_decode_tb(engine(), &tb, q->max_iterations);
+  int ret = srsb200_decode_tb(engine_for(softbuffer), &tb, q->max_iterations);
   free(ri);
   if (ret == SRSB200_ERROR_NO_DEVICE) {
     ERROR("srsran_b200: %s", srsb200_last_error());
@@ -442,10 +568,62 @@ static void splice_bits(uint8_t* dst, uint32_t off, const uint8_t* src, uint32_t
 }
 
 /*
+ * data == NULL (sch.c:305 `if (data)`): the reference then re-reads the circular buffers softbuffer->buffer_b that an earlier
+ * call WITH data filled, i.e. it retransmits the payload of that call. The device encoder works from the payload, so the shim
+ * keeps the payload of the last call with data in the (otherwise unused) buffer_b arrays of the same soft buffer - same
+ * lifetime and ownership as the reference's state, no allocation: an 8-byte header in buffer_b[0], then PAYLOAD_CHUNK bytes
+ * per code-block buffer.
+ */
+#define PAYLOAD_MAGIC 0xB2005EEDu
+#define PAYLOAD_CHUNK 16384u
+static int payload_fits(const srsran_softbuffer_tx_t* sb, uint32_t nbytes)
+{
+  if (sb->buffer_b == NULL || sb->max_cb_size < PAYLOAD_CHUNK + 8) {
+    return 0;
+  }
+  return (nbytes + PAYLOAD_CHUNK - 1) / PAYLOAD_CHUNK <= sb->max_cb;
+}
+static void payload_store(srsran_softbuffer_tx_t* sb, uint32_t tbs, const uint8_t* data)
+{
+  uint32_t nbytes = tbs / 8;
+  if (!payload_fits(sb, nbytes) || sb->buffer_b[0] == NULL) {
+    return;
+  }
+  for (uint32_t i = 0, off = 0; off < nbytes; i++, off += PAYLOAD_CHUNK) {
+    if (sb->buffer_b[i] == NULL) {
+      return;
+    }
+    uint32_t n = nbytes - off < PAYLOAD_CHUNK ? nbytes - off : PAYLOAD_CHUNK;
+    memcpy(sb->buffer_b[i] + 8, &data[off], n);
+  }
+  uint32_t hdr[2] = {PAYLOAD_MAGIC, tbs};
+  memcpy(sb->buffer_b[0], hdr, sizeof(hdr));
+}
+/* -> malloc'd copy of the payload stored for this transport block size, or NULL */
+static uint8_t* payload_load(const srsran_softbuffer_tx_t* sb, uint32_t tbs)
+{
+  uint32_t nbytes = tbs / 8, hdr[2];
+  if (!payload_fits(sb, nbytes) || sb->buffer_b[0] == NULL) {
+    return NULL;
+  }
+  memcpy(hdr, sb->buffer_b[0], sizeof(hdr));
+  if (hdr[0] != PAYLOAD_MAGIC || hdr[1] != tbs) {
+    return NULL;
+  }
+  uint8_t* p = malloc(nbytes + 8);
+  for (uint32_t i = 0, off = 0; p && off < nbytes; i++, off += PAYLOAD_CHUNK) {
+    uint32_t n = nbytes - off < PAYLOAD_CHUNK ? nbytes - off : PAYLOAD_CHUNK;
+    memcpy(&p[off], sb->buffer_b[i] + 8, n);
+  }
+  return p;
+}
+
+/*
  * Drop-in body of sch.c's static encode_tb_off(): same arguments and return codes. CRC attach, turbo encoding and rate
  * matching of all code blocks run on the device as one submission; the bits land at bit offset w_offset of e_bits and
  * the rest of e_bits is preserved, as srsran_rm_turbo_tx_lut + srsran_bit_copy leave it. The transmit soft buffer
- * (softbuffer->buffer_b, the per-block circular buffers) is not used: every redundancy version is produced from `data`.
+ * (softbuffer->buffer_b, the per-block circular buffers) holds the payload instead of the coded circular buffers (above):
+ * every redundancy version is produced from the payload, with or without `data`.
  */
 int srsran_b200_encode_tb(srsran_sch_t*           q,
                           srsran_softbuffer_tx_t* softbuffer,
@@ -461,13 +639,21 @@ int srsran_b200_encode_tb(srsran_sch_t*           q,
     ERROR("Invalid parameters: e_bits=%d, cb_segm=%d, softbuffer=%d", e_bits != 0, cb_segm != 0, softbuffer != 0);
     return SRSRAN_ERROR_INVALID_INPUTS;
   }
+  uint8_t* kept = NULL;
   if (data == NULL && cb_segm->C > 0 && !cb_segm->F && Qm) {
-    ERROR("srsran_b200: retransmission without payload is not offloaded (no device-side circular buffer)");
-    return SRSRAN_ERROR;
+    kept = payload_load(softbuffer, cb_segm->tbs); /* HARQ retransmission: the payload of the last call with data */
+    if (kept == NULL) {
+      ERROR("srsran_b200: retransmission without payload, and this soft buffer holds none for tbs=%d", cb_segm->tbs);
+      return SRSRAN_ERROR;
+    }
+    data = kept;
+  } else if (data != NULL && cb_segm->C > 0 && !cb_segm->F) {
+    payload_store(softbuffer, cb_segm->tbs, data);
   }
   uint32_t nbytes = (nof_e_bits + 7) / 8;
   uint8_t* tmp    = w_offset || (Qm && nof_e_bits % Qm) || (nof_e_bits & 7u) ? malloc(nbytes + 8) : e_bits;
   if (!tmp) {
+    free(kept);
     return SRSRAN_ERROR;
   }
   srsb200_tb_tx_t tb;
@@ -479,7 +665,7 @@ int srsran_b200_encode_tb(srsran_sch_t*           q,
   tb.max_cb     = softbuffer->max_cb;
   tb.data       = data ? data : (const uint8_t*)"";
   tb.e_bits     = tmp;
-  int ret = srsb200_encode_tb(engine(), &tb);
+  int ret = srsb200_encode_tb(engine_for(softbuffer), &tb);
   if (ret == SRSB200_ERROR_NO_DEVICE) {
     ERROR("srsran_b200: %s", srsb200_last_error());
     ret = SRSRAN_ERROR;
@@ -490,6 +676,7 @@ int srsran_b200_encode_tb(srsran_sch_t*           q,
     }
     free(tmp);
   }
+  free(kept);
   return ret;
 }
 

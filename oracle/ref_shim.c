@@ -792,6 +792,33 @@ int ref_dlsch_encode_cw(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_b
   return ret;
 }
 
+/* HARQ retransmission WITHOUT payload (sch.c:305 `if (data)`): rv 0 with data on a fresh soft buffer, then redundancy version rv
+ * with data == NULL on the same soft buffer; e_bits receives the second transmission */
+int ref_dlsch_encode_retx_null(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, uint8_t* data, uint8_t* e_bits)
+{
+  ref_init();
+  pthread_mutex_lock(&g_lock);
+  int ret = -1;
+  if (sch_ready() == 0) {
+    srsran_softbuffer_tx_t sb;
+    if (srsran_softbuffer_tx_init(&sb, 110) == 0) {
+      srsran_pdsch_cfg_t cfg;
+      cw_cfg_fill(&cfg, tbs, Qm, 0, nof_e_bits, 0, 1);
+      cfg.softbuffers.tx[0] = &sb;
+      uint8_t* scratch      = calloc((nof_e_bits + 7) / 8 + 64, 1);
+      ret                   = srsran_dlsch_encode2(&g_sch, &cfg, data, scratch, 0, 1);
+      free(scratch);
+      if (ret == 0) {
+        cfg.grant.tb[0].rv = (int)rv;
+        ret                = srsran_dlsch_encode2(&g_sch, &cfg, NULL, e_bits, 0, 1);
+      }
+      srsran_softbuffer_tx_free(&sb);
+    }
+  }
+  pthread_mutex_unlock(&g_lock);
+  return ret;
+}
+
 uint32_t ref_dlsch_rx_max_cb(void* h)
 {
   return ((srsran_softbuffer_rx_t*)h)->max_cb;

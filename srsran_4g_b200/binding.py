@@ -44,7 +44,15 @@ def lib():
         L.srsb200_host_register.argtypes = [vp, C.c_size_t]
         L.srsb200_host_unregister.argtypes = [vp]
         L.srsb200_engine_profile.argtypes = [vp, i32]
+        L.srsb200_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i32]
+        L.srsb200_multi_destroy.argtypes = [vp]; L.srsb200_multi_destroy.restype = None
+        L.srsb200_multi_nof_devices.argtypes = [vp]
+        L.srsb200_multi_engine.argtypes = [vp, i32]; L.srsb200_multi_engine.restype = vp
+        L.srsb200_multi_device_of.argtypes = [vp, u64]
+        L.srsb200_multi_decode_tb_batch.argtypes = [vp, vp, u32, vp, u32]
+        L.srsb200_multi_tdec_batch.argtypes = [vp, u32, vp, vp, vp, vp, u64, u32, u32, i32, vp, vp, u64, vp, vp]
         L.srsb200_engine_set_subbatches.argtypes = [vp, i32]
+        L.srsb200_engine_inject_alloc_failure.argtypes = [vp, i32]
         L.srsb200_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
         L.srsb200_cbsize.argtypes = [u32]
         L.srsb200_cbindex.argtypes = [u32]
@@ -115,7 +123,7 @@ class _TbStruct(C.Structure):
                 ("max_cb", C.c_uint32), ("data", C.c_void_p), ("cb_noi", C.c_void_p), ("avg_iterations", C.c_float), ("ret", C.c_int),
                 ("q_bits", C.c_void_p), ("H_prime_total", C.c_uint32), ("N_pusch_symbs", C.c_uint32), ("ri_positions", C.c_void_p),
                 ("nof_ri_bits", C.c_uint32), ("e_offset", C.c_uint32), ("g_bits", C.c_void_p), ("nof_g_out", C.c_uint32),
-                ("descramble", C.c_uint32), ("c_init", C.c_uint32)]
+                ("descramble", C.c_uint32), ("c_init", C.c_uint32), ("max_iterations", C.c_uint32)]
 
 
 class _TbTxStruct(C.Structure):
@@ -205,6 +213,9 @@ class Engine:
     def set_subbatches(self, n):
         _check(self._L.srsb200_engine_set_subbatches(self._h, n), "srsb200_engine_set_subbatches")
 
+    def inject_alloc_failure(self, nth):
+        _check(self._L.srsb200_engine_inject_alloc_failure(self._h, nth), "srsb200_engine_inject_alloc_failure")
+
     def profile(self, enable):
         _check(self._L.srsb200_engine_profile(self._h, int(enable)), "srsb200_engine_profile")
 
@@ -281,11 +292,13 @@ class Engine:
         _check(self._L.srsb200_softbuffer_release(self._h, tb._bf, tb.max_cb), "srsb200_softbuffer_release")
 
     # ---- transport blocks
-    def decode_tb_batch(self, reqs, max_iterations):
-        """reqs: list of (TransportBlock, Qm, rv, e_bits)"""
+    def decode_tb_batch(self, reqs, max_iterations, limits=None):
+        """reqs: list of (TransportBlock, Qm, rv, e_bits); limits: optional per-TB half-iteration limits (0 = max_iterations)"""
         arr = (_TbStruct * len(reqs))()
-        for s, (tb, Qm, rv, e) in zip(arr, reqs):
+        for i, (s, (tb, Qm, rv, e)) in enumerate(zip(arr, reqs)):
             tb.fill(s, Qm, rv, e)
+            if limits is not None:
+                s.max_iterations = int(limits[i])
         ret = self._L.srsb200_decode_tb_batch(self._h, arr, len(reqs), max_iterations)
         for s, (tb, _, _, _) in zip(arr, reqs):
             tb.ret, tb.avg_iterations = s.ret, s.avg_iterations
@@ -380,3 +393,60 @@ class Tdec:
         out = np.zeros(K // 8, np.uint8)
         ret = self._L.srsb200_tdec_run_all(self._h, _ptr(llr), _ptr(out), nof_iterations, K)
         return ret, out
+
+
+class Multi:
+    """srsb200_multi_*: one process, several GPUs; transport blocks are placed by owner key modulo the device count"""
+
+    def __init__(self, devices=None):
+        self._L = lib()
+        self._h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(self._L.srsb200_multi_create(C.byref(self._h), arr, len(devices)), "srsb200_multi_create")
+        else:
+            _check(self._L.srsb200_multi_create(C.byref(self._h), None, 0), "srsb200_multi_create")
+
+    def close(self):
+        if self._h:
+            self._L.srsb200_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def nof_devices(self):
+        return self._L.srsb200_multi_nof_devices(self._h)
+
+    def launch_counts(self):
+        return [int(self._L.srsb200_engine_launch_count(self._L.srsb200_multi_engine(self._h, i))) for i in range(self.nof_devices)]
+
+    def device_of(self, owner):
+        return self._L.srsb200_multi_device_of(self._h, owner)
+
+    def decode_tb_batch(self, reqs, max_iterations, owners=None):
+        """reqs: list of (TransportBlock, Qm, rv, e_bits); owners: optional per-TB owner keys (cell ids)"""
+        arr = (_TbStruct * len(reqs))()
+        for s, (tb, Qm, rv, e) in zip(arr, reqs):
+            tb.fill(s, Qm, rv, e)
+        own = np.ascontiguousarray(owners, np.uint64) if owners is not None else None
+        ret = self._L.srsb200_multi_decode_tb_batch(self._h, arr, len(reqs), _ptr(own) if own is not None else None, max_iterations)
+        for s, (tb, _, _, _) in zip(arr, reqs):
+            tb.ret, tb.avg_iterations = s.ret, s.avg_iterations
+        return ret
+
+    def tdec_batch(self, K, llr, max_iter, early_stop=True, min_iter=2, crc_kind=CRC_24B):
+        """uniform K: llr [n, 3K+12] int16 -> (out [n, K/8], noi, ok), split over the devices"""
+        llr = np.ascontiguousarray(llr, np.int16)
+        n = llr.shape[0]
+        Ks = np.full(n, K, np.uint32); kinds = np.full(n, crc_kind, np.uint8)
+        loff = np.arange(n, dtype=np.uint64) * np.uint64(3 * K + 12)
+        ooff = np.arange(n, dtype=np.uint64) * np.uint64(K // 8)
+        out = np.zeros((n, K // 8), np.uint8); noi = np.zeros(n, np.uint8); ok = np.zeros(n, np.uint8)
+        _check(self._L.srsb200_multi_tdec_batch(self._h, n, _ptr(Ks), _ptr(kinds), _ptr(llr), _ptr(loff), llr.size, max_iter, min_iter, int(early_stop),
+                                                _ptr(out), _ptr(ooff), out.size, _ptr(noi), _ptr(ok)), "srsb200_multi_tdec_batch")
+        return out, noi, ok

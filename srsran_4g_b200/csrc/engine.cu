@@ -207,6 +207,7 @@ struct srsb200_engine {
   cudaStream_t sub[MAX_SUB] = {nullptr};
   cudaEvent_t  ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
 
+  int fail_alloc_countdown = 0;  // > 0: the n-th ensure_scratch call from now fails (tests of the error paths)
   // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
   bool profiling = false;
   struct ProfEv { cudaEvent_t a, b; int kind; };
@@ -254,6 +255,8 @@ struct ProfScope {
 
 static int ensure_scratch(srsb200_engine* e, int slot, size_t bytes, void** out)
 {
+  // fault injection (srsb200_engine_inject_alloc_failure / SRSB200_FAIL_ALLOC): the n-th scratch request from now on fails
+  if (e->fail_alloc_countdown > 0 && --e->fail_alloc_countdown == 0) return fail(SRSB200_ERROR, "injected allocation failure (scratch slot %d)", slot);
   if (e->scratch_cap[slot] < bytes) {
     if (e->d_scratch[slot]) cudaFree(e->d_scratch[slot]);
     e->d_scratch[slot]   = nullptr;
@@ -372,14 +375,22 @@ struct Stager {
         maxb      = std::max<uint64_t>(maxb, j.bytes);
       }
     }
-    if (k && ce == cudaSuccess) {
-      gather_copy_kernel<<<dim3((unsigned)((maxb + 16383) / 16384), (unsigned)k), 256, 0, st>>>(list);
+    for (size_t k0 = 0; k0 < k && ce == cudaSuccess; k0 += MAX_GRID_Y) {  // gridDim.y <= 65535
+      const size_t kn = std::min<size_t>(MAX_GRID_Y, k - k0);
+      gather_copy_kernel<<<dim3((unsigned)std::max<uint64_t>(1, (maxb + 16383) / 16384), (unsigned)kn), 256, 0, st>>>(list + k0);
       e->launches++;
       ce = cudaGetLastError();
     }
     return ce;
   }
   static constexpr uint64_t BIG = 32768;
+  static constexpr size_t   MAX_GRID_Y = 65535;
+  // error path: forget what has not been issued (the caller drains the stream)
+  void drop()
+  {
+    q.clear();
+    outs.clear();
+  }
   // after the stream has been synchronised
   void finish()
   {
@@ -525,8 +536,11 @@ extern "C" int srsb200_softbuffer_reset(srsb200_engine_t* e, int16_t** buffer_f,
   void* d_list;
   if (ensure_scratch(e, 5, sizeof(int16_t*) * nof_cb, &d_list)) return SRSB200_ERROR;
   CUDA_TRY(cudaMemcpyAsync(d_list, list.data(), sizeof(int16_t*) * nof_cb, cudaMemcpyHostToDevice, e->stream));
-  zero_slots_kernel<<<dim3((SOFTSLOT_ELEMS / 8 + 255) / 256, nof_cb), 256, 0, e->stream>>>((int16_t* const*)d_list, (uint32_t)(SOFTSLOT_ELEMS / 8));
-  e->launches++;
+  for (uint32_t c0 = 0; c0 < nof_cb; c0 += 65535u) {  // gridDim.y <= 65535
+    zero_slots_kernel<<<dim3((SOFTSLOT_ELEMS / 8 + 255) / 256, std::min(65535u, nof_cb - c0)), 256, 0, e->stream>>>((int16_t* const*)d_list + c0,
+                                                                                                                 (uint32_t)(SOFTSLOT_ELEMS / 8));
+    e->launches++;
+  }
   CUDA_TRY(cudaStreamSynchronize(e->stream));  // `list` (pageable) must stay alive until the copy has been issued and consumed
   return SRSB200_SUCCESS;
 }
@@ -643,6 +657,7 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   memset(e->d_rm_inv, 0, sizeof(e->d_rm_inv));
   memset(e->h_ktab, 0, sizeof(e->h_ktab));
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  if (const char* env = getenv("SRSB200_FAIL_ALLOC")) e->fail_alloc_countdown = std::max(0, atoi(env));
   if (const char* env = getenv("SRSB200_SUBBATCHES")) e->n_sub = std::max(1, std::min((int)srsb200_engine::MAX_SUB, atoi(env)));
   if (const char* env = getenv("SRSB200_SUBBATCHES_DEV")) e->n_sub_dev = std::max(1, std::min((int)srsb200_engine::MAX_SUB, atoi(env)));
   for (int i = 0; i < srsb200_engine::MAX_SUB; i++) {
@@ -735,6 +750,14 @@ extern "C" int srsb200_engine_set_subbatches(srsb200_engine_t* e, int n)
   return SRSB200_SUCCESS;
 }
 
+extern "C" int srsb200_engine_inject_alloc_failure(srsb200_engine_t* e, int nth)
+{
+  if (!e || nth < 0) return SRSB200_ERROR_INVALID_INPUTS;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  e->fail_alloc_countdown = nth;
+  return SRSB200_SUCCESS;
+}
+
 extern "C" uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e) { return e ? e->launches : 0; }
 extern "C" void*    srsb200_engine_stream(const srsb200_engine_t* e) { return e ? (void*)e->stream : nullptr; }
 extern "C" void* srsb200_host_alloc(size_t bytes)
@@ -796,6 +819,8 @@ struct srsb200_plan {
   uint64_t* d_llr_off = nullptr;
   uint64_t* d_out_off = nullptr;
   uint32_t* d_out_len = nullptr;  // optional [n_cb] bytes to emit per code block (nullptr: K/8)
+  uint8_t*  d_cb_max_iter = nullptr;  // optional [n_cb] half-iteration limit per code block (use_cb_max_iter)
+  bool      use_cb_max_iter = false;
   // decode state that lives across the launches of one decode (and across srsb200_tdec_iteration calls)
   uint32_t* d_crc_acc = nullptr;  // [n_cb] running CRC of the current half-iteration
   uint8_t*  d_done = nullptr;     // [n_cb]
@@ -805,18 +830,24 @@ struct srsb200_plan {
   int       lane = 0;            // which pair of sub-stream sets runs its device-resident submissions
   uint32_t  wpj = WPJ;           // windows per job warp: 16 for machine-filling batches (throughput), 8 otherwise (latency)
   // the launch chain of a small (single-range) decode as an instantiated CUDA graph, valid for exactly these arguments
-  cudaGraphExec_t graph = nullptr;
+  static const int N_GRAPHS = 4;  // a caller alternating a few buffer sets (double buffering, two codewords) re-uses, not re-captures
   struct GraphKey {
-    const void *llr, *out, *noi, *ok;
+    const void *llr, *out, *noi, *ok, *mi;
     uint32_t max_iter, min_iter, start_iter;
     int early_stop, do_extract;
     bool operator==(const GraphKey& o) const
     {
-      return llr == o.llr && out == o.out && noi == o.noi && ok == o.ok && max_iter == o.max_iter && min_iter == o.min_iter &&
+      return llr == o.llr && out == o.out && noi == o.noi && ok == o.ok && mi == o.mi && max_iter == o.max_iter && min_iter == o.min_iter &&
              start_iter == o.start_iter && early_stop == o.early_stop && do_extract == o.do_extract;
     }
-  } graph_key{};
-  uint32_t graph_launches = 0;
+  };
+  struct CachedGraph {
+    cudaGraphExec_t exec = nullptr;
+    GraphKey        key{};
+    uint32_t        launches = 0;
+    uint64_t        last_use = 0;
+  } graphs[N_GRAPHS];
+  uint64_t graph_clock = 0;
   bool      contiguous = false;  // one (K, crc) bucket and code block i at llr offset i*(3K+12), output offset i*K/8
 };
 
@@ -915,12 +946,14 @@ extern "C" void srsb200_plan_destroy(srsb200_plan_t* p)
 {
   if (!p) return;
   if (p->e) cudaSetDevice(p->e->device);
-  if (p->graph) cudaGraphExecDestroy(p->graph);
+  for (auto& cg : p->graphs)
+    if (cg.exec) cudaGraphExecDestroy(cg.exec);
   cudaFree(p->d_groups);
   cudaFree(p->d_ws);
   cudaFree(p->d_llr_off);
   cudaFree(p->d_out_off);
   cudaFree(p->d_out_len);
+  cudaFree(p->d_cb_max_iter);
   cudaFree(p->d_crc_acc);
   cudaFree(p->d_done);
   cudaFree(p->d_active);
@@ -982,7 +1015,7 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
       ProfScope ps(e, 6, st);
 #define SRSB200_JOB(M, WP)                                                                                                                    \
   job_kernel<M, WP><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, \
-                                             max_iter, min_iter, early_stop)
+                                             max_iter, min_iter, early_stop, p->use_cb_max_iter ? p->d_cb_max_iter : nullptr)
       if (p->wpj == 16) {
         if (mode == 0) SRSB200_JOB(0, 16); else if (mode == 1) SRSB200_JOB(1, 16); else SRSB200_JOB(2, 16);
       } else {
@@ -1046,10 +1079,17 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
   // process-wide driver lock. Their chain is captured once per (plan, arguments) into a CUDA graph and replayed.
   static const bool use_graphs = getenv("SRSB200_NO_GRAPHS") == nullptr;
   if (use_graphs && S == 1 && !lazy && !io && !e->profiling && start_iter == 0 && do_extract) {
-    const srsb200_plan::GraphKey key{d_llr, d_out, d_noi, d_ok, max_iter, min_iter, start_iter, early_stop, do_extract ? 1 : 0};
-    if (!p->graph || !(p->graph_key == key)) {
-      if (p->graph) cudaGraphExecDestroy(p->graph);
-      p->graph = nullptr;
+    const srsb200_plan::GraphKey key{d_llr, d_out, d_noi, d_ok, p->use_cb_max_iter ? p->d_cb_max_iter : nullptr, max_iter, min_iter, start_iter, early_stop, do_extract ? 1 : 0};
+    srsb200_plan::CachedGraph* slot = nullptr;
+    for (auto& cg : p->graphs)
+      if (cg.exec && cg.key == key) slot = &cg;
+    if (!slot) {
+      // least recently used slot
+      slot = &p->graphs[0];
+      for (auto& cg : p->graphs)
+        if (!cg.exec) { slot = &cg; break; } else if (cg.last_use < slot->last_use) slot = &cg;
+      if (slot->exec) cudaGraphExecDestroy(slot->exec);
+      slot->exec = nullptr;
       cudaGraph_t g = nullptr;
       const uint64_t l0 = e->launches;
       if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -1059,20 +1099,21 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
           launch_one(e, p, rg[0], 2, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
         }
         launch_one(e, p, rg[0], 4, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
-        if (cudaStreamEndCapture(e->stream, &g) == cudaSuccess && g && cudaGraphInstantiate(&p->graph, g, 0) == cudaSuccess) {
-          p->graph_key      = key;
-          p->graph_launches = (uint32_t)(e->launches - l0);
+        if (cudaStreamEndCapture(e->stream, &g) == cudaSuccess && g && cudaGraphInstantiate(&slot->exec, g, 0) == cudaSuccess) {
+          slot->key      = key;
+          slot->launches = (uint32_t)(e->launches - l0);
         } else {
-          p->graph = nullptr;
+          slot->exec = nullptr;
         }
         if (g) cudaGraphDestroy(g);
       }
       e->launches = l0;
       cudaGetLastError();
     }
-    if (p->graph) {
-      CUDA_TRY(cudaGraphLaunch(p->graph, e->stream));
-      e->launches += p->graph_launches;
+    if (slot->exec) {
+      slot->last_use = ++p->graph_clock;
+      CUDA_TRY(cudaGraphLaunch(slot->exec, e->stream));
+      e->launches += slot->launches;
       return SRSB200_SUCCESS;
     }
   }
@@ -1136,6 +1177,7 @@ extern "C" int srsb200_tdec_run_plan_dev(srsb200_engine_t* e, srsb200_plan_t* pl
                                          uint32_t min_iter, int early_stop, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_crc_ok)
 {
   if (!e || !plan || !d_llr || !d_out || !d_noi || !d_crc_ok) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
+  if ((uintptr_t)d_llr & 1u) return fail(SRSB200_ERROR_INVALID_INPUTS, "d_llr must be 2-byte aligned");
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
   // (profiling runs the submission on the engine stream itself: order it after whatever is still in flight on the lanes)
@@ -1203,7 +1245,22 @@ extern "C" int srsb200_tdec_batch(srsb200_engine_t* e, uint32_t n, const uint32_
     ce = cudaMemcpyAsync(d_llr, llr, llr_len * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream);
     if (ce == cudaSuccess)
       r = launch_plan(e, p, (const int16_t*)d_llr, max_iter, min_iter, early_stop, 0, true, (uint8_t*)d_out, (uint8_t*)d_noi, (uint8_t*)d_ok);
-    if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(out_bytes, d_out, out_len, cudaMemcpyDeviceToHost, e->stream);
+    // only [out_offset[i], +K[i]/8) of every code block is written (the header's contract): gaps in the caller's buffer keep
+    // their content and never see scratch bytes of an earlier submission. Neighbouring ranges merge into one transfer.
+    if (ce == cudaSuccess && r == 0) {
+      std::vector<std::pair<uint64_t, uint64_t>> rg(n);
+      for (uint32_t i = 0; i < n; i++) rg[i] = {out_offset[i], out_offset[i] + K[i] / 8};
+      std::sort(rg.begin(), rg.end());
+      uint64_t a = rg[0].first, b = rg[0].second;
+      for (uint32_t i = 1; i <= n && ce == cudaSuccess; i++) {
+        if (i < n && rg[i].first <= b) {
+          b = std::max(b, rg[i].second);
+          continue;
+        }
+        ce = cudaMemcpyAsync(out_bytes + a, (uint8_t*)d_out + a, b - a, cudaMemcpyDeviceToHost, e->stream);
+        if (i < n) { a = rg[i].first; b = rg[i].second; }
+      }
+    }
     if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(noi, d_noi, n, cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess && r == 0) ce = cudaMemcpyAsync(crc_ok, d_ok, n, cudaMemcpyDeviceToHost, e->stream);
   }
@@ -1438,7 +1495,7 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
   CUDA_TRY(cudaMemsetAsync(d_g, 0, ng * sizeof(int16_t), e->stream));  // the nof_ri_bits values past the data are left stale by the reference
   {
     ProfScope ps(e, 3);
-    ulsch_deint_kernel<<<dim3(std::min<uint32_t>(64u, (uint32_t)(ng + 255) / 256), 1), 256, 0, e->stream>>>((const DeintJob*)d_dj);
+    ulsch_deint_kernel<<<dim3(std::max(1u, std::min<uint32_t>(64u, (uint32_t)(ng + 255) / 256)), 1), 256, 0, e->stream>>>((const DeintJob*)d_dj);
     e->launches++;
   }
   CUDA_TRY(stg.d2h(g_bits, d_g, ng * sizeof(int16_t), e->stream));
@@ -1450,3 +1507,4 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
 
 #include "tb_decode.inc"
 #include "tb_encode.inc"
+#include "multi.inc"

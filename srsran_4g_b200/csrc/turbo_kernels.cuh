@@ -547,7 +547,7 @@ template <int MODE, int WPJ_T>
 __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws,
                                             uint8_t* __restrict__ group_active, uint8_t* __restrict__ done, uint32_t* __restrict__ crc_acc,
                                             uint32_t* __restrict__ arrivals, uint8_t* __restrict__ noi, uint8_t* __restrict__ ok, uint32_t cnt,
-                                            uint32_t max_iter, uint32_t min_iter, int early_stop)
+                                            uint32_t max_iter, uint32_t min_iter, int early_stop, const uint8_t* __restrict__ max_iter_cb)
 {
   if (!group_active[blockIdx.y]) return;
   __shared__ uint32_t s_last;
@@ -740,7 +740,8 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
         const uint32_t okv = (g.crc_kind != 0 && __ldcg(&crc_acc[cb]) == 0u) ? 1u : 0u;
         noi[cb] = (uint8_t)cnt;
         ok[cb]  = (uint8_t)okv;
-        if ((early_stop && okv && cnt >= min_iter) || cnt >= max_iter) done[cb] = 1;
+        // (max_iter_cb: transport blocks of one submission may carry different limits - one srsran_sch_t each)
+        if ((early_stop && okv && cnt >= min_iter) || cnt >= (max_iter_cb ? (uint32_t)max_iter_cb[cb] : max_iter)) done[cb] = 1;
         else active = 1;
       }
       crc_acc[cb] = 0u;
@@ -795,7 +796,7 @@ extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const
         for (uint32_t i = l8; i < nwords; i += 8) tile[cbl][i] = 0u;
       } else {
         const uint64_t off = llr_off[cb] + 3ull * k0;
-        if ((off & 3ull) == 0) {
+        if ((reinterpret_cast<uintptr_t>(llr + off) & 7u) == 0) {  // the ADDRESS, not the offset: the base may be a slice
           const uint2* src = reinterpret_cast<const uint2*>(llr + off);
           for (uint32_t i = l8; i < npairs; i += 8) {
             const uint2 v = __ldg(src + i);
@@ -933,7 +934,7 @@ emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, 
     // the last, because the next block's bytes overwrite the 24 CRC bits: sch.c:430 writes at cb_idx * rlen / 8)
     const uint32_t total = out_len ? out_len[cb] : K / 8;
     const uint32_t nb    = (4 * word >= total) ? 0u : min(nt / 8, total - 4 * word);
-    if (nb == 4 && ((out_off[cb] & 3ull) == 0)) {
+    if (nb == 4 && ((reinterpret_cast<uintptr_t>(o) & 3u) == 0)) {
       *reinterpret_cast<uint32_t*>(o) = __byte_perm(v, 0, 0x0123);
     } else {
       for (uint32_t b = 0; b < nb; b++) o[b] = (uint8_t)(v >> (24 - 8 * b));

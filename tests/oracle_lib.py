@@ -80,6 +80,7 @@ class _Lib:
             L.ref_dlsch_decode.restype = C.c_int
             L.ref_dlsch_decode_cw.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [i16p, C.c_uint32, u8p, u8p, u8p, C.POINTER(C.c_float)] + [C.c_uint32] * 3
             L.ref_dlsch_decode_cw.restype = C.c_int
+            L.ref_dlsch_encode_retx_null.argtypes = [C.c_uint32] * 4 + [u8p, u8p]; L.ref_dlsch_encode_retx_null.restype = C.c_int
             L.ref_dlsch_encode_cw.argtypes = [C.c_uint32] * 4 + [u8p, u8p] + [C.c_uint32] * 3; L.ref_dlsch_encode_cw.restype = C.c_int
             L.ref_ulsch_deinterleave.argtypes = [i16p, C.c_uint32, C.c_uint32, C.c_uint32, i16p, u32p, C.c_uint32]
             i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
@@ -256,6 +257,13 @@ class _Lib:
         cbc = np.zeros(ncb, np.uint8); tbc = np.zeros(1, np.uint8); avg = C.c_float(0)
         ret = self.lib.ref_dlsch_decode_cw(h, tbs, Qm, rv, len(e_bits), e_bits, max_iterations, data, cbc, tbc, C.byref(avg), tb_idx, nof_layers, nof_tb)
         return dict(ret=ret, data=data, cb_crc=cbc, tb_crc=int(tbc[0]), avg_iterations=avg.value)
+
+    def dlsch_encode_retx_null(self, tbs, Qm, rv, nof_e_bits, data):
+        """srsran_dlsch_encode2 with data, then again with data == NULL and redundancy version rv on the same tx soft buffer"""
+        data = np.ascontiguousarray(data, np.uint8).copy()
+        e = np.zeros((nof_e_bits + 7) // 8 + 64, np.uint8)
+        ret = self.lib.ref_dlsch_encode_retx_null(tbs, Qm, rv, nof_e_bits, data, e)
+        return ret, e[:(nof_e_bits + 7) // 8]
 
     def dlsch_encode_cw(self, tbs, Qm, rv, nof_e_bits, data, tb_idx, nof_layers, nof_tb):
         data = np.ascontiguousarray(data, np.uint8).copy()

@@ -698,3 +698,102 @@ def test_bench_path_vs_oracle(sb, o):
             e.plan_destroy(p)
     finally:
         e.close()
+
+
+# ---------------------------------------------------------------- robustness of the C ABI
+def test_decode_tb_batch_error_paths_fault_injection(sb, o):
+    """srsb200_engine_inject_alloc_failure: whichever scratch request of a transport-block submission fails, the call returns an
+    error with every queued block's ret = -1, nothing is left in flight, and the very next submission is bit-exact again"""
+    e = sb.Engine(0)
+    try:
+        cases = [(36696, 43200, 6, 1.0), (6200, 9000, 4, 0.5), (12216, 19200, 6, 2.5)]
+        es = [vecgen.make_tb(tbs, Gb, Qm, 0, eb, 400 + i)[1] for i, (tbs, Gb, Qm, eb) in enumerate(cases)]
+        exp = [o.decode_tb(tbs, Qm, 0, ev, 8) for (tbs, Gb, Qm, eb), ev in zip(cases, es)]
+        failed = 0
+        for nth in range(1, 12):
+            tbo = [sb.TransportBlock(c[0]) for c in cases]
+            reqs = [(tb, c[2], 0, ev) for tb, c, ev in zip(tbo, cases, es)]
+            e.inject_alloc_failure(nth)
+            ret = e.decode_tb_batch(reqs, 8)
+            e.inject_alloc_failure(0)
+            if ret != 0:
+                failed += 1
+                assert all(tb.ret == -1 for tb in tbo), (nth, [tb.ret for tb in tbo])
+            tbo = [sb.TransportBlock(c[0]) for c in cases]
+            reqs = [(tb, c[2], 0, ev) for tb, c, ev in zip(tbo, cases, es)]
+            assert e.decode_tb_batch(reqs, 8) == 0
+            for tb, r in zip(tbo, exp):
+                _check_tb(r, tb, r["state"])
+        assert failed >= 5
+    finally:
+        e.close()
+
+
+def test_decode_tb_batch_per_tb_iteration_limits(sb, eng, o):
+    """transport blocks of one submission with different half-iteration limits (one srsran_sch_t each): every block
+    must stop at ITS limit, as decode_tb called once per TB does"""
+    cases = [(36696, 43200, 6, 0.3, 2), (36696, 43200, 6, 0.3, 8), (6200, 9000, 4, 0.2, 3), (12216, 19200, 6, 0.6, 5)]
+    tbo, reqs, exp = [], [], []
+    for i, (tbs, Gb, Qm, eb, lim) in enumerate(cases):
+        _, ev = vecgen.make_tb(tbs, Gb, Qm, 0, eb, 500 + i // 2)
+        tb = sb.TransportBlock(tbs)
+        tbo.append(tb); reqs.append((tb, Qm, 0, ev)); exp.append(o.decode_tb(tbs, Qm, 0, ev, lim))
+    assert eng.decode_tb_batch(reqs, 8, limits=[c[4] for c in cases]) == 0
+    for tb, r in zip(tbo, exp):
+        _check_tb(r, tb, r["state"])
+    assert exp[0]["cb_noi"].max() == 2 and exp[1]["cb_noi"].max() > 2   # same e-bits, different limits: they do differ
+
+
+def test_tdec_batch_scattered_output_keeps_gaps(sb, eng, o):
+    """srsb200_tdec_batch with non-contiguous output offsets writes exactly [out_offset[i], +K/8): the bytes between
+    and after the blocks keep the caller's content"""
+    import ctypes as C
+    K = 512
+    _, llr = vecgen.make_cb_batch(K, 3, 2.0, 808)
+    _, oo, on, ook = o.tdec_batch(K, llr, 6, True)
+    Ks = np.full(3, K, np.uint32); kinds = np.full(3, sb.CRC_24B, np.uint8)
+    loff = (np.arange(3, dtype=np.uint64) * np.uint64(3 * K + 12))
+    ooff = np.array([5, 100, 301], np.uint64)   # odd offsets, gaps
+    out = np.full(400, 0xA5, np.uint8); noi = np.zeros(3, np.uint8); ok = np.zeros(3, np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    flat = np.ascontiguousarray(llr.reshape(-1))
+    assert sb.lib().srsb200_tdec_batch(eng.handle, 3, vp(Ks), vp(kinds), vp(flat), vp(loff), len(flat), 6, 2, 1, vp(out), vp(ooff), len(out), vp(noi), vp(ok)) == 0
+    mask = np.ones(400, bool)
+    for i in range(3):
+        assert (out[int(ooff[i]):int(ooff[i]) + K // 8] == oo[i]).all() and noi[i] == on[i] and ok[i] == ook[i]
+        mask[int(ooff[i]):int(ooff[i]) + K // 8] = False
+    assert (out[mask] == 0xA5).all()
+
+
+def test_multi_device_dispatcher(sb, o):
+    """srsb200_multi_*: transport blocks placed by owner key modulo the device count, flat batches split by sum(K); every result
+    equals the oracle's whatever the number of devices; with two or more devices every one of them must have launched kernels"""
+    import torch
+    m = sb.Multi()
+    try:
+        nd = m.nof_devices
+        assert nd == torch.cuda.device_count() >= 1
+        cases = [(36696, 43200, 6, 1.0), (6200, 9000, 4, 0.5), (12216, 19200, 6, 2.5), (75376, 86400, 6, 6.0), (6120, 14400, 2, 3.0), (40, 300, 2, 3.0)]
+        for round_ in range(2):   # second round: HARQ retransmission, every owner must land on the same device again
+            rv = (0, 2)[round_]
+            if round_ == 0:
+                tbo = [sb.TransportBlock(c[0]) for c in cases]
+                st = [None] * len(cases)
+            reqs, exp = [], []
+            for i, (tbs, Gb, Qm, eb) in enumerate(cases):
+                _, ev = vecgen.make_tb(tbs, Gb, Qm, rv, eb - 1.5, 600 + i)
+                reqs.append((tbo[i], Qm, rv, ev))
+                r = o.decode_tb(tbs, Qm, rv, ev, 8, st[i]); st[i] = r["state"]; exp.append(r)
+                tbo[i].data[:] = 0
+            assert m.decode_tb_batch(reqs, 8, owners=list(range(len(cases)))) == 0
+            for tb, r, s_ in zip(tbo, exp, st):
+                _check_tb(r, tb, s_)
+        assert [m.device_of(i) for i in range(6)] == [i % nd for i in range(6)]
+        K = 1024
+        _, llr = vecgen.make_cb_batch(K, 70, 1.2, 4321)
+        _, oo, on, ook = o.tdec_batch(K, llr, 7, True, nthreads=4)
+        out, noi, ok = m.tdec_batch(K, llr, 7)
+        assert (out == oo).all() and (noi == on).all() and (ok == ook).all()
+        assert all(c > 0 for c in m.launch_counts())
+    finally:
+        m.close()

@@ -84,6 +84,18 @@ def test_dlsch_encode2_on_the_engine(phy):
         assert r0 == r1 == 0 and np.array_equal(np.unpackbits(e0)[:nb], np.unpackbits(e1)[:nb])
 
 
+@pytest.mark.parametrize("tbs,Qm,rv,G", [(12216, 6, 2, 19200), (75376, 6, 3, 86400), (6120, 2, 1, 9000), (40, 2, 2, 120)])
+def test_dlsch_encode2_retransmission_without_payload(phy, tbs, Qm, rv, G):
+    """srsran_dlsch_encode2(..., data = NULL, ...) on a soft buffer that saw the payload - the reference
+    retransmits from its circular buffers (sch.c:305), the drop-in from the payload it kept in the same soft buffer"""
+    o = ol.oracle()
+    data = np.random.default_rng(tbs + 5).integers(0, 256, tbs // 8, dtype=np.uint8)
+    r0, e0 = o.encode_tb(tbs, Qm, rv, G, data)
+    r1, e1 = phy.dlsch_encode_retx_null(tbs, Qm, rv, G, data)
+    nb = Qm * (G // Qm)
+    assert r0 == r1 == 0 and np.array_equal(np.unpackbits(e0)[:nb], np.unpackbits(e1)[:nb])
+
+
 @pytest.mark.parametrize("tbs,Qm,nprb,nsymb,ri_len", [(2984, 2, 15, 12, 0), (12216, 4, 25, 12, 1), (36696, 6, 50, 12, 1), (75376, 6, 100, 12, 0)])
 def test_ulsch_decode_on_the_engine(phy, tbs, Qm, nprb, nsymb, ri_len):
     """srsran_ulsch_decode with the de-interleaver + decode fused on the device (grants with and without RI)"""

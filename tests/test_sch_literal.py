@@ -183,3 +183,14 @@ def test_encode_tb_layers_codewords_vs_srsran_dlsch_encode2(tbs, Qm, G, kill, tb
     r1, e1 = ref.dlsch_encode_cw(tbs, Qm, rv, G, data, tb_idx, nof_layers, nof_tb)
     assert r0 == r1 == 0
     assert np.array_equal(np.unpackbits(e0)[:G], np.unpackbits(e1)[:G])
+
+
+@pytest.mark.parametrize("tbs,Qm,rv,G", [(12216, 6, 2, 19200), (75376, 6, 3, 86400), (6120, 2, 1, 9000), (40, 2, 2, 120)])
+def test_encode_retransmission_without_payload_literal(tbs, Qm, rv, G):
+    """sch.c:305: data == NULL re-reads the circular buffers of the previous call = the same bits as encoding the payload at that rv"""
+    o = ol.oracle()
+    data = np.random.default_rng(tbs + 5).integers(0, 256, tbs // 8, dtype=np.uint8)
+    r0, e0 = o.encode_tb(tbs, Qm, rv, G, data)
+    r1, e1 = ref.dlsch_encode_retx_null(tbs, Qm, rv, G, data)
+    nb = Qm * (G // Qm)
+    assert r0 == r1 == 0 and np.array_equal(np.unpackbits(e0)[:nb], np.unpackbits(e1)[:nb])

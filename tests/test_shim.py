@@ -155,3 +155,46 @@ def test_shim_ulsch_decode_tb(shim):
         if ret == 0:
             assert (data[:tbs // 8] == res["data"][:tbs // 8]).all()
     assert ret == 0
+
+
+@pytest.mark.gpu
+def test_shim_thread_engines_are_destroyed_at_thread_exit(shim):
+    """the per-thread engines must not outlive their thread (streams, pinned arenas, device tables). 24 short-lived
+    threads each decode one K=6144 block through srsran_tdec_run_all; the device memory in use afterwards must be back to where it
+    was after the first few (a leak of one engine per thread would pile up tens of MB each)."""
+    import threading
+    import torch
+    o = ol.oracle()
+    K = 6144
+    _, llr = vecgen.make_cb(K, 1.5, 77)
+    ref = o.tdec_run_all(K, llr, 4)
+    shim.srsran_b200_selftest_sizeof_tdec.restype = C.c_size_t
+    sz = shim.srsran_b200_selftest_sizeof_tdec() + 64
+    errs = []
+
+    def work():
+        try:
+            h = C.create_string_buffer(sz)
+            out = np.zeros(K // 8, np.uint8)
+            assert shim.srsran_tdec_init(h, K) == 0
+            assert shim.srsran_tdec_run_all(h, llr.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 4, K) == 0
+            assert (out == ref).all()
+            shim.srsran_tdec_free(h)
+        except BaseException as ex:  # noqa: BLE001
+            errs.append(ex)
+
+    def run(n):
+        for _ in range(n):
+            t = threading.Thread(target=work)
+            t.start()
+            t.join()
+
+    run(4)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    run(20)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert not errs, errs[0]
+    assert free0 - free1 < 32 * 2 ** 20, "device memory grew by %.1f MB over 20 thread lifetimes" % ((free0 - free1) / 2 ** 20)
+    assert shim.srsran_b200_nof_devices() >= 1

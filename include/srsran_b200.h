@@ -140,6 +140,23 @@ int  srsb200_tdec_run_all(srsb200_tdec_t* h, const int16_t* input, uint8_t* outp
  * the north-star's "get_hard_decision"); -1 before the first half-iteration */
 int  srsb200_tdec_get_hard_decision(srsb200_tdec_t* h, uint8_t* output);
 
+/* ------------------------------------------------------------------ 8-bit LLR mode: srsran_tdec_*_8bit, srsran_rm_turbo_rx_lut_8bit */
+/*
+ * The reference's 8-bit mode is not the generic algorithm in fewer bits: srsran_tdec_iteration_8bit (turbodecoder.c:458-484,
+ * 551-555) runs the windowed SIMD decoders of turbodecoder_win.h with llr_t = int8_t (saturating arithmetic, 32 or 16
+ * windows with 40-step warm-up, max-normalisation, extrinsic >> 1). The engine reproduces them bit for bit (win8_kernels.cuh;
+ * the CPU checker of the test suite is pinned to the compiled reference). srsb200_tdec8_windows: number of windows for this K, 0 = the
+ * reference does not decode this size in 8-bit arithmetic (it widens to int16 SSE decoders, turbodecoder.c:443-476).
+ */
+uint32_t srsb200_tdec8_windows(uint32_t K);
+/* srsb200_tdec_batch with int8 LLRs (natural order, 3K+12 per block; llr_offset / llr_len in elements = bytes); every K must have
+ * srsb200_tdec8_windows(K) != 0 */
+int srsb200_tdec_batch8(srsb200_engine_t* e, uint32_t n, const uint32_t* K, const uint8_t* crc_kind, const int8_t* llr, const uint64_t* llr_offset,
+                        uint64_t llr_len, uint32_t max_iter, uint32_t min_iter, int early_stop, uint8_t* out_bytes, const uint64_t* out_offset,
+                        uint64_t out_len, uint8_t* noi, uint8_t* crc_ok);
+/* replaces srsran_rm_turbo_rx_lut_8bit (rm_turbo.c:447-483): output[T[i mod (3K+12)]] += input[i] in wrapping int8, natural layout */
+int srsb200_rm_turbo_rx_lut8(srsb200_engine_t* e, const int8_t* input, int8_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx);
+
 /* ------------------------------------------------------------------ rate de-matching: srsran_rm_turbo_rx_lut */
 /* replaces srsran_rm_turbo_gentables / srsran_rm_turbo_free_tables (rm_turbo.h:54,56); idempotent, thread-safe */
 int  srsb200_rm_turbo_gentables(srsb200_engine_t* e);
@@ -199,6 +216,13 @@ typedef struct {
   /* Half-iteration limit of THIS transport block (q->max_iterations of its srsran_sch_t, sch.c:223-230); 0 = the
    * max_iterations argument of the call. Blocks of one submission may differ. */
   uint32_t        max_iterations;
+  /* q->llr_is_8bit (lib/include/srsran/phy/phch/sch.h:57): e_bits points to int8 LLRs and buffer_f[r] to int8[SRSB200_SOFTBUFFER_SIZE]
+   * (the reference casts the same arrays, sch.c:410,428). Rate de-matching is srsran_rm_turbo_rx_lut_8bit (wrapping int8), the
+   * decoder what srsran_tdec_iteration_8bit runs in AUTO mode - the windowed saturating int8 decoders - bit for bit. Accepted
+   * for transport blocks whose code-block sizes have an 8-bit decoder in the reference (srsb200_tdec8_windows(K) != 0: K > 800
+   * and K % 16 == 0; the reference widens smaller blocks to its SSE int16 decoders, the drop-in leaves those to the reference's
+   * own loop), without q_bits / descramble. All transport blocks of one submission must agree on this flag. */
+  uint32_t        llr_is_8bit;
 } srsb200_tb_t;
 
 /*

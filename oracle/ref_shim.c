@@ -222,6 +222,49 @@ int ref_tdec_trace(int impl, uint32_t K, int16_t* in, uint32_t nof_iter, uint8_t
   return 0;
 }
 
+/*
+ * The 8-BIT mode (turbodecoder.c:458-484,551-555): srsran_tdec_iteration_8bit in AUTO mode on natural-order int8 input
+ * (srsran_tdec_force_not_sb => tdec_win*_extract_input does the window interleaving). dump[it][3][K] = ext1, ext2, app1 of the
+ * decoder object after every half-iteration, brought back from the window-interleaved storage to natural order
+ * (element n lives at (n % S) * NW + n / S, S = K / NW: turbodecoder_win.h:883-921). Returns the number of windows the
+ * reference used (0 = it left 8-bit arithmetic for this K: turbodecoder.c:443-476) or < 0.
+ */
+int ref_tdec8_trace(uint32_t K, int8_t* in, uint32_t nof_iter, uint8_t* out_bytes, int8_t* dump)
+{
+  srsran_tdec_t h;
+  if (srsran_tdec_init(&h, K)) {
+    return -1;
+  }
+  srsran_tdec_force_not_sb(&h);
+  if (srsran_tdec_new_cb(&h, K)) {
+    srsran_tdec_free(&h);
+    return -2;
+  }
+  uint32_t NW = srsran_tdec_autoimp_get_subblocks_8bit(K);
+  uint32_t nw = (NW == 32 || NW == 16) ? NW : 0;
+  for (uint32_t it = 0; it < nof_iter; it++) {
+    srsran_tdec_iteration_8bit(&h, in, &out_bytes[it * (K / 8)]);
+    if (dump && nw) {
+      const int8_t* src[3] = {(const int8_t*)h.ext1, (const int8_t*)h.ext2, (const int8_t*)h.app1};
+      uint32_t      S      = K / nw;
+      for (int a = 0; a < 3; a++) {
+        for (uint32_t n = 0; n < K; n++) {
+          dump[(it * 3 + a) * K + n] = src[a][(n % S) * nw + n / S];
+        }
+      }
+    }
+  }
+  srsran_tdec_free(&h);
+  return (int)nw;
+}
+
+/* srsran_rm_turbo_rx_lut_8bit itself: writes the sub-block layout of srsran_tdec_autoimp_get_subblocks_8bit(K) */
+int ref_rm_rx8(int8_t* e, int8_t* buf, uint32_t E, uint32_t cb_idx, uint32_t rv)
+{
+  ref_init();
+  return srsran_rm_turbo_rx_lut_8bit(e, buf, E, cb_idx, rv);
+}
+
 /* srsran_tdec_run_all on one CB */
 int ref_tdec_run_all(int impl, uint32_t K, int16_t* in, uint32_t nof_iter, uint8_t* out_bytes)
 {
@@ -923,6 +966,7 @@ int ref_ulsch_decode(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t n
 }
 
 /* srsran_dlsch_decode2 in 8-bit LLR mode (q->llr_is_8bit: rate de-matching and turbo decoding on int8 values) */
+static float g_last_avg_noi = 0;
 int ref_dlsch_decode8(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, int8_t* e_bits, uint32_t max_iterations, uint8_t* data,
                       uint8_t* cb_crc, uint8_t* tb_crc)
 {
@@ -948,9 +992,15 @@ int ref_dlsch_decode8(void* h, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t 
       cb_crc[i] = sb->cb_crc[i] ? 1 : 0;
     }
     *tb_crc = sb->tb_crc ? 1 : 0;
+    g_last_avg_noi = srsran_sch_last_noi(&g_sch);
   }
   pthread_mutex_unlock(&g_lock);
   return ret;
+}
+/* srsran_sch_last_noi after the latest ref_dlsch_decode8 (kept out of its signature, which the drop-in tests bind) */
+float ref_last_avg_iterations(void)
+{
+  return g_last_avg_noi;
 }
 
 /* srsran_sequence_apply_s itself (lib/src/phy/common/sequence.c:507-561) */

@@ -70,6 +70,18 @@ int orc_ulsch_deinterleave(const int16_t* q_bits, uint32_t Qm, uint32_t H_prime_
 void orc_sequence_bits(uint32_t c_init, uint8_t* c, uint32_t len);
 void orc_sequence_apply_s(const int16_t* in, int16_t* out, uint32_t len, uint32_t c_init);
 
+/* ------------------------------------------------------------------ 8-bit LLR mode (turbo_oracle8.c)
+ * The reference's windowed saturating int8 decoders (turbodecoder_win.h with llr_t = int8_t) restated in natural order.
+ * orc_tdec8_windows: 32 / 16 = number of windows the reference's AUTO mode uses for this K, 0 = not decoded in 8-bit
+ * arithmetic there (K <= 800 or K not a multiple of 16). */
+uint32_t orc_tdec8_windows(uint32_t K);
+int orc_tdec8_trace(uint32_t K, const int8_t* in, uint32_t nof_iter, uint8_t* out_bytes, int8_t* dump);
+double orc_tdec8_batch(uint32_t K, const int8_t* in, uint32_t n, uint32_t max_iter, int early_stop, int nthreads, uint8_t* out, uint8_t* noi,
+                       uint8_t* crc_ok);
+int orc_rm_rx8(const int8_t* e, int8_t* buf, uint32_t E, uint32_t cb_idx, uint32_t rv);
+int orc_decode_tb8(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, const int8_t* e_bits, uint32_t max_iterations, int8_t* buffer_b,
+                   uint8_t* sb_data, uint8_t* cb_crc, uint8_t* tb_crc, uint8_t* data, uint32_t* cb_noi, float* avg_iterations);
+
 #ifdef __cplusplus
 }
 #endif

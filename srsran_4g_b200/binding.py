@@ -51,6 +51,9 @@ def lib():
         L.srsb200_multi_device_of.argtypes = [vp, u64]
         L.srsb200_multi_decode_tb_batch.argtypes = [vp, vp, u32, vp, u32]
         L.srsb200_multi_tdec_batch.argtypes = [vp, u32, vp, vp, vp, vp, u64, u32, u32, i32, vp, vp, u64, vp, vp]
+        L.srsb200_tdec8_windows.argtypes = [u32]; L.srsb200_tdec8_windows.restype = u32
+        L.srsb200_tdec_batch8.argtypes = [vp, u32, vp, vp, vp, vp, u64, u32, u32, i32, vp, vp, u64, vp, vp]
+        L.srsb200_rm_turbo_rx_lut8.argtypes = [vp, vp, vp, u32, u32, u32]
         L.srsb200_engine_set_subbatches.argtypes = [vp, i32]
         L.srsb200_engine_inject_alloc_failure.argtypes = [vp, i32]
         L.srsb200_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
@@ -100,6 +103,10 @@ def cbsize(idx):
     return lib().srsb200_cbsize(idx)
 
 
+def tdec8_windows(K):
+    return int(lib().srsb200_tdec8_windows(K))
+
+
 def cbindex(K):
     return lib().srsb200_cbindex(K)
 
@@ -123,7 +130,7 @@ class _TbStruct(C.Structure):
                 ("max_cb", C.c_uint32), ("data", C.c_void_p), ("cb_noi", C.c_void_p), ("avg_iterations", C.c_float), ("ret", C.c_int),
                 ("q_bits", C.c_void_p), ("H_prime_total", C.c_uint32), ("N_pusch_symbs", C.c_uint32), ("ri_positions", C.c_void_p),
                 ("nof_ri_bits", C.c_uint32), ("e_offset", C.c_uint32), ("g_bits", C.c_void_p), ("nof_g_out", C.c_uint32),
-                ("descramble", C.c_uint32), ("c_init", C.c_uint32), ("max_iterations", C.c_uint32)]
+                ("descramble", C.c_uint32), ("c_init", C.c_uint32), ("max_iterations", C.c_uint32), ("llr_is_8bit", C.c_uint32)]
 
 
 class _TbTxStruct(C.Structure):
@@ -149,8 +156,14 @@ class TransportBlock:
         self.ret, self.avg_iterations = None, 0.0
         self._e = None
 
-    def fill(self, s, Qm, rv, e_bits, nof_e_bits=None):
-        self._e = np.ascontiguousarray(e_bits, np.int16)
+    @property
+    def buffer_b(self):
+        """the soft buffers as the 8-bit mode sees them: (int8_t*)softbuffer->buffer_f[r] (sch.c:410)"""
+        return self.buffer_f.view(np.int8)
+
+    def fill(self, s, Qm, rv, e_bits, nof_e_bits=None, llr8=False):
+        self._e = np.ascontiguousarray(e_bits, np.int8 if llr8 else np.int16)
+        s.llr_is_8bit = 1 if llr8 else 0
         s.tbs, s.Qm, s.rv = self.tbs, Qm, rv
         s.nof_e_bits = len(self._e) if nof_e_bits is None else nof_e_bits
         s.e_bits = self._e.ctypes.data
@@ -256,6 +269,22 @@ class Engine:
             return out.reshape(n, K // 8), noi, ok
         return [out[int(o):int(o) + int(b)] for o, b in zip(ooff, obytes)], noi, ok
 
+    def tdec_batch8(self, K, llr8, max_iter, early_stop=True, min_iter=2, crc_kind=CRC_24B):
+        """8-bit LLR mode, uniform K: llr8 [n, 3K+12] int8 -> (out [n, K/8], noi, crc_ok)"""
+        llr8 = np.ascontiguousarray(llr8, np.int8)
+        n = llr8.shape[0]
+        Ks = np.full(n, K, np.uint32); kinds = np.full(n, crc_kind, np.uint8)
+        loff = np.arange(n, dtype=np.uint64) * np.uint64(3 * K + 12)
+        ooff = np.arange(n, dtype=np.uint64) * np.uint64(K // 8)
+        out = np.zeros((n, K // 8), np.uint8); noi = np.zeros(n, np.uint8); ok = np.zeros(n, np.uint8)
+        _check(self._L.srsb200_tdec_batch8(self._h, n, _ptr(Ks), _ptr(kinds), _ptr(llr8), _ptr(loff), llr8.size, max_iter, min_iter, int(early_stop),
+                                           _ptr(out), _ptr(ooff), out.size, _ptr(noi), _ptr(ok)), "srsb200_tdec_batch8")
+        return out, noi, ok
+
+    def rm_turbo_rx_lut8(self, e8, buf8, cb_idx, rv):
+        e8 = np.ascontiguousarray(e8, np.int8)
+        return self._L.srsb200_rm_turbo_rx_lut8(self._h, _ptr(e8), _ptr(buf8), len(e8), cb_idx, rv)
+
     # ---- device-resident plan API (raw device pointers, e.g. torch tensor .data_ptr())
     def plan_uniform(self, n, K, crc_kind=CRC_24B):
         p = C.c_void_p()
@@ -292,11 +321,12 @@ class Engine:
         _check(self._L.srsb200_softbuffer_release(self._h, tb._bf, tb.max_cb), "srsb200_softbuffer_release")
 
     # ---- transport blocks
-    def decode_tb_batch(self, reqs, max_iterations, limits=None):
-        """reqs: list of (TransportBlock, Qm, rv, e_bits); limits: optional per-TB half-iteration limits (0 = max_iterations)"""
+    def decode_tb_batch(self, reqs, max_iterations, limits=None, llr8=False):
+        """reqs: list of (TransportBlock, Qm, rv, e_bits); limits: optional per-TB half-iteration limits (0 = max_iterations);
+        llr8: q->llr_is_8bit - int8 e-bits and soft buffers, the reference's windowed saturating decoders"""
         arr = (_TbStruct * len(reqs))()
         for i, (s, (tb, Qm, rv, e)) in enumerate(zip(arr, reqs)):
-            tb.fill(s, Qm, rv, e)
+            tb.fill(s, Qm, rv, e, llr8=llr8)
             if limits is not None:
                 s.max_iterations = int(limits[i])
         ret = self._L.srsb200_decode_tb_batch(self._h, arr, len(reqs), max_iterations)
@@ -345,10 +375,11 @@ class Engine:
             r[0].ret, r[0].avg_iterations = s.ret, s.avg_iterations
         return ret
 
-    def decode_tb(self, tb, Qm, rv, e_bits, max_iterations, nof_e_bits=None, c_init=None):
-        """c_init: the e_bits are still scrambled; descramble them on the device with the Gold sequence of that seed"""
+    def decode_tb(self, tb, Qm, rv, e_bits, max_iterations, nof_e_bits=None, c_init=None, llr8=False):
+        """c_init: the e_bits are still scrambled; descramble them on the device with the Gold sequence of that seed;
+        llr8: q->llr_is_8bit (int8 e-bits and soft buffers)"""
         s = _TbStruct()
-        tb.fill(s, Qm, rv, e_bits, nof_e_bits)
+        tb.fill(s, Qm, rv, e_bits, nof_e_bits, llr8=llr8)
         if c_init is not None:
             s.descramble, s.c_init = 1, c_init
         ret = self._L.srsb200_decode_tb(self._h, C.byref(s), max_iterations)

@@ -8,6 +8,7 @@
 #include "turbo_kernels.cuh"
 #include "rm_kernels.cuh"
 #include "tx_kernels.cuh"
+#include "win8_kernels.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -225,6 +226,14 @@ struct srsb200_engine {
   std::vector<uint8_t>  tb_kind;
   std::vector<uint64_t> tb_boff, tb_ooff;
 
+  // 8-bit LLR mode (win8.inc): tables + the last plans of srsb200_tdec_batch8 / the 8-bit transport-block path
+  void* w8 = nullptr;
+  struct srsb200_plan8* cached_plan8 = nullptr;
+  struct srsb200_plan8* tb_plan8 = nullptr;
+  std::vector<uint32_t> tb8_K, tb8_olen;
+  std::vector<uint8_t>  tb8_kind;
+  std::vector<uint64_t> tb8_boff, tb8_ooff;
+
   // last plan built by srsb200_tdec_batch, reused when the next submission has the same shape
   struct srsb200_plan* cached_plan = nullptr;
   std::vector<uint32_t> cached_K;
@@ -233,6 +242,8 @@ struct srsb200_engine {
 };
 
 static int join_pending(srsb200_engine* e);
+static void plan8_destroy(struct srsb200_plan8* p);
+static void w8_engine_free(srsb200_engine* e);
 
 struct ProfScope {
   srsb200_engine* e; int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
@@ -697,6 +708,9 @@ extern "C" void srsb200_engine_destroy(srsb200_engine_t* e)
   cudaStreamSynchronize(e->stream);
   if (e->cached_plan) srsb200_plan_destroy(e->cached_plan);
   if (e->tb_plan) srsb200_plan_destroy(e->tb_plan);
+  plan8_destroy(e->cached_plan8);
+  plan8_destroy(e->tb_plan8);
+  w8_engine_free(e);
   for (void* p : e->softslot_chunks) cudaFree(p);
   for (void* p : e->owned) cudaFree(p);
   for (int i = 0; i < 16; i++)
@@ -1505,6 +1519,7 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
   return SRSB200_SUCCESS;
 }
 
+#include "win8.inc"
 #include "tb_decode.inc"
 #include "tb_encode.inc"
 #include "multi.inc"

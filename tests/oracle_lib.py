@@ -17,14 +17,15 @@ CRC24B = 0x1800063
 SOFTBUFFER_SIZE = 18600
 
 i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
 u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
 u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 
 
 def build_oracle(force=False):
-    src = os.path.join(ORACLE_DIR, "turbo_oracle.c")
-    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("turbo_oracle.c", "turbo_oracle8.c", "turbo_oracle.h")]
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
     return ORACLE_SO
 
@@ -83,8 +84,10 @@ class _Lib:
             L.ref_dlsch_encode_retx_null.argtypes = [C.c_uint32] * 4 + [u8p, u8p]; L.ref_dlsch_encode_retx_null.restype = C.c_int
             L.ref_dlsch_encode_cw.argtypes = [C.c_uint32] * 4 + [u8p, u8p] + [C.c_uint32] * 3; L.ref_dlsch_encode_cw.restype = C.c_int
             L.ref_ulsch_deinterleave.argtypes = [i16p, C.c_uint32, C.c_uint32, C.c_uint32, i16p, u32p, C.c_uint32]
-            i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
             L.ref_dlsch_decode8.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [i8p, C.c_uint32, u8p, u8p, u8p]
+            L.ref_last_avg_iterations.restype = C.c_float
+            L.ref_tdec8_trace.argtypes = [C.c_uint32, i8p, C.c_uint32, u8p, C.c_void_p]; L.ref_tdec8_trace.restype = C.c_int
+            L.ref_rm_rx8.argtypes = [i8p, i8p, C.c_uint32, C.c_uint32, C.c_uint32]; L.ref_rm_rx8.restype = C.c_int
             L.ref_dlsch_decode8.restype = C.c_int
             L.ref_ulsch_encode.argtypes = [C.c_uint32] * 7 + [u8p, u8p]; L.ref_ulsch_encode.restype = C.c_int
             L.ref_ulsch_decode.argtypes = [C.c_void_p] + [C.c_uint32] * 6 + [i16p, C.c_uint32, u8p, u8p, u8p, C.POINTER(C.c_float), u8p]
@@ -92,6 +95,12 @@ class _Lib:
         else:
             self._trace = L.orc_tdec_trace; self._trace.argtypes = [C.c_uint32, i16p, C.c_uint32, u8p, C.c_void_p]
             self._run_all = L.orc_tdec_run_all; self._run_all.argtypes = [C.c_uint32, i16p, C.c_uint32, u8p]
+            L.orc_tdec8_windows.argtypes = [C.c_uint32]; L.orc_tdec8_windows.restype = C.c_uint32
+            L.orc_tdec8_trace.argtypes = [C.c_uint32, i8p, C.c_uint32, u8p, C.c_void_p]; L.orc_tdec8_trace.restype = C.c_int
+            L.orc_tdec8_batch.argtypes = [C.c_uint32, i8p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, u8p, u8p, u8p]; L.orc_tdec8_batch.restype = C.c_double
+            L.orc_rm_rx8.argtypes = [i8p, i8p, C.c_uint32, C.c_uint32, C.c_uint32]; L.orc_rm_rx8.restype = C.c_int
+            L.orc_decode_tb8.argtypes = [C.c_uint32] * 4 + [i8p, C.c_uint32, i8p, u8p, u8p, u8p, u8p, u32p, C.POINTER(C.c_float)]
+            L.orc_decode_tb8.restype = C.c_int
             self._batch = L.orc_tdec_batch
             self._batch.argtypes = [C.c_uint32, i16p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, u8p, u8p, u8p]
             L.orc_ulsch_deinterleave.argtypes = [i16p, C.c_uint32, C.c_uint32, C.c_uint32, i16p, u32p, C.c_uint32]
@@ -207,6 +216,47 @@ class _Lib:
         avg = C.c_float(0)
         ret = self._dec_tb(tbs, Qm, rv, G, e_bits, max_iterations, state["buffer_f"], state["sb_data"], state["cb_crc"],
                            tb_crc, data, noi, C.byref(avg))
+        return dict(ret=ret, data=data, cb_noi=noi, tb_crc=int(tb_crc[0]), avg_iterations=avg.value, state=state, seg=seg)
+
+    # ---- 8-bit LLR mode
+    def tdec8_windows(self, K):
+        return int(self.lib.orc_tdec8_windows(K))
+
+    def tdec8_trace(self, K, llr8, nof_iter, dump=False):
+        """hard decisions after every half-iteration of the 8-bit window decoder; dump -> (out, [it][3][K] ext1, ext2, app1)"""
+        llr8 = np.ascontiguousarray(llr8, np.int8)
+        out = np.zeros((nof_iter, K // 8), np.uint8)
+        d = np.zeros((nof_iter, 3, K), np.int8) if dump else None
+        dp = d.ctypes.data_as(C.c_void_p) if dump else None
+        ret = getattr(self.lib, self.p + "tdec8_trace")(K, llr8, nof_iter, out, dp)
+        assert ret >= 0, ret
+        return (out, d) if dump else out
+
+    def tdec8_batch(self, K, llr8, max_iter, early_stop, nthreads=1):
+        llr8 = np.ascontiguousarray(llr8, np.int8)
+        n = llr8.shape[0]
+        out = np.zeros((n, K // 8), np.uint8); noi = np.zeros(n, np.uint8); ok = np.zeros(n, np.uint8)
+        secs = self.lib.orc_tdec8_batch(K, llr8, n, max_iter, int(early_stop), nthreads, out, noi, ok)
+        assert secs >= 0
+        return secs, out, noi, ok
+
+    def rm_rx8(self, e8, buf8, cb_idx, rv):
+        """in-place accumulate into buf8 (oracle: natural layout; compiled reference: its sub-block layout)"""
+        e8 = np.ascontiguousarray(e8, np.int8)
+        assert getattr(self.lib, self.p + "rm_rx8")(e8, buf8, len(e8), cb_idx, rv) == 0
+        return buf8
+
+    def decode_tb8(self, tbs, Qm, rv, e_bits8, max_iterations, state=None):
+        """the decode_tb loop with q->llr_is_8bit; state = dict(buffer_b[C,18600] i8, sb_data, cb_crc)"""
+        _, seg = self.cbsegm(tbs)
+        Cn = max(seg["C"], 1)
+        if state is None:
+            state = dict(buffer_b=np.zeros((Cn, SOFTBUFFER_SIZE), np.int8), sb_data=np.zeros((Cn, SOFTBUFFER_SIZE // 8), np.uint8),
+                         cb_crc=np.zeros(Cn, np.uint8))
+        e = np.ascontiguousarray(e_bits8, np.int8)
+        data = np.zeros(Cn * 768 + 8, np.uint8); noi = np.zeros(Cn, np.uint32); tb_crc = np.zeros(1, np.uint8); avg = C.c_float(0)
+        ret = self.lib.orc_decode_tb8(tbs, Qm, rv, len(e), e, max_iterations, state["buffer_b"], state["sb_data"], state["cb_crc"], tb_crc, data, noi,
+                                      C.byref(avg))
         return dict(ret=ret, data=data, cb_noi=noi, tb_crc=int(tb_crc[0]), avg_iterations=avg.value, state=state, seg=seg)
 
     def sequence_apply_s(self, llr, c_init):

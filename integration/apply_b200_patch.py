@@ -16,6 +16,7 @@ PROTOS = '''
 #ifdef SRSRAN_B200
 int srsran_b200_decode_tb(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer, srsran_cbsegm_t* cb_segm, uint32_t Qm, uint32_t rv,
                           uint32_t nof_e_bits, int16_t* e_bits, uint8_t* data);
+int srsran_b200_takes_tb(srsran_sch_t* q, srsran_cbsegm_t* cb_segm);
 int srsran_b200_encode_tb(srsran_sch_t* q, srsran_softbuffer_tx_t* softbuffer, srsran_cbsegm_t* cb_segm, uint32_t Qm, uint32_t rv,
                           uint32_t nof_e_bits, uint8_t* data, uint8_t* e_bits, uint32_t w_offset);
 int srsran_b200_ulsch_decode_tb(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer, srsran_cbsegm_t* cb_segm, uint32_t Qm, uint32_t rv,
@@ -41,7 +42,7 @@ def main():
     last_inc = [m for m in re.finditer(r'^#include .*$', src, re.M)][-1]
     src = src[:last_inc.end()] + "\n" + PROTOS + src[last_inc.end():]
     src = insert_after_open_brace(src, r'static int decode_tb\(srsran_sch_t\*\s+q,[^)]*\)',
-                                  "#ifdef SRSRAN_B200\n  if (q != NULL && !q->llr_is_8bit) {\n    return srsran_b200_decode_tb(q, softbuffer, cb_segm, Qm, rv, nof_e_bits, e_bits, data);\n  }\n#endif\n")
+                                  "#ifdef SRSRAN_B200\n  if (q != NULL && srsran_b200_takes_tb(q, cb_segm)) { /* int16 LLRs, and 8-bit LLRs of sizes with an 8-bit decoder */\n    return srsran_b200_decode_tb(q, softbuffer, cb_segm, Qm, rv, nof_e_bits, e_bits, data);\n  }\n#endif\n")
     src = insert_after_open_brace(src, r'static int encode_tb_off\(srsran_sch_t\*\s+q,[^)]*\)',
                                   "#ifdef SRSRAN_B200\n  return srsran_b200_encode_tb(q, softbuffer, cb_segm, Qm, rv, nof_e_bits, data, e_bits, w_offset);\n#endif\n")
     # srsran_ulsch_decode: right after Q_prime_ri is known

@@ -239,21 +239,28 @@ int srsran_tdec_run_all(srsran_tdec_t* h, int16_t* input, uint8_t* output, uint3
 }
 
 /*
- * 8-bit LLR entry points (turbodecoder.h:118-121), so that the shim replaces turbodecoder.c completely at link time. The
- * reference's 8-bit decoders are saturating SIMD variants with their own numerics (not the parity target); here the LLRs
- * are widened to int16 and decoded by the exact int16 engine - same API, results of the generic decoder on those values.
- * (sch.c reaches these only when q->llr_is_8bit; its own per-code-block loop then runs unchanged, see INTEGRATION.md.)
+ * 8-bit LLR entry points (turbodecoder.h:118-121). The reference's 8-bit mode runs its windowed saturating int8 decoders
+ * (turbodecoder_win.h with llr_t = int8_t) for K > 800 with K % 16 == 0; the engine reproduces those bit for bit
+ * (srsb200_tdec_batch8). For the smaller sizes the reference itself leaves 8-bit arithmetic (it widens to its SSE int16
+ * decoders, turbodecoder.c:443-476); there the LLRs are widened and decoded by the exact int16 engine - same API, results of the
+ * generic decoder on those values. No allocation per call: one scratch buffer per thread.
  */
-static int16_t* widen_llr8(const int8_t* input, uint32_t long_cb)
+static __thread int16_t t_widen[3 * 6144 + 12];
+static int tdec8_run(srsran_tdec_t* h, int8_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb)
 {
-  uint32_t n   = 3 * long_cb + 12;
-  int16_t* tmp = malloc(n * sizeof(int16_t));
-  if (tmp) {
-    for (uint32_t i = 0; i < n; i++) {
-      tmp[i] = input[i];
-    }
+  uint32_t K = long_cb, kind = 0;
+  uint64_t loff = 0, ooff = 0;
+  uint8_t  noi = 0, ok = 0;
+  uint8_t  kind8 = (uint8_t)kind;
+  /* stateless: half-iteration n of the 8-bit decoder is a pure function of the input, so "one more half-iteration" is the decode
+   * run to n + 1 from the start (the transport-block path, where it matters, submits whole decodes through the sch.c hook) */
+  int r = srsb200_tdec_batch8(engine_for(h), 1, &K, &kind8, input, &loff, 3ull * K + 12, nof_iterations ? nof_iterations : 1, 1, 0, output, &ooff, K / 8,
+                              &noi, &ok);
+  if (r != SRSB200_SUCCESS) {
+    ERROR("srsran_b200: %s", srsb200_last_error());
+    return SRSRAN_ERROR;
   }
-  return tmp;
+  return SRSRAN_SUCCESS;
 }
 void srsran_tdec_iteration_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output)
 {
@@ -261,21 +268,38 @@ void srsran_tdec_iteration_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output
     ERROR("Error CB index not set (call srsran_tdec_new_cb() first");
     return;
   }
-  int16_t* tmp = widen_llr8(input, h->current_long_cb);
-  if (tmp) {
-    srsran_tdec_iteration(h, tmp, output);
-    free(tmp);
+  if (srsb200_tdec8_windows(h->current_long_cb)) {
+    if (tdec8_run(h, input, output, (uint32_t)h->n_iter + 1, h->current_long_cb) == SRSRAN_SUCCESS) {
+      h->n_iter++;
+    }
+    return;
   }
+  uint32_t n = 3 * h->current_long_cb + 12;
+  for (uint32_t i = 0; i < n; i++) {
+    t_widen[i] = input[i];
+  }
+  srsran_tdec_iteration(h, t_widen, output);
 }
 int srsran_tdec_run_all_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb)
 {
-  int16_t* tmp = widen_llr8(input, long_cb);
-  if (!tmp) {
+  if (srsb200_tdec8_windows(long_cb)) {
+    if (srsran_tdec_new_cb(h, long_cb)) {
+      return SRSRAN_ERROR;
+    }
+    int ret = tdec8_run(h, input, output, nof_iterations, long_cb);
+    if (ret == SRSRAN_SUCCESS) {
+      h->n_iter = nof_iterations ? (int)nof_iterations : 1;
+    }
+    return ret;
+  }
+  if (long_cb > 6144) {
     return SRSRAN_ERROR;
   }
-  int ret = srsran_tdec_run_all(h, tmp, output, nof_iterations, long_cb);
-  free(tmp);
-  return ret;
+  uint32_t n = 3 * long_cb + 12;
+  for (uint32_t i = 0; i < n; i++) {
+    t_widen[i] = input[i];
+  }
+  return srsran_tdec_run_all(h, t_widen, output, nof_iterations, long_cb);
 }
 
 /* Names the reference does not have but integrators ask for: thin aliases. */
@@ -302,6 +326,26 @@ int srsran_rm_turbo_rx_lut_(int16_t* input, int16_t* output, uint32_t in_len, ui
 int srsran_rm_turbo_rx_lut(int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx)
 {
   return srsran_rm_turbo_rx_lut_(input, output, in_len, cb_idx, rv_idx, true);
+}
+
+/* rm_turbo.h:86-87: wrapping int8 accumulation, natural layout (srsran_tdec_autoimp_get_subblocks_8bit reports 0 here) */
+int srsran_rm_turbo_rx_lut_8bit(int8_t* input, int8_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx)
+{
+  return srsb200_rm_turbo_rx_lut8(engine(), input, output, in_len, cb_idx, rv_idx);
+}
+
+/* Does the batched entry point take this transport block? int16 LLRs: always. q->llr_is_8bit: when its code-block sizes run in the
+ * reference's 8-bit window decoders (K > 800, K % 16 == 0) - smaller blocks stay in the reference's own loop (sch.c:371-494), which
+ * then calls the per-block 8-bit symbols above. */
+int srsran_b200_takes_tb(srsran_sch_t* q, srsran_cbsegm_t* cb_segm)
+{
+  if (q == NULL || cb_segm == NULL || !q->llr_is_8bit) {
+    return 1;
+  }
+  if (cb_segm->C == 0) {
+    return 1;
+  }
+  return srsb200_tdec8_windows(cb_segm->K1) != 0 && (cb_segm->C2 == 0 || srsb200_tdec8_windows(cb_segm->K2) != 0);
 }
 
 /* ------------------------------------------------------------------ decode_tb (sch.c:509-573) */
@@ -351,9 +395,8 @@ static int decode_tb_common(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer,
     ERROR("Missing inputs: data=%d, softbuffer=%d, e_bits=%d, cb_segm=%d Qm=%d", data != 0, softbuffer != 0, e_bits != 0, cb_segm != 0, Qm);
     return SRSRAN_ERROR_INVALID_INPUTS;
   }
-  if (q->llr_is_8bit) {
-    /* the sch.c hook only comes here for int16 LLRs (the 8-bit mode keeps the reference's per-code-block loop) */
-    ERROR("srsran_b200: 8-bit LLR mode does not use the batched entry point");
+  if (q->llr_is_8bit && (descramble || !srsran_b200_takes_tb(q, cb_segm))) {
+    ERROR("srsran_b200: this 8-bit transport block stays in the reference's per-code-block loop (srsran_b200_takes_tb)");
     return SRSRAN_ERROR_INVALID_INPUTS;
   }
   uint8_t      tb_crc = 0;
@@ -371,8 +414,9 @@ static int decode_tb_common(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer,
   tb.max_cb     = softbuffer->max_cb;
   tb.data       = data;
   tb.cb_noi     = NULL;
-  tb.descramble = descramble ? 1u : 0u;
-  tb.c_init     = c_init;
+  tb.descramble  = descramble ? 1u : 0u;
+  tb.c_init      = c_init;
+  tb.llr_is_8bit = q->llr_is_8bit ? 1u : 0u; /* e_bits / buffer_f then point to int8 data, exactly as sch.c:410,428 casts them */
   int ret = srsb200_decode_tb(engine_for(softbuffer), &tb, q->max_iterations);
   if (ret == SRSB200_ERROR_NO_DEVICE) {
     ERROR("srsran_b200: %s", srsb200_last_error());

@@ -135,11 +135,36 @@ def test_ulsch_decode_on_the_engine(phy, tbs, Qm, nprb, nsymb, ri_len):
 
 
 def test_dlsch_decode2_8bit_mode_on_the_engine(phy):
-    """q->llr_is_8bit: the hooks leave sch.c's own per-code-block loop in place; it calls the reference's 8-bit rate
-    de-matcher and the shim's srsran_tdec_iteration_8bit (LLRs widened into the exact int16 engine). The reference's 8-bit
-    SIMD decoder has different numerics, so the comparison is on what a clean channel pins: return code, flags, bytes."""
+    """q->llr_is_8bit through the patched sch.c: transport blocks whose code blocks have an 8-bit decoder in the reference (K > 800,
+    K % 16 == 0) take the batched hook and run the reference's windowed saturating int8 algorithm on the GPU - return code, bytes,
+    flags AND the average half-iteration count equal the oracle's 8-bit loop (itself pinned to the literal sch.c with llr_is_8bit)
+    over a HARQ sequence at an operating point where the first transmission fails; smaller blocks stay in sch.c's own loop."""
+    o = ol.oracle()
     ref = ol.ref()
-    for tbs, Qm, G in [(12216, 4, 4 * 4500), (36696, 6, 6 * 8000), (6120, 2, 2 * 5000)]:
+    for tbs, Qm, G, eb in [(75376, 6, 86400, 1.0), (36696, 6, 6 * 8000, 0.3), (12960, 4, 4 * 5000, 0.5)]:
+        h = phy.dlsch_rx_new()
+        st = None
+        rets = []
+        try:
+            for rv in (0, 2, 3):
+                _, e = vecgen.make_tb(tbs, G, Qm, rv, eb, 131 + tbs, scale=12)
+                e8 = np.clip(e, -127, 127).astype(np.int8)
+                a = o.decode_tb8(tbs, Qm, rv, e8, 8, st)
+                st = a["state"]
+                b = phy.dlsch_decode8(h, tbs, Qm, rv, e8, 8)
+                Cn = a["seg"]["C"]
+                rets.append(a["ret"])
+                assert a["ret"] == b["ret"] and a["tb_crc"] == b["tb_crc"]
+                assert np.array_equal(st["cb_crc"][:Cn], b["cb_crc"][:Cn])
+                assert np.float32(a["avg_iterations"]) == np.float32(phy.lib.ref_last_avg_iterations())
+                if a["ret"] == 0:
+                    assert np.array_equal(a["data"][:tbs // 8], b["data"][:tbs // 8])
+        finally:
+            phy.dlsch_rx_free(h)
+        assert 0 in rets
+    # a transport block of small code blocks (K = 6144/... <= 800 is not reachable with C > 1; single block K = 512): stays in the
+    # reference loop, which calls the shim's per-block 8-bit symbols (LLRs widened into the exact int16 engine)
+    for tbs, Qm, G in [(488, 2, 2 * 700)]:
         payload, e = vecgen.make_tb(tbs, G, Qm, 0, 9.0, 21 + tbs, scale=20)
         e8 = np.clip(e, -127, 127).astype(np.int8)
         h = phy.dlsch_rx_new()

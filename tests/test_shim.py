@@ -21,7 +21,7 @@ def test_shim_builds_against_reference_headers():
     import __graft_entry__ as g
     g.build()
     out = subprocess.check_output(["make", "-s", "-C", os.path.join(ROOT, "integration"), "check"]).decode()
-    assert "exports all 22" in out
+    assert "exports all 24" in out
 
 
 @pytest.fixture(scope="module")
@@ -55,11 +55,20 @@ def test_shim_tdec_symbols(shim):
         assert shim.srsran_tdec_get_hard_decision(h, again.ctypes.data_as(C.c_void_p), K) == 0   # north-star alias
         assert (again == hard[2]).all()
         assert shim.srsran_tdec_get_hard_decision(h, again.ctypes.data_as(C.c_void_p), K + 8) == -2
-        # 8-bit LLR entry points: widened to int16 and decoded by the same exact engine
+        # 8-bit LLR entry points: the reference's windowed int8 decoder where it has one (K > 800, K % 16 == 0), else widened into
+        # the exact int16 engine
         l8 = np.clip(llr // 8, -127, 127).astype(np.int8)
         out8 = np.zeros(K // 8, np.uint8)
         assert shim.srsran_tdec_run_all_8bit(h, l8.ctypes.data_as(C.c_void_p), out8.ctypes.data_as(C.c_void_p), 4, K) == 0
-        assert (out8 == o.tdec_run_all(K, l8.astype(np.int16), 4)).all()
+        if o.tdec8_windows(K):
+            tr = o.tdec8_trace(K, l8, 4)
+            assert (out8 == tr[3]).all()
+            assert shim.srsran_tdec_new_cb(h, K) == 0
+            for it in range(3):
+                shim.srsran_tdec_iteration_8bit(h, l8.ctypes.data_as(C.c_void_p), out8.ctypes.data_as(C.c_void_p))
+                assert (out8 == tr[it]).all() and shim.srsran_tdec_get_nof_iterations(h) == it + 1
+        else:
+            assert (out8 == o.tdec_run_all(K, l8.astype(np.int16), 4)).all()
     shim.srsran_tdec_free(h)
 
 

@@ -223,6 +223,20 @@ typedef struct {
    * and K % 16 == 0; the reference widens smaller blocks to its SSE int16 decoders, the drop-in leaves those to the reference's
    * own loop), without q_bits / descramble. All transport blocks of one submission must agree on this flag. */
   uint32_t        llr_is_8bit;
+  /* Optional modulation-symbol source: with symbols != NULL the soft demodulator runs on the device -
+   * srsran_demod_soft_demodulate_s (lib/src/phy/modem/demod_soft.c:871-894; called at pdsch.c:696 and pusch.c:422) bit for bit,
+   * including which symbols the reference's SSE / AVX2 bodies round and which its scalar tails truncate - and e_bits (downlink)
+   * or q_bits (uplink: H_prime_total != 0) are ignored: the host sends 8 bytes per resource element instead of 2 * Qm.
+   * symbols = nof_symbols (re, im) float pairs of equalised symbols (q->d), mod = srsran_mod_t (0 BPSK, 1 QPSK, 2 16QAM, 3 64QAM,
+   * 4 256QAM). Usually combined with descramble / c_init: downlink as above; uplink the interleaved stream is descrambled as
+   * a whole (srsran_sequence_pusch_apply_s, pusch.c:439-441) before the de-interleaver, and the host-side UCI decoding gets the
+   * descrambled LLRs it reads back through q_gather: q_gather_out[i] = q[q_gather_pos[i]] (RI / ACK positions). int16 mode only. */
+  const float*    symbols;
+  uint32_t        nof_symbols;
+  uint32_t        mod;
+  const uint32_t* q_gather_pos;
+  int16_t*        q_gather_out;
+  uint32_t        nof_q_gather;
 } srsb200_tb_t;
 
 /*
@@ -238,6 +252,10 @@ int srsb200_softbuffer_set_resident(srsb200_engine_t* e, int resident);
 int srsb200_softbuffer_reset(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);
 int srsb200_softbuffer_sync_to_host(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);
 int srsb200_softbuffer_release(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);
+
+/* replaces srsran_demod_soft_demodulate_s (lib/src/phy/modem/demod_soft.c:871-894), host in / host out: llr receives
+ * nsymbols * bits-per-symbol values; -1 for an unknown modulation (like the reference) */
+int srsb200_demod_soft_demodulate_s(srsb200_engine_t* e, uint32_t mod, const float* symbols, int16_t* llr, uint32_t nsymbols);
 
 /* UL-SCH channel de-interleaver alone (host in, host out): g_bits receives H_prime_total*Qm values, of which the first
  * H_prime_total*Qm - nof_ri_bits are defined (as in the reference) */

@@ -429,6 +429,65 @@ static int decode_tb_common(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer,
   return ret;
 }
 
+/*
+ * The whole receive tail of srsran_pdsch_decode for one codeword (pdsch.c:693-740) in one device submission: the equalised symbols
+ * q->d[cw] go to the device as they are (8 bytes per resource element instead of 2 * Qm bytes of LLRs), soft demodulation
+ * (srsran_demod_soft_demodulate_s), descrambling (srsran_sequence_pdsch_apply_s) and decode_tb run there. A caller in pdsch.c
+ * replaces its three calls by this one; mod is the codeword's srsran_mod_t, Qm what srsran_dlsch_decode2 would pass to decode_tb
+ * (bits per symbol x Nl), c_init the scrambling seed as for srsran_b200_decode_tb_scrambled.
+ */
+int srsran_b200_decode_tb_symbols(srsran_sch_t*           q,
+                                  srsran_softbuffer_rx_t* softbuffer,
+                                  srsran_cbsegm_t*        cb_segm,
+                                  srsran_mod_t            mod,
+                                  uint32_t                Qm,
+                                  uint32_t                rv,
+                                  uint32_t                nof_e_bits,
+                                  cf_t*                   symbols,
+                                  uint32_t                nof_symbols,
+                                  uint32_t                c_init,
+                                  uint8_t*                data)
+{
+  if (q == NULL || data == NULL || softbuffer == NULL || symbols == NULL || cb_segm == NULL || Qm == 0 || q->llr_is_8bit) {
+    return SRSRAN_ERROR_INVALID_INPUTS;
+  }
+  uint8_t      tb_crc = 0;
+  srsb200_tb_t tb;
+  memset(&tb, 0, sizeof(tb));
+  tb.tbs         = cb_segm->tbs;
+  tb.Qm          = Qm;
+  tb.rv          = rv;
+  tb.nof_e_bits  = nof_e_bits;
+  tb.buffer_f    = softbuffer->buffer_f;
+  tb.sb_data     = softbuffer->data;
+  tb.cb_crc      = (uint8_t*)softbuffer->cb_crc;
+  tb.tb_crc      = &tb_crc;
+  tb.max_cb      = softbuffer->max_cb;
+  tb.data        = data;
+  tb.symbols     = (const float*)symbols;
+  tb.nof_symbols = nof_symbols;
+  tb.mod         = (uint32_t)mod;
+  tb.descramble  = 1;
+  tb.c_init      = c_init;
+  int ret = srsb200_decode_tb(engine_for(softbuffer), &tb, q->max_iterations);
+  if (ret == SRSB200_ERROR_NO_DEVICE) {
+    ERROR("srsran_b200: %s", srsb200_last_error());
+    return SRSRAN_ERROR;
+  }
+  if (cb_segm->tbs != 0 && cb_segm->C != 0 && ret != SRSRAN_ERROR_INVALID_INPUTS) {
+    softbuffer->tb_crc = tb_crc != 0;
+    q->avg_iterations  = tb.avg_iterations;
+  }
+  return ret;
+}
+
+/* srsran_demod_soft_demodulate_s (demod_soft.h) on the device, same return codes */
+int srsran_b200_demod_soft_demodulate_s(srsran_mod_t modulation, const cf_t* symbols, short* llr, int nsymbols)
+{
+  int r = srsb200_demod_soft_demodulate_s(engine(), (uint32_t)modulation, (const float*)symbols, llr, nsymbols < 0 ? 0u : (uint32_t)nsymbols);
+  return r == SRSB200_SUCCESS ? 0 : -1;
+}
+
 int srsran_sch_decode(srsran_sch_t* q, srsran_softbuffer_rx_t* softbuffer, srsran_cbsegm_t* cb_segm, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits,
                       int16_t* e_bits, uint8_t* data)
 {

@@ -1009,3 +1009,20 @@ void ref_sequence_apply_s(const int16_t* in, int16_t* out, uint32_t len, uint32_
 {
   srsran_sequence_apply_s(in, out, len, c_init);
 }
+
+/* srsran_demod_soft_demodulate_s itself (lib/src/phy/modem/demod_soft.c:871-894); symbols must be 32-byte aligned (_mm_load_ps) */
+#include "srsran/phy/modem/demod_soft.h"
+int ref_demod_soft_demodulate_s(int mod, const float* symbols, int16_t* llr, int nsymbols)
+{
+  cf_t*    s = srsran_vec_cf_malloc(nsymbols + 8);
+  int16_t* l = srsran_vec_i16_malloc(8 * nsymbols + 64);
+  memcpy(s, symbols, sizeof(cf_t) * nsymbols);
+  int r = srsran_demod_soft_demodulate_s((srsran_mod_t)mod, s, l, nsymbols);
+  static const int bps[5] = {1, 2, 4, 6, 8};
+  if (r == 0) {
+    memcpy(llr, l, sizeof(int16_t) * (size_t)bps[mod] * nsymbols);
+  }
+  free(s);
+  free(l);
+  return r;
+}

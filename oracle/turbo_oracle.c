@@ -810,3 +810,110 @@ void orc_sequence_apply_s(const int16_t* in, int16_t* out, uint32_t len, uint32_
   }
   free(c);
 }
+
+/* ------------------------------------------------------------------ soft demodulation to int16 LLRs */
+/*
+ * srsran_demod_soft_demodulate_s (lib/src/phy/modem/demod_soft.c:871-894) as the reference's AVX2 / SSE build computes it. The
+ * 16QAM and 64QAM bodies handle four symbols per SSE trip with ROUND-TO-NEAREST-EVEN conversion and a saturating pack
+ * (_mm_cvtps_epi32, _mm_packs_epi32, :250-287 and :569-629) and the last nsymbols % 4 symbols in scalar code that TRUNCATES
+ * (:290-298, :631-643) - the 16QAM tail also subtracts its threshold in floating point before truncating; QPSK goes through
+ * srsran_vec_convert_fi (vector_simd.c:436-472): truncation everywhere, but the 16 values of an AVX2 trip are SATURATED by the pack
+ * (simd.h:1866-1871) while the last (2 n) % 16 go through a plain C cast;
+ * BPSK and 256QAM are scalar (double resp. float arithmetic, truncation). mod: 0 BPSK, 1 QPSK, 2 16QAM, 3 64QAM, 4 256QAM
+ * (srsran_mod_t, phy_common.h:285-292). symbols: nsymbols pairs (re, im). Returns -1 for an unknown modulation.
+ */
+#include <math.h>
+static inline int32_t cvt_rne(float v)
+{
+  /* _mm_cvtps_epi32 in the default rounding mode; out of range / NaN -> the "integer indefinite" value */
+  if (!(v > -2147483904.0f && v < 2147483648.0f)) {
+    return INT32_MIN;
+  }
+  return (int32_t)lrintf(v); /* round to nearest even (default FP environment) */
+}
+static inline int16_t packs32(int32_t v)
+{
+  return (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
+}
+static inline int16_t abs16_wrap(int16_t v)
+{
+  return (int16_t)(v < 0 ? (uint16_t)(0u - (uint16_t)v) : (uint16_t)v); /* _mm_abs_epi16: |-32768| stays -32768 */
+}
+int orc_demod_soft_demodulate_s(int mod, const float* symbols, int16_t* llr, int nsymbols)
+{
+  switch (mod) {
+    case 0: /* BPSK, demod_soft.c:96-101 */
+      for (int i = 0; i < nsymbols; i++) {
+        llr[i] = (int16_t)(-100 * (symbols[2 * i] + symbols[2 * i + 1]) * M_SQRT1_2);
+      }
+      return 0;
+    case 1: { /* QPSK, :115-118 */
+      const float scale = (float)(-100 * M_SQRT2);
+      const int   len = 2 * nsymbols, nsimd = len - len % 16;
+      for (int i = 0; i < len; i++) {
+        /* SIMD body: _mm256_cvttps_epi32 (truncation) + saturating pack (simd.h:1866-1871); tail: plain C cast */
+        const float v = symbols[i] * scale;
+        llr[i]        = i < nsimd ? packs32((v > -2147483904.0f && v < 2147483648.0f) ? (int32_t)v : INT32_MIN) : (int16_t)v;
+      }
+      return 0;
+    }
+    case 2: { /* 16QAM, :250-299 */
+      const int16_t offset = (int16_t)(2 * 400 / sqrtf(10));
+      const int     nsimd  = 4 * (nsymbols / 4);
+      for (int i = 0; i < nsymbols; i++) {
+        for (int c = 0; c < 2; c++) {
+          const float v = symbols[2 * i + c];
+          if (i < nsimd) {
+            const int16_t y    = packs32(cvt_rne(v * -400.0f));
+            llr[4 * i + c]     = y;
+            llr[4 * i + 2 + c] = (int16_t)(uint16_t)((uint16_t)abs16_wrap(y) - (uint16_t)offset);
+          } else {
+            const short y      = (short)(400 * v);
+            llr[4 * i + c]     = (short)-y;
+            llr[4 * i + 2 + c] = (short)(abs(y) - 2 * 400 / sqrtf(10));
+          }
+        }
+      }
+      return 0;
+    }
+    case 3: { /* 64QAM, :569-643 */
+      const int16_t off1 = (int16_t)(4 * 700 / sqrtf(42)), off2 = (int16_t)(2 * 700 / sqrtf(42));
+      const int     nsimd = 4 * (nsymbols / 4);
+      for (int i = 0; i < nsymbols; i++) {
+        for (int c = 0; c < 2; c++) {
+          const float v = symbols[2 * i + c];
+          if (i < nsimd) {
+            const int16_t y    = packs32(cvt_rne(v * -700.0f));
+            const int16_t a1   = (int16_t)(uint16_t)((uint16_t)abs16_wrap(y) - (uint16_t)off1);
+            const int16_t a2   = (int16_t)(uint16_t)((uint16_t)abs16_wrap(a1) - (uint16_t)off2);
+            llr[6 * i + c]     = y;
+            llr[6 * i + 2 + c] = a1;
+            llr[6 * i + 4 + c] = a2;
+          } else {
+            const int16_t y    = (int16_t)(700 * v);
+            llr[6 * i + c]     = (int16_t)-y;
+            llr[6 * i + 2 + c] = (int16_t)((int16_t)abs(y) - off1);
+            llr[6 * i + 4 + c] = (int16_t)((int16_t)abs(llr[6 * i + 2 + c]) - off2);
+          }
+        }
+      }
+      return 0;
+    }
+    case 4: /* 256QAM, :824-844: float arithmetic, truncation */
+      for (int i = 0; i < nsymbols; i++) {
+        for (int c = 0; c < 2; c++) {
+          volatile float r   = -symbols[2 * i + c];
+          llr[8 * i + c]     = (int16_t)(1000 * r);
+          r                  = fabsf(r) - 8.0f / sqrtf(170.0f);
+          llr[8 * i + 2 + c] = (int16_t)(1000 * r);
+          r                  = fabsf(r) - 4.0f / sqrtf(170.0f);
+          llr[8 * i + 4 + c] = (int16_t)(1000 * r);
+          r                  = fabsf(r) - 2.0f / sqrtf(170.0f);
+          llr[8 * i + 6 + c] = (int16_t)(1000 * r);
+        }
+      }
+      return 0;
+    default:
+      return -1;
+  }
+}

@@ -70,6 +70,10 @@ int orc_ulsch_deinterleave(const int16_t* q_bits, uint32_t Qm, uint32_t H_prime_
 void orc_sequence_bits(uint32_t c_init, uint8_t* c, uint32_t len);
 void orc_sequence_apply_s(const int16_t* in, int16_t* out, uint32_t len, uint32_t c_init);
 
+/* soft demodulation to int16 LLRs as srsran_demod_soft_demodulate_s computes it in the AVX2 build (SIMD body rounds to nearest even
+ * and saturates, the scalar tails truncate); mod 0..4 = BPSK, QPSK, 16QAM, 64QAM, 256QAM; symbols = (re, im) float pairs */
+int orc_demod_soft_demodulate_s(int mod, const float* symbols, int16_t* llr, int nsymbols);
+
 /* ------------------------------------------------------------------ 8-bit LLR mode (turbo_oracle8.c)
  * The reference's windowed saturating int8 decoders (turbodecoder_win.h with llr_t = int8_t) restated in natural order.
  * orc_tdec8_windows: 32 / 16 = number of windows the reference's AUTO mode uses for this K, 0 = not decoded in 8-bit

@@ -51,6 +51,7 @@ def lib():
         L.srsb200_multi_device_of.argtypes = [vp, u64]
         L.srsb200_multi_decode_tb_batch.argtypes = [vp, vp, u32, vp, u32]
         L.srsb200_multi_tdec_batch.argtypes = [vp, u32, vp, vp, vp, vp, u64, u32, u32, i32, vp, vp, u64, vp, vp]
+        L.srsb200_demod_soft_demodulate_s.argtypes = [vp, u32, vp, vp, u32]
         L.srsb200_tdec8_windows.argtypes = [u32]; L.srsb200_tdec8_windows.restype = u32
         L.srsb200_tdec_batch8.argtypes = [vp, u32, vp, vp, vp, vp, u64, u32, u32, i32, vp, vp, u64, vp, vp]
         L.srsb200_rm_turbo_rx_lut8.argtypes = [vp, vp, vp, u32, u32, u32]
@@ -130,7 +131,9 @@ class _TbStruct(C.Structure):
                 ("max_cb", C.c_uint32), ("data", C.c_void_p), ("cb_noi", C.c_void_p), ("avg_iterations", C.c_float), ("ret", C.c_int),
                 ("q_bits", C.c_void_p), ("H_prime_total", C.c_uint32), ("N_pusch_symbs", C.c_uint32), ("ri_positions", C.c_void_p),
                 ("nof_ri_bits", C.c_uint32), ("e_offset", C.c_uint32), ("g_bits", C.c_void_p), ("nof_g_out", C.c_uint32),
-                ("descramble", C.c_uint32), ("c_init", C.c_uint32), ("max_iterations", C.c_uint32), ("llr_is_8bit", C.c_uint32)]
+                ("descramble", C.c_uint32), ("c_init", C.c_uint32), ("max_iterations", C.c_uint32), ("llr_is_8bit", C.c_uint32),
+                ("symbols", C.c_void_p), ("nof_symbols", C.c_uint32), ("mod", C.c_uint32), ("q_gather_pos", C.c_void_p),
+                ("q_gather_out", C.c_void_p), ("nof_q_gather", C.c_uint32)]
 
 
 class _TbTxStruct(C.Structure):
@@ -171,6 +174,25 @@ class TransportBlock:
         s.cb_crc, s.tb_crc = self.cb_crc.ctypes.data, self.tb_crc.ctypes.data
         s.max_cb = self.max_cb
         s.data, s.cb_noi = self.data.ctypes.data, self.cb_noi.ctypes.data
+
+    def fill_symbols(self, s, Qm, rv, symbols, mod, nof_e_bits, c_init=None, ul=None, q_gather=()):
+        """symbol source: the soft demodulator (and the descrambling) run on the device. ul = dict(H_prime_total, N_pusch_symbs,
+        ri_positions, e_offset) for the uplink chain (de-interleaver in between); q_gather: positions of q returned to the host"""
+        self.fill(s, Qm, rv, np.zeros(0, np.int16), nof_e_bits)
+        s.e_bits = None
+        self._sym = np.ascontiguousarray(symbols, np.complex64)
+        s.symbols, s.nof_symbols, s.mod = self._sym.ctypes.data, len(self._sym), mod
+        if c_init is not None:
+            s.descramble, s.c_init = 1, c_init
+        if ul is not None:
+            self._ri = np.ascontiguousarray(np.array(list(ul.get("ri_positions", ())), np.uint32))
+            s.H_prime_total, s.N_pusch_symbs = ul["H_prime_total"], ul["N_pusch_symbs"]
+            s.ri_positions = self._ri.ctypes.data if len(self._ri) else None
+            s.nof_ri_bits, s.e_offset = len(self._ri), ul.get("e_offset", 0)
+            self._gp = np.ascontiguousarray(np.array(list(q_gather), np.uint32))
+            self.q_gather_out = np.zeros(max(len(self._gp), 1), np.int16)
+            if len(self._gp):
+                s.q_gather_pos, s.q_gather_out, s.nof_q_gather = self._gp.ctypes.data, self.q_gather_out.ctypes.data, len(self._gp)
 
     def fill_ul(self, s, Qm, rv, q_bits, H_prime_total, N_pusch_symbs, nof_e_bits, ri_positions=(), e_offset=0, nof_g_out=0):
         """UL-SCH source: the e-bits are produced on the device by the channel de-interleaver from q_bits"""
@@ -281,6 +303,13 @@ class Engine:
                                            _ptr(out), _ptr(ooff), out.size, _ptr(noi), _ptr(ok)), "srsb200_tdec_batch8")
         return out, noi, ok
 
+    def demod_soft_demodulate_s(self, mod, symbols):
+        """mod 0..4 = BPSK, QPSK, 16QAM, 64QAM, 256QAM; symbols complex64[n] -> (ret, int16 LLRs)"""
+        s = np.ascontiguousarray(symbols, np.complex64)
+        llr = np.zeros(len(s) * (1, 2, 4, 6, 8)[mod if mod < 5 else 0], np.int16)
+        ret = self._L.srsb200_demod_soft_demodulate_s(self._h, mod, _ptr(s), _ptr(llr), len(s))
+        return ret, llr
+
     def rm_turbo_rx_lut8(self, e8, buf8, cb_idx, rv):
         e8 = np.ascontiguousarray(e8, np.int8)
         return self._L.srsb200_rm_turbo_rx_lut8(self._h, _ptr(e8), _ptr(buf8), len(e8), cb_idx, rv)
@@ -364,6 +393,13 @@ class Engine:
         ri = np.ascontiguousarray(np.array(list(ri_positions), np.uint32))
         ret = self._L.srsb200_ulsch_deinterleave(self._h, _ptr(q), Qm, H_prime_total, N_pusch_symbs, _ptr(g), _ptr(ri) if len(ri) else None, len(ri))
         return ret, g
+
+    def decode_tb_symbols(self, tb, Qm, rv, symbols, mod, nof_e_bits, max_iterations, c_init=None, ul=None, q_gather=()):
+        s = _TbStruct()
+        tb.fill_symbols(s, Qm, rv, symbols, mod, nof_e_bits, c_init, ul, q_gather)
+        ret = self._L.srsb200_decode_tb(self._h, C.byref(s), max_iterations)
+        tb.ret, tb.avg_iterations = s.ret, s.avg_iterations
+        return ret
 
     def ulsch_decode_batch(self, reqs, max_iterations):
         """reqs: list of (TransportBlock, Qm, rv, q_bits, H_prime_total, N_pusch_symbs, nof_e_bits, ri_positions, e_offset, nof_g_out)"""

@@ -1519,6 +1519,42 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
   return SRSB200_SUCCESS;
 }
 
+extern "C" int srsb200_demod_soft_demodulate_s(srsb200_engine_t* e, uint32_t mod, const float* symbols, int16_t* llr, uint32_t nsymbols)
+{
+  if (!e) return fail(SRSB200_ERROR_NO_DEVICE, "no engine (no CUDA device?)");
+  if (mod > 4) {
+    fprintf(stderr, "Invalid modulation %d\n", mod);
+    return SRSB200_ERROR;
+  }
+  if (!symbols || !llr) return SRSB200_ERROR_INVALID_INPUTS;
+  if (nsymbols == 0) return SRSB200_SUCCESS;
+  static const uint32_t bps_of[5] = {1, 2, 4, 6, 8};
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
+  const size_t nb_in = (size_t)nsymbols * 2 * sizeof(float), nb_out = (size_t)nsymbols * bps_of[mod] * sizeof(int16_t);
+  void *d_sym, *d_llr, *d_job;
+  if (ensure_scratch(e, 14, nb_in, &d_sym) || ensure_scratch(e, 4, nb_out, &d_llr) || ensure_scratch(e, 15, sizeof(DemodJob), &d_job)) return SRSB200_ERROR;
+  DemodJob j;
+  j.sym = (const float*)d_sym; j.llr = (int16_t*)d_llr; j.nsym = nsymbols; j.mod = mod;
+  Stager stg(e);
+  if (stg.reserve(nb_in + sizeof(j) + 4096, nb_out + 4096)) return SRSB200_ERROR;
+  CUDA_TRY(stg.h2d(d_sym, symbols, nb_in, e->stream));
+  CUDA_TRY(stg.h2d(d_job, &j, sizeof(j), e->stream));
+  CUDA_TRY(stg.flush(e->stream));
+  {
+    ProfScope ps(e, 3);
+    demod_kernel<<<dim3(std::max(1u, std::min(1024u, (nsymbols + 255) / 256)), 1), 256, 0, e->stream>>>((const DemodJob*)d_job);
+    e->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(stg.d2h(llr, d_llr, nb_out, e->stream));
+  CUDA_TRY(stg.flush(e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  stg.finish();
+  return SRSB200_SUCCESS;
+}
+
 #include "win8.inc"
 #include "tb_decode.inc"
 #include "tb_encode.inc"

@@ -232,3 +232,147 @@ __global__ void __launch_bounds__(256) gather_copy_kernel(const CopyJob* __restr
 }
 
 }  // namespace srsb200
+
+namespace srsb200 {
+/*
+ * Soft demodulation to int16 LLRs: srsran_demod_soft_demodulate_s (lib/src/phy/modem/demod_soft.c:871-894) as the reference's
+ * AVX2 / SSE build computes it, bit for bit - including WHICH symbols take which rounding: the 16QAM / 64QAM SSE bodies convert
+ * four symbols per trip with round-to-nearest-even and a saturating pack (:250-287, :569-629), the last nsymbols % 4 symbols go
+ * through scalar code that truncates (the 16QAM tail subtracts its threshold in floating point first, :290-298); QPSK truncates
+ * everywhere but only the 16 values of an AVX2 trip are saturated (srsran_vec_convert_fi, vector_simd.c:436-472, simd.h:1866-1871);
+ * BPSK is double arithmetic, 256QAM float arithmetic with truncation. One thread per symbol, coalesced 8-byte loads, the Qm LLRs
+ * of a symbol are one contiguous store run. HBM-bound: 8 bytes in, 2 Qm bytes out per symbol.
+ */
+struct DemodJob {
+  const float* sym;   // (re, im) pairs
+  int16_t*     llr;   // nsym * bits per symbol
+  uint32_t     nsym;
+  uint32_t     mod;   // srsran_mod_t: 0 BPSK, 1 QPSK, 2 16QAM, 3 64QAM, 4 256QAM
+};
+// _mm_cvtps_epi32 / _mm_cvttps_epi32: out of range and NaN give the "integer indefinite" value 0x80000000
+__device__ __forceinline__ int32_t dm_cvt_rne(float v) { return (v > -2147483904.0f && v < 2147483648.0f) ? __float2int_rn(v) : INT32_MIN; }
+__device__ __forceinline__ int32_t dm_cvt_trunc(float v) { return (v > -2147483904.0f && v < 2147483648.0f) ? __float2int_rz(v) : INT32_MIN; }
+__device__ __forceinline__ int16_t dm_packs(int32_t v) { return (int16_t)min(32767, max(-32768, v)); }
+__device__ __forceinline__ int16_t dm_abs16(int16_t v) { return (int16_t)(v < 0 ? (uint16_t)(0u - (uint16_t)v) : (uint16_t)v); }  // |-32768| = -32768
+// the C cast (short)(float) of the scalar tails on x86: cvttss2si to 32 bits, then the low half
+__device__ __forceinline__ int16_t dm_cast16(float v) { return (int16_t)dm_cvt_trunc(v); }
+
+__global__ void __launch_bounds__(256) demod_kernel(const DemodJob* __restrict__ jobs)
+{
+  const DemodJob j = jobs[blockIdx.y];
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < j.nsym; i += gridDim.x * 256) {
+    const float2 s = *reinterpret_cast<const float2*>(j.sym + 2 * (size_t)i);
+    const float  v[2] = {s.x, s.y};
+    switch (j.mod) {
+      case 0: {
+        const double d = (double)__fmul_rn(-100.0f, __fadd_rn(s.x, s.y)) * 0.70710678118654752440;  // -SCALE * (re + im) in float, * M_SQRT1_2 in double
+        j.llr[i] = (d > -2147483649.0 && d < 2147483648.0) ? (int16_t)__double2int_rz(d) : (int16_t)0;
+      } break;
+      case 1: {
+        const float    scale = (float)(-100 * 1.41421356237309504880);
+        const uint32_t len = 2 * j.nsym, nsimd = len - len % 16;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const float t = __fmul_rn(v[c], scale);
+          j.llr[2 * (size_t)i + c] = (2 * i + c < nsimd) ? dm_packs(dm_cvt_trunc(t)) : dm_cast16(t);
+        }
+      } break;
+      case 2: {
+        const int16_t offset = 252;  // (short)(2 * 400 / sqrtf(10))
+        const bool    simd   = i < 4 * (j.nsym / 4);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          int16_t l0, l1;
+          if (simd) {
+            l0 = dm_packs(dm_cvt_rne(__fmul_rn(v[c], -400.0f)));
+            l1 = (int16_t)(uint16_t)((uint16_t)dm_abs16(l0) - (uint16_t)offset);
+          } else {
+            const int16_t y = dm_cast16(__fmul_rn(400.0f, v[c]));
+            l0 = (int16_t)-y;
+            l1 = dm_cast16(__fsub_rn((float)abs((int)y), __fdiv_rn(800.0f, __fsqrt_rn(10.0f))));  // abs(yre) - 2 * 400 / sqrtf(10): int - float
+          }
+          j.llr[4 * (size_t)i + c]     = l0;
+          j.llr[4 * (size_t)i + 2 + c] = l1;
+        }
+      } break;
+      case 3: {
+        const int16_t off1 = 432, off2 = 216;  // (short)(4 * 700 / sqrtf(42)), (short)(2 * 700 / sqrtf(42))
+        const bool    simd = i < 4 * (j.nsym / 4);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          int16_t y, a1, a2;
+          if (simd) {
+            y  = dm_packs(dm_cvt_rne(__fmul_rn(v[c], -700.0f)));
+            a1 = (int16_t)(uint16_t)((uint16_t)dm_abs16(y) - (uint16_t)off1);
+            a2 = (int16_t)(uint16_t)((uint16_t)dm_abs16(a1) - (uint16_t)off2);
+          } else {
+            const int16_t t = dm_cast16(__fmul_rn(700.0f, v[c]));
+            y  = (int16_t)-t;
+            a1 = (int16_t)((int16_t)abs((int)t) - off1);
+            a2 = (int16_t)((int16_t)abs((int)a1) - off2);
+          }
+          j.llr[6 * (size_t)i + c]     = y;
+          j.llr[6 * (size_t)i + 2 + c] = a1;
+          j.llr[6 * (size_t)i + 4 + c] = a2;
+        }
+      } break;
+      default: {
+        // 256QAM: real = fabsf(real) - 8 / sqrtf(170) ... in float, every LLR = (short)(1000 * real)
+        const float sq = __fsqrt_rn(170.0f), c8 = __fdiv_rn(8.0f, sq), c4 = __fdiv_rn(4.0f, sq), c2 = __fdiv_rn(2.0f, sq);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          float r = -v[c];
+          j.llr[8 * (size_t)i + c]     = dm_cast16(__fmul_rn(1000.0f, r));
+          r = __fsub_rn(fabsf(r), c8);
+          j.llr[8 * (size_t)i + 2 + c] = dm_cast16(__fmul_rn(1000.0f, r));
+          r = __fsub_rn(fabsf(r), c4);
+          j.llr[8 * (size_t)i + 4 + c] = dm_cast16(__fmul_rn(1000.0f, r));
+          r = __fsub_rn(fabsf(r), c2);
+          j.llr[8 * (size_t)i + 6 + c] = dm_cast16(__fmul_rn(1000.0f, r));
+        }
+      } break;
+    }
+  }
+}
+}  // namespace srsb200
+
+namespace srsb200 {
+/*
+ * Descrambling of int16 LLRs in place (srsran_sequence_apply_s, lib/src/phy/common/sequence.c:507-561, as called by
+ * srsran_sequence_pusch_apply_s / _pdsch_apply_s, lib/src/phy/phch/sequences.c:95-146): q[i] = c(i) ? -q[i] : q[i] with int16 wrap.
+ * A thread owns 32 consecutive positions: it jumps the two LFSR windows of the Gold sequence to its word (GF(2) matrix powers,
+ * like rm_rx_kernel<true>) and steps them 32 times. x1 / x2 = windows at sequence position 0 (after Nc = 1600).
+ */
+struct ScrJob {
+  int16_t* q;
+  uint32_t n, x1, x2;
+};
+__global__ void __launch_bounds__(256) descramble_kernel(const ScrJob* __restrict__ jobs, const uint32_t* __restrict__ gold)
+{
+  const ScrJob   j    = jobs[blockIdx.y];
+  const uint32_t word = blockIdx.x * 256 + threadIdx.x;
+  if (32ull * word >= j.n) return;
+  uint32_t w1 = gold_jump(gold, j.x1, 32 * word), w2 = gold_jump(gold + 32 * GOLD_POWERS, j.x2, 32 * word);
+  const uint32_t end = min(j.n, 32 * word + 32);
+  for (uint32_t i = 32 * word; i < end; i++) {
+    if ((w1 ^ w2) & 1u) j.q[i] = (int16_t)(uint16_t)(0u - (uint16_t)j.q[i]);
+    w1 = (w1 >> 1) | ((uint32_t)(__popc(w1 & 0x9u) & 1) << 30);
+    w2 = (w2 >> 1) | ((uint32_t)(__popc(w2 & 0xFu) & 1) << 30);
+  }
+}
+// out[i] = q[pos[i]]: the handful of (descrambled) LLRs the host-side UCI decoding reads (RI / ACK positions)
+struct GatherJob {
+  const int16_t*  q;
+  const uint32_t* pos;
+  int16_t*        out;
+  uint32_t        n, qlen;
+};
+__global__ void __launch_bounds__(256) gather16_kernel(const GatherJob* __restrict__ jobs)
+{
+  const GatherJob j = jobs[blockIdx.y];
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < j.n; i += gridDim.x * 256) {
+    const uint32_t p = j.pos[i];
+    j.out[i] = p < j.qlen ? j.q[p] : (int16_t)0;
+  }
+}
+}  // namespace srsb200

@@ -43,18 +43,21 @@ struct Unit8 {
   int32_t  cb[4];                     // code-block ids: pair p = lanes [p*NW, (p+1)*NW), cb[2p] low half, cb[2p+1] high half; -1 = empty
   uint32_t pad_;
 };
-// per code block: six int8 arrays of pitch KP = K + 16: syst, par0, par1, app1, app2, ext1 (natural order; syst / par0 / par1 /
-// app2 carry the three termination values at K..K+2)
+// per code block: seven int8 arrays of pitch KP = K + 16: syst, par0, par1, app1, app2, ext1, nd (natural order; syst / par0 / par1 /
+// app2 carry the three termination values at K..K+2; nd = scratch for DEC2's decisions on their way back to natural order)
 __host__ __device__ inline uint32_t w8_pitch(uint32_t K) { return (K + 16 + 15) & ~15u; }
-__host__ __device__ inline uint64_t w8_cb_bytes(uint32_t K) { return 6ull * w8_pitch(K); }
+__host__ __device__ inline uint64_t w8_cb_bytes(uint32_t K) { return 7ull * w8_pitch(K); }
 
+// Shared memory of a warp: the two input streams of the constituent decode, window-interleaved. 25 KB => eight warps per SM. Everything
+// else lives in registers or goes through global memory in coalesced pieces: the beta checkpoints (one 512-byte row per 8 steps,
+// written and read back by the same lanes, the next one prefetched a block ahead), the a-priori values the DEC1 glue needs again at
+// the output, DEC2's decisions on their way to natural order. (The first version kept all of it in shared memory - 54 KB, four
+// warps per SM, one per scheduler - and ran at a quarter of an instruction per cycle and scheduler: profiles/r02_win8_ncu.md.)
 struct alignas(16) W8Smem {
-  uint8_t  X[W8_MAX_S * W8_PITCH];     // systematic (+ a-priori) per step; scratch for the natural-order decisions afterwards
-  uint8_t  Y[W8_MAX_S * W8_PITCH];     // parity; hard decisions after the alpha pass
-  uint8_t  A[W8_MAX_S * W8_PITCH];     // a-priori (DEC1 with a-priori); extrinsic output after the alpha pass
-  uint4    ck[W8_MAX_CK][32];          // beta checkpoints: 8 states x 2 code blocks as bytes
-  uint32_t hard[4][W8_MAX_S];          // decoded bits of each of the unit's code blocks, 32 steps per word (MSB first)
+  uint8_t X[W8_MAX_S * W8_PITCH];  // systematic (+ a-priori) per step; overwritten step by step with the extrinsic output
+  uint8_t Y[W8_MAX_S * W8_PITCH];  // parity; overwritten step by step with the hard decisions
 };
+constexpr size_t W8_CK_UNIT = (size_t)W8_MAX_CK * 32;  // uint4 per unit in the global checkpoint scratch
 
 // ---- int8 values in int16x2 lanes
 // PRMT with the sign-replicating selectors (nibble 8 | n = the sign of byte n in all eight bits). Inline PTX on purpose: the
@@ -132,9 +135,8 @@ __device__ __forceinline__ void w8_ck_store(uint4* dst, const uint32_t (&o)[8])
 {
   *dst = make_uint4(__byte_perm(o[0], o[1], 0x6420u), __byte_perm(o[2], o[3], 0x6420u), __byte_perm(o[4], o[5], 0x6420u), __byte_perm(o[6], o[7], 0x6420u));
 }
-__device__ __forceinline__ void w8_ck_load(const uint4* src, uint32_t (&o)[8])
+__device__ __forceinline__ void w8_ck_unpack(const uint4 v, uint32_t (&o)[8])
 {
-  const uint4 v = *src;
   o[0] = w8_prmt(v.x, 0u, 0x9180u); o[1] = w8_prmt(v.x, 0u, 0xB3A2u);
   o[2] = w8_prmt(v.y, 0u, 0x9180u); o[3] = w8_prmt(v.y, 0u, 0xB3A2u);
   o[4] = w8_prmt(v.z, 0u, 0x9180u); o[5] = w8_prmt(v.z, 0u, 0xB3A2u);
@@ -150,66 +152,88 @@ struct W8Tables {
  * MODE 0: DEC1, first half-iteration     x = syst                         y = par0
  * MODE 1: DEC1 with a-priori             a = app1 - ext1 (glue), x = a + syst   y = par0
  * MODE 2: DEC2                           x = app2                         y = par1
- * grid = n_units, block = 32. crcw[kind][m] = x^(m+24) mod g (kind 1: CRC24A, 2: CRC24B), m < 6144.
+ * grid = n_units, block = 32. crcw_a / crcw_b[m] = x^(m+24) mod g (CRC24A / CRC24B), m < 6144. ckg: W8_CK_UNIT uint4 per unit.
  */
 template <int MODE>
 __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ units, const W8Tables* __restrict__ tabs, uint8_t* __restrict__ ws,
-                                                  const uint64_t* __restrict__ ws_off, uint8_t* __restrict__ done, uint8_t* __restrict__ noi,
-                                                  uint8_t* __restrict__ ok, uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off,
-                                                  const uint32_t* __restrict__ out_len, const uint32_t* __restrict__ crcw_a,
-                                                  const uint32_t* __restrict__ crcw_b, uint32_t cnt, uint32_t max_iter, uint32_t min_iter, int early_stop,
-                                                  const uint8_t* __restrict__ max_iter_cb)
+                                                  const uint64_t* __restrict__ ws_off, uint4* __restrict__ ckg, uint8_t* __restrict__ done,
+                                                  uint8_t* __restrict__ noi, uint8_t* __restrict__ ok, uint8_t* __restrict__ out,
+                                                  const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_len,
+                                                  const uint32_t* __restrict__ crcw_a, const uint32_t* __restrict__ crcw_b, uint32_t cnt, uint32_t max_iter,
+                                                  uint32_t min_iter, int early_stop, const uint8_t* __restrict__ max_iter_cb)
 {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   W8Smem&        sm   = *reinterpret_cast<W8Smem*>(smem_raw);
-  const Unit8    u    = units[blockIdx.x];
+  // (every field of the unit goes into its own register: a local copy of the struct indexed with a runtime code-block number lands
+  //  in local memory, and the first version spent a quarter of its stall samples on those loads - profiles/r02_win8_ncu.md)
+  const Unit8*   up   = units + blockIdx.x;
   const int      lane = threadIdx.x;
-  const uint32_t K = u.K, NW = u.NW, S = u.S, KP = w8_pitch(K);
+  const uint32_t K = up->K, NW = up->NW, S = up->S, KP = w8_pitch(K), crc_kind = up->crc_kind;
+  const int      cb0 = up->cb[0], cb1 = up->cb[1], cb2 = up->cb[2], cb3 = up->cb[3];
   const int      npairs = 32 / (int)NW;  // 1 or 2
   const int      ncb    = 2 * npairs;
+  auto cb_of = [&](int c) { return c == 0 ? cb0 : (c == 1 ? cb1 : (c == 2 ? cb2 : cb3)); };
   // ---- anything left to do?
-  bool live[4];
-  bool any = false;
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    live[c] = c < ncb && u.cb[c] >= 0 && !done[u.cb[c]];
-    any |= live[c];
-  }
-  if (!any) return;
-  const W8Tables tb = tabs[u.kidx];
+  const bool live0 = cb0 >= 0 && !done[cb0], live1 = cb1 >= 0 && !done[cb1];
+  const bool live2 = ncb > 2 && cb2 >= 0 && !done[cb2], live3 = ncb > 2 && cb3 >= 0 && !done[cb3];
+  auto live_of = [&](int c) { return c == 0 ? live0 : (c == 1 ? live1 : (c == 2 ? live2 : live3)); };
+  if (!(live0 || live1 || live2 || live3)) return;
+  const W8Tables tb = tabs[up->kidx];
+  uint4*         ck = ckg + (size_t)blockIdx.x * W8_CK_UNIT;
   // sub_glue: srsran_vec_sub_bbb saturates, except (AVX2 build) on the last K % 32 elements of the window-interleaved array, which
   // its scalar tail subtracts with wrap-around: interleaved index = step * NW + window >= K - K % 32  <=>  (K % 32 != 0 and step == S-1)
   const bool wrap_tail = (K & 31u) != 0;
 
   // ---------------------------------------------------------------- stage: global natural order -> shared [step][lane] byte pairs
-  for (int c = 0; c < ncb; c++) {
-    const int      col0 = (c >> 1) * (int)NW;  // first lane of this code block's pair
-    const int      half = c & 1;
-    const int      cb   = u.cb[c];
-    if (cb < 0) {
-      for (uint32_t n = lane; n < K; n += 32) {
-        const uint32_t w = n / S, k = n - w * S, a = k * W8_PITCH + 2 * (col0 + w) + half;
-        sm.X[a] = 0; sm.Y[a] = 0; sm.A[a] = 0;
+  // Four consecutive trellis positions per lane and 32-bit global loads (the arrays are 16-byte aligned), four trips in flight:
+  // every load of a batch is issued before the first value is used, so the warp pays the DRAM latency once per 512 positions.
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    if (c >= ncb) break;
+    const int     col0 = (c >> 1) * (int)NW;  // first lane of this code block's pair
+    const int     half = c & 1;
+    const int     cb   = cb_of(c);
+    uint8_t*      base = (cb >= 0) ? ws + ws_off[cb] : nullptr;
+    constexpr int UN   = 4;
+    for (uint32_t n0 = 0; n0 < K; n0 += 128 * UN) {
+      uint32_t vx[UN], vy[UN], va[UN], ve[UN];
+#pragma unroll
+      for (int t = 0; t < UN; t++) {
+        const uint32_t n = n0 + 128 * t + 4 * lane;
+        vx[t] = vy[t] = va[t] = ve[t] = 0u;
+        if (n < K && base) {
+          // MODE 0/1: syst + par0 (+ app1, ext1); MODE 2: app2 + par1
+          vx[t] = *reinterpret_cast<const uint32_t*>(base + (MODE == 2 ? 4 * KP : 0) + n);
+          vy[t] = *reinterpret_cast<const uint32_t*>(base + (MODE == 2 ? 2 * KP : KP) + n);
+          if (MODE == 1) {
+            va[t] = *reinterpret_cast<const uint32_t*>(base + 3 * KP + n);
+            ve[t] = *reinterpret_cast<const uint32_t*>(base + 5 * KP + n);
+          }
+        }
       }
-      continue;
-    }
-    const int8_t* base = reinterpret_cast<const int8_t*>(ws + ws_off[cb]);
-    const int8_t *pS = base, *pP0 = base + KP, *pP1 = base + 2 * KP, *pA1 = base + 3 * KP, *pA2 = base + 4 * KP, *pE1 = base + 5 * KP;
-    for (uint32_t n = lane; n < K; n += 32) {
-      const uint32_t w = n / S, k = n - w * S, a = k * W8_PITCH + 2 * (col0 + w) + half;
-      int x, y, ap = 0;
-      if (MODE == 0) {
-        x = pS[n]; y = pP0[n];
-      } else if (MODE == 1) {
-        const int d = (int)pA1[n] - (int)pE1[n];
-        ap = (wrap_tail && k == S - 1) ? (int)(int8_t)d : w8_sat_i(d);  // app1 <- app1 - ext1 (turbodecoder_iter.h:106-108)
-        x  = w8_sat_i(ap + (int)pS[n]);                                // simd_add(ap, x), turbodecoder_win.h:608-611
-        y  = pP0[n];
-      } else {
-        x = pA2[n]; y = pP1[n];
+#pragma unroll
+      for (int t = 0; t < UN; t++) {
+        const uint32_t n = n0 + 128 * t + 4 * lane;
+        if (n >= K) continue;
+        uint32_t w = n / S, k = n - w * S, apw = 0;
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++) {
+          // (K is a multiple of 8, so the four positions exist together; they may straddle a window boundary)
+          const uint32_t a = k * W8_PITCH + 2 * (col0 + w) + half;
+          int x = (int)(int8_t)(vx[t] >> (8 * bb)), y = (int)(int8_t)(vy[t] >> (8 * bb));
+          if (MODE == 1) {
+            const int d  = (int)(int8_t)(va[t] >> (8 * bb)) - (int)(int8_t)(ve[t] >> (8 * bb));
+            const int ap = (wrap_tail && k == S - 1) ? (int)(int8_t)d : w8_sat_i(d);  // app1 <- app1 - ext1 (turbodecoder_iter.h:106-108)
+            x            = w8_sat_i(ap + x);                                         // simd_add(ap, x), turbodecoder_win.h:608-611
+            apw |= ((uint32_t)ap & 0xffu) << (8 * bb);
+          }
+          sm.X[a] = (uint8_t)x;
+          sm.Y[a] = (uint8_t)y;
+          if (++k == S) { k = 0; w++; }
+        }
+        // the updated a-priori values go back where they came from: the output side subtracts them again (ext1 <- ext1 - app1)
+        if (MODE == 1 && base) *reinterpret_cast<uint32_t*>(base + 3 * KP + n) = apw;
       }
-      sm.X[a] = (uint8_t)x; sm.Y[a] = (uint8_t)y;
-      if (MODE == 1) sm.A[a] = (uint8_t)ap;
     }
   }
   __syncwarp();
@@ -232,37 +256,37 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
 #pragma unroll
     for (int i = 0; i < 8; i++) t[i] = __shfl_down_sync(0xffffffffu, o[i], 1, (int)NW);
     if (w_lane == (int)NW - 1) {
-      int st[2][8];
+#pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int cb = u.cb[2 * pair + h];
-#pragma unroll
-        for (int i = 0; i < 8; i++) st[h][i] = 0;
-        if (cb < 0) continue;
-        const int8_t* base = reinterpret_cast<const int8_t*>(ws + ws_off[cb]);
-        const int8_t* pin  = (MODE == 2) ? base + 4 * KP : base;           // app2 (second encoder's termination systematic) / syst
-        const int8_t* ppa  = (MODE == 2) ? base + 2 * KP : base + KP;      // par1 / par0
-        for (int k = (int)K + 2; k >= (int)K; k--) {
-          const int xv = pin[k], yv = ppa[k], xy = w8_sadd_tail(xv, yv);
-          const int a[8] = {w8_sadd_tail(st[h][4], xy), st[h][4], w8_sadd_tail(st[h][5], yv), w8_sadd_tail(st[h][5], xv),
-                            w8_sadd_tail(st[h][6], xv), w8_sadd_tail(st[h][6], yv), st[h][7], w8_sadd_tail(st[h][7], xy)};
-          const int b[8] = {st[h][0], w8_sadd_tail(st[h][0], xy), w8_sadd_tail(st[h][1], xv), w8_sadd_tail(st[h][1], yv),
-                            w8_sadd_tail(st[h][2], yv), w8_sadd_tail(st[h][2], xv), w8_sadd_tail(st[h][3], xy), st[h][3]};
-#pragma unroll
-          for (int i = 0; i < 8; i++) st[h][i] = max(a[i], b[i]);
+        int st0 = 0, st1 = 0, st2 = 0, st3 = 0, st4 = 0, st5 = 0, st6 = 0, st7 = 0;
+        const int cb = pair ? (h ? cb3 : cb2) : (h ? cb1 : cb0);
+        if (cb >= 0) {
+          const int8_t* base = reinterpret_cast<const int8_t*>(ws + ws_off[cb]);
+          const int8_t* pin  = (MODE == 2) ? base + 4 * KP : base;       // app2 (second encoder's termination systematic) / syst
+          const int8_t* ppa  = (MODE == 2) ? base + 2 * KP : base + KP;  // par1 / par0
+          for (int k = (int)K + 2; k >= (int)K; k--) {
+            const int xv = pin[k], yv = ppa[k], xy = w8_sadd_tail(xv, yv);
+            const int n0 = max(w8_sadd_tail(st4, xy), st0), n1 = max(st4, w8_sadd_tail(st0, xy));
+            const int n2 = max(w8_sadd_tail(st5, yv), w8_sadd_tail(st1, xv)), n3 = max(w8_sadd_tail(st5, xv), w8_sadd_tail(st1, yv));
+            const int n4 = max(w8_sadd_tail(st6, xv), w8_sadd_tail(st2, yv)), n5 = max(w8_sadd_tail(st6, yv), w8_sadd_tail(st2, xv));
+            const int n6 = max(st7, w8_sadd_tail(st3, xy)), n7 = max(w8_sadd_tail(st7, xy), st3);
+            st0 = n0; st1 = n1; st2 = n2; st3 = n3; st4 = n4; st5 = n5; st6 = n6; st7 = n7;
+          }
         }
-      }
+        const int      sv[8] = {st0, st1, st2, st3, st4, st5, st6, st7};
 #pragma unroll
-      for (int i = 0; i < 8; i++) t[i] = ((uint32_t)st[0][i] & 0xffffu) | ((uint32_t)st[1][i] << 16);
+        for (int i = 0; i < 8; i++) t[i] = h ? ((t[i] & 0xffffu) | ((uint32_t)sv[i] << 16)) : ((uint32_t)sv[i] & 0xffffu);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) o[i] = t[i];
   }
   // ---------------------------------------------------------------- beta: main pass, checkpoint B[k] (before normalisation) at k = 8, 16, ... and B[S]
   const int ck_top = ((int)S + 7) / 8;  // slot of B[S]; B[8c] lives in slot c
-  w8_ck_store(&sm.ck[ck_top][lane], o);
+  w8_ck_store(&ck[ck_top * 32 + lane], o);
   for (int k = (int)S - 1; k >= 0; k--) {
     w8_bstep(o, ldx(k), ldy(k));
-    if (k && (k & 7) == 0) w8_ck_store(&sm.ck[k >> 3][lane], o);
+    if (k && (k & 7) == 0) w8_ck_store(&ck[(k >> 3) * 32 + lane], o);
     if (k) w8_norm(o);
   }
   // ---------------------------------------------------------------- alpha: warm-up over the window's own last 40 steps
@@ -281,7 +305,6 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
     for (int i = 0; i < 8; i++) o[i] = (w_lane == 0) ? 0u : t[i];  // first window: the known state {0, -INF x 7}, INF = 0
   }
   // ---------------------------------------------------------------- alpha: main pass, 8 steps at a time with beta recomputed into registers
-  __syncwarp();
   // one step: branch sums, LLR against beta[k+1] (b), extrinsic / decision into the consumed slots, state update
   auto astep_out = [&](int k, const uint32_t (&b)[8]) {
     const uint32_t x = ldx(k), y = ldy(k);
@@ -300,23 +323,23 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
 #pragma unroll
     for (int i = 0; i < 8; i++) o[i] = __vmaxs2(z[i], w[i]);
     if (k) w8_norm(o);
-    // what the next half-iteration reads, and the decision (tdec_win*_decision_byte: > 0) of this one
-    uint32_t r = ext;
-    if (MODE == 1) {
-      const uint32_t ap = w8_unpack(*reinterpret_cast<const uint16_t*>(&sm.A[k * W8_PITCH + 2 * lane]));
-      // ext1 <- ext1 - app1 (turbodecoder_iter.h:116-118), same saturate / wrap rule as on the way in
-      r = (wrap_tail && k == (int)S - 1) ? __vsub2(ext, ap) : w8_subs(ext, ap);
-    }
-    *reinterpret_cast<uint16_t*>(&sm.A[k * W8_PITCH + 2 * lane]) = (uint16_t)w8_pack(r);
+    // x[k] and y[k] have been consumed (the beta recompute of this block ran first): the extrinsic value and the decision
+    // (tdec_win*_decision_byte: > 0) take their places
+    *reinterpret_cast<uint16_t*>(&sm.X[k * W8_PITCH + 2 * lane]) = (uint16_t)w8_pack(ext);
     const uint32_t pos = __vadd2(__vmaxs2(ext, 0u), 0x7fff7fffu) & 0x80008000u;  // bit 15 / 31 set iff the value is > 0
     *reinterpret_cast<uint16_t*>(&sm.Y[k * W8_PITCH + 2 * lane]) = (uint16_t)(((pos >> 15) & 1u) | ((pos >> 23) & 0x100u));
   };
+  uint4 ck_next = ck[(8 >= (int)S ? ck_top : 1) * 32 + lane];
   for (int k0 = 0; k0 < (int)S; k0 += 8) {
     const int len = min(8, (int)S - k0), top = k0 + len;
     // B[j] = beta[k0 + 1 + j] as stored (before normalisation): what the LLR of step k0 + j reads; B[len-1] is the checkpoint
     uint32_t B[8][8];
     uint32_t s[8];
-    w8_ck_load(&sm.ck[top == (int)S ? ck_top : (top >> 3)][lane], s);
+    w8_ck_unpack(ck_next, s);
+    if (top < (int)S) {  // the next block's checkpoint is fetched now and used after this block's ~1000 instructions
+      const int ntop = min(top + 8, (int)S);
+      ck_next        = ck[(ntop == (int)S ? ck_top : (ntop >> 3)) * 32 + lane];
+    }
     if (len == 8) {
 #pragma unroll
       for (int i = 0; i < 8; i++) B[7][i] = s[i];
@@ -332,86 +355,120 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
 #pragma unroll
       for (int j = 0; j < 8; j++) astep_out(k0 + j, B[j]);
     } else {
-      // the short last block of a window whose length is not a multiple of 8 (top == S): same recursion, predicated
+      // the short last block of a window whose length is not a multiple of 8 (top == S, at most 7 steps, once per window): beta of
+      // every step is recomputed from the checkpoint on its own - no register window with a runtime length (an array indexed
+      // by `len` would push the whole window into local memory, for the full blocks too)
+      for (int j = 0; j < len; j++) {
+        uint32_t t[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (j == len - 1) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) B[j][i] = s[i];
+        for (int i = 0; i < 8; i++) t[i] = s[i];
+        if (j < len - 1 && top < (int)S) w8_norm(t);
+        for (int kk = top - 1; kk >= k0 + 1 + j; kk--) {
+          w8_bstep(t, ldx(kk), ldy(kk));
+          if (kk > k0 + 1 + j) w8_norm(t);  // kk >= 1; the last one stays as stored: before normalisation
         }
-      if (top < (int)S) w8_norm(s);
-#pragma unroll
-      for (int j = 6; j >= 0; j--) {
-        if (j <= len - 2) {
-          const int kk = k0 + 1 + j;
-          w8_bstep(s, ldx(kk), ldy(kk));
-#pragma unroll
-          for (int i = 0; i < 8; i++) B[j][i] = s[i];
-          w8_norm(s);
-        }
+        astep_out(k0 + j, t);
       }
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (j < len) astep_out(k0 + j, B[j]);
     }
   }
   __syncwarp();
 
   // ---------------------------------------------------------------- emit: natural order, QPP scatter, hard bits, CRC, verdict
-  const uint32_t nwords = (K + 31) / 32;
-  for (int c = 0; c < ncb; c++) {
-    const int cb = u.cb[c];
-    if (cb < 0) continue;  // (done code blocks of a live unit are recomputed but nothing of them is stored)
+  // Lanes walk consecutive trellis positions (coalesced byte accesses; the ballot of 32 decisions is one output word). Per 256
+  // positions every global load (QPP table, a-priori bytes) is issued before the first value is used.
+  const uint32_t nbytes = K / 8;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    if (c >= ncb) break;
+    const int cb = cb_of(c);
+    if (cb < 0 || !live_of(c)) continue;  // (done code blocks of a live unit are recomputed but nothing of them is stored)
     const int col0 = (c >> 1) * (int)NW, half = c & 1;
     int8_t*   base = reinterpret_cast<int8_t*>(ws + ws_off[cb]);
     int8_t *  pA1 = base + 3 * KP, *pA2 = base + 4 * KP, *pE1 = base + 5 * KP;
-    uint8_t*  natd = sm.X;  // decisions in natural order (DEC2 produces them in interleaved order)
-    if (!live[c]) continue;
-    if (MODE == 2) {
-      for (uint32_t n = lane; n < K; n += 32) {
-        const uint32_t w = n / S, k = n - w * S, a = k * W8_PITCH + 2 * (col0 + w) + half;
-        const uint32_t f = tb.fwd[n];
-        pA1[f]  = (int8_t)sm.A[a];  // app1[fwd[i]] = ext2[i] (turbodecoder_iter.h:127)
-        natd[f] = sm.Y[a];
-      }
-      __syncwarp();
-    }
-    uint32_t crc = 0;
-    const uint32_t* crcw = (u.crc_kind == 1) ? crcw_a : crcw_b;
-    for (uint32_t n0 = 0; n0 < K; n0 += 32) {
-      const uint32_t n = n0 + lane;
-      uint32_t       d = 0;
-      if (n < K) {
-        if (MODE == 2) {
-          d = natd[n];
-        } else {
-          const uint32_t w = n / S, k = n - w * S, a = k * W8_PITCH + 2 * (col0 + w) + half;
-          const int8_t   r = (int8_t)sm.A[a];
-          pE1[n]           = r;            // ext1 (after the subtraction) stays for the next DEC1's glue
-          pA2[tb.rev[n]]   = r;            // app2[rev[i]] = ext1[i] (turbodecoder_iter.h:120)
-          d                = sm.Y[a];
+    uint8_t*  pND = reinterpret_cast<uint8_t*>(base + 6 * KP);
+    const uint16_t* perm  = (MODE == 2) ? tb.fwd : tb.rev;
+    const uint32_t* crcw  = (crc_kind == 1) ? crcw_a : crcw_b;
+    uint8_t*        dst   = out + out_off[cb];
+    const uint32_t  total = out_len ? out_len[cb] : nbytes;
+    uint32_t        crc   = 0;
+    constexpr int   UE    = 8;
+    // 32 x UE decisions -> 32 output bytes: lane l takes byte l of the batch; its CRC contribution by linearity, eight consecutive
+    // table words per byte (crcw[m] = x^(m+24) mod g; bit 7 of a byte = the earliest position = the highest m)
+    auto finish_words = [&](const uint32_t (&bal)[UE], uint32_t n0) {
+      uint32_t wv = 0;
+#pragma unroll
+      for (int t = 0; t < UE; t++)
+        if ((lane >> 2) == t) wv = bal[t];
+      const uint32_t b = (n0 >> 3) + lane;
+      if (b < nbytes) {
+        const uint32_t v = (__brev(wv) >> (24 - 8 * (lane & 3))) & 0xffu;  // position n in bit 31 - (n mod 32): MSB-first bytes
+        if (b < total) dst[b] = (uint8_t)v;
+        if (crc_kind && v) {
+          const uint4* wq = reinterpret_cast<const uint4*>(crcw + (K - 8 - 8 * b));  // 32-byte aligned
+          const uint4  lo = __ldg(wq), hi = __ldg(wq + 1);
+          crc ^= (lo.x & (0u - (v & 1u))) ^ (lo.y & (0u - ((v >> 1) & 1u))) ^ (lo.z & (0u - ((v >> 2) & 1u))) ^ (lo.w & (0u - ((v >> 3) & 1u)));
+          crc ^= (hi.x & (0u - ((v >> 4) & 1u))) ^ (hi.y & (0u - ((v >> 5) & 1u))) ^ (hi.z & (0u - ((v >> 6) & 1u))) ^ (hi.w & (0u - (v >> 7)));
         }
-        if (d && u.crc_kind) crc ^= __ldg(&crcw[K - 1 - n]);
       }
-      const uint32_t bal = __ballot_sync(0xffffffffu, d != 0);
-      if (lane == 0) sm.hard[c][n0 >> 5] = __brev(bal);  // step n0 in bit 31: MSB-first bytes once stored big-endian
+    };
+    uint32_t w = 0, k = (uint32_t)lane;  // position n = n0 + 32 t + lane walks (window, step) incrementally: S > 32
+    for (uint32_t n0 = 0; n0 < K; n0 += 32 * UE) {
+      uint32_t pv[UE], av[UE], bal[UE];
+#pragma unroll
+      for (int t = 0; t < UE; t++) {
+        const uint32_t n = n0 + 32 * t + lane;
+        pv[t] = (n < K) ? (uint32_t)__ldg(perm + n) : 0u;
+        av[t] = (MODE == 1 && n < K) ? (uint32_t)(uint8_t)pA1[n] : 0u;
+      }
+#pragma unroll
+      for (int t = 0; t < UE; t++) {
+        const uint32_t n = n0 + 32 * t + lane;
+        uint32_t       d = 0;
+        if (n < K) {
+          const uint32_t a = k * W8_PITCH + 2 * (col0 + w) + half;
+          int            r = (int)(int8_t)sm.X[a];
+          d                = sm.Y[a];
+          if (MODE == 1) {
+            // ext1 <- ext1 - app1 (turbodecoder_iter.h:116-118), same saturate / wrap rule as on the way in
+            const int df = r - (int)(int8_t)av[t];
+            r            = (wrap_tail && k == S - 1) ? (int)(int8_t)df : w8_sat_i(df);
+          }
+          if (MODE == 2) {
+            pA1[pv[t]] = (int8_t)r;   // app1[fwd[i]] = ext2[i] (turbodecoder_iter.h:127)
+            pND[pv[t]] = (uint8_t)d;  // the decision of step i belongs to natural position fwd[i]
+          } else {
+            pE1[n]     = (int8_t)r;   // ext1 (after the subtraction) stays for the next DEC1's glue
+            pA2[pv[t]] = (int8_t)r;   // app2[rev[i]] = ext1[i] (turbodecoder_iter.h:120)
+          }
+        }
+        k += 32;
+        if (k >= S) { k -= S; w++; }
+        bal[t] = __ballot_sync(0xffffffffu, d != 0);
+      }
+      if (MODE != 2) finish_words(bal, n0);
+    }
+    if (MODE == 2) {
+      __syncwarp();  // the scattered decisions of all lanes are visible to all lanes
+      for (uint32_t n0 = 0; n0 < K; n0 += 32 * UE) {
+        uint32_t dv[UE], bal[UE];
+#pragma unroll
+        for (int t = 0; t < UE; t++) {
+          const uint32_t n = n0 + 32 * t + lane;
+          dv[t] = (n < K) ? (uint32_t)pND[n] : 0u;
+        }
+#pragma unroll
+        for (int t = 0; t < UE; t++) bal[t] = __ballot_sync(0xffffffffu, dv[t] != 0);
+        finish_words(bal, n0);
+      }
     }
     crc = __reduce_xor_sync(0xffffffffu, crc);
-    __syncwarp();
-    // decoded bytes (every half-iteration: the latest decision is what a finished block keeps)
-    {
-      uint8_t*       dst   = out + out_off[cb];
-      const uint32_t total = out_len ? out_len[cb] : K / 8;
-      for (uint32_t b = lane; b < total; b += 32) dst[b] = (uint8_t)(sm.hard[c][b >> 2] >> (24 - 8 * (b & 3u)));
-    }
     if (lane == 0) {
-      const uint32_t okv = (u.crc_kind != 0 && crc == 0u) ? 1u : 0u;
+      const uint32_t okv = (crc_kind != 0 && crc == 0u) ? 1u : 0u;
       noi[cb] = (uint8_t)cnt;
       ok[cb]  = (uint8_t)okv;
       if ((early_stop && okv && cnt >= min_iter) || cnt >= (max_iter_cb ? (uint32_t)max_iter_cb[cb] : max_iter)) done[cb] = 1;
     }
     __syncwarp();
-    (void)nwords;
   }
 }
 

@@ -59,6 +59,8 @@ class _Lib:
         self._dec_tb = f("decode_tb")
         self._dec_tb.argtypes = [C.c_uint32] * 4 + [i16p, C.c_uint32, i16p, u8p, u8p, u8p, u8p, u32p, C.POINTER(C.c_float)]
         self._dec_tb.restype = C.c_int
+        self._demod = f("demod_soft_demodulate_s")
+        self._demod.argtypes = [C.c_int, np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), i16p, C.c_int]; self._demod.restype = C.c_int
         self._seq = f("sequence_apply_s"); self._seq.argtypes = [i16p, i16p, C.c_uint32, C.c_uint32]; self._seq.restype = None
         self._enc_tb = f("encode_tb")
         self._enc_tb.argtypes = [C.c_uint32] * 4 + [u8p, u8p]
@@ -258,6 +260,14 @@ class _Lib:
         ret = self.lib.orc_decode_tb8(tbs, Qm, rv, len(e), e, max_iterations, state["buffer_b"], state["sb_data"], state["cb_crc"], tb_crc, data, noi,
                                       C.byref(avg))
         return dict(ret=ret, data=data, cb_noi=noi, tb_crc=int(tb_crc[0]), avg_iterations=avg.value, state=state, seg=seg)
+
+    def demod_soft_demodulate_s(self, mod, symbols):
+        """mod 0..4 = BPSK, QPSK, 16QAM, 64QAM, 256QAM; symbols complex64[n] -> int16 LLRs [n * bits per symbol]"""
+        s = np.ascontiguousarray(symbols, np.complex64).view(np.float32)
+        n = len(s) // 2
+        llr = np.zeros(n * (1, 2, 4, 6, 8)[mod] + 16, np.int16)
+        assert self._demod(mod, s, llr, n) == 0
+        return llr[:n * (1, 2, 4, 6, 8)[mod]]
 
     def sequence_apply_s(self, llr, c_init):
         """(de)scrambling of int16 LLRs with the LTE Gold sequence of seed c_init"""

@@ -797,3 +797,102 @@ def test_multi_device_dispatcher(sb, o):
         assert all(c > 0 for c in m.launch_counts())
     finally:
         m.close()
+
+
+# ---------------------------------------------------------------- soft demodulation + descrambling on the device
+QAM_NORM = {1: np.sqrt(2.0), 2: np.sqrt(10.0), 3: np.sqrt(42.0), 4: np.sqrt(170.0)}
+
+
+def _modulate(bits, mod):
+    """36.211 7.1 constellations from hard bits (test-signal generation only) -> complex64 symbols"""
+    bps = (1, 2, 4, 6, 8)[mod]
+    b = 1.0 - 2.0 * np.asarray(bits, np.float64).reshape(-1, bps)   # bit 0 -> +1
+    if mod == 0:
+        v = b[:, 0] / np.sqrt(2.0)
+        return (v + 1j * v).astype(np.complex64)
+
+    def axis(first):
+        cols = list(range(first, bps, 2))
+        level = [1, 2, 4, 8][:len(cols)][::-1]          # e.g. 64QAM: 4, 2, 1
+        acc = np.full(len(b), float(level[-1]))
+        for j in range(len(cols) - 1, 0, -1):           # innermost term first: (2 - (1 - 2 b4)) ...
+            acc = level[j - 1] - b[:, cols[j]] * acc
+        return b[:, cols[0]] * acc
+    return ((axis(0) + 1j * axis(1)) / QAM_NORM[mod]).astype(np.complex64)
+
+
+@pytest.mark.parametrize("mod", [0, 1, 2, 3, 4])
+def test_demod_soft_demodulate_s(sb, eng, o, mod):
+    rng = np.random.default_rng(50 + mod)
+    for n in (1, 3, 4, 5, 8, 9, 17, 1201, 14400):
+        for amp in (0.3, 1.0, 30.0, 200.0):
+            s = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * amp).astype(np.complex64)
+            ret, llr = eng.demod_soft_demodulate_s(mod, s)
+            assert ret == 0 and np.array_equal(llr, o.demod_soft_demodulate_s(mod, s)), (mod, n, amp)
+    assert eng.demod_soft_demodulate_s(7, np.zeros(4, np.complex64))[0] == -1
+
+
+@pytest.mark.parametrize("tbs,nre,mod,eb", [(75376, 14400, 3, 18.0), (36696, 7201, 3, 18.0), (12216, 4803, 2, 10.0), (6120, 7200, 1, 4.0), (75376, 11000, 4, 26.0)])
+def test_decode_tb_from_symbols_downlink(sb, eng, o, tbs, nre, mod, eb):
+    """pdsch.c:693-740 on the device: equalised symbols -> soft demodulation -> descrambling -> rate de-matching -> decode, against
+    the oracle chain demod -> sequence_apply_s -> decode_tb on the same symbols (odd symbol counts exercise the scalar tails)"""
+    Qm = (1, 2, 4, 6, 8)[mod]
+    G = nre * Qm
+    rng = np.random.default_rng(tbs + mod)
+    c_init = (0x1234 << 14) | (3 << 9) | 77
+    payload, e_clean = vecgen.make_tb(tbs, G, Qm, 0, 60.0, 5 + mod, scale=1)   # noiseless +-1 "LLRs": sign = transmitted bit
+    tx_bits = (e_clean > 0).astype(np.uint8)
+    scr = o.sequence_apply_s(np.ones(G, np.int16), c_init) < 0
+    sym = _modulate(tx_bits ^ scr.astype(np.uint8), mod)
+    sigma = vecgen.sigma_for(eb, tbs / float(G)) / np.sqrt(2.0)
+    sym = (sym + sigma * (rng.standard_normal(nre) + 1j * rng.standard_normal(nre))).astype(np.complex64)
+    llr = o.sequence_apply_s(o.demod_soft_demodulate_s(mod, sym), c_init)
+    ref_res = o.decode_tb(tbs, Qm, 0, llr, 8)
+    tb = sb.TransportBlock(tbs)
+    assert eng.decode_tb_symbols(tb, Qm, 0, sym, mod, G, 8, c_init=c_init) == ref_res["ret"]
+    _check_tb(ref_res, tb, ref_res["state"])
+    assert ref_res["ret"] == 0 and np.array_equal(ref_res["data"][:tbs // 8], payload[:tbs // 8])
+
+
+@pytest.mark.parametrize("tbs,nprb,nsymb,mod,ri", [(36696, 50, 12, 3, True), (12216, 25, 12, 2, False), (6120, 30, 11, 1, True)])
+def test_decode_tb_from_symbols_uplink(sb, eng, o, tbs, nprb, nsymb, mod, ri):
+    """pusch.c:418-455 on the device: symbols -> demodulation -> descrambling of the interleaved stream -> channel de-interleaver ->
+    decode; the descrambled LLRs at the RI positions come back for the host-side UCI decoding"""
+    Qm = (1, 2, 4, 6, 8)[mod]
+    H = nprb * 12 * nsymb
+    rows = H // nsymb
+    c_init = (0x4321 << 14) | (7 << 9) | 301
+    pos = []
+    if ri:
+        for n_ in range(8):
+            r_ = rows - 1 - n_ // 4
+            c_ = (1, 4, 7, 10)[n_ % 4]
+            pos += [r_ * Qm + c_ * rows * Qm + k for k in range(Qm)]
+    G = H * Qm - len(pos)
+    rng = np.random.default_rng(tbs + 9)
+    payload, e_clean = vecgen.make_tb(tbs, G, Qm, 0, 60.0, 8 + mod, scale=1)
+    # interleave the clean bits the way the de-interleaver will undo it: build q so that deinterleave(q) = e
+    idx = o.ulsch_deinterleave(np.arange(H * Qm, dtype=np.int32).astype(np.int16) * 0, Qm, H, nsymb, pos)   # shape probe
+    q_bits = np.zeros(H * Qm, np.uint8)
+    # (find the permutation with unique markers in two passes of 15-bit values)
+    marks = np.arange(H * Qm, dtype=np.int64)
+    lo = o.ulsch_deinterleave((marks & 0x7fff).astype(np.int16), Qm, H, nsymb, pos).astype(np.int64) & 0x7fff
+    hi = o.ulsch_deinterleave((marks >> 15).astype(np.int16), Qm, H, nsymb, pos).astype(np.int64)
+    src = (hi << 15) | lo           # g[r] = q[src[r]]
+    q_bits[src[:G]] = (e_clean > 0).astype(np.uint8)
+    scr = o.sequence_apply_s(np.ones(H * Qm, np.int16), c_init) < 0
+    sym = _modulate(q_bits ^ scr.astype(np.uint8), mod)
+    sigma = vecgen.sigma_for({1: 4.0, 2: 10.0, 3: 18.0}[mod], tbs / float(G)) / np.sqrt(2.0)
+    sym = (sym + sigma * (rng.standard_normal(H) + 1j * rng.standard_normal(H))).astype(np.complex64)
+    q = o.sequence_apply_s(o.demod_soft_demodulate_s(mod, sym), c_init)
+    g = o.ulsch_deinterleave(q, Qm, H, nsymb, pos)
+    ref_res = o.decode_tb(tbs, Qm, 0, g[:G], 8)
+    tb = sb.TransportBlock(tbs)
+    ret = eng.decode_tb_symbols(tb, Qm, 0, sym, mod, G, 8, c_init=c_init, ul=dict(H_prime_total=H, N_pusch_symbs=nsymb, ri_positions=pos),
+                                q_gather=pos[:11] + [0, H * Qm - 1])
+    assert ret == ref_res["ret"]
+    _check_tb(ref_res, tb, ref_res["state"])
+    exp = q[np.array(pos[:11] + [0, H * Qm - 1], np.int64)]
+    assert np.array_equal(tb.q_gather_out[:len(exp)], exp)
+    assert ref_res["ret"] == 0 and np.array_equal(ref_res["data"][:tbs // 8], payload[:tbs // 8])
+    del idx

@@ -163,3 +163,15 @@ def test_scrambling_sequence_vs_reference(libs, c_init):
         x = rng.integers(-32768, 32768, n).astype(np.int16)
         x[0] = -32768
         assert np.array_equal(o.sequence_apply_s(x, c_init), r.sequence_apply_s(x, c_init)), n
+
+
+@pytest.mark.parametrize("mod", [0, 1, 2, 3, 4])
+def test_demod_soft_demodulate_s_vs_reference(mod):
+    """srsran_demod_soft_demodulate_s: the SIMD bodies and the scalar tails round differently - every symbol
+    count class (n mod 4, 2n mod 16), amplitudes up to far beyond the int16 range (saturating packs vs wrapping casts)"""
+    o, r = ol.oracle(), ol.ref()
+    rng = np.random.default_rng(40 + mod)
+    for n in (1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 100, 1201, 14400):
+        for amp in (0.3, 1.0, 3.0, 30.0, 200.0):
+            s = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * amp).astype(np.complex64)
+            assert np.array_equal(o.demod_soft_demodulate_s(mod, s), r.demod_soft_demodulate_s(mod, s)), (mod, n, amp)

@@ -484,10 +484,11 @@ static int ensure_rm_table(srsb200_engine* e, uint32_t cb_idx, uint32_t rv)
   if (e->d_rm[cb_idx][rv]) return 0;
   std::vector<uint16_t> T;
   rm_table_host(cb_idx, rv, T);
-  std::vector<uint16_t> both(2 * T.size());
+  const size_t Lp = (T.size() + 7) & ~(size_t)7;  // the inverse table starts 16-byte aligned (rm_rx_kernel reads it 128 bits at a time)
+  std::vector<uint16_t> both(Lp + T.size() + 8, 0);
   for (size_t n = 0; n < T.size(); n++) {
-    both[n]                   = T[n];
-    both[T.size() + T[n]]     = (uint16_t)n;  // inverse permutation
+    both[n]         = T[n];
+    both[Lp + T[n]] = (uint16_t)n;  // inverse permutation
   }
   uint16_t* d;
   CUDA_TRY(cudaMalloc(&d, both.size() * sizeof(uint16_t)));
@@ -495,7 +496,7 @@ static int ensure_rm_table(srsb200_engine* e, uint32_t cb_idx, uint32_t rv)
   CUDA_TRY(cudaMemcpyAsync(d, both.data(), both.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   e->d_rm[cb_idx][rv]     = d;
-  e->d_rm_inv[cb_idx][rv] = d + T.size();  // L = 3K+12 is even: the inverse table starts 4-byte aligned
+  e->d_rm_inv[cb_idx][rv] = d + Lp;
   return 0;
 }
 
@@ -683,8 +684,8 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   CUDA_TRY(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<0>)));
   CUDA_TRY(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<1>)));
   CUDA_TRY(cudaFuncSetAttribute(scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanSmemT<2>)));
-  CUDA_TRY(cudaFuncSetAttribute(rm_rx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RM_SMEM_ELEMS * sizeof(int16_t))));
-  CUDA_TRY(cudaFuncSetAttribute(rm_rx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RM_SMEM_ELEMS * sizeof(int16_t))));
+  CUDA_TRY(cudaFuncSetAttribute(rm_rx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((RM_SMEM_ELEMS + 8) * sizeof(int16_t))));
+  CUDA_TRY(cudaFuncSetAttribute(rm_rx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((RM_SMEM_ELEMS + 8) * sizeof(int16_t))));
   gold_build(e->h_gold);
   CUDA_TRY(cudaMalloc(&e->d_gold, sizeof(e->h_gold)));
   CUDA_TRY(cudaMemcpy(e->d_gold, e->h_gold, sizeof(e->h_gold), cudaMemcpyHostToDevice));
@@ -1443,7 +1444,7 @@ extern "C" int srsb200_rm_turbo_rx_lut(srsb200_engine_t* e, const int16_t* input
   void* d_job;
   if (ensure_scratch(e, 6, sizeof(RmJob), &d_job)) return SRSB200_ERROR;
   CUDA_TRY(cudaMemcpyAsync(d_job, &job, sizeof(job), cudaMemcpyHostToDevice, e->stream));
-  rm_rx_kernel<false><<<1, RM_THREADS, std::min(in_len, RM_SMEM_ELEMS) * sizeof(int16_t), e->stream>>>((const RmJob*)d_job, e->d_gold);
+  rm_rx_kernel<false><<<1, RM_THREADS, (std::min(in_len, RM_SMEM_ELEMS) + 8) * sizeof(int16_t), e->stream>>>((const RmJob*)d_job, e->d_gold);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(output, d_buf, (size_t)L * 2, cudaMemcpyDeviceToHost, e->stream));
@@ -1509,7 +1510,7 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
   CUDA_TRY(cudaMemsetAsync(d_g, 0, ng * sizeof(int16_t), e->stream));  // the nof_ri_bits values past the data are left stale by the reference
   {
     ProfScope ps(e, 3);
-    ulsch_deint_kernel<<<dim3(std::max(1u, std::min<uint32_t>(64u, (uint32_t)(ng + 255) / 256)), 1), 256, 0, e->stream>>>((const DeintJob*)d_dj);
+    ulsch_deint_kernel<<<dim3(std::max(1u, std::min<uint32_t>(128u, (j.rows + DT_ROWS - 1) / DT_ROWS)), 1), 256, 0, e->stream>>>((const DeintJob*)d_dj);
     e->launches++;
   }
   CUDA_TRY(stg.d2h(g_bits, d_g, ng * sizeof(int16_t), e->stream));

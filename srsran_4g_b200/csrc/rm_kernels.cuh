@@ -69,11 +69,24 @@ __device__ __forceinline__ uint32_t warp_gold_jump(const uint32_t* __restrict__ 
 template <bool SCR>
 __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restrict__ jobs, const uint32_t* __restrict__ gold)
 {
-  extern __shared__ __align__(16) int16_t se[];
+  extern __shared__ __align__(16) int16_t se_raw[];
   __shared__ uint32_t sc[SCR ? RM_SC_WORDS : 1];
   const RmJob    j  = jobs[blockIdx.x];
   const uint32_t ns = min(j.E, RM_SMEM_ELEMS);
-  for (uint32_t i = threadIdx.x; i < ns; i += RM_THREADS) se[i] = j.e[i];
+  // ---- stage the received LLRs: 128-bit global loads and 128-bit shared stores. The e-bits of a code block start anywhere
+  //      (2-byte aligned): the shared copy is shifted by the same number of elements, so that element i sits 16-byte aligned in
+  //      shared memory exactly when it does in global memory; a scalar head and tail cover the rest.
+  const uint32_t sh = (uint32_t)((reinterpret_cast<uintptr_t>(j.e) >> 1) & 7u);  // elements past a 16-byte boundary
+  int16_t*       se = se_raw + sh;                                               // (8 spare elements are allocated for the shift)
+  {
+    const uint32_t head = min(ns, (8u - sh) & 7u);
+    if (threadIdx.x < head) se[threadIdx.x] = j.e[threadIdx.x];
+    const uint32_t nv = (ns - head) / 8;
+    const uint4*   gv = reinterpret_cast<const uint4*>(j.e + head);
+    uint4*         sv = reinterpret_cast<uint4*>(se + head);
+    for (uint32_t i = threadIdx.x; i < nv; i += RM_THREADS) sv[i] = __ldg(gv + i);
+    for (uint32_t i = head + 8 * nv + threadIdx.x; i < ns; i += RM_THREADS) se[i] = j.e[i];
+  }
   if (SCR && j.scramble) {
     // The block's part of the scrambling sequence, 32 bits per word. A matrix-vector product over GF(2) is one popc per row:
     // the 32 lanes of a warp take one row each and a ballot collects the new window, so a warp jumps both LFSR windows to
@@ -106,15 +119,41 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
     }
     return v;
   };
-  // two soft-buffer elements per thread (L is even, buf is 4-byte aligned): 128-byte accesses per warp
+  // what soft-buffer position p receives: e[n], e[n + L], ... with n = Tinv[p] (repetition when E > L)
+  auto gathered = [&](uint32_t n) -> uint32_t {
+    uint32_t sum = 0;
+    for (uint32_t i = n; i < j.E; i += j.L) sum += llr(i);
+    return sum;
+  };
+  // ---- read-modify-write of the soft buffer, EIGHT positions (one uint4) per thread: the table entries and the old values
+  //      are fetched with one 128-bit load each before the first shared-memory read, results leave with one 128-bit store.
+  //      Table and soft buffer are 16-byte aligned (the engine allocates them so); L = 3K + 12 = 4 mod 8: the last four
+  //      positions are done two at a time.
+  const bool     wide = ((reinterpret_cast<uintptr_t>(j.buf) | reinterpret_cast<uintptr_t>(j.table)) & 15u) == 0;
+  const uint32_t L8   = wide ? j.L / 8 : 0u;
+  for (uint32_t p8 = threadIdx.x; p8 < L8; p8 += RM_THREADS) {
+    const uint4 tt = __ldg(reinterpret_cast<const uint4*>(j.table) + p8);
+    const uint32_t tw[4] = {tt.x, tt.y, tt.z, tt.w};
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) any |= (tw[q] & 0xffffu) < j.E || (tw[q] >> 16) < j.E;
+    if (!any) continue;  // nothing received for these eight positions (punctured region): no traffic at all
+    uint4    old = reinterpret_cast<uint4*>(j.buf)[p8];
+    uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint32_t s0 = gathered(tw[q] & 0xffffu), s1 = gathered(tw[q] >> 16);
+      ow[q] = ((ow[q] + s0) & 0xffffu) | ((((ow[q] >> 16) + s1) & 0xffffu) << 16);
+    }
+    reinterpret_cast<uint4*>(j.buf)[p8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+  // two soft-buffer elements per thread for the rest (L is even, buf is 4-byte aligned)
   uint32_t* buf2 = reinterpret_cast<uint32_t*>(j.buf);
-  for (uint32_t p2 = threadIdx.x; p2 < j.L / 2; p2 += RM_THREADS) {
+  for (uint32_t p2 = 4 * L8 + threadIdx.x; p2 < j.L / 2; p2 += RM_THREADS) {
     const uint32_t tt = reinterpret_cast<const uint32_t*>(j.table)[p2];
     uint32_t       n0 = tt & 0xffffu, n1 = tt >> 16;
     if (n0 >= j.E && n1 >= j.E) continue;  // nothing received for these two positions
-    uint32_t s0 = 0, s1 = 0;
-    for (uint32_t i = n0; i < j.E; i += j.L) s0 += llr(i);
-    for (uint32_t i = n1; i < j.E; i += j.L) s1 += llr(i);
+    const uint32_t s0 = gathered(n0), s1 = gathered(n1);
     const uint32_t old = buf2[p2];
     buf2[p2] = ((old + s0) & 0xffffu) | ((((old >> 16) + s1) & 0xffffu) << 16);
   }
@@ -174,28 +213,58 @@ struct DeintJob {
   const uint32_t* ri_scan;  // sorted scan-order indices of the RI positions
   uint32_t        nri, rows, cols, Qm, p_star;
 };
+// Version 2 (round 2): the matrix is rows x cols items of Qm LLRs; q holds it column by column, g row by row. A block takes DT_ROWS
+// consecutive rows: per column that is ONE contiguous run of DT_ROWS * Qm LLRs in q - read with coalesced 32-bit loads into shared
+// memory - and the block's part of g is one contiguous range, written in scan order from shared memory (32-bit stores whenever no
+// RI position shifts the pairing). Round 1 let every thread read its Qm values straight from q (12 bytes out of every 32-byte
+// sector per request, columns rows * Qm * 2 bytes apart): 1.5 TB/s.
+constexpr int DT_ROWS = 32;
+constexpr int DT_MAXC = 14;  // columns = PUSCH symbols carrying data: 12 (normal CP), 10 / 11 with SRS or extended CP
 __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __restrict__ jobs)
 {
-  const DeintJob j  = jobs[blockIdx.y];
-  const uint32_t np = j.rows * j.cols;  // (row, column) pairs = modulation symbols; a thread moves the Qm values of one
-  for (uint32_t sp = blockIdx.x * 256 + threadIdx.x; sp < np; sp += gridDim.x * 256) {
-    const uint32_t row = sp / j.cols, col = sp - row * j.cols;
-    const uint32_t s0  = sp * j.Qm;                                   // scan index of its first value
-    const int16_t* src = j.q + (size_t)row * j.Qm + (size_t)col * j.rows * j.Qm;
-    // number of RI scan indices < s0 (binary search), then walk the list together with the Qm values
-    uint32_t lo = 0, hi = j.nri;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (j.ri_scan[mid] < s0) lo = mid + 1; else hi = mid;
+  __shared__ int16_t tile[DT_MAXC][DT_ROWS * 8 + 2];
+  const DeintJob j = jobs[blockIdx.y];
+  const uint32_t ntiles = (j.rows + DT_ROWS - 1) / DT_ROWS;
+  const bool     tiled  = j.cols <= DT_MAXC && j.Qm <= 8 && (j.Qm & 1u) == 0 && ((reinterpret_cast<uintptr_t>(j.q) & 3u) == 0) && ((j.rows * j.Qm) & 1u) == 0;
+  for (uint32_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+    const uint32_t row0 = tix * DT_ROWS, nr = min((uint32_t)DT_ROWS, j.rows - row0), run = nr * j.Qm;  // LLRs per column of this tile
+    if (tiled) {
+      __syncthreads();  // the previous tile has been written out
+      const uint32_t rw = run / 2;  // 32-bit words per column run (Qm is even)
+      for (uint32_t idx = threadIdx.x; idx < j.cols * rw; idx += 256) {
+        const uint32_t col = idx / rw, wq = idx - col * rw;
+        const uint32_t v   = reinterpret_cast<const uint32_t*>(j.q + (size_t)col * j.rows * j.Qm + (size_t)row0 * j.Qm)[wq];
+        *reinterpret_cast<uint32_t*>(&tile[col][2 * wq]) = v;
+      }
+      __syncthreads();
     }
-    for (uint32_t bit = 0; bit < j.Qm; bit++) {
-      const uint32_t s = s0 + bit;
-      if (lo < j.nri && j.ri_scan[lo] == s) {
-        lo++;
+    for (uint32_t it = threadIdx.x; it < nr * j.cols; it += 256) {
+      const uint32_t r = it / j.cols, col = it - r * j.cols, row = row0 + r;
+      const uint32_t s0  = (row * j.cols + col) * j.Qm;  // scan index of the item's first LLR
+      const int16_t* src = tiled ? &tile[col][r * j.Qm] : j.q + (size_t)row * j.Qm + (size_t)col * j.rows * j.Qm;
+      // number of RI scan indices < s0 (binary search), then walk the list together with the Qm values
+      uint32_t lo = 0, hi = j.nri;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (j.ri_scan[mid] < s0) lo = mid + 1; else hi = mid;
+      }
+      const bool clean = (lo >= j.nri || j.ri_scan[lo] >= s0 + j.Qm) && ((s0 - lo) & 1u) == 0 && s0 != lo && tiled &&
+                         ((reinterpret_cast<uintptr_t>(j.g) & 3u) == 0);
+      if (clean) {
+        // no RI inside the item, even rank, not the item that owns g[0]: Qm / 2 aligned 32-bit stores
+        uint32_t* dst = reinterpret_cast<uint32_t*>(j.g + (s0 - lo));
+        for (uint32_t w2 = 0; w2 < j.Qm / 2; w2++) dst[w2] = *reinterpret_cast<const uint32_t*>(src + 2 * w2);
         continue;
       }
-      const uint32_t rank = s - lo;
-      j.g[rank] = rank == 0 ? j.q[j.p_star] : src[bit];
+      for (uint32_t bit = 0; bit < j.Qm; bit++) {
+        const uint32_t s = s0 + bit;
+        if (lo < j.nri && j.ri_scan[lo] == s) {
+          lo++;
+          continue;
+        }
+        const uint32_t rank = s - lo;
+        j.g[rank] = rank == 0 ? j.q[j.p_star] : src[bit];
+      }
     }
   }
 }

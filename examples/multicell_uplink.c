@@ -6,7 +6,11 @@
  *
  *   gcc -O2 -std=gnu99 examples/multicell_uplink.c -Iinclude -Lsrsran_4g_b200 -lsrsran_b200 -lpthread -lm \
  *       -Wl,-rpath,'$ORIGIN/../srsran_4g_b200' -o examples/multicell_uplink
- *   examples/multicell_uplink [threads=4] [cells=64] [subframes=20] [pinned=1]
+ *   examples/multicell_uplink [threads per GPU=4] [cells per worker=64] [subframes=20] [pinned=1] [gpus=1]
+ *
+ * gpus > 1 (BASELINE config 5: 8 GPUs x 64 cells): the worker threads are spread over the devices, worker i on device i mod gpus
+ * - cells, their HARQ soft-buffer mirrors and their host threads belong to one GPU for good; nothing crosses between devices
+ * (independent units, no collective). Weak scaling: the work per GPU is fixed, the aggregate is reported.
  */
 #include <math.h>
 #include <pthread.h>
@@ -24,7 +28,7 @@
 #define SOFTBUFFER_SIZE 18600
 #define MAX_CB 13
 
-static int               pinned = 1;
+static int               pinned = 1, gpus = 1;
 static pthread_barrier_t g_start; /* every worker finishes its warm-up (allocations, table builds) before any is timed */
 
 typedef struct {
@@ -56,7 +60,7 @@ static void* worker(void* arg)
 {
   worker_t*         w = (worker_t*)arg;
   srsb200_engine_t* e = NULL;
-  if (srsb200_engine_create(&e, 0) != SRSB200_SUCCESS) {
+  if (srsb200_engine_create(&e, w->id % gpus) != SRSB200_SUCCESS) {
     fprintf(stderr, "worker %d: %s\n", w->id, srsb200_last_error());
     return NULL;
   }
@@ -143,6 +147,12 @@ int main(int argc, char** argv)
 {
   int T = argc > 1 ? atoi(argv[1]) : 4, cells = argc > 2 ? atoi(argv[2]) : 64, sfs = argc > 3 ? atoi(argv[3]) : 20;
   if (argc > 4) pinned = atoi(argv[4]);
+  if (argc > 5) gpus = atoi(argv[5]);
+  if (gpus < 1 || gpus > srsb200_device_count()) {
+    fprintf(stderr, "gpus=%d but %d CUDA device(s) visible\n", gpus, srsb200_device_count());
+    return 2;
+  }
+  T *= gpus; /* threads per GPU x GPUs */
   if (T < 1 || T > 64 || cells < 1 || sfs < 1) return 2;
   pthread_t th[64];
   worker_t  w[64];
@@ -163,10 +173,10 @@ int main(int argc, char** argv)
     fprintf(stderr, "no subframe decoded\n");
     return 1;
   }
-  printf("{\"workload\": \"%d worker threads x %d subframes x %d cells x TBS %u (13 code blocks), 64QAM, rate 0.87, device-resident soft buffers, %s e-bit/data buffers\", "
+  printf("{\"gpus\": %d, \"workload\": \"%d worker threads x %d subframes x %d cells x TBS %u (13 code blocks), 64QAM, rate 0.87, device-resident soft buffers, %s e-bit/data buffers\", "
          "\"transport_blocks\": %llu, \"crc_ok\": %llu, \"crc_ok_but_payload_differs\": %llu, \"seconds_slowest_worker\": %.6f, "
          "\"ms_per_subframe_aggregate\": %.4f, \"info_Gbit_s\": %.3f}\n",
-         T, sfs, cells, TBS, pinned ? "page-locked" : "pageable", (unsigned long long)tot, (unsigned long long)ok, (unsigned long long)bad, slowest,
+         gpus, T, sfs, cells, TBS, pinned ? "page-locked" : "pageable", (unsigned long long)tot, (unsigned long long)ok, (unsigned long long)bad, slowest,
          slowest / ((double)T * sfs) * 1e3, (double)tot * TBS / slowest / 1e9);
   return bad == 0 ? 0 : 1;
 }

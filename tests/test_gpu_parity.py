@@ -832,7 +832,7 @@ def test_demod_soft_demodulate_s(sb, eng, o, mod):
     assert eng.demod_soft_demodulate_s(7, np.zeros(4, np.complex64))[0] == -1
 
 
-@pytest.mark.parametrize("tbs,nre,mod,eb", [(75376, 14400, 3, 18.0), (36696, 7201, 3, 18.0), (12216, 4803, 2, 10.0), (6120, 7200, 1, 4.0), (75376, 11000, 4, 26.0)])
+@pytest.mark.parametrize("tbs,nre,mod,eb", [(75376, 14400, 3, 12.5), (36696, 7201, 3, 12.0), (12216, 4803, 2, 6.5), (6120, 7200, 1, 2.5), (75376, 11000, 4, 18.5)])
 def test_decode_tb_from_symbols_downlink(sb, eng, o, tbs, nre, mod, eb):
     """pdsch.c:693-740 on the device: equalised symbols -> soft demodulation -> descrambling -> rate de-matching -> decode, against
     the oracle chain demod -> sequence_apply_s -> decode_tb on the same symbols (odd symbol counts exercise the scalar tails)"""
@@ -840,11 +840,11 @@ def test_decode_tb_from_symbols_downlink(sb, eng, o, tbs, nre, mod, eb):
     G = nre * Qm
     rng = np.random.default_rng(tbs + mod)
     c_init = (0x1234 << 14) | (3 << 9) | 77
-    payload, e_clean = vecgen.make_tb(tbs, G, Qm, 0, 60.0, 5 + mod, scale=1)   # noiseless +-1 "LLRs": sign = transmitted bit
+    payload, e_clean = vecgen.make_tb(tbs, G, Qm, 0, 60.0, 5 + mod, scale=8)   # noiseless LLRs: sign = transmitted bit
     tx_bits = (e_clean > 0).astype(np.uint8)
     scr = o.sequence_apply_s(np.ones(G, np.int16), c_init) < 0
     sym = _modulate(tx_bits ^ scr.astype(np.uint8), mod)
-    sigma = vecgen.sigma_for(eb, tbs / float(G)) / np.sqrt(2.0)
+    sigma = vecgen.sigma_for(eb, tbs / float(G)) / np.sqrt(float(Qm))   # per component, unit symbol energy: N0 / 2 = 1 / (2 Qm R Eb/N0)
     sym = (sym + sigma * (rng.standard_normal(nre) + 1j * rng.standard_normal(nre))).astype(np.complex64)
     llr = o.sequence_apply_s(o.demod_soft_demodulate_s(mod, sym), c_init)
     ref_res = o.decode_tb(tbs, Qm, 0, llr, 8)
@@ -870,7 +870,7 @@ def test_decode_tb_from_symbols_uplink(sb, eng, o, tbs, nprb, nsymb, mod, ri):
             pos += [r_ * Qm + c_ * rows * Qm + k for k in range(Qm)]
     G = H * Qm - len(pos)
     rng = np.random.default_rng(tbs + 9)
-    payload, e_clean = vecgen.make_tb(tbs, G, Qm, 0, 60.0, 8 + mod, scale=1)
+    payload, e_clean = vecgen.make_tb(tbs, G, Qm, 0, 60.0, 8 + mod, scale=8)
     # interleave the clean bits the way the de-interleaver will undo it: build q so that deinterleave(q) = e
     idx = o.ulsch_deinterleave(np.arange(H * Qm, dtype=np.int32).astype(np.int16) * 0, Qm, H, nsymb, pos)   # shape probe
     q_bits = np.zeros(H * Qm, np.uint8)
@@ -882,7 +882,7 @@ def test_decode_tb_from_symbols_uplink(sb, eng, o, tbs, nprb, nsymb, mod, ri):
     q_bits[src[:G]] = (e_clean > 0).astype(np.uint8)
     scr = o.sequence_apply_s(np.ones(H * Qm, np.int16), c_init) < 0
     sym = _modulate(q_bits ^ scr.astype(np.uint8), mod)
-    sigma = vecgen.sigma_for({1: 4.0, 2: 10.0, 3: 18.0}[mod], tbs / float(G)) / np.sqrt(2.0)
+    sigma = vecgen.sigma_for({1: 2.5, 2: 6.5, 3: 12.5}[mod], tbs / float(G)) / np.sqrt(float(Qm))
     sym = (sym + sigma * (rng.standard_normal(H) + 1j * rng.standard_normal(H))).astype(np.complex64)
     q = o.sequence_apply_s(o.demod_soft_demodulate_s(mod, sym), c_init)
     g = o.ulsch_deinterleave(q, Qm, H, nsymb, pos)

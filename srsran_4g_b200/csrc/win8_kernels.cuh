@@ -14,16 +14,24 @@
  * saturation to [-128, 127] is a min / max against constants - sm_100a has no s8x4 min / max / saturating add). With 16
  * windows a warp carries four code blocks (two pairs of 16 lanes).
  *
+ * Data layout = compute layout. The reference keeps its 8-bit arrays window-interleaved (element of window w, step k at index
+ * k * NW + w: tdec_win*_extract_input, turbodecoder_win.h:883-921) and so does this engine, with the two code blocks of a pair
+ * packed byte by byte: every stream of a warp's UNIT is a [step][32 lanes] array of byte pairs, 64 bytes per step, in HBM
+ * exactly as in shared memory. Staging a stream is a straight 128-bit copy, every per-step access of the decode loop is one
+ * coalesced 64-byte row, the QPP interleaver is a table of destination offsets in the same layout (shared by both blocks of a
+ * pair: one 2-byte scatter store moves both), and the CRC is a table of per-position remainders in that order. The first
+ * version kept natural-order arrays and transposed in and out of shared memory every half-iteration: the transposing emit pass
+ * cost as many instructions as the decode itself (profiles/r02_win8_ncu.md).
+ *
  * Per half-iteration one launch, one warp per unit:
- *   stage   natural-order int8 streams of the unit's code blocks -> shared memory [step][lane] byte pairs (coalesced global
- *           reads, the a-priori glue of turbodecoder_iter.h:104-128 applied on the way in);
- *   beta    warm-up, shuffle, main pass storing the state every 8 steps (checkpoints, shared memory);
- *   alpha   warm-up, shuffle, main pass: per 8 steps beta is recomputed from its checkpoint into registers, then alpha + LLR;
- *           extrinsic bytes and hard decisions overwrite the consumed a-priori / parity slots;
- *   emit    extrinsic back to natural order in global memory + QPP scatter for the next half-iteration, hard bits by warp
- *           ballot (32 trellis steps per word), CRC24 by linearity, per-code-block verdict (sch.c:426-456), decoded bytes.
+ *   stage   x and y streams -> shared memory (DEC1 with a-priori: x = sat(sat(app1 - ext1) + syst), turbodecoder_iter.h:104-128);
+ *   beta    warm-up, shuffle, main pass with the state checkpointed every 8 steps (global scratch, coalesced, read back by the
+ *           same lanes one block ahead of use);
+ *   alpha   warm-up, shuffle, main pass: per 8 steps beta is recomputed from its checkpoint into registers, then alpha + LLR,
+ *           and every step stores its extrinsic value in place and through the QPP table, its hard decision, and folds its
+ *           CRC contribution; the per-code-block verdict (sch.c:426-456) closes the launch.
  * Units whose code blocks are all done return at once: early termination works per warp, not per 64-block group.
- * HBM traffic per code-block step and half-iteration: 3-4 bytes in, 2 out - the kernel is bound by integer issue.
+ * HBM traffic per code-block step and half-iteration: 2-4 bytes in, 3 out - the kernel is bound by integer issue.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -31,31 +39,29 @@
 
 namespace srsb200 {
 
-constexpr int      W8_OVERLAP  = 40;   // win_overlap_len
-constexpr int      W8_MAX_S    = 192;  // longest window: 6144 / 32
-constexpr int      W8_PITCH    = 66;   // bytes per shared-memory row of 32 byte pairs (+2: the transposing stores of the staging spread over all banks)
-constexpr int      W8_MAX_CK   = W8_MAX_S / 8 + 2;
-constexpr uint32_t W8_M128     = 0xFF80FF80u;  // two int16 of -128
-constexpr uint32_t W8_P127     = 0x007F007Fu;  // two int16 of +127
+constexpr int      W8_OVERLAP = 40;   // win_overlap_len
+constexpr int      W8_MAX_S   = 192;  // longest window: 6144 / 32
+constexpr int      W8_ROW     = 64;   // bytes per step row: 32 lanes x 2 code blocks
+constexpr int      W8_MAX_CK  = W8_MAX_S / 8 + 2;
+constexpr uint32_t W8_M128    = 0xFF80FF80u;  // two int16 of -128
+constexpr uint32_t W8_P127    = 0x007F007Fu;  // two int16 of +127
 
 struct Unit8 {
   uint32_t K, NW, S, kidx, crc_kind;  // NW windows of S steps; crc_kind 0 none, 1 CRC24A, 2 CRC24B
-  int32_t  cb[4];                     // code-block ids: pair p = lanes [p*NW, (p+1)*NW), cb[2p] low half, cb[2p+1] high half; -1 = empty
+  int32_t  cb[4];                     // code-block ids: pair p = lanes [p*NW, (p+1)*NW), cb[2p] low byte, cb[2p+1] high byte; -1 = empty
   uint32_t pad_;
+  uint64_t ws_off;                    // byte offset of the unit's arrays
 };
-// per code block: seven int8 arrays of pitch KP = K + 16: syst, par0, par1, app1, app2, ext1, nd (natural order; syst / par0 / par1 /
-// app2 carry the three termination values at K..K+2; nd = scratch for DEC2's decisions on their way back to natural order)
-__host__ __device__ inline uint32_t w8_pitch(uint32_t K) { return (K + 16 + 15) & ~15u; }
-__host__ __device__ inline uint64_t w8_cb_bytes(uint32_t K) { return 7ull * w8_pitch(K); }
+// unit workspace: seven [S][64] arrays - syst, par0, par1, app1, app2, ext1, nd (hard decisions at their natural position) - and a
+// 64-byte block with the 3 termination values of {syst, par0, app2, par1} per code block: tail[cb slot][stream][4]
+enum { W8_SYST = 0, W8_PAR0, W8_PAR1, W8_APP1, W8_APP2, W8_EXT1, W8_ND, W8_NARR };
+__host__ __device__ inline uint64_t w8_arr_bytes(uint32_t S) { return (uint64_t)S * W8_ROW; }
+__host__ __device__ inline uint64_t w8_unit_bytes(uint32_t S) { return W8_NARR * w8_arr_bytes(S) + 64; }
 
-// Shared memory of a warp: the two input streams of the constituent decode, window-interleaved. 25 KB => eight warps per SM. Everything
-// else lives in registers or goes through global memory in coalesced pieces: the beta checkpoints (one 512-byte row per 8 steps,
-// written and read back by the same lanes, the next one prefetched a block ahead), the a-priori values the DEC1 glue needs again at
-// the output, DEC2's decisions on their way to natural order. (The first version kept all of it in shared memory - 54 KB, four
-// warps per SM, one per scheduler - and ran at a quarter of an instruction per cycle and scheduler: profiles/r02_win8_ncu.md.)
+// Shared memory of a warp: the two input streams of the constituent decode. 24 KB => nine warps per SM.
 struct alignas(16) W8Smem {
-  uint8_t X[W8_MAX_S * W8_PITCH];  // systematic (+ a-priori) per step; overwritten step by step with the extrinsic output
-  uint8_t Y[W8_MAX_S * W8_PITCH];  // parity; overwritten step by step with the hard decisions
+  uint8_t X[W8_MAX_S * W8_ROW];  // systematic (+ a-priori) per step
+  uint8_t Y[W8_MAX_S * W8_ROW];  // parity
 };
 constexpr size_t W8_CK_UNIT = (size_t)W8_MAX_CK * 32;  // uint4 per unit in the global checkpoint scratch
 
@@ -69,10 +75,13 @@ __device__ __forceinline__ uint32_t w8_prmt(uint32_t a, uint32_t b, uint32_t sel
   return d;
 }
 __device__ __forceinline__ uint32_t w8_unpack(uint32_t pair) { return w8_prmt(pair, 0u, 0x9180u); }  // bytes (lo, hi) -> two sign-extended int16
-__device__ __forceinline__ uint32_t w8_pack(uint32_t v) { return __byte_perm(v, 0u, 0x4420u) & 0xffffu; }
+__device__ __forceinline__ uint32_t w8_unpack_hi(uint32_t w) { return w8_prmt(w, 0u, 0xB3A2u); }     // the same for bytes 2, 3 of a word
+__device__ __forceinline__ uint32_t w8_pack(uint32_t v) { return __byte_perm(v, 0u, 0x4420u); }      // two int16 -> bytes (lo, hi), upper half zero
 __device__ __forceinline__ uint32_t w8_sat(uint32_t v) { return __vmins2(__vmaxs2(v, W8_M128), W8_P127); }
 __device__ __forceinline__ uint32_t w8_adds(uint32_t a, uint32_t b) { return __vmins2(__viaddmax_s16x2(a, b, W8_M128), W8_P127); }
 __device__ __forceinline__ uint32_t w8_subs(uint32_t a, uint32_t b) { return w8_sat(__vsub2(a, b)); }
+// int8 wrap-around of a 16-bit lane value (the scalar tail of srsran_vec_sub_bbb): sign-extend the low byte of each half
+__device__ __forceinline__ uint32_t w8_wrap8(uint32_t v) { return w8_prmt(v, 0u, 0xA280u); }
 // max(sat(a + b), c) for c already in range: the lower clamp is implied by c
 __device__ __forceinline__ uint32_t w8_addmax_hi(uint32_t a, uint32_t b, uint32_t c) { return __vmins2(__viaddmax_s16x2(a, b, c), W8_P127); }
 
@@ -122,8 +131,6 @@ __device__ __forceinline__ void w8_astep(uint32_t (&o)[8], uint32_t x, uint32_t 
   o[0] = n0; o[1] = n1; o[2] = n2; o[3] = n3; o[4] = n4; o[5] = n5; o[6] = n6; o[7] = n7;
 }
 
-// scalar helpers of the staging / termination code
-__device__ __forceinline__ int w8_sat_i(int v) { return min(127, max(-128, v)); }
 // the termination steps' helper: saturates upwards only, wraps below -128 (turbodecoder_win.h:469-477)
 __device__ __forceinline__ int w8_sadd_tail(int a, int b)
 {
@@ -137,115 +144,120 @@ __device__ __forceinline__ void w8_ck_store(uint4* dst, const uint32_t (&o)[8])
 }
 __device__ __forceinline__ void w8_ck_unpack(const uint4 v, uint32_t (&o)[8])
 {
-  o[0] = w8_prmt(v.x, 0u, 0x9180u); o[1] = w8_prmt(v.x, 0u, 0xB3A2u);
-  o[2] = w8_prmt(v.y, 0u, 0x9180u); o[3] = w8_prmt(v.y, 0u, 0xB3A2u);
-  o[4] = w8_prmt(v.z, 0u, 0x9180u); o[5] = w8_prmt(v.z, 0u, 0xB3A2u);
-  o[6] = w8_prmt(v.w, 0u, 0x9180u); o[7] = w8_prmt(v.w, 0u, 0xB3A2u);
+  o[0] = w8_unpack(v.x); o[1] = w8_unpack_hi(v.x);
+  o[2] = w8_unpack(v.y); o[3] = w8_unpack_hi(v.y);
+  o[4] = w8_unpack(v.z); o[5] = w8_unpack_hi(v.z);
+  o[6] = w8_unpack(v.w); o[7] = w8_unpack_hi(v.w);
+}
+// a load the compiler must leave where it is written (it sinks plain loads to their first use, which puts the whole
+// global-memory latency in front of the consumer: measured as a quarter of the stall samples before)
+__device__ __forceinline__ uint4 w8_ld_v4(const uint4* p)
+{
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
 }
 
+// per block size, everything indexed by the window-interleaved position k * NW + w
 struct W8Tables {
-  const uint16_t* fwd;   // QPP pi(i)
-  const uint16_t* rev;   // inverse
+  const uint16_t* dst1;     // DEC1: where the extrinsic value of position (w, k) goes in app2: (k' * 32 + w') of natural position rev[wS + k]
+  const uint16_t* dst2;     // DEC2: the same into app1 / nd through fwd[]
+  const uint32_t* crc1[3];  // [crc kind]: x^(K-1-n+24) mod g for the natural position n = wS + k (DEC1 decides in natural order)
+  const uint32_t* crc2[3];  // the same for position fwd[wS + k] (DEC2 decides in interleaved order); kind 0 aliases kind 2
 };
 
 /*
  * MODE 0: DEC1, first half-iteration     x = syst                         y = par0
  * MODE 1: DEC1 with a-priori             a = app1 - ext1 (glue), x = a + syst   y = par0
  * MODE 2: DEC2                           x = app2                         y = par1
- * grid = n_units, block = 32. crcw_a / crcw_b[m] = x^(m+24) mod g (CRC24A / CRC24B), m < 6144. ckg: W8_CK_UNIT uint4 per unit.
+ * grid = n_units, block = 32. ckg: W8_CK_UNIT uint4 per unit.
  */
 template <int MODE>
 __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ units, const W8Tables* __restrict__ tabs, uint8_t* __restrict__ ws,
-                                                  const uint64_t* __restrict__ ws_off, uint4* __restrict__ ckg, uint8_t* __restrict__ done,
-                                                  uint8_t* __restrict__ noi, uint8_t* __restrict__ ok, uint8_t* __restrict__ out,
-                                                  const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_len,
-                                                  const uint32_t* __restrict__ crcw_a, const uint32_t* __restrict__ crcw_b, uint32_t cnt, uint32_t max_iter,
-                                                  uint32_t min_iter, int early_stop, const uint8_t* __restrict__ max_iter_cb)
+                                                  uint4* __restrict__ ckg, uint8_t* __restrict__ done, uint8_t* __restrict__ noi,
+                                                  uint8_t* __restrict__ ok, uint32_t cnt, uint32_t max_iter, uint32_t min_iter, int early_stop,
+                                                  const uint8_t* __restrict__ max_iter_cb)
 {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   W8Smem&        sm   = *reinterpret_cast<W8Smem*>(smem_raw);
-  // (every field of the unit goes into its own register: a local copy of the struct indexed with a runtime code-block number lands
-  //  in local memory, and the first version spent a quarter of its stall samples on those loads - profiles/r02_win8_ncu.md)
   const Unit8*   up   = units + blockIdx.x;
   const int      lane = threadIdx.x;
-  const uint32_t K = up->K, NW = up->NW, S = up->S, KP = w8_pitch(K), crc_kind = up->crc_kind;
-  const int      cb0 = up->cb[0], cb1 = up->cb[1], cb2 = up->cb[2], cb3 = up->cb[3];
-  const int      npairs = 32 / (int)NW;  // 1 or 2
-  const int      ncb    = 2 * npairs;
-  auto cb_of = [&](int c) { return c == 0 ? cb0 : (c == 1 ? cb1 : (c == 2 ? cb2 : cb3)); };
-  // ---- anything left to do?
-  const bool live0 = cb0 >= 0 && !done[cb0], live1 = cb1 >= 0 && !done[cb1];
-  const bool live2 = ncb > 2 && cb2 >= 0 && !done[cb2], live3 = ncb > 2 && cb3 >= 0 && !done[cb3];
-  auto live_of = [&](int c) { return c == 0 ? live0 : (c == 1 ? live1 : (c == 2 ? live2 : live3)); };
-  if (!(live0 || live1 || live2 || live3)) return;
+  const uint32_t K = up->K, NW = up->NW, S = up->S, crc_kind = up->crc_kind;
+  const int      pair = lane / (int)NW, w_lane = lane % (int)NW;
+  // the two code blocks of this lane's pair (pair 1 exists with 16 windows only)
+  const int      cb_lo = pair ? up->cb[2] : up->cb[0], cb_hi = pair ? up->cb[3] : up->cb[1];
+  const bool     live_lo = cb_lo >= 0 && !done[cb_lo], live_hi = cb_hi >= 0 && !done[cb_hi];
+  if (!__any_sync(0xffffffffu, live_lo || live_hi)) return;
   const W8Tables tb = tabs[up->kidx];
-  uint4*         ck = ckg + (size_t)blockIdx.x * W8_CK_UNIT;
+  uint8_t*       base = ws + up->ws_off;
+  const uint64_t ab   = w8_arr_bytes(S);
+  uint4*         ck   = ckg + (size_t)blockIdx.x * W8_CK_UNIT;
   // sub_glue: srsran_vec_sub_bbb saturates, except (AVX2 build) on the last K % 32 elements of the window-interleaved array, which
   // its scalar tail subtracts with wrap-around: interleaved index = step * NW + window >= K - K % 32  <=>  (K % 32 != 0 and step == S-1)
   const bool wrap_tail = (K & 31u) != 0;
+  auto glue = [&](uint32_t a, uint32_t b, int k) { return (wrap_tail && k == (int)S - 1) ? w8_wrap8(__vsub2(a, b)) : w8_subs(a, b); };
 
-  // ---------------------------------------------------------------- stage: global natural order -> shared [step][lane] byte pairs
-  // Four consecutive trellis positions per lane and 32-bit global loads (the arrays are 16-byte aligned), four trips in flight:
-  // every load of a batch is issued before the first value is used, so the warp pays the DRAM latency once per 512 positions.
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    if (c >= ncb) break;
-    const int     col0 = (c >> 1) * (int)NW;  // first lane of this code block's pair
-    const int     half = c & 1;
-    const int     cb   = cb_of(c);
-    uint8_t*      base = (cb >= 0) ? ws + ws_off[cb] : nullptr;
-    constexpr int UN   = 4;
-    for (uint32_t n0 = 0; n0 < K; n0 += 128 * UN) {
-      uint32_t vx[UN], vy[UN], va[UN], ve[UN];
+  // ---------------------------------------------------------------- stage: the x and y streams of the unit -> shared memory
+  // 128-bit loads, four trips in flight (every load of a batch is issued before the first value is used)
+  {
+    const uint4* gx  = reinterpret_cast<const uint4*>(base + (MODE == 2 ? W8_APP2 : W8_SYST) * ab);
+    const uint4* gy  = reinterpret_cast<const uint4*>(base + (MODE == 2 ? W8_PAR1 : W8_PAR0) * ab);
+    uint4*       ga  = reinterpret_cast<uint4*>(base + W8_APP1 * ab);
+    const uint4* ge  = reinterpret_cast<const uint4*>(base + W8_EXT1 * ab);
+    uint4*       sx  = reinterpret_cast<uint4*>(sm.X);
+    uint4*       sy  = reinterpret_cast<uint4*>(sm.Y);
+    const int    nv  = (int)S * (W8_ROW / 16);  // uint4 per stream: four per step row
+    constexpr int UN = 4;
+    for (int i0 = 0; i0 < nv; i0 += 32 * UN) {
+      uint4 vx[UN], vy[UN], va[UN], ve[UN];
 #pragma unroll
       for (int t = 0; t < UN; t++) {
-        const uint32_t n = n0 + 128 * t + 4 * lane;
-        vx[t] = vy[t] = va[t] = ve[t] = 0u;
-        if (n < K && base) {
-          // MODE 0/1: syst + par0 (+ app1, ext1); MODE 2: app2 + par1
-          vx[t] = *reinterpret_cast<const uint32_t*>(base + (MODE == 2 ? 4 * KP : 0) + n);
-          vy[t] = *reinterpret_cast<const uint32_t*>(base + (MODE == 2 ? 2 * KP : KP) + n);
+        const int i = i0 + 32 * t + lane;
+        if (i < nv) {
+          vx[t] = gx[i];
+          vy[t] = gy[i];
           if (MODE == 1) {
-            va[t] = *reinterpret_cast<const uint32_t*>(base + 3 * KP + n);
-            ve[t] = *reinterpret_cast<const uint32_t*>(base + 5 * KP + n);
+            va[t] = ga[i];
+            ve[t] = ge[i];
           }
         }
       }
 #pragma unroll
       for (int t = 0; t < UN; t++) {
-        const uint32_t n = n0 + 128 * t + 4 * lane;
-        if (n >= K) continue;
-        uint32_t w = n / S, k = n - w * S, apw = 0;
+        const int i = i0 + 32 * t + lane;
+        if (i >= nv) continue;
+        if (MODE == 1) {
+          // app1 <- app1 - ext1 (turbodecoder_iter.h:106-108), x = sat(app1 + syst) (simd_add(ap, x), turbodecoder_win.h:608-611);
+          // eight byte pairs per uint4, two per word
+          const int      k = i / (W8_ROW / 16);
+          const uint32_t xa[4] = {vx[t].x, vx[t].y, vx[t].z, vx[t].w}, aa[4] = {va[t].x, va[t].y, va[t].z, va[t].w},
+                         ea[4] = {ve[t].x, ve[t].y, ve[t].z, ve[t].w};
+          uint32_t xo[4], ao[4];
 #pragma unroll
-        for (int bb = 0; bb < 4; bb++) {
-          // (K is a multiple of 8, so the four positions exist together; they may straddle a window boundary)
-          const uint32_t a = k * W8_PITCH + 2 * (col0 + w) + half;
-          int x = (int)(int8_t)(vx[t] >> (8 * bb)), y = (int)(int8_t)(vy[t] >> (8 * bb));
-          if (MODE == 1) {
-            const int d  = (int)(int8_t)(va[t] >> (8 * bb)) - (int)(int8_t)(ve[t] >> (8 * bb));
-            const int ap = (wrap_tail && k == S - 1) ? (int)(int8_t)d : w8_sat_i(d);  // app1 <- app1 - ext1 (turbodecoder_iter.h:106-108)
-            x            = w8_sat_i(ap + x);                                         // simd_add(ap, x), turbodecoder_win.h:608-611
-            apw |= ((uint32_t)ap & 0xffu) << (8 * bb);
+          for (int q = 0; q < 4; q++) {
+            const uint32_t ap0 = glue(w8_unpack(aa[q]), w8_unpack(ea[q]), k), ap1 = glue(w8_unpack_hi(aa[q]), w8_unpack_hi(ea[q]), k);
+            const uint32_t x0 = w8_adds(ap0, w8_unpack(xa[q])), x1 = w8_adds(ap1, w8_unpack_hi(xa[q]));
+            ao[q] = __byte_perm(ap0, ap1, 0x6420u);
+            xo[q] = __byte_perm(x0, x1, 0x6420u);
           }
-          sm.X[a] = (uint8_t)x;
-          sm.Y[a] = (uint8_t)y;
-          if (++k == S) { k = 0; w++; }
+          sx[i] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+          ga[i] = make_uint4(ao[0], ao[1], ao[2], ao[3]);  // the output side subtracts the updated a-priori values again
+        } else {
+          sx[i] = vx[t];
         }
-        // the updated a-priori values go back where they came from: the output side subtracts them again (ext1 <- ext1 - app1)
-        if (MODE == 1 && base) *reinterpret_cast<uint32_t*>(base + 3 * KP + n) = apw;
+        sy[i] = vy[t];
       }
     }
   }
   __syncwarp();
-  const int w_lane = lane % (int)NW;  // window of this lane within its pair
-  const int pair   = lane / (int)NW;
-  auto ldx = [&](int k) { return w8_unpack(*reinterpret_cast<const uint16_t*>(&sm.X[k * W8_PITCH + 2 * lane])); };
-  auto ldy = [&](int k) { return w8_unpack(*reinterpret_cast<const uint16_t*>(&sm.Y[k * W8_PITCH + 2 * lane])); };
+  auto ldx = [&](int k) { return w8_unpack(*reinterpret_cast<const uint16_t*>(&sm.X[k * W8_ROW + 2 * lane])); };
+  auto ldy = [&](int k) { return w8_unpack(*reinterpret_cast<const uint16_t*>(&sm.Y[k * W8_ROW + 2 * lane])); };
 
   uint32_t o[8];
   // ---------------------------------------------------------------- beta: warm-up over the window's own first 40 steps
 #pragma unroll
   for (int i = 0; i < 8; i++) o[i] = 0u;  // simd_set1(-INF), INF = 0
+#pragma unroll 2
   for (int k = W8_OVERLAP - 1; k >= 0; k--) {
     w8_bstep(o, ldx(k), ldy(k));
     if (k) w8_norm(o);
@@ -256,16 +268,15 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
 #pragma unroll
     for (int i = 0; i < 8; i++) t[i] = __shfl_down_sync(0xffffffffu, o[i], 1, (int)NW);
     if (w_lane == (int)NW - 1) {
+      const int8_t* tail = reinterpret_cast<const int8_t*>(base + W8_NARR * ab);  // [cb slot][stream: syst, par0, app2, par1][4]
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         int st0 = 0, st1 = 0, st2 = 0, st3 = 0, st4 = 0, st5 = 0, st6 = 0, st7 = 0;
-        const int cb = pair ? (h ? cb3 : cb2) : (h ? cb1 : cb0);
-        if (cb >= 0) {
-          const int8_t* base = reinterpret_cast<const int8_t*>(ws + ws_off[cb]);
-          const int8_t* pin  = (MODE == 2) ? base + 4 * KP : base;       // app2 (second encoder's termination systematic) / syst
-          const int8_t* ppa  = (MODE == 2) ? base + 2 * KP : base + KP;  // par1 / par0
-          for (int k = (int)K + 2; k >= (int)K; k--) {
-            const int xv = pin[k], yv = ppa[k], xy = w8_sadd_tail(xv, yv);
+        if ((h ? cb_hi : cb_lo) >= 0) {
+          const int8_t* pin = tail + (2 * pair + h) * 16 + (MODE == 2 ? 8 : 0);   // app2 (second encoder's termination systematic) / syst
+          const int8_t* ppa = tail + (2 * pair + h) * 16 + (MODE == 2 ? 12 : 4);  // par1 / par0
+          for (int r = 2; r >= 0; r--) {
+            const int xv = pin[r], yv = ppa[r], xy = w8_sadd_tail(xv, yv);
             const int n0 = max(w8_sadd_tail(st4, xy), st0), n1 = max(st4, w8_sadd_tail(st0, xy));
             const int n2 = max(w8_sadd_tail(st5, yv), w8_sadd_tail(st1, xv)), n3 = max(w8_sadd_tail(st5, xv), w8_sadd_tail(st1, yv));
             const int n4 = max(w8_sadd_tail(st6, xv), w8_sadd_tail(st2, yv)), n5 = max(w8_sadd_tail(st6, yv), w8_sadd_tail(st2, xv));
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
             st0 = n0; st1 = n1; st2 = n2; st3 = n3; st4 = n4; st5 = n5; st6 = n6; st7 = n7;
           }
         }
-        const int      sv[8] = {st0, st1, st2, st3, st4, st5, st6, st7};
+        const int sv[8] = {st0, st1, st2, st3, st4, st5, st6, st7};
 #pragma unroll
         for (int i = 0; i < 8; i++) t[i] = h ? ((t[i] & 0xffffu) | ((uint32_t)sv[i] << 16)) : ((uint32_t)sv[i] & 0xffffu);
       }
@@ -284,6 +295,7 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
   // ---------------------------------------------------------------- beta: main pass, checkpoint B[k] (before normalisation) at k = 8, 16, ... and B[S]
   const int ck_top = ((int)S + 7) / 8;  // slot of B[S]; B[8c] lives in slot c
   w8_ck_store(&ck[ck_top * 32 + lane], o);
+#pragma unroll 2
   for (int k = (int)S - 1; k >= 0; k--) {
     w8_bstep(o, ldx(k), ldy(k));
     if (k && (k & 7) == 0) w8_ck_store(&ck[(k >> 3) * 32 + lane], o);
@@ -292,6 +304,7 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
   // ---------------------------------------------------------------- alpha: warm-up over the window's own last 40 steps
 #pragma unroll
   for (int i = 0; i < 8; i++) o[i] = 0u;
+#pragma unroll 2
   for (int j = 0; j < W8_OVERLAP; j++) {
     const int k = (int)S - W8_OVERLAP + j;
     w8_astep(o, ldx(k), ldy(k));
@@ -305,42 +318,77 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
     for (int i = 0; i < 8; i++) o[i] = (w_lane == 0) ? 0u : t[i];  // first window: the known state {0, -INF x 7}, INF = 0
   }
   // ---------------------------------------------------------------- alpha: main pass, 8 steps at a time with beta recomputed into registers
-  // one step: branch sums, LLR against beta[k+1] (b), extrinsic / decision into the consumed slots, state update
-  auto astep_out = [&](int k, const uint32_t (&b)[8]) {
-    const uint32_t x = ldx(k), y = ldy(k);
-    uint32_t       z[8], w[8];
-    w8_abranches(o, x, y, z, w);
-    // max_i sat(b_i + z_i) = sat(max_i (b_i + z_i)): saturation is monotone
-    const uint32_t p0 = __vadd2(b[0], z[0]), p1 = __vadd2(b[1], z[1]), p2 = __vadd2(b[2], z[2]), p3 = __vadd2(b[3], z[3]);
-    const uint32_t p4 = __vadd2(b[4], z[4]), p5 = __vadd2(b[5], z[5]), p6 = __vadd2(b[6], z[6]), p7 = __vadd2(b[7], z[7]);
-    const uint32_t q0 = __vadd2(b[0], w[0]), q1 = __vadd2(b[1], w[1]), q2 = __vadd2(b[2], w[2]), q3 = __vadd2(b[3], w[3]);
-    const uint32_t q4 = __vadd2(b[4], w[4]), q5 = __vadd2(b[5], w[5]), q6 = __vadd2(b[6], w[6]), q7 = __vadd2(b[7], w[7]);
-    const uint32_t m0 = w8_sat(__vmaxs2(__vimax3_s16x2(__vimax3_s16x2(p0, p1, p2), p6, p7), __vimax3_s16x2(p3, p4, p5)));
-    const uint32_t m1 = w8_sat(__vmaxs2(__vimax3_s16x2(__vimax3_s16x2(q0, q1, q2), q6, q7), __vimax3_s16x2(q3, q4, q5)));
-    const uint32_t l  = w8_subs(m1, m0);
-    // out = l >> 1, arithmetic, per element (simd_rb_shift, divide_output = 1)
-    const uint32_t ext = ((l >> 1) & 0x7fff7fffu) | (l & 0x80008000u);
-#pragma unroll
-    for (int i = 0; i < 8; i++) o[i] = __vmaxs2(z[i], w[i]);
-    if (k) w8_norm(o);
-    // x[k] and y[k] have been consumed (the beta recompute of this block ran first): the extrinsic value and the decision
-    // (tdec_win*_decision_byte: > 0) take their places
-    *reinterpret_cast<uint16_t*>(&sm.X[k * W8_PITCH + 2 * lane]) = (uint16_t)w8_pack(ext);
-    const uint32_t pos = __vadd2(__vmaxs2(ext, 0u), 0x7fff7fffu) & 0x80008000u;  // bit 15 / 31 set iff the value is > 0
-    *reinterpret_cast<uint16_t*>(&sm.Y[k * W8_PITCH + 2 * lane]) = (uint16_t)(((pos >> 15) & 1u) | ((pos >> 23) & 0x100u));
+  // Every step also finishes its own output: the extrinsic value goes to ext1 in place (DEC1) and through the QPP table to the
+  // other decoder's input, the hard decision to its natural position, the CRC contribution into the running remainder. All of
+  // these are 2-byte accesses of one 64-byte row per warp - or one byte when the other block of the pair is done and must keep
+  // what it has.
+  const uint16_t* dtab  = (MODE == 2) ? tb.dst2 : tb.dst1;
+  const uint32_t* ctab  = (MODE == 2) ? tb.crc2[crc_kind] : tb.crc1[crc_kind];
+  uint8_t*        pOUT  = base + (MODE == 2 ? W8_APP1 : W8_APP2) * ab;  // scatter target
+  uint8_t*        pE1   = base + W8_EXT1 * ab;
+  uint8_t*        pND   = base + W8_ND * ab;
+  const uint8_t*  pAP   = base + W8_APP1 * ab;
+  const uint32_t  lane2 = 2u * (uint32_t)lane, pcol = 2u * (uint32_t)(pair * (int)NW);
+  uint32_t        crc_lo = 0, crc_hi = 0;
+  // a 2-byte pair store that leaves the byte of a finished code block alone
+  auto st_pair = [&](uint8_t* p, uint32_t v) {
+    if (live_lo && live_hi) *reinterpret_cast<uint16_t*>(p) = (uint16_t)v;
+    else if (live_lo) p[0] = (uint8_t)v;
+    else if (live_hi) p[1] = (uint8_t)(v >> 8);
   };
-  uint4 ck_next = ck[(8 >= (int)S ? ck_top : 1) * 32 + lane];
+  uint4 ck_next = w8_ld_v4(&ck[(8 >= (int)S ? ck_top : 1) * 32 + lane]);
   for (int k0 = 0; k0 < (int)S; k0 += 8) {
     const int len = min(8, (int)S - k0), top = k0 + len;
+    // per-step table entries and a-priori values of this block, fetched before the block's ~900 instructions
+    uint32_t dv[8], cv[8], av[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int kk = min(k0 + j, (int)S - 1);
+      dv[j] = __ldg(dtab + kk * (int)NW + w_lane);
+      cv[j] = __ldg(ctab + kk * (int)NW + w_lane);
+      av[j] = (MODE == 1) ? (uint32_t) * reinterpret_cast<const uint16_t*>(pAP + kk * W8_ROW + lane2) : 0u;
+    }
     // B[j] = beta[k0 + 1 + j] as stored (before normalisation): what the LLR of step k0 + j reads; B[len-1] is the checkpoint
-    uint32_t B[8][8];
     uint32_t s[8];
     w8_ck_unpack(ck_next, s);
-    if (top < (int)S) {  // the next block's checkpoint is fetched now and used after this block's ~1000 instructions
+    if (top < (int)S) {  // the next block's checkpoint is fetched now and used after this block
       const int ntop = min(top + 8, (int)S);
-      ck_next        = ck[(ntop == (int)S ? ck_top : (ntop >> 3)) * 32 + lane];
+      ck_next        = w8_ld_v4(&ck[(ntop == (int)S ? ck_top : (ntop >> 3)) * 32 + lane]);
     }
+    // one step: branch sums, LLR against beta[k+1] (b), outputs, state update
+    auto astep_out = [&](int k, uint32_t dvj, uint32_t cvj, uint32_t avj, const uint32_t (&b)[8]) {
+      const uint32_t x = ldx(k), y = ldy(k);
+      uint32_t       z[8], w[8];
+      w8_abranches(o, x, y, z, w);
+      // max_i sat(b_i + z_i) = sat(max_i (b_i + z_i)): saturation is monotone
+      const uint32_t p0 = __vadd2(b[0], z[0]), p1 = __vadd2(b[1], z[1]), p2 = __vadd2(b[2], z[2]), p3 = __vadd2(b[3], z[3]);
+      const uint32_t p4 = __vadd2(b[4], z[4]), p5 = __vadd2(b[5], z[5]), p6 = __vadd2(b[6], z[6]), p7 = __vadd2(b[7], z[7]);
+      const uint32_t q0 = __vadd2(b[0], w[0]), q1 = __vadd2(b[1], w[1]), q2 = __vadd2(b[2], w[2]), q3 = __vadd2(b[3], w[3]);
+      const uint32_t q4 = __vadd2(b[4], w[4]), q5 = __vadd2(b[5], w[5]), q6 = __vadd2(b[6], w[6]), q7 = __vadd2(b[7], w[7]);
+      const uint32_t m0 = w8_sat(__vmaxs2(__vimax3_s16x2(__vimax3_s16x2(p0, p1, p2), p6, p7), __vimax3_s16x2(p3, p4, p5)));
+      const uint32_t m1 = w8_sat(__vmaxs2(__vimax3_s16x2(__vimax3_s16x2(q0, q1, q2), q6, q7), __vimax3_s16x2(q3, q4, q5)));
+      const uint32_t l  = w8_subs(m1, m0);
+      // out = l >> 1, arithmetic, per element (simd_rb_shift, divide_output = 1)
+      const uint32_t ext = ((l >> 1) & 0x7fff7fffu) | (l & 0x80008000u);
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] = __vmaxs2(z[i], w[i]);
+      if (k) w8_norm(o);
+      // what the next half-iteration reads: DEC1 ext1 <- ext1 - app1 (turbodecoder_iter.h:116-118; first half-iteration: ext1
+      // as it is), app2[rev[i]] = ext1[i] (:120); DEC2 app1[fwd[i]] = ext2[i] (:127)
+      uint32_t r = ext;
+      if (MODE == 1) r = glue(ext, w8_unpack(avj), k);
+      const uint32_t rp = w8_pack(r);
+      if (MODE != 2) st_pair(pE1 + k * W8_ROW + lane2, rp);
+      st_pair(pOUT + 2u * dvj + pcol, rp);
+      // the decision (tdec_win*_decision_byte: > 0) at its natural position, and its CRC contribution
+      const uint32_t pos = __vadd2(__vmaxs2(ext, 0u), 0x7fff7fffu) & 0x80008000u;  // bit 15 / 31 set iff the value is > 0
+      const uint32_t dp  = ((pos >> 15) & 1u) | ((pos >> 23) & 0x100u);
+      st_pair(pND + (MODE == 2 ? 2u * dvj + pcol : (uint32_t)k * W8_ROW + lane2), dp);
+      crc_lo ^= cvj & (0u - (dp & 1u));
+      crc_hi ^= cvj & (0u - (dp >> 8));
+    };
     if (len == 8) {
+      uint32_t B[8][8];
 #pragma unroll
       for (int i = 0; i < 8; i++) B[7][i] = s[i];
       if (top < (int)S) w8_norm(s);  // the recursion went on from the normalised state; the start state B[S] is used as it is
@@ -353,150 +401,120 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
         w8_norm(s);
       }
 #pragma unroll
-      for (int j = 0; j < 8; j++) astep_out(k0 + j, B[j]);
+      for (int j = 0; j < 8; j++) astep_out(k0 + j, dv[j], cv[j], av[j], B[j]);
     } else {
       // the short last block of a window whose length is not a multiple of 8 (top == S, at most 7 steps, once per window): beta of
       // every step is recomputed from the checkpoint on its own - no register window with a runtime length (an array indexed
       // by `len` would push the whole window into local memory, for the full blocks too)
-      for (int j = 0; j < len; j++) {
-        uint32_t t[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) t[i] = s[i];
-        if (j < len - 1 && top < (int)S) w8_norm(t);
-        for (int kk = top - 1; kk >= k0 + 1 + j; kk--) {
-          w8_bstep(t, ldx(kk), ldy(kk));
-          if (kk > k0 + 1 + j) w8_norm(t);  // kk >= 1; the last one stays as stored: before normalisation
+      for (int j = 0; j < 7; j++) {
+        if (j < len) {
+          uint32_t t[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) t[i] = s[i];
+          if (j < len - 1 && top < (int)S) w8_norm(t);
+          for (int kk = top - 1; kk >= k0 + 1 + j; kk--) {
+            w8_bstep(t, ldx(kk), ldy(kk));
+            if (kk > k0 + 1 + j) w8_norm(t);  // kk >= 1; the last one stays as stored: before normalisation
+          }
+          astep_out(k0 + j, dv[j], cv[j], av[j], t);
         }
-        astep_out(k0 + j, t);
       }
     }
   }
-  __syncwarp();
-
-  // ---------------------------------------------------------------- emit: natural order, QPP scatter, hard bits, CRC, verdict
-  // Lanes walk consecutive trellis positions (coalesced byte accesses; the ballot of 32 decisions is one output word). Per 256
-  // positions every global load (QPP table, a-priori bytes) is issued before the first value is used.
-  const uint32_t nbytes = K / 8;
+  // ---------------------------------------------------------------- verdict per code block (sch.c:426-456): CRC of all windows, counts, done flags
+  for (int off = (int)NW / 2; off > 0; off >>= 1) {
+    crc_lo ^= __shfl_xor_sync(0xffffffffu, crc_lo, off, (int)NW);
+    crc_hi ^= __shfl_xor_sync(0xffffffffu, crc_hi, off, (int)NW);
+  }
+  if (w_lane == 0) {
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
-    if (c >= ncb) break;
-    const int cb = cb_of(c);
-    if (cb < 0 || !live_of(c)) continue;  // (done code blocks of a live unit are recomputed but nothing of them is stored)
-    const int col0 = (c >> 1) * (int)NW, half = c & 1;
-    int8_t*   base = reinterpret_cast<int8_t*>(ws + ws_off[cb]);
-    int8_t *  pA1 = base + 3 * KP, *pA2 = base + 4 * KP, *pE1 = base + 5 * KP;
-    uint8_t*  pND = reinterpret_cast<uint8_t*>(base + 6 * KP);
-    const uint16_t* perm  = (MODE == 2) ? tb.fwd : tb.rev;
-    const uint32_t* crcw  = (crc_kind == 1) ? crcw_a : crcw_b;
-    uint8_t*        dst   = out + out_off[cb];
-    const uint32_t  total = out_len ? out_len[cb] : nbytes;
-    uint32_t        crc   = 0;
-    constexpr int   UE    = 8;
-    // 32 x UE decisions -> 32 output bytes: lane l takes byte l of the batch; its CRC contribution by linearity, eight consecutive
-    // table words per byte (crcw[m] = x^(m+24) mod g; bit 7 of a byte = the earliest position = the highest m)
-    auto finish_words = [&](const uint32_t (&bal)[UE], uint32_t n0) {
-      uint32_t wv = 0;
-#pragma unroll
-      for (int t = 0; t < UE; t++)
-        if ((lane >> 2) == t) wv = bal[t];
-      const uint32_t b = (n0 >> 3) + lane;
-      if (b < nbytes) {
-        const uint32_t v = (__brev(wv) >> (24 - 8 * (lane & 3))) & 0xffu;  // position n in bit 31 - (n mod 32): MSB-first bytes
-        if (b < total) dst[b] = (uint8_t)v;
-        if (crc_kind && v) {
-          const uint4* wq = reinterpret_cast<const uint4*>(crcw + (K - 8 - 8 * b));  // 32-byte aligned
-          const uint4  lo = __ldg(wq), hi = __ldg(wq + 1);
-          crc ^= (lo.x & (0u - (v & 1u))) ^ (lo.y & (0u - ((v >> 1) & 1u))) ^ (lo.z & (0u - ((v >> 2) & 1u))) ^ (lo.w & (0u - ((v >> 3) & 1u)));
-          crc ^= (hi.x & (0u - ((v >> 4) & 1u))) ^ (hi.y & (0u - ((v >> 5) & 1u))) ^ (hi.z & (0u - ((v >> 6) & 1u))) ^ (hi.w & (0u - (v >> 7)));
-        }
-      }
-    };
-    uint32_t w = 0, k = (uint32_t)lane;  // position n = n0 + 32 t + lane walks (window, step) incrementally: S > 32
-    for (uint32_t n0 = 0; n0 < K; n0 += 32 * UE) {
-      uint32_t pv[UE], av[UE], bal[UE];
-#pragma unroll
-      for (int t = 0; t < UE; t++) {
-        const uint32_t n = n0 + 32 * t + lane;
-        pv[t] = (n < K) ? (uint32_t)__ldg(perm + n) : 0u;
-        av[t] = (MODE == 1 && n < K) ? (uint32_t)(uint8_t)pA1[n] : 0u;
-      }
-#pragma unroll
-      for (int t = 0; t < UE; t++) {
-        const uint32_t n = n0 + 32 * t + lane;
-        uint32_t       d = 0;
-        if (n < K) {
-          const uint32_t a = k * W8_PITCH + 2 * (col0 + w) + half;
-          int            r = (int)(int8_t)sm.X[a];
-          d                = sm.Y[a];
-          if (MODE == 1) {
-            // ext1 <- ext1 - app1 (turbodecoder_iter.h:116-118), same saturate / wrap rule as on the way in
-            const int df = r - (int)(int8_t)av[t];
-            r            = (wrap_tail && k == S - 1) ? (int)(int8_t)df : w8_sat_i(df);
-          }
-          if (MODE == 2) {
-            pA1[pv[t]] = (int8_t)r;   // app1[fwd[i]] = ext2[i] (turbodecoder_iter.h:127)
-            pND[pv[t]] = (uint8_t)d;  // the decision of step i belongs to natural position fwd[i]
-          } else {
-            pE1[n]     = (int8_t)r;   // ext1 (after the subtraction) stays for the next DEC1's glue
-            pA2[pv[t]] = (int8_t)r;   // app2[rev[i]] = ext1[i] (turbodecoder_iter.h:120)
-          }
-        }
-        k += 32;
-        if (k >= S) { k -= S; w++; }
-        bal[t] = __ballot_sync(0xffffffffu, d != 0);
-      }
-      if (MODE != 2) finish_words(bal, n0);
-    }
-    if (MODE == 2) {
-      __syncwarp();  // the scattered decisions of all lanes are visible to all lanes
-      for (uint32_t n0 = 0; n0 < K; n0 += 32 * UE) {
-        uint32_t dv[UE], bal[UE];
-#pragma unroll
-        for (int t = 0; t < UE; t++) {
-          const uint32_t n = n0 + 32 * t + lane;
-          dv[t] = (n < K) ? (uint32_t)pND[n] : 0u;
-        }
-#pragma unroll
-        for (int t = 0; t < UE; t++) bal[t] = __ballot_sync(0xffffffffu, dv[t] != 0);
-        finish_words(bal, n0);
-      }
-    }
-    crc = __reduce_xor_sync(0xffffffffu, crc);
-    if (lane == 0) {
-      const uint32_t okv = (crc_kind != 0 && crc == 0u) ? 1u : 0u;
+    for (int h = 0; h < 2; h++) {
+      const int cb = h ? cb_hi : cb_lo;
+      if (cb < 0 || !(h ? live_hi : live_lo)) continue;
+      const uint32_t okv = (crc_kind != 0 && (h ? crc_hi : crc_lo) == 0u) ? 1u : 0u;
       noi[cb] = (uint8_t)cnt;
       ok[cb]  = (uint8_t)okv;
       if ((early_stop && okv && cnt >= min_iter) || cnt >= (max_iter_cb ? (uint32_t)max_iter_cb[cb] : max_iter)) done[cb] = 1;
     }
-    __syncwarp();
   }
 }
 
 /*
  * De-multiplex natural-order int8 LLRs (s p p' triples + 12 termination values: tdec_win*_extract_input, turbodecoder_win.h:
- * 883-921, in natural order) into the per-code-block arrays and re-arm the decode state. grid = (ceil(K_max / 256), n_cb).
+ * 883-921) into the unit's window-interleaved, pair-packed arrays and re-arm the decode state. One block per unit: the triples
+ * are read coalesced, transposed in shared memory and leave as whole 64-byte rows. Dynamic shared memory: 3 * S * 66 bytes.
  */
-__global__ void __launch_bounds__(256) extract8_kernel(const int8_t* __restrict__ llr, const uint64_t* __restrict__ llr_off, const uint32_t* __restrict__ cbK,
-                                                       uint8_t* __restrict__ ws, const uint64_t* __restrict__ ws_off, uint8_t* __restrict__ done)
+__global__ void __launch_bounds__(256) extract8_kernel(const int8_t* __restrict__ llr, const uint64_t* __restrict__ llr_off, const Unit8* __restrict__ units,
+                                                       uint8_t* __restrict__ ws, uint8_t* __restrict__ done)
 {
-  const uint32_t cb = blockIdx.y, K = cbK[cb], KP = w8_pitch(K);
-  const int8_t*  in = llr + llr_off[cb];
-  int8_t*        b  = reinterpret_cast<int8_t*>(ws + ws_off[cb]);
-  const uint32_t n  = blockIdx.x * 256 + threadIdx.x;
-  if (n < K) {
-    b[n]          = in[3 * n];
-    b[KP + n]     = in[3 * n + 1];
-    b[2 * KP + n] = in[3 * n + 2];
-  }
-  if (blockIdx.x == 0) {
+  extern __shared__ __align__(16) uint8_t xs[];  // [3][S][66]: rows padded by 2 bytes so that the transposing stores spread over the banks
+  const Unit8    u = units[blockIdx.x];
+  const uint32_t K = u.K, NW = u.NW, S = u.S, PITCH = W8_ROW + 2;
+  uint8_t*       base = ws + u.ws_off;
+  const uint64_t ab   = w8_arr_bytes(S);
+  const int      ncb  = 2 * (32 / (int)NW);
+  for (uint32_t i = threadIdx.x; i < 3 * S * PITCH / 2; i += 256) reinterpret_cast<uint16_t*>(xs)[i] = 0;
+  __syncthreads();
+  for (int c = 0; c < ncb; c++) {
+    const int cb = u.cb[c];
+    if (cb < 0) continue;
+    const int8_t*  in  = llr + llr_off[cb];
+    const uint32_t col = 2u * ((c >> 1) * NW) + (c & 1);
+    for (uint32_t n = threadIdx.x; n < K; n += 256) {
+      const uint32_t w = n / S, k = n - w * S, a = k * PITCH + 2 * w + col;
+      xs[a]                 = (uint8_t)in[3 * n];
+      xs[S * PITCH + a]     = (uint8_t)in[3 * n + 1];
+      xs[2 * S * PITCH + a] = (uint8_t)in[3 * n + 2];
+    }
     if (threadIdx.x < 3) {
       const uint32_t j = threadIdx.x;
-      b[K + j]          = in[3 * K + 2 * j];          // syst termination
-      b[KP + K + j]     = in[3 * K + 2 * j + 1];      // par0
-      b[4 * KP + K + j] = in[3 * K + 6 + 2 * j];      // app2: second encoder's termination systematic
-      b[2 * KP + K + j] = in[3 * K + 6 + 2 * j + 1];  // par1
+      int8_t* tail = reinterpret_cast<int8_t*>(base + W8_NARR * ab) + c * 16;
+      tail[j]      = in[3 * K + 2 * j];          // syst termination
+      tail[4 + j]  = in[3 * K + 2 * j + 1];      // par0
+      tail[8 + j]  = in[3 * K + 6 + 2 * j];      // app2: second encoder's termination systematic
+      tail[12 + j] = in[3 * K + 6 + 2 * j + 1];  // par1
     }
     if (threadIdx.x == 0) done[cb] = 0;
+  }
+  __syncthreads();
+  // rows out: 3 streams x S rows x 16 words
+  for (uint32_t i = threadIdx.x; i < 3 * S * 16; i += 256) {
+    const uint32_t a = i / (S * 16), r = i - a * S * 16, k = r / 16, wq = r - k * 16;
+    const uint8_t* src = xs + a * S * PITCH + k * PITCH + 4 * wq;
+    const uint32_t v   = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+    reinterpret_cast<uint32_t*>(base + a * ab)[k * 16 + wq] = v;  // arrays 0, 1, 2 = syst, par0, par1
+  }
+}
+
+/*
+ * Decoded bytes of every code block from the unit's decision array (tdec_win*_decision_byte, MSB first): position n = w S + k sits
+ * in row k, column w of its pair. One warp per unit; 32 positions per ballot.
+ */
+__global__ void __launch_bounds__(32) emit8_kernel(const Unit8* __restrict__ units, const uint8_t* __restrict__ ws, uint8_t* __restrict__ out,
+                                                   const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_len)
+{
+  const Unit8    u    = units[blockIdx.x];
+  const int      lane = threadIdx.x;
+  const uint32_t K = u.K, NW = u.NW, S = u.S;
+  const uint8_t* nd  = ws + u.ws_off + W8_ND * w8_arr_bytes(S);
+  const int      ncb = 2 * (32 / (int)NW);
+  for (int c = 0; c < ncb; c++) {
+    const int cb = u.cb[c];
+    if (cb < 0) continue;
+    const uint32_t col   = 2u * ((c >> 1) * NW) + (c & 1);
+    uint8_t*       dst   = out + out_off[cb];
+    const uint32_t total = out_len ? out_len[cb] : K / 8;
+    uint32_t       w = 0, k = (uint32_t)lane;  // position n0 + lane walks (window, step) incrementally: S > 32
+    for (uint32_t n0 = 0; n0 < K; n0 += 32) {
+      const uint32_t n = n0 + lane;
+      const uint32_t d = (n < K) ? nd[k * W8_ROW + 2 * w + col] : 0u;
+      k += 32;
+      if (k >= S) { k -= S; w++; }
+      const uint32_t word = __brev(__ballot_sync(0xffffffffu, d != 0));  // position n0 in bit 31: MSB-first bytes
+      const uint32_t b    = (n0 >> 3) + (uint32_t)lane;
+      if (lane < 4 && b < total && b < K / 8) dst[b] = (uint8_t)(word >> (24 - 8 * lane));
+    }
   }
 }
 

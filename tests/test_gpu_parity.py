@@ -882,7 +882,7 @@ def test_decode_tb_from_symbols_uplink(sb, eng, o, tbs, nprb, nsymb, mod, ri):
     q_bits[src[:G]] = (e_clean > 0).astype(np.uint8)
     scr = o.sequence_apply_s(np.ones(H * Qm, np.int16), c_init) < 0
     sym = _modulate(q_bits ^ scr.astype(np.uint8), mod)
-    sigma = vecgen.sigma_for({1: 2.5, 2: 6.5, 3: 12.5}[mod], tbs / float(G)) / np.sqrt(float(Qm))
+    sigma = vecgen.sigma_for({1: 6.0, 2: 10.5, 3: 12.5}[mod], tbs / float(G)) / np.sqrt(float(Qm))
     sym = (sym + sigma * (rng.standard_normal(H) + 1j * rng.standard_normal(H))).astype(np.complex64)
     q = o.sequence_apply_s(o.demod_soft_demodulate_s(mod, sym), c_init)
     g = o.ulsch_deinterleave(q, Qm, H, nsymb, pos)

@@ -785,7 +785,7 @@ def test_multi_device_dispatcher(sb, o):
                 reqs.append((tbo[i], Qm, rv, ev))
                 r = o.decode_tb(tbs, Qm, rv, ev, 8, st[i]); st[i] = r["state"]; exp.append(r)
                 tbo[i].data[:] = 0
-            assert m.decode_tb_batch(reqs, 8, owners=list(range(len(cases)))) == 0
+            assert m.decode_tb_batch(reqs, 8, owners=list(range(len(cases)))) == 0, sb.lib().srsb200_last_error().decode()
             for tb, r, s_ in zip(tbo, exp, st):
                 _check_tb(r, tb, s_)
         assert [m.device_of(i) for i in range(6)] == [i % nd for i in range(6)]

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Measures the BASELINE.json configs that are not the bench line (1, 3, 4, 5) on one B200 and checks a sample of each
-against the oracle. Writes profiles/r01_configs.json. Usage: python tools/run_configs.py"""
+against the oracle. Writes profiles/r02_configs.json. Usage: python tools/run_configs.py"""
 import json
 import os
 import sys
@@ -40,6 +40,14 @@ for nit in (4, 8):
     dt = timeit(lambda: t.run_all(llr, nit, K), reps=10)
     res["config1_single_cb_K6144_%d_half_iterations" % nit] = {"latency_us": dt * 1e6, "info_Mbit_s": K / dt / 1e6, "parity": "bit-exact vs oracle"}
 t.free()
+
+# ---- config 1 in the reference's 8-bit LLR mode: the windowed decoder has no K-long dependency chain (one warp, 32 windows)
+l8 = np.clip(vecgen.make_cb(K, 1.5, 1, scale=12)[1], -127, 127).astype(np.int8)
+for nit in (4, 8):
+    out8, _, _ = eng.tdec_batch8(K, l8[None, :], nit, early_stop=False, crc_kind=sb.CRC_NONE)
+    assert (out8[0] == o.tdec8_trace(K, l8, nit)[nit - 1]).all()
+    dt = timeit(lambda: eng.tdec_batch8(K, l8[None, :], nit, early_stop=False, crc_kind=sb.CRC_NONE), reps=10)
+    res["config1_single_cb_K6144_%d_half_iterations_llr8" % nit] = {"latency_us": dt * 1e6, "info_Mbit_s": K / dt / 1e6, "parity": "bit-exact vs the 8-bit oracle"}
 
 # ---- config 4: all 188 LTE sizes in one submission (8 blocks each), CRC early stop
 Ks, llrs = [], []
@@ -114,6 +122,35 @@ def one_pdsch():
 dt = timeit(one_pdsch, reps=10)
 res["config3_pdsch_2cw_steady"] = {"ms_per_subframe_host_to_host": dt * 1e3, "info_Mbit_s": 2 * tbs / dt / 1e6, "code_blocks": 26}
 
+# ---- config 3, the two-layer single-TB variant (TBS 149776, C = 25, K = 6016, Qm * Nl = 12) and the 8-bit mode of both
+tbs2, G2 = 149776, 12 * 14400
+tb2 = sb.TransportBlock(tbs2)
+e2 = vecgen.make_tb(tbs2, G2, 12, 0, 5.5, 61, scale=700)[1]
+r2 = o.decode_tb(tbs2, 12, 0, e2, 8)
+assert eng.decode_tb(tb2, 12, 0, e2, 8) == r2["ret"] and (tb2.cb_noi[:25] == r2["cb_noi"][:25]).all()
+def one_2layer():
+    tb2.buffer_f[:] = 0; tb2.cb_crc[:] = 0
+    eng.decode_tb(tb2, 12, 0, e2, 8)
+dt = timeit(one_2layer, reps=10)
+res["config3_pdsch_2layer_1tb_steady"] = {"ms_per_subframe_host_to_host": dt * 1e3, "info_Mbit_s": tbs2 / dt / 1e6, "code_blocks": 25, "ret": int(tb2.ret),
+                                          "parity": "return code and iteration counts bit-exact vs oracle"}
+for name, (tbsx, Gx, Qx, nblk) in {"2cw": (tbs, G, Qm, 26), "2layer_1tb": (tbs2, G2, 12, 25)}.items():
+    ntb = 2 if name == "2cw" else 1
+    tbx = [sb.TransportBlock(tbsx) for _ in range(ntb)]
+    ex = [np.clip(vecgen.make_tb(tbsx, Gx, Qx, 0, 1.0, 70 + c, scale=12)[1], -127, 127).astype(np.int8) for c in range(ntb)]
+    rx = [o.decode_tb8(tbsx, Qx, 0, ex[c], 8) for c in range(ntb)]
+    assert eng.decode_tb_batch([(tbx[c], Qx, 0, ex[c]) for c in range(ntb)], 8, llr8=True) == 0
+    for c in range(ntb):
+        assert tbx[c].ret == rx[c]["ret"] and (tbx[c].cb_noi[:rx[c]["seg"]["C"]] == rx[c]["cb_noi"][:rx[c]["seg"]["C"]]).all()
+    def one8():
+        for c in range(ntb):
+            tbx[c].buffer_f[:] = 0; tbx[c].cb_crc[:] = 0
+        eng.decode_tb_batch([(tbx[c], Qx, 0, ex[c]) for c in range(ntb)], 8, llr8=True)
+    dt = timeit(one8, reps=10)
+    res["config3_pdsch_%s_steady_llr8" % name] = {"ms_per_subframe_host_to_host": dt * 1e3, "info_Mbit_s": ntb * tbsx / dt / 1e6, "code_blocks": nblk,
+                                                 "ret": [int(t_.ret) for t_ in tbx], "avg_half_iterations": [float(t_.avg_iterations) for t_ in tbx],
+                                                 "parity": "return codes and iteration counts bit-exact vs the 8-bit oracle"}
+
 # ---- config 5: 64 cells x one 100-PRB PUSCH TB (13 CB, K=5824) per subframe on one GPU, one batched submission per subframe
 cells = 64
 el = [vecgen.make_tb(tbs, G, Qm, 0, 6.0, 500 + c, scale=700)[1] for c in range(4)]
@@ -172,6 +209,6 @@ eng.close()
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 for d_ in ("profiles", "gpurun_out"):
     os.makedirs(os.path.join(ROOT, d_), exist_ok=True)
-    with open(os.path.join(ROOT, d_, "r01_configs.json"), "w") as f:
+    with open(os.path.join(ROOT, d_, "r02_configs.json"), "w") as f:
         json.dump(res, f, indent=1)
 print(json.dumps(res, indent=1))

@@ -99,12 +99,12 @@ class ClockSampler(threading.Thread):
 
 
 def kernel_source_sha():
-    """fingerprint of the CUDA sources: ncu-derived figures (profiles/dram_traffic.json) are only printed for the kernels they
-    were captured on"""
+    """fingerprint of the source of the decode kernels the roofline is about (scan / job / extract / emit: turbo_kernels.cuh):
+    ncu-derived figures (profiles/dram_traffic.json) are only printed for the kernels they were captured on"""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "srsran_4g_b200", "csrc")
-    for f in sorted(os.listdir(d)):
+    for f in ("turbo_kernels.cuh",):
         h.update(f.encode())
         with open(os.path.join(d, f), "rb") as fh:
             h.update(fh.read())

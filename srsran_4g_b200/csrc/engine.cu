@@ -1054,7 +1054,8 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
  * H2D of range s+1 overlaps the decode of range s, and its D2H overlaps the decode of range s+2 (the PCIe copies are
  * the long pole of the end-to-end path: 6.1 bytes per information bit). Device-resident submissions run as one chain:
  * overlapping the latency-bound scans of one range with the window jobs of another was measured and does not pay
- * (scan warps sharing a sub-partition with job warps slow down as much as the overlap gains; profiles/r01_notes.md).
+ * (scan warps sharing a sub-partition with job warps slow down as much as the overlap gains; DESIGN.md section 5 design history,
+ * profiles/r02_trailing_experiment.md).
  */
 struct HostIO {
   const int16_t* h_llr = nullptr;
@@ -1510,7 +1511,7 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
   CUDA_TRY(cudaMemsetAsync(d_g, 0, ng * sizeof(int16_t), e->stream));  // the nof_ri_bits values past the data are left stale by the reference
   {
     ProfScope ps(e, 3);
-    ulsch_deint_kernel<<<dim3(std::max(1u, std::min<uint32_t>(128u, (j.rows + DT_ROWS - 1) / DT_ROWS)), 1), 256, 0, e->stream>>>((const DeintJob*)d_dj);
+    ulsch_deint_kernel<<<dim3(1, std::max(1u, std::min<uint32_t>(128u, (j.rows + DT_ROWS - 1) / DT_ROWS))), 256, 0, e->stream>>>((const DeintJob*)d_dj);
     e->launches++;
   }
   CUDA_TRY(stg.d2h(g_bits, d_g, ng * sizeof(int16_t), e->stream));

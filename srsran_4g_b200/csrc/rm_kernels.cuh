@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace srsb200 {
 
@@ -106,8 +107,9 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
     }
   }
   __syncthreads();
-  auto llr = [&](uint32_t i) -> uint32_t {
-    uint32_t v = (uint16_t)(i < ns ? se[i] : j.e[i]);
+  // one received LLR (descrambled if asked for). STAGED: every i < E lies in shared memory (E <= RM_SMEM_ELEMS, the usual case)
+  auto llr = [&](uint32_t i, auto staged) -> uint32_t {
+    uint32_t v = (uint16_t)((decltype(staged)::value || i < ns) ? se[i] : j.e[i]);
     if (SCR && j.scramble) {
       uint32_t c;
       if ((i >> 5) < RM_SC_WORDS) {
@@ -119,44 +121,59 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
     }
     return v;
   };
-  // what soft-buffer position p receives: e[n], e[n + L], ... with n = Tinv[p] (repetition when E > L)
-  auto gathered = [&](uint32_t n) -> uint32_t {
-    uint32_t sum = 0;
-    for (uint32_t i = n; i < j.E; i += j.L) sum += llr(i);
-    return sum;
-  };
+  // What soft-buffer position p receives: e[n], e[n + L], ... with n = Tinv[p] (repetition when E > L). The trip count over the
+  // repetitions is the same for the whole block (reps = ceil(E / L), 1 at every operating point without repetition), so the
+  // shared-memory reads of a thread's eight positions are independent, predicated loads issued back to back (the first round-2
+  // version walked i = n, n + L, ... per position: eight data-dependent loops, 27 instructions per LLR, issue-bound).
+  const uint32_t reps = (j.E + j.L - 1) / j.L;
   // ---- read-modify-write of the soft buffer, EIGHT positions (one uint4) per thread: the table entries and the old values
   //      are fetched with one 128-bit load each before the first shared-memory read, results leave with one 128-bit store.
   //      Table and soft buffer are 16-byte aligned (the engine allocates them so); L = 3K + 12 = 4 mod 8: the last four
   //      positions are done two at a time.
   const bool     wide = ((reinterpret_cast<uintptr_t>(j.buf) | reinterpret_cast<uintptr_t>(j.table)) & 15u) == 0;
   const uint32_t L8   = wide ? j.L / 8 : 0u;
-  for (uint32_t p8 = threadIdx.x; p8 < L8; p8 += RM_THREADS) {
-    const uint4 tt = __ldg(reinterpret_cast<const uint4*>(j.table) + p8);
-    const uint32_t tw[4] = {tt.x, tt.y, tt.z, tt.w};
-    bool any = false;
+  auto rmw = [&](auto staged) {
+    for (uint32_t p8 = threadIdx.x; p8 < L8; p8 += RM_THREADS) {
+      const uint4    tt    = __ldg(reinterpret_cast<const uint4*>(j.table) + p8);
+      const uint32_t tw[4] = {tt.x, tt.y, tt.z, tt.w};
+      uint32_t       n[8];
+      bool           any = false;
 #pragma unroll
-    for (int q = 0; q < 4; q++) any |= (tw[q] & 0xffffu) < j.E || (tw[q] >> 16) < j.E;
-    if (!any) continue;  // nothing received for these eight positions (punctured region): no traffic at all
-    uint4    old = reinterpret_cast<uint4*>(j.buf)[p8];
-    uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+      for (int q = 0; q < 4; q++) {
+        n[2 * q]     = tw[q] & 0xffffu;
+        n[2 * q + 1] = tw[q] >> 16;
+        any |= n[2 * q] < j.E || n[2 * q + 1] < j.E;
+      }
+      if (!any) continue;  // nothing received for these eight positions (punctured region): no traffic at all
+      uint4    old   = reinterpret_cast<uint4*>(j.buf)[p8];
+      uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+      uint32_t sum[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      for (uint32_t r = 0, base = 0; r < reps; r++, base += j.L) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const uint32_t s0 = gathered(tw[q] & 0xffffu), s1 = gathered(tw[q] >> 16);
-      ow[q] = ((ow[q] + s0) & 0xffffu) | ((((ow[q] >> 16) + s1) & 0xffffu) << 16);
+        for (int q = 0; q < 8; q++) {
+          const uint32_t i = n[q] + base;
+          if (i < j.E) sum[q] += llr(i, staged);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) ow[q] = __vadd2(ow[q], __byte_perm(sum[2 * q], sum[2 * q + 1], 0x5410));  // two wrapping 16-bit sums
+      reinterpret_cast<uint4*>(j.buf)[p8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
-    reinterpret_cast<uint4*>(j.buf)[p8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-  }
-  // two soft-buffer elements per thread for the rest (L is even, buf is 4-byte aligned)
-  uint32_t* buf2 = reinterpret_cast<uint32_t*>(j.buf);
-  for (uint32_t p2 = 4 * L8 + threadIdx.x; p2 < j.L / 2; p2 += RM_THREADS) {
-    const uint32_t tt = reinterpret_cast<const uint32_t*>(j.table)[p2];
-    uint32_t       n0 = tt & 0xffffu, n1 = tt >> 16;
-    if (n0 >= j.E && n1 >= j.E) continue;  // nothing received for these two positions
-    const uint32_t s0 = gathered(n0), s1 = gathered(n1);
-    const uint32_t old = buf2[p2];
-    buf2[p2] = ((old + s0) & 0xffffu) | ((((old >> 16) + s1) & 0xffffu) << 16);
-  }
+    // two soft-buffer elements per thread for the rest (L is even, buf is 4-byte aligned)
+    uint32_t* buf2 = reinterpret_cast<uint32_t*>(j.buf);
+    for (uint32_t p2 = 4 * L8 + threadIdx.x; p2 < j.L / 2; p2 += RM_THREADS) {
+      const uint32_t tt = reinterpret_cast<const uint32_t*>(j.table)[p2];
+      const uint32_t n0 = tt & 0xffffu, n1 = tt >> 16;
+      if (n0 >= j.E && n1 >= j.E) continue;  // nothing received for these two positions
+      uint32_t s0 = 0, s1 = 0;
+      for (uint32_t r = 0, base = 0; r < reps; r++, base += j.L) {
+        if (n0 + base < j.E) s0 += llr(n0 + base, staged);
+        if (n1 + base < j.E) s1 += llr(n1 + base, staged);
+      }
+      buf2[p2] = __vadd2(buf2[p2], __byte_perm(s0, s1, 0x5410));
+    }
+  };
+  if (j.E <= RM_SMEM_ELEMS) rmw(std::true_type{}); else rmw(std::false_type{});
 }
 
 // zero a list of soft-buffer mirrors (srsran_softbuffer_rx_reset forwarded to the device): grid = (ceil(n16/256), n_slots)
@@ -213,30 +230,71 @@ struct DeintJob {
   const uint32_t* ri_scan;  // sorted scan-order indices of the RI positions
   uint32_t        nri, rows, cols, Qm, p_star;
 };
-// Version 2 (round 2): the matrix is rows x cols items of Qm LLRs; q holds it column by column, g row by row. A block takes DT_ROWS
-// consecutive rows: per column that is ONE contiguous run of DT_ROWS * Qm LLRs in q - read with coalesced 32-bit loads into shared
-// memory - and the block's part of g is one contiguous range, written in scan order from shared memory (32-bit stores whenever no
-// RI position shifts the pairing). Round 1 let every thread read its Qm values straight from q (12 bytes out of every 32-byte
-// sector per request, columns rows * Qm * 2 bytes apart): 1.5 TB/s.
-constexpr int DT_ROWS = 32;
+// The matrix is rows x cols items of Qm LLRs; q holds it column by column, g row by row. A block takes DT_ROWS consecutive rows:
+// per column that is ONE contiguous run of DT_ROWS * Qm LLRs in q - read with coalesced 32-bit loads, several in flight per
+// thread, into shared memory - and the block's part of g is one contiguous range. A tile without RI positions inside (all but
+// the last rows of a subframe) leaves as a linear stream of 32-bit words, word w of the range taken from (row, column, bit) =
+// w's scan position (divisions by multiply-high with per-block constants); tiles with RI positions, or behind an odd number of
+// them, go item by item with the rank found by binary search. Round 1 let every thread read its Qm values straight from q
+// (12 bytes out of every 32-byte sector per request): 1.5 TB/s; 32-row tiles with per-item stores: 2.1 TB/s.
+// grid = (jobs, tiles per job: any number >= 1, tiles are strided over gridDim.y), block = 256
+constexpr int DT_ROWS = 64;
 constexpr int DT_MAXC = 14;  // columns = PUSCH symbols carrying data: 12 (normal CP), 10 / 11 with SRS or extended CP
+// floor(n / d) = umulhi(n, magic) while n * d < 2^32 and d >= 2; magic 0 stands for d = 1
+__device__ __forceinline__ uint32_t dt_magic(uint32_t d) { return d < 2 ? 0u : 0xffffffffu / d + 1u; }
+__device__ __forceinline__ uint32_t dt_div(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
 __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __restrict__ jobs)
 {
-  __shared__ int16_t tile[DT_MAXC][DT_ROWS * 8 + 2];
-  const DeintJob j = jobs[blockIdx.y];
+  __shared__ __align__(16) int16_t tile[DT_MAXC][DT_ROWS * 8 + 2];
+  const DeintJob j = jobs[blockIdx.x];
   const uint32_t ntiles = (j.rows + DT_ROWS - 1) / DT_ROWS;
   const bool     tiled  = j.cols <= DT_MAXC && j.Qm <= 8 && (j.Qm & 1u) == 0 && ((reinterpret_cast<uintptr_t>(j.q) & 3u) == 0) && ((j.rows * j.Qm) & 1u) == 0;
-  for (uint32_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+  const bool     g32ok  = (reinterpret_cast<uintptr_t>(j.g) & 3u) == 0;
+  const uint32_t item_w = j.Qm / 2, line_w = j.cols * item_w;  // 32-bit words per item / per matrix row (tiled: Qm even)
+  const uint32_t m_item = dt_magic(max(item_w, 1u)), m_line = dt_magic(max(line_w, 1u));
+  for (uint32_t tix = blockIdx.y; tix < ntiles; tix += gridDim.y) {
     const uint32_t row0 = tix * DT_ROWS, nr = min((uint32_t)DT_ROWS, j.rows - row0), run = nr * j.Qm;  // LLRs per column of this tile
+    bool           fast = false;
+    uint32_t       c0   = 0;
     if (tiled) {
       __syncthreads();  // the previous tile has been written out
-      const uint32_t rw = run / 2;  // 32-bit words per column run (Qm is even)
-      for (uint32_t idx = threadIdx.x; idx < j.cols * rw; idx += 256) {
-        const uint32_t col = idx / rw, wq = idx - col * rw;
-        const uint32_t v   = reinterpret_cast<const uint32_t*>(j.q + (size_t)col * j.rows * j.Qm + (size_t)row0 * j.Qm)[wq];
-        *reinterpret_cast<uint32_t*>(&tile[col][2 * wq]) = v;
+      const uint32_t rw = run / 2, nw = j.cols * rw, m_rw = dt_magic(rw);  // 32-bit words per column run
+      for (uint32_t i0 = threadIdx.x; i0 < nw; i0 += 256 * 4) {
+        uint32_t v[4], at[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t idx = i0 + 256 * u;
+          if (idx < nw) {
+            const uint32_t col = dt_div(idx, m_rw), wq = idx - col * rw;
+            at[u] = col * (DT_ROWS * 8 + 2) + 2 * wq;
+            v[u]  = __ldg(reinterpret_cast<const uint32_t*>(j.q + (size_t)col * j.rows * j.Qm + (size_t)row0 * j.Qm) + wq);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (i0 + 256 * u < nw) *reinterpret_cast<uint32_t*>(&tile[0][0] + at[u]) = v[u];
       }
+      // number of RI scan indices before the tile, and whether one lies inside it (every thread the same search: broadcast loads)
+      const uint32_t s_lo = row0 * j.cols * j.Qm, s_hi = s_lo + nr * j.cols * j.Qm;
+      uint32_t       lo = 0, hi = j.nri;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(j.ri_scan + mid) < s_lo) lo = mid + 1; else hi = mid;
+      }
+      c0   = lo;
+      fast = g32ok && (c0 & 1u) == 0 && (c0 >= j.nri || __ldg(j.ri_scan + c0) >= s_hi);
       __syncthreads();
+      if (fast) {
+        uint32_t*      dst = reinterpret_cast<uint32_t*>(j.g) + (s_lo - c0) / 2;
+        const uint32_t now = nr * line_w;
+        for (uint32_t w = threadIdx.x; w < now; w += 256) {
+          const uint32_t r = dt_div(w, m_line), rem = w - r * line_w, col = dt_div(rem, m_item), k = rem - col * item_w;
+          uint32_t       v = *reinterpret_cast<const uint32_t*>(&tile[col][r * j.Qm + 2 * k]);
+          if (w == 0 && s_lo == c0) v = (v & 0xffff0000u) | (uint16_t)j.q[j.p_star];  // g[0]: see above
+          dst[w] = v;
+        }
+        continue;
+      }
     }
     for (uint32_t it = threadIdx.x; it < nr * j.cols; it += 256) {
       const uint32_t r = it / j.cols, col = it - r * j.cols, row = row0 + r;
@@ -248,8 +306,7 @@ __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __rest
         const uint32_t mid = (lo + hi) >> 1;
         if (j.ri_scan[mid] < s0) lo = mid + 1; else hi = mid;
       }
-      const bool clean = (lo >= j.nri || j.ri_scan[lo] >= s0 + j.Qm) && ((s0 - lo) & 1u) == 0 && s0 != lo && tiled &&
-                         ((reinterpret_cast<uintptr_t>(j.g) & 3u) == 0);
+      const bool clean = (lo >= j.nri || j.ri_scan[lo] >= s0 + j.Qm) && ((s0 - lo) & 1u) == 0 && s0 != lo && tiled && g32ok;
       if (clean) {
         // no RI inside the item, even rank, not the item that owns g[0]: Qm / 2 aligned 32-bit stores
         uint32_t* dst = reinterpret_cast<uint32_t*>(j.g + (s0 - lo));

@@ -85,49 +85,68 @@ __device__ __forceinline__ uint32_t w8_wrap8(uint32_t v) { return w8_prmt(v, 0u,
 // max(sat(a + b), c) for c already in range: the lower clamp is implied by c
 __device__ __forceinline__ uint32_t w8_addmax_hi(uint32_t a, uint32_t b, uint32_t c) { return __vmins2(__viaddmax_s16x2(a, b, c), W8_P127); }
 
+/*
+ * State metrics live NEGATED AND BIASED: m" = 127 - m, a value in [0, 255] held in an int16 lane. The map is a monotone
+ * bijection, so every result is the same bit for bit, and
+ *   max becomes min;   the upper saturation bound +127 becomes 0 - the .RELU of VIMNMX / VIMNMX3 / VIADDMNMX -
+ *   and the lower bound -128 becomes a min against 255, which is the third operand of those instructions or implied by a
+ *   min against a value that is in range already.
+ * A saturating add of a branch metric g is ONE instruction, max(min(m" + (-g), 255), 0), instead of two; a state update
+ * max(sat(a + g), c) is one, max(min(a" + (-g), c"), 0). The branch metrics arrive negated: shared memory holds ~x and ~y.
+ * First version (values as they are): 146 min / max-pipe instructions per window step, this one 101.
+ */
+constexpr uint32_t W8_C255 = 0x00FF00FFu, W8_C128 = 0x00800080u, W8_M127 = 0xFF81FF81u, W8_ONE = 0x00010001u;
+// max(sat(a + g), c)  ->  min-form with ng = -g, c" in range
+__device__ __forceinline__ uint32_t w8n_addmin(uint32_t a, uint32_t ng, uint32_t c) { return __viaddmin_s16x2_relu(a, ng, c); }
+// sat(a + g)
+__device__ __forceinline__ uint32_t w8n_adds(uint32_t a, uint32_t ng) { return __viaddmin_s16x2_relu(a, ng, W8_C255); }
+// -sat(x + y) from nx = -x, ny = -y
+__device__ __forceinline__ uint32_t w8n_nxy(uint32_t nx, uint32_t ny) { return __vmins2(__viaddmax_s16x2(nx, ny, W8_M127), W8_C128); }
+
 __device__ __forceinline__ void w8_norm(uint32_t (&o)[8])
 {
-  // normalize_max (turbodecoder_win.h:479-497): subtract the maximum, saturating (the difference is <= 0: only the lower clamp)
-  const uint32_t m  = __vmaxs2(__vimax3_s16x2(__vimax3_s16x2(__vimax3_s16x2(o[0], o[1], o[2]), o[3], o[4]), o[5], o[6]), o[7]);
-  const uint32_t nm = __vsub2(0u, m);
+  // normalize_max (turbodecoder_win.h:479-497): subtract the maximum, saturating. Here: add 127 - min", clamp at 255
+  const uint32_t m = __vmins2(__vimin3_s16x2(__vimin3_s16x2(__vimin3_s16x2(o[0], o[1], o[2]), o[3], o[4]), o[5], o[6]), o[7]);
+  const uint32_t c = __vsub2(W8_P127, m);
 #pragma unroll
-  for (int i = 0; i < 8; i++) o[i] = __viaddmax_s16x2(o[i], nm, W8_M128);
+  for (int i = 0; i < 8; i++) o[i] = __viaddmin_s16x2(o[i], c, W8_C255);
 }
-// backward step, turbodecoder_win.h:613-636
-__device__ __forceinline__ void w8_bstep(uint32_t (&o)[8], uint32_t x, uint32_t y)
+// backward step, turbodecoder_win.h:613-636 (nx = -x, ny = -y)
+__device__ __forceinline__ void w8_bstep(uint32_t (&o)[8], uint32_t nx, uint32_t ny)
 {
-  const uint32_t xy = w8_adds(x, y);
-  const uint32_t n0 = w8_addmax_hi(o[4], xy, o[0]);
-  const uint32_t n1 = w8_addmax_hi(o[0], xy, o[4]);
-  const uint32_t n6 = w8_addmax_hi(o[3], xy, o[7]);
-  const uint32_t n7 = w8_addmax_hi(o[7], xy, o[3]);
-  const uint32_t n2 = w8_sat(__viaddmax_s16x2(o[5], y, __vadd2(o[1], x)));
-  const uint32_t n3 = w8_sat(__viaddmax_s16x2(o[5], x, __vadd2(o[1], y)));
-  const uint32_t n4 = w8_sat(__viaddmax_s16x2(o[6], x, __vadd2(o[2], y)));
-  const uint32_t n5 = w8_sat(__viaddmax_s16x2(o[6], y, __vadd2(o[2], x)));
+  const uint32_t nxy = w8n_nxy(nx, ny);
+  const uint32_t n0 = w8n_addmin(o[4], nxy, o[0]);
+  const uint32_t n1 = w8n_addmin(o[0], nxy, o[4]);
+  const uint32_t n6 = w8n_addmin(o[3], nxy, o[7]);
+  const uint32_t n7 = w8n_addmin(o[7], nxy, o[3]);
+  // sat(max(a + g, b + h)) = max(min(a" - g, b" - h, 255), 0): saturation is monotone
+  const uint32_t n2 = __vimin3_s16x2_relu(__vadd2(o[5], ny), __vadd2(o[1], nx), W8_C255);
+  const uint32_t n3 = __vimin3_s16x2_relu(__vadd2(o[5], nx), __vadd2(o[1], ny), W8_C255);
+  const uint32_t n4 = __vimin3_s16x2_relu(__vadd2(o[6], nx), __vadd2(o[2], ny), W8_C255);
+  const uint32_t n5 = __vimin3_s16x2_relu(__vadd2(o[6], ny), __vadd2(o[2], nx), W8_C255);
   o[0] = n0; o[1] = n1; o[2] = n2; o[3] = n3; o[4] = n4; o[5] = n5; o[6] = n6; o[7] = n7;
 }
 // branch sums of a forward step, turbodecoder_win.h:724-741: z = information bit 0 into state i, w = information bit 1
-__device__ __forceinline__ void w8_abranches(const uint32_t (&o)[8], uint32_t x, uint32_t y, uint32_t (&z)[8], uint32_t (&w)[8])
+__device__ __forceinline__ void w8_abranches(const uint32_t (&o)[8], uint32_t nx, uint32_t ny, uint32_t (&z)[8], uint32_t (&w)[8])
 {
-  const uint32_t xy = w8_adds(x, y);
-  z[0] = o[0]; z[1] = w8_adds(o[3], y); z[2] = w8_adds(o[4], y); z[3] = o[7];
-  z[4] = o[1]; z[5] = w8_adds(o[2], y); z[6] = w8_adds(o[5], y); z[7] = o[6];
-  w[0] = w8_adds(o[1], xy); w[1] = w8_adds(o[2], x); w[2] = w8_adds(o[5], x); w[3] = w8_adds(o[6], xy);
-  w[4] = w8_adds(o[0], xy); w[5] = w8_adds(o[3], x); w[6] = w8_adds(o[4], x); w[7] = w8_adds(o[7], xy);
+  const uint32_t nxy = w8n_nxy(nx, ny);
+  z[0] = o[0]; z[1] = w8n_adds(o[3], ny); z[2] = w8n_adds(o[4], ny); z[3] = o[7];
+  z[4] = o[1]; z[5] = w8n_adds(o[2], ny); z[6] = w8n_adds(o[5], ny); z[7] = o[6];
+  w[0] = w8n_adds(o[1], nxy); w[1] = w8n_adds(o[2], nx); w[2] = w8n_adds(o[5], nx); w[3] = w8n_adds(o[6], nxy);
+  w[4] = w8n_adds(o[0], nxy); w[5] = w8n_adds(o[3], nx); w[6] = w8n_adds(o[4], nx); w[7] = w8n_adds(o[7], nxy);
 }
-// forward step without output (warm-up): max(sat(u), sat(v)) = sat(max(u, v))
-__device__ __forceinline__ void w8_astep(uint32_t (&o)[8], uint32_t x, uint32_t y)
+// forward step without output (warm-up)
+__device__ __forceinline__ void w8_astep(uint32_t (&o)[8], uint32_t nx, uint32_t ny)
 {
-  const uint32_t xy = w8_adds(x, y);
-  const uint32_t n0 = w8_addmax_hi(o[1], xy, o[0]);
-  const uint32_t n3 = w8_addmax_hi(o[6], xy, o[7]);
-  const uint32_t n4 = w8_addmax_hi(o[0], xy, o[1]);
-  const uint32_t n7 = w8_addmax_hi(o[7], xy, o[6]);
-  const uint32_t n1 = w8_sat(__viaddmax_s16x2(o[3], y, __vadd2(o[2], x)));
-  const uint32_t n2 = w8_sat(__viaddmax_s16x2(o[4], y, __vadd2(o[5], x)));
-  const uint32_t n5 = w8_sat(__viaddmax_s16x2(o[2], y, __vadd2(o[3], x)));
-  const uint32_t n6 = w8_sat(__viaddmax_s16x2(o[5], y, __vadd2(o[4], x)));
+  const uint32_t nxy = w8n_nxy(nx, ny);
+  const uint32_t n0 = w8n_addmin(o[1], nxy, o[0]);
+  const uint32_t n3 = w8n_addmin(o[6], nxy, o[7]);
+  const uint32_t n4 = w8n_addmin(o[0], nxy, o[1]);
+  const uint32_t n7 = w8n_addmin(o[7], nxy, o[6]);
+  const uint32_t n1 = __vimin3_s16x2_relu(__vadd2(o[3], ny), __vadd2(o[2], nx), W8_C255);
+  const uint32_t n2 = __vimin3_s16x2_relu(__vadd2(o[4], ny), __vadd2(o[5], nx), W8_C255);
+  const uint32_t n5 = __vimin3_s16x2_relu(__vadd2(o[2], ny), __vadd2(o[3], nx), W8_C255);
+  const uint32_t n6 = __vimin3_s16x2_relu(__vadd2(o[5], ny), __vadd2(o[4], nx), W8_C255);
   o[0] = n0; o[1] = n1; o[2] = n2; o[3] = n3; o[4] = n4; o[5] = n5; o[6] = n6; o[7] = n7;
 }
 
@@ -144,10 +163,11 @@ __device__ __forceinline__ void w8_ck_store(uint4* dst, const uint32_t (&o)[8])
 }
 __device__ __forceinline__ void w8_ck_unpack(const uint4 v, uint32_t (&o)[8])
 {
-  o[0] = w8_unpack(v.x); o[1] = w8_unpack_hi(v.x);
-  o[2] = w8_unpack(v.y); o[3] = w8_unpack_hi(v.y);
-  o[4] = w8_unpack(v.z); o[5] = w8_unpack_hi(v.z);
-  o[6] = w8_unpack(v.w); o[7] = w8_unpack_hi(v.w);
+  // zero-extending: the stored bytes are 0..255 (negated and biased metrics)
+  o[0] = __byte_perm(v.x, 0u, 0x4140u); o[1] = __byte_perm(v.x, 0u, 0x4342u);
+  o[2] = __byte_perm(v.y, 0u, 0x4140u); o[3] = __byte_perm(v.y, 0u, 0x4342u);
+  o[4] = __byte_perm(v.z, 0u, 0x4140u); o[5] = __byte_perm(v.z, 0u, 0x4342u);
+  o[6] = __byte_perm(v.w, 0u, 0x4140u); o[7] = __byte_perm(v.w, 0u, 0x4342u);
 }
 // a load the compiler must leave where it is written (it sinks plain loads to their first use, which puts the whole
 // global-memory latency in front of the consumer: measured as a quarter of the stall samples before)
@@ -240,23 +260,24 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
             ao[q] = __byte_perm(ap0, ap1, 0x6420u);
             xo[q] = __byte_perm(x0, x1, 0x6420u);
           }
-          sx[i] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+          sx[i] = make_uint4(~xo[0], ~xo[1], ~xo[2], ~xo[3]);
           ga[i] = make_uint4(ao[0], ao[1], ao[2], ao[3]);  // the output side subtracts the updated a-priori values again
         } else {
-          sx[i] = vx[t];
+          sx[i] = make_uint4(~vx[t].x, ~vx[t].y, ~vx[t].z, ~vx[t].w);
         }
-        sy[i] = vy[t];
+        sy[i] = make_uint4(~vy[t].x, ~vy[t].y, ~vy[t].z, ~vy[t].w);
       }
     }
   }
   __syncwarp();
-  auto ldx = [&](int k) { return w8_unpack(*reinterpret_cast<const uint16_t*>(&sm.X[k * W8_ROW + 2 * lane])); };
-  auto ldy = [&](int k) { return w8_unpack(*reinterpret_cast<const uint16_t*>(&sm.Y[k * W8_ROW + 2 * lane])); };
+  // shared memory holds the complemented bytes: sign-extended ~v = -v - 1, plus one = the NEGATED branch metric
+  auto ldx = [&](int k) { return __vadd2(w8_unpack(*reinterpret_cast<const uint16_t*>(&sm.X[k * W8_ROW + 2 * lane])), W8_ONE); };
+  auto ldy = [&](int k) { return __vadd2(w8_unpack(*reinterpret_cast<const uint16_t*>(&sm.Y[k * W8_ROW + 2 * lane])), W8_ONE); };
 
   uint32_t o[8];
   // ---------------------------------------------------------------- beta: warm-up over the window's own first 40 steps
 #pragma unroll
-  for (int i = 0; i < 8; i++) o[i] = 0u;  // simd_set1(-INF), INF = 0
+  for (int i = 0; i < 8; i++) o[i] = W8_P127;  // simd_set1(-INF), INF = 0; negated and biased: 127
 #pragma unroll 2
   for (int k = W8_OVERLAP - 1; k >= 0; k--) {
     w8_bstep(o, ldx(k), ldy(k));
@@ -286,7 +307,7 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
         }
         const int sv[8] = {st0, st1, st2, st3, st4, st5, st6, st7};
 #pragma unroll
-        for (int i = 0; i < 8; i++) t[i] = h ? ((t[i] & 0xffffu) | ((uint32_t)sv[i] << 16)) : ((uint32_t)sv[i] & 0xffffu);
+        for (int i = 0; i < 8; i++) t[i] = h ? ((t[i] & 0xffffu) | ((uint32_t)(127 - sv[i]) << 16)) : (uint32_t)(127 - sv[i]);
       }
     }
 #pragma unroll
@@ -303,7 +324,7 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
   }
   // ---------------------------------------------------------------- alpha: warm-up over the window's own last 40 steps
 #pragma unroll
-  for (int i = 0; i < 8; i++) o[i] = 0u;
+  for (int i = 0; i < 8; i++) o[i] = W8_P127;
 #pragma unroll 2
   for (int j = 0; j < W8_OVERLAP; j++) {
     const int k = (int)S - W8_OVERLAP + j;
@@ -315,7 +336,7 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
 #pragma unroll
     for (int i = 0; i < 8; i++) t[i] = __shfl_up_sync(0xffffffffu, o[i], 1, (int)NW);
 #pragma unroll
-    for (int i = 0; i < 8; i++) o[i] = (w_lane == 0) ? 0u : t[i];  // first window: the known state {0, -INF x 7}, INF = 0
+    for (int i = 0; i < 8; i++) o[i] = (w_lane == 0) ? W8_P127 : t[i];  // first window: the known state {0, -INF x 7}, INF = 0
   }
   // ---------------------------------------------------------------- alpha: main pass, 8 steps at a time with beta recomputed into registers
   // Every step also finishes its own output: the extrinsic value goes to ext1 in place (DEC1) and through the QPP table to the
@@ -357,21 +378,22 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
     }
     // one step: branch sums, LLR against beta[k+1] (b), outputs, state update
     auto astep_out = [&](int k, uint32_t dvj, uint32_t cvj, uint32_t avj, const uint32_t (&b)[8]) {
-      const uint32_t x = ldx(k), y = ldy(k);
+      const uint32_t nx = ldx(k), ny = ldy(k);
       uint32_t       z[8], w[8];
-      w8_abranches(o, x, y, z, w);
-      // max_i sat(b_i + z_i) = sat(max_i (b_i + z_i)): saturation is monotone
+      w8_abranches(o, nx, ny, z, w);
+      // max_i sat(b_i + z_i) = sat(max_i (b_i + z_i)): saturation is monotone. Negated: b" + z" = 254 - (b + z), the maximum is
+      // the minimum M of those, and 127 - sat(254 - M) = max(min(M - 127, 255), 0)
       const uint32_t p0 = __vadd2(b[0], z[0]), p1 = __vadd2(b[1], z[1]), p2 = __vadd2(b[2], z[2]), p3 = __vadd2(b[3], z[3]);
       const uint32_t p4 = __vadd2(b[4], z[4]), p5 = __vadd2(b[5], z[5]), p6 = __vadd2(b[6], z[6]), p7 = __vadd2(b[7], z[7]);
       const uint32_t q0 = __vadd2(b[0], w[0]), q1 = __vadd2(b[1], w[1]), q2 = __vadd2(b[2], w[2]), q3 = __vadd2(b[3], w[3]);
       const uint32_t q4 = __vadd2(b[4], w[4]), q5 = __vadd2(b[5], w[5]), q6 = __vadd2(b[6], w[6]), q7 = __vadd2(b[7], w[7]);
-      const uint32_t m0 = w8_sat(__vmaxs2(__vimax3_s16x2(__vimax3_s16x2(p0, p1, p2), p6, p7), __vimax3_s16x2(p3, p4, p5)));
-      const uint32_t m1 = w8_sat(__vmaxs2(__vimax3_s16x2(__vimax3_s16x2(q0, q1, q2), q6, q7), __vimax3_s16x2(q3, q4, q5)));
-      const uint32_t l  = w8_subs(m1, m0);
+      const uint32_t m0 = __viaddmin_s16x2_relu(__vmins2(__vimin3_s16x2(__vimin3_s16x2(p0, p1, p2), p6, p7), __vimin3_s16x2(p3, p4, p5)), W8_M127, W8_C255);
+      const uint32_t m1 = __viaddmin_s16x2_relu(__vmins2(__vimin3_s16x2(__vimin3_s16x2(q0, q1, q2), q6, q7), __vimin3_s16x2(q3, q4, q5)), W8_M127, W8_C255);
+      const uint32_t l  = w8_subs(m0, m1);  // sat(max1 - max0) = sat(m0" - m1")
       // out = l >> 1, arithmetic, per element (simd_rb_shift, divide_output = 1)
       const uint32_t ext = ((l >> 1) & 0x7fff7fffu) | (l & 0x80008000u);
 #pragma unroll
-      for (int i = 0; i < 8; i++) o[i] = __vmaxs2(z[i], w[i]);
+      for (int i = 0; i < 8; i++) o[i] = __vmins2(z[i], w[i]);
       if (k) w8_norm(o);
       // what the next half-iteration reads: DEC1 ext1 <- ext1 - app1 (turbodecoder_iter.h:116-118; first half-iteration: ext1
       // as it is), app2[rev[i]] = ext1[i] (:120); DEC2 app1[fwd[i]] = ext2[i] (:127)
@@ -380,12 +402,12 @@ __global__ void __launch_bounds__(32) win8_kernel(const Unit8* __restrict__ unit
       const uint32_t rp = w8_pack(r);
       if (MODE != 2) st_pair(pE1 + k * W8_ROW + lane2, rp);
       st_pair(pOUT + 2u * dvj + pcol, rp);
-      // the decision (tdec_win*_decision_byte: > 0) at its natural position, and its CRC contribution
-      const uint32_t pos = __vadd2(__vmaxs2(ext, 0u), 0x7fff7fffu) & 0x80008000u;  // bit 15 / 31 set iff the value is > 0
-      const uint32_t dp  = ((pos >> 15) & 1u) | ((pos >> 23) & 0x100u);
-      st_pair(pND + (MODE == 2 ? 2u * dvj + pcol : (uint32_t)k * W8_ROW + lane2), dp);
-      crc_lo ^= cvj & (0u - (dp & 1u));
-      crc_hi ^= cvj & (0u - (dp >> 8));
+      // the decision (tdec_win*_decision_byte: ext > 0, i.e. l >= 2) at its natural position - stored as 0xFF / 0x00 - and its CRC
+      // contribution: l + 0x7FFE has its sign bit set exactly when l >= 2; PRMT replicates the sign of a byte over a byte
+      const uint32_t sg = __vadd2(l, 0x7ffe7ffeu);
+      st_pair(pND + (MODE == 2 ? 2u * dvj + pcol : (uint32_t)k * W8_ROW + lane2), w8_prmt(sg, 0u, 0x44B9u));
+      crc_lo ^= cvj & w8_prmt(sg, 0u, 0x9999u);
+      crc_hi ^= cvj & w8_prmt(sg, 0u, 0xBBBBu);
     };
     if (len == 8) {
       uint32_t B[8][8];
@@ -528,14 +550,52 @@ struct RmJob8 {
   const uint16_t* table;  // Tinv
   uint32_t        E, L;
 };
-__global__ void __launch_bounds__(256) rm_rx8_kernel(const RmJob8* __restrict__ jobs)
+constexpr uint32_t RM8_SMEM    = 32768;  // e-bits staged per block; the rest of a longer e (heavy repetition) is read from global
+constexpr int      RM8_THREADS = 512;
+// grid = code blocks, block = RM8_THREADS, dynamic shared memory = min(max E, RM8_SMEM) + 16 bytes
+__global__ void __launch_bounds__(RM8_THREADS) rm_rx8_kernel(const RmJob8* __restrict__ jobs)
 {
-  const RmJob8 j = jobs[blockIdx.x];
-  for (uint32_t p = threadIdx.x; p < j.L; p += 256) {
+  extern __shared__ __align__(16) int8_t se8_raw[];
+  const RmJob8   j  = jobs[blockIdx.x];
+  const uint32_t ns = min(j.E, RM8_SMEM);
+  // staged copy shifted like the source, so that 128-bit loads and stores line up (see rm_rx_kernel)
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(j.e) & 15u);
+  int8_t*        se = se8_raw + sh;
+  {
+    const uint32_t head = min(ns, (16u - sh) & 15u);
+    if (threadIdx.x < head) se[threadIdx.x] = j.e[threadIdx.x];
+    const uint32_t nv = (ns - head) / 16;
+    const uint4*   gv = reinterpret_cast<const uint4*>(j.e + head);
+    uint4*         sv = reinterpret_cast<uint4*>(se + head);
+    for (uint32_t i = threadIdx.x; i < nv; i += RM8_THREADS) sv[i] = __ldg(gv + i);
+    for (uint32_t i = head + 16 * nv + threadIdx.x; i < ns; i += RM8_THREADS) se[i] = j.e[i];
+  }
+  __syncthreads();
+  const uint32_t reps = (j.E + j.L - 1) / j.L;  // block-uniform trip count over the repetitions (1 without repetition)
+  auto llr = [&](uint32_t i) -> uint32_t { return (uint8_t)(i < ns ? se[i] : j.e[i]); };
+  // four soft-buffer positions (one 32-bit word, L = 3K + 12 is a multiple of 4) per thread: 64-bit table load, wrapping byte adds
+  const bool     wide = (reinterpret_cast<uintptr_t>(j.buf) & 3u) == 0 && (reinterpret_cast<uintptr_t>(j.table) & 7u) == 0;
+  const uint32_t L4   = wide ? j.L / 4 : 0u;
+  for (uint32_t p4 = threadIdx.x; p4 < L4; p4 += RM8_THREADS) {
+    const uint2    tt   = __ldg(reinterpret_cast<const uint2*>(j.table) + p4);
+    const uint32_t n[4] = {tt.x & 0xffffu, tt.x >> 16, tt.y & 0xffffu, tt.y >> 16};
+    if (n[0] >= j.E && n[1] >= j.E && n[2] >= j.E && n[3] >= j.E) continue;  // punctured region
+    const uint32_t old    = reinterpret_cast<uint32_t*>(j.buf)[p4];
+    uint32_t       sum[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t r = 0, base = 0; r < reps; r++, base += j.L) {
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (n[q] + base < j.E) sum[q] += llr(n[q] + base);
+    }
+    const uint32_t add = (sum[0] & 0xffu) | ((sum[1] & 0xffu) << 8) | ((sum[2] & 0xffu) << 16) | (sum[3] << 24);
+    reinterpret_cast<uint32_t*>(j.buf)[p4] = __vadd4(old, add);
+  }
+  for (uint32_t p = 4 * L4 + threadIdx.x; p < j.L; p += RM8_THREADS) {
     const uint32_t t = j.table[p];
-    int            acc = 0;
-    for (uint32_t i = t; i < j.E; i += j.L) acc += j.e[i];
-    if (t < j.E) j.buf[p] = (int8_t)((int)j.buf[p] + acc);
+    if (t >= j.E) continue;
+    uint32_t acc = 0;
+    for (uint32_t i = t; i < j.E; i += j.L) acc += llr(i);
+    j.buf[p] = (int8_t)(uint8_t)((uint8_t)j.buf[p] + acc);
   }
 }
 

@@ -841,6 +841,12 @@ struct srsb200_plan {
   uint8_t*  d_done = nullptr;     // [n_cb]
   uint8_t*  d_active = nullptr;   // [n_groups]
   uint32_t* d_arrivals = nullptr; // [n_groups] job blocks of the group that have finished the current half-iteration
+  // regrouping of the unfinished code blocks (turbo_kernels.cuh, regroup_plan_kernel): plans of one block size with enough groups
+  // carry n_new spare group slots behind their own groups (table, workspace, activity flags, arrival counters)
+  uint32_t  n_new = 0;
+  int32_t*  d_home = nullptr;     // [n_cb] group (relative to the range's first) whose decision arrays hold the block's bits
+  int32_t*  d_src = nullptr;      // [n_new][64] where each lane of a new group took its state from
+  uint32_t* d_rg_state = nullptr; // [MAX_SUB] per running range: 0, or the regrouping point that regrouped it
   bool      uniform = false;
   int       lane = 0;            // which pair of sub-stream sets runs its device-resident submissions
   uint32_t  wpj = WPJ;           // windows per job warp: 16 for machine-filling batches (throughput), 8 otherwise (latency)
@@ -917,6 +923,19 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
   // job kernel (a warp walks its run sequentially: 256 steps x ~144 cycles at 16 windows)
   p->wpj = p->n_groups >= 128 ? 16u : (uint32_t)WPJ;
   for (auto& g : p->h_groups) g.wpj = p->wpj;
+  // spare slots for regrouped survivors: a quarter of the groups (+ one per range: launch_plan gives range [g0, g1) the slots
+  // n_groups + g0 / 4 + s ... n_groups + g1 / 4 + s)
+  static const bool no_regroup = getenv("SRSB200_NO_REGROUP") != nullptr;
+  if (!no_regroup && buckets.size() == 1 && p->n_groups >= 64) {
+    p->n_new = p->n_groups / 4 + srsb200_engine::MAX_SUB + 1;
+    Group g  = p->h_groups[0];
+    for (int j = 0; j < 64; j++) g.cb[j] = -1;
+    for (uint32_t i = 0; i < p->n_new; i++) {
+      g.ws_off = off;
+      off += ((group_ws_words(g.R) * 4 + 255) / 256) * 256;
+      p->h_groups.push_back(g);
+    }
+  }
   p->ws_bytes = off;
   p->contiguous = buckets.size() == 1;
   for (uint32_t i = 0; i < n && p->contiguous; i++) {
@@ -924,15 +943,20 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
     if ((llr_off && llr_off[i] != (uint64_t)i * (3ull * k + 12)) || (out_off && out_off[i] != (uint64_t)i * (k / 8))) p->contiguous = false;
   }
   cudaError_t ce;
-  if ((ce = cudaMalloc(&p->d_groups, sizeof(Group) * std::max<uint32_t>(1, p->n_groups))) != cudaSuccess ||
+  const uint32_t n_slots = std::max<uint32_t>(1, p->n_groups + p->n_new);
+  if ((ce = cudaMalloc(&p->d_groups, sizeof(Group) * n_slots)) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_ws, std::max<uint64_t>(256, p->ws_bytes))) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_llr_off, sizeof(uint64_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_out_off, sizeof(uint64_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_crc_acc, sizeof(uint32_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
       (ce = cudaMalloc(&p->d_done, std::max<uint32_t>(1, n))) != cudaSuccess ||
-      (ce = cudaMalloc(&p->d_active, std::max<uint32_t>(1, p->n_groups))) != cudaSuccess ||
-      (ce = cudaMalloc(&p->d_arrivals, sizeof(uint32_t) * std::max<uint32_t>(1, p->n_groups))) != cudaSuccess ||
-      (ce = cudaMemset(p->d_arrivals, 0, sizeof(uint32_t) * std::max<uint32_t>(1, p->n_groups))) != cudaSuccess) {
+      (ce = cudaMalloc(&p->d_active, n_slots)) != cudaSuccess || (ce = cudaMemset(p->d_active, 0, n_slots)) != cudaSuccess ||
+      (ce = cudaMalloc(&p->d_arrivals, sizeof(uint32_t) * n_slots)) != cudaSuccess ||
+      (ce = cudaMemset(p->d_arrivals, 0, sizeof(uint32_t) * n_slots)) != cudaSuccess ||
+      (p->n_new && ((ce = cudaMalloc(&p->d_home, sizeof(int32_t) * std::max<uint32_t>(1, n))) != cudaSuccess ||
+                    (ce = cudaMalloc(&p->d_src, sizeof(int32_t) * 64 * p->n_new)) != cudaSuccess ||
+                    (ce = cudaMalloc(&p->d_rg_state, sizeof(uint32_t) * srsb200_engine::MAX_SUB)) != cudaSuccess ||
+                    (ce = cudaMemset(p->d_rg_state, 0, sizeof(uint32_t) * srsb200_engine::MAX_SUB)) != cudaSuccess))) {
     cudaGetLastError();
     srsb200_plan_destroy(p);
     return fail(SRSB200_ERROR, "plan allocation failed: %s", cudaGetErrorString(ce));
@@ -944,7 +968,7 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
     oo[i]      = out_off ? out_off[i] : (uint64_t)i * (k / 8);
   }
   if (n) {
-    cudaMemcpyAsync(p->d_groups, p->h_groups.data(), sizeof(Group) * p->n_groups, cudaMemcpyHostToDevice, e->stream);
+    cudaMemcpyAsync(p->d_groups, p->h_groups.data(), sizeof(Group) * p->h_groups.size(), cudaMemcpyHostToDevice, e->stream);
     cudaMemcpyAsync(p->d_llr_off, lo.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream);
     cudaMemcpyAsync(p->d_out_off, oo.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream);
   }
@@ -973,6 +997,9 @@ extern "C" void srsb200_plan_destroy(srsb200_plan_t* p)
   cudaFree(p->d_done);
   cudaFree(p->d_active);
   cudaFree(p->d_arrivals);
+  cudaFree(p->d_home);
+  cudaFree(p->d_src);
+  cudaFree(p->d_rg_state);
   delete p;
 }
 
@@ -990,6 +1017,10 @@ extern "C" int srsb200_tdec_plan_uniform(srsb200_engine_t* e, uint32_t n, uint32
 struct RangeArgs {
   uint32_t       g0, g1;
   cudaStream_t   st;
+  // regrouping (plans with spare slots, device-resident full decodes): the range's slots [slot0, slot0 + cap) of the group table,
+  // its state word, and whether a regrouping point has been enqueued yet (from then on the launches cover the slots too)
+  uint32_t       slot0 = 0, cap = 0, rg_idx = 0;
+  bool           rg = false, rg_started = false;
 };
 
 // one launch of the decode chain of a group range; kind: 0 extract, 1 scan, 2 job (+ per-block verdict), 4 emit
@@ -1007,7 +1038,9 @@ static int join_pending(srsb200_engine* e)
 static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, int kind, uint32_t n, const int16_t* d_llr, uint32_t max_iter,
                        uint32_t min_iter, int early_stop, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_ok)
 {
-  const uint32_t ng = r.g1 - r.g0;
+  const uint32_t ng0 = r.g1 - r.g0;                       // the range's own groups
+  const uint32_t ng  = ng0 + (r.rg_started ? r.cap : 0);  // + its slots for regrouped survivors, once a regrouping point has passed
+  const uint32_t so  = r.slot0 - r.g0;                    // the slots' index relative to the range's first group
   const Group*   dg = p->d_groups + r.g0;
   uint8_t*       da = p->d_active + r.g0;
   cudaStream_t   st = r.st;
@@ -1015,22 +1048,24 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
   const uint32_t nwin_max = (p->max_R + WC - 1) / WC;
   const dim3     sgrid((ng + 1) / 2), jgrid((nwin_max + 4 * p->wpj - 1) / (4 * p->wpj), ng);
   const size_t   jsm = 4 * sizeof(JobWarpSmem);
+  int32_t*       home = r.rg ? p->d_home : nullptr;
+  uint32_t*      rgs  = r.rg ? p->d_rg_state + r.rg_idx : nullptr;
   switch (kind) {
     case 0: {
       ProfScope ps(e, 0, st);
-      extract_kernel<<<dim3(p->max_R / XT, ng), 256, 0, st>>>(dg, p->d_ws, d_llr, p->d_llr_off, da, p->d_done, p->d_crc_acc);
+      extract_kernel<<<dim3(p->max_R / XT, ng0), 256, 0, st>>>(dg, p->d_ws, d_llr, p->d_llr_off, da, p->d_done, p->d_crc_acc, home, rgs, 0u);
     } break;
     case 1: {
       ProfScope ps(e, 5, st);
-      if (mode == 0) scan_kernel<0><<<sgrid, 160, sizeof(ScanSmemT<0>), st>>>(dg, p->d_ws, da, ng);
-      else if (mode == 1) scan_kernel<1><<<sgrid, 160, sizeof(ScanSmemT<1>), st>>>(dg, p->d_ws, da, ng);
-      else scan_kernel<2><<<sgrid, 160, sizeof(ScanSmemT<2>), st>>>(dg, p->d_ws, da, ng);
+      if (mode == 0) scan_kernel<0><<<sgrid, 160, sizeof(ScanSmemT<0>), st>>>(dg, p->d_ws, da, ng, ng0, so);
+      else if (mode == 1) scan_kernel<1><<<sgrid, 160, sizeof(ScanSmemT<1>), st>>>(dg, p->d_ws, da, ng, ng0, so);
+      else scan_kernel<2><<<sgrid, 160, sizeof(ScanSmemT<2>), st>>>(dg, p->d_ws, da, ng, ng0, so);
     } break;
     case 2: {
       ProfScope ps(e, 6, st);
 #define SRSB200_JOB(M, WP)                                                                                                                    \
   job_kernel<M, WP><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, \
-                                             max_iter, min_iter, early_stop, p->use_cb_max_iter ? p->d_cb_max_iter : nullptr)
+                                             max_iter, min_iter, early_stop, p->use_cb_max_iter ? p->d_cb_max_iter : nullptr, ng0, so)
       if (p->wpj == 16) {
         if (mode == 0) SRSB200_JOB(0, 16); else if (mode == 1) SRSB200_JOB(1, 16); else SRSB200_JOB(2, 16);
       } else {
@@ -1038,9 +1073,22 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
       }
 #undef SRSB200_JOB
     } break;
+    case 3: {
+      // regrouping point after half-iteration n (0-based): plan, then - only if the plan kernel regrouped - the channel streams
+      // and the state stream of the new groups. n even: the last half-iteration was a DEC1, its output app2 carries the state
+      ProfScope ps(e, 0, st);  // (profiled with the extract kernel: layout work)
+      const uint32_t attempt = n + 1;
+      regroup_plan_kernel<<<1, 256, 0, st>>>(p->d_groups + r.g0, ng0, so, r.cap, da, p->d_done, p->d_home, p->d_src + 64ull * (r.slot0 - p->n_groups), rgs, attempt);
+      extract_kernel<<<dim3(p->max_R / XT, r.cap), 256, 0, st>>>(p->d_groups + r.slot0, p->d_ws, d_llr, p->d_llr_off, p->d_active + r.slot0, p->d_done,
+                                                                 p->d_crc_acc, nullptr, rgs, attempt);
+      regroup_fill_kernel<<<dim3(p->max_R / 64, r.cap), 256, 0, st>>>(p->d_groups + r.slot0, p->d_active + r.slot0, dg, p->d_src + 64ull * (r.slot0 - p->n_groups),
+                                                                      e->d_ktab, p->d_ws, rgs, attempt, (n & 1u) ? 0 : 1);
+      e->launches += 2;
+    } break;
     default: {
       ProfScope ps(e, 2, st);
-      emit_kernel<<<dim3(ng, EMIT_SPLIT), 256, emit_smem_bytes(p->max_R, p->max_R), st>>>(dg, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off, p->d_out_len);
+      emit_kernel<<<dim3(ng, EMIT_SPLIT), 256, emit_smem_bytes(p->max_R, p->max_R), st>>>(dg, e->d_ktab, p->d_ws, d_noi, d_out, p->d_out_off, p->d_out_len, home,
+                                                                                          ng0, so);
     } break;
   }
   e->launches++;
@@ -1089,6 +1137,13 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     wacc += wgt[s];
     rg[s].g1 = (uint32_t)((uint64_t)p->n_groups * wacc / wsum);
     rg[s].st = (S == 1 && !lazy) ? e->stream : e->sub[sbase + s];
+    // regrouping of the survivors: full device-resident decodes of plans that carry spare slots
+    if (p->n_new && !io && do_extract && start_iter == 0 && max_iter >= 6) {
+      rg[s].rg     = true;
+      rg[s].slot0  = p->n_groups + rg[s].g0 / 4 + s;
+      rg[s].cap    = rg[s].g1 / 4 - rg[s].g0 / 4 + 1;
+      rg[s].rg_idx = (S == 1 && !lazy) ? 0u : sbase + s;
+    }
   }
   // Small decodes (one range on the engine stream: a transport block, a single code block) are launch-bound: extract +
   // 2 x max_iter + emit kernels of tens of microseconds each, and in a multi-threaded PHY every launch takes the
@@ -1154,6 +1209,11 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     for (uint32_t n = start_iter; n < max_iter; n++) {
       launch_one(e, p, rg[s], 1, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
       launch_one(e, p, rg[s], 2, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+      // regrouping points after the 4th, 5th and 6th half-iteration (the first one that finds few enough survivors regroups)
+      if (rg[s].rg && n + 1 >= 4 && n + 1 <= 6 && n + 1 < max_iter) {
+        launch_one(e, p, rg[s], 3, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
+        rg[s].rg_started = true;
+      }
     }
     launch_one(e, p, rg[s], 4, 0, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
     if (io) {

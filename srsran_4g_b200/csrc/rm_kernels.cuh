@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
   extern __shared__ __align__(16) int16_t se_raw[];
   __shared__ uint32_t sc[SCR ? RM_SC_WORDS : 1];
   const RmJob    j  = jobs[blockIdx.x];
+  const uint32_t nthr = blockDim.x;  // <= RM_THREADS
   const uint32_t ns = min(j.E, RM_SMEM_ELEMS);
   // ---- stage the received LLRs: 128-bit global loads and 128-bit shared stores. The e-bits of a code block start anywhere
   //      (2-byte aligned): the shared copy is shifted by the same number of elements, so that element i sits 16-byte aligned in
@@ -85,8 +86,8 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
     const uint32_t nv = (ns - head) / 8;
     const uint4*   gv = reinterpret_cast<const uint4*>(j.e + head);
     uint4*         sv = reinterpret_cast<uint4*>(se + head);
-    for (uint32_t i = threadIdx.x; i < nv; i += RM_THREADS) sv[i] = __ldg(gv + i);
-    for (uint32_t i = head + 8 * nv + threadIdx.x; i < ns; i += RM_THREADS) se[i] = j.e[i];
+    for (uint32_t i = threadIdx.x; i < nv; i += nthr) sv[i] = __ldg(gv + i);
+    for (uint32_t i = head + 8 * nv + threadIdx.x; i < ns; i += nthr) se[i] = j.e[i];
   }
   if (SCR && j.scramble) {
     // The block's part of the scrambling sequence, 32 bits per word. A matrix-vector product over GF(2) is one popc per row:
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
     // its first word (offset c_off + 32 * first word, by powers A^(2^k)) and then walks word by word with A^32. 31 bits of a
     // word come straight out of the windows (bit b = x(n + b)), the 32nd is the feedback bit.
     const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t nw   = min((j.E + 31) / 32, RM_SC_WORDS), per = (nw + RM_THREADS / 32 - 1) / (RM_THREADS / 32);
+    const uint32_t nw   = min((j.E + 31) / 32, RM_SC_WORDS), per = (nw + nthr / 32 - 1) / (nthr / 32);
     const uint32_t w0 = wid * per, w1 = min(w0 + per, nw);
     if (w0 < w1) {
       uint32_t a = warp_gold_jump(gold, j.x1, j.c_off + 32 * w0, lane), b = warp_gold_jump(gold + 32 * GOLD_POWERS, j.x2, j.c_off + 32 * w0, lane);
@@ -133,35 +134,49 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
   const bool     wide = ((reinterpret_cast<uintptr_t>(j.buf) | reinterpret_cast<uintptr_t>(j.table)) & 15u) == 0;
   const uint32_t L8   = wide ? j.L / 8 : 0u;
   auto rmw = [&](auto staged) {
-    for (uint32_t p8 = threadIdx.x; p8 < L8; p8 += RM_THREADS) {
-      const uint4    tt    = __ldg(reinterpret_cast<const uint4*>(j.table) + p8);
-      const uint32_t tw[4] = {tt.x, tt.y, tt.z, tt.w};
-      uint32_t       n[8];
-      bool           any = false;
+    // two uint4 per thread and trip: both table loads and both old values are in flight before the first shared-memory read
+    constexpr int U = 2;
+    for (uint32_t p0 = threadIdx.x; p0 < L8; p0 += U * nthr) {
+      uint4 tt[U], old[U];
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        n[2 * q]     = tw[q] & 0xffffu;
-        n[2 * q + 1] = tw[q] >> 16;
-        any |= n[2 * q] < j.E || n[2 * q + 1] < j.E;
-      }
-      if (!any) continue;  // nothing received for these eight positions (punctured region): no traffic at all
-      uint4    old   = reinterpret_cast<uint4*>(j.buf)[p8];
-      uint32_t ow[4] = {old.x, old.y, old.z, old.w};
-      uint32_t sum[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      for (uint32_t r = 0, base = 0; r < reps; r++, base += j.L) {
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const uint32_t i = n[q] + base;
-          if (i < j.E) sum[q] += llr(i, staged);
+      for (int u = 0; u < U; u++) {
+        const uint32_t p8 = p0 + u * nthr;
+        if (p8 < L8) {
+          tt[u]  = __ldg(reinterpret_cast<const uint4*>(j.table) + p8);
+          old[u] = reinterpret_cast<const uint4*>(j.buf)[p8];
         }
       }
 #pragma unroll
-      for (int q = 0; q < 4; q++) ow[q] = __vadd2(ow[q], __byte_perm(sum[2 * q], sum[2 * q + 1], 0x5410));  // two wrapping 16-bit sums
-      reinterpret_cast<uint4*>(j.buf)[p8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      for (int u = 0; u < U; u++) {
+        const uint32_t p8 = p0 + u * nthr;
+        if (p8 >= L8) continue;
+        const uint32_t tw[4] = {tt[u].x, tt[u].y, tt[u].z, tt[u].w};
+        uint32_t       n[8];
+        bool           any = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          n[2 * q]     = tw[q] & 0xffffu;
+          n[2 * q + 1] = tw[q] >> 16;
+          any |= n[2 * q] < j.E || n[2 * q + 1] < j.E;
+        }
+        if (!any) continue;  // nothing received for these eight positions (punctured region): nothing written
+        uint32_t ow[4]  = {old[u].x, old[u].y, old[u].z, old[u].w};
+        uint32_t sum[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        for (uint32_t r = 0, base = 0; r < reps; r++, base += j.L) {
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const uint32_t i = n[q] + base;
+            if (i < j.E) sum[q] += llr(i, staged);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) ow[q] = __vadd2(ow[q], __byte_perm(sum[2 * q], sum[2 * q + 1], 0x5410));  // two wrapping 16-bit sums
+        reinterpret_cast<uint4*>(j.buf)[p8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
     }
     // two soft-buffer elements per thread for the rest (L is even, buf is 4-byte aligned)
     uint32_t* buf2 = reinterpret_cast<uint32_t*>(j.buf);
-    for (uint32_t p2 = 4 * L8 + threadIdx.x; p2 < j.L / 2; p2 += RM_THREADS) {
+    for (uint32_t p2 = 4 * L8 + threadIdx.x; p2 < j.L / 2; p2 += nthr) {
       const uint32_t tt = reinterpret_cast<const uint32_t*>(j.table)[p2];
       const uint32_t n0 = tt & 0xffffu, n1 = tt >> 16;
       if (n0 >= j.E && n1 >= j.E) continue;  // nothing received for these two positions
@@ -238,7 +253,7 @@ struct DeintJob {
 // them, go item by item with the rank found by binary search. Round 1 let every thread read its Qm values straight from q
 // (12 bytes out of every 32-byte sector per request): 1.5 TB/s; 32-row tiles with per-item stores: 2.1 TB/s.
 // grid = (jobs, tiles per job: any number >= 1, tiles are strided over gridDim.y), block = 256
-constexpr int DT_ROWS = 64;
+constexpr int DT_ROWS = 128;  // 32 / 64 / 128 rows per tile: 2.1 / 2.7-3.1 / see profiles TB/s on 512 transport blocks (bytes in flight per SM)
 constexpr int DT_MAXC = 14;  // columns = PUSCH symbols carrying data: 12 (normal CP), 10 / 11 with SRS or extended CP
 // floor(n / d) = umulhi(n, magic) while n * d < 2^32 and d >= 2; magic 0 stands for d = 1
 __device__ __forceinline__ uint32_t dt_magic(uint32_t d) { return d < 2 ? 0u : 0xffffffffu / d + 1u; }
@@ -259,10 +274,11 @@ __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __rest
     if (tiled) {
       __syncthreads();  // the previous tile has been written out
       const uint32_t rw = run / 2, nw = j.cols * rw, m_rw = dt_magic(rw);  // 32-bit words per column run
-      for (uint32_t i0 = threadIdx.x; i0 < nw; i0 += 256 * 4) {
-        uint32_t v[4], at[4];
+      constexpr int UN = 8;  // loads in flight per thread
+      for (uint32_t i0 = threadIdx.x; i0 < nw; i0 += 256 * UN) {
+        uint32_t v[UN], at[UN];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < UN; u++) {
           const uint32_t idx = i0 + 256 * u;
           if (idx < nw) {
             const uint32_t col = dt_div(idx, m_rw), wq = idx - col * rw;
@@ -271,7 +287,7 @@ __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __rest
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < UN; u++)
           if (i0 + 256 * u < nw) *reinterpret_cast<uint32_t*>(&tile[0][0] + at[u]) = v[u];
       }
       // number of RI scan indices before the tile, and whether one lies inside it (every thread the same search: broadcast loads)

@@ -92,6 +92,10 @@ __host__ __device__ inline GroupPtrs group_ptrs(uint8_t* ws, const Group& g)
   return p;
 }
 
+// Launches that follow a regrouping point (regroup_plan_kernel below) cover a range's own groups - relative indices
+// [0, n_first) - and then the slots of its regrouped survivors, which sit further back in the group table
+__device__ __forceinline__ uint32_t seg_index(uint32_t b, uint32_t n_first, uint32_t second_off) { return b < n_first ? b : b - n_first + second_off; }
+
 // ---------------------------------------------------------------- packed int16x2 arithmetic (wrapping)
 __device__ __forceinline__ uint32_t padd(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 __device__ __forceinline__ uint32_t psub(uint32_t a, uint32_t b) { return __vsub2(a, b); }
@@ -291,7 +295,7 @@ __device__ __forceinline__ void alpha_block(const ScanStageT<MODE>& st, int r0, 
  */
 template <int MODE>
 __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const uint8_t* __restrict__ group_active,
-                                                   uint32_t n_groups)
+                                                   uint32_t n_groups, uint32_t n_first, uint32_t second_off)
 {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanSmemT<MODE>* sm   = reinterpret_cast<ScanSmemT<MODE>*>(smem_raw);
@@ -313,10 +317,10 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
     const uint32_t* src[4][3];
     int             nchunk[4], cK4[4];
     for (int w = 0; w < 4; w++) {
-      const uint32_t gi = blockIdx.x * 2 + (w >> 1);
+      const uint32_t bi = blockIdx.x * 2 + (w >> 1), gi = seg_index(bi, n_first, second_off);
       nchunk[w] = 0;
       cK4[w]    = 0;
-      if (gi < n_groups && group_active[gi]) {
+      if (bi < n_groups && group_active[gi]) {
         const Group&    g  = groups[gi];
         const GroupPtrs gp = group_ptrs(ws, g);
         src[w][0] = (MODE == 2) ? gp.app2 : (MODE == 1 ? gp.xa1 : gp.syst);
@@ -358,9 +362,9 @@ __global__ void __launch_bounds__(160) scan_kernel(const Group* __restrict__ gro
   }
 
   // ---------------- recursion warps
-  const uint32_t gi  = blockIdx.x * 2 + (wid >> 1);
+  const uint32_t bi  = blockIdx.x * 2 + (wid >> 1), gi = seg_index(bi, n_first, second_off);
   const int      dir = wid & 1;  // 0 = backward (beta), 1 = forward (alpha)
-  if (gi >= n_groups || !group_active[gi]) return;
+  if (bi >= n_groups || !group_active[gi]) return;
 #ifdef SCAN_PROBE
   const long long probe_t0 = clock64();
 #endif
@@ -547,15 +551,17 @@ template <int MODE, int WPJ_T>
 __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws,
                                             uint8_t* __restrict__ group_active, uint8_t* __restrict__ done, uint32_t* __restrict__ crc_acc,
                                             uint32_t* __restrict__ arrivals, uint8_t* __restrict__ noi, uint8_t* __restrict__ ok, uint32_t cnt,
-                                            uint32_t max_iter, uint32_t min_iter, int early_stop, const uint8_t* __restrict__ max_iter_cb)
+                                            uint32_t max_iter, uint32_t min_iter, int early_stop, const uint8_t* __restrict__ max_iter_cb,
+                                            uint32_t n_first, uint32_t second_off)
 {
-  if (!group_active[blockIdx.y]) return;
+  const uint32_t gi = seg_index(blockIdx.y, n_first, second_off);
+  if (!group_active[gi]) return;
   __shared__ uint32_t s_last;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int       wid  = threadIdx.x >> 5;
   const int       lane = threadIdx.x & 31;
   JobWarpSmem*    sm   = reinterpret_cast<JobWarpSmem*>(smem_raw) + wid;
-  const Group&    g    = groups[blockIdx.y];
+  const Group&    g    = groups[gi];
   const uint32_t  K    = g.K;
   const int       nwin = (int)((K + WC - 1) / WC);
   constexpr int   wpj  = WPJ_T;  // == g.wpj (the host picks the instantiation)
@@ -728,7 +734,7 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   // half-iteration count, CRC == 0 accepted from the min_iter-th on, done flags, group activity for the next launches
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&arrivals[blockIdx.y], 1u) == gridDim.x - 1) ? 1u : 0u;
+  if (threadIdx.x == 0) s_last = (atomicAdd(&arrivals[gi], 1u) == gridDim.x - 1) ? 1u : 0u;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -749,8 +755,8 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   }
   active = __syncthreads_or(active);
   if (threadIdx.x == 0) {
-    group_active[blockIdx.y] = (uint8_t)(active ? 1 : 0);
-    arrivals[blockIdx.y]     = 0u;
+    group_active[gi] = (uint8_t)(active ? 1 : 0);
+    arrivals[gi]     = 0u;
   }
 }
 #undef LOAD_XY
@@ -765,20 +771,25 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
 constexpr int XT = 64;  // rows per tile
 __global__ void __launch_bounds__(256)
 extract_kernel(const Group* __restrict__ groups, uint8_t* __restrict__ ws, const int16_t* __restrict__ llr, const uint64_t* __restrict__ llr_off,
-               uint8_t* __restrict__ active, uint8_t* __restrict__ done, uint32_t* __restrict__ crc_acc)
+               uint8_t* __restrict__ active, uint8_t* __restrict__ done, uint32_t* __restrict__ crc_acc, int32_t* __restrict__ home,
+               uint32_t* __restrict__ rg_state, uint32_t rg_attempt)
 {
+  // rg_attempt != 0: the channel streams of the groups that regrouping point rg_attempt has just formed (nothing is re-armed)
+  if (rg_attempt && (*rg_state != rg_attempt || !active[blockIdx.y])) return;
   constexpr int ROWW = 3 * XT / 2 + 1;      // words per tile row: 96 int16 + pad (odd => conflict-free column reads)
   __shared__ uint32_t tile[64][ROWW];
   const Group&    g  = groups[blockIdx.y];
   const uint32_t  K  = g.K;
   const uint32_t  k0 = blockIdx.x * XT;  // first row of this tile
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && !rg_attempt) {
     // a new decode starts here: re-arm the group and its code blocks (stream-ordered before the first scan)
     if (threadIdx.x < 64 && g.cb[threadIdx.x] >= 0) {
       done[g.cb[threadIdx.x]]    = 0;
       crc_acc[g.cb[threadIdx.x]] = 0;
+      if (home) home[g.cb[threadIdx.x]] = (int32_t)blockIdx.y;  // the group whose decision arrays will hold the block's bits
     }
     if (threadIdx.x == 0) active[blockIdx.y] = 1;
+    if (threadIdx.x == 0 && blockIdx.y == 0 && rg_state) *rg_state = 0u;
   }
   if (k0 >= g.R) return;
   const GroupPtrs gp   = group_ptrs(ws, g);
@@ -879,11 +890,14 @@ __host__ __device__ inline size_t emit_smem_bytes(uint32_t R, uint32_t K)
 }
 __global__ void __launch_bounds__(256)
 emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws, const uint8_t* __restrict__ noi,
-            uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_len)
+            uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ out_len,
+            const int32_t* __restrict__ home, uint32_t n_first, uint32_t second_off)
 {
+  // home (plans that may regroup): a code block is emitted by the group it ran its last half-iteration in
   extern __shared__ __align__(16) uint8_t esm[];
   constexpr uint32_t NL = LANES / EMIT_SPLIT, NC = 2 * NL;  // lanes / code blocks of this block
-  const Group&    g    = groups[blockIdx.x];
+  const uint32_t  gi   = seg_index(blockIdx.x, n_first, second_off);
+  const Group&    g    = groups[gi];
   const GroupPtrs gp   = group_ptrs(ws, g);
   const uint32_t  K    = g.K;
   const uint32_t  NP   = (K + 15) / 16;             // pieces actually used
@@ -894,7 +908,10 @@ emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, 
   uint16_t*       srev = T2 + NC * P;
   const int       tid  = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   bool any = false;
-  for (uint32_t c = 0; c < NC; c++) any |= g.cb[(c / NL) * 32 + L0 + (c % NL)] >= 0;
+  for (uint32_t c = 0; c < NC; c++) {
+    const int cb = g.cb[(c / NL) * 32 + L0 + (c % NL)];
+    any |= cb >= 0 && (!home || home[cb] == (int32_t)gi);
+  }
   if (!any) return;
   for (uint32_t idx = tid; idx < NP * NL; idx += 256) {
     const uint32_t p = idx / NL, l = idx % NL;
@@ -911,7 +928,7 @@ emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, 
   for (uint32_t task = wid; task < NC * nchunk; task += 8) {
     const uint32_t c = task / nchunk, word = (task % nchunk) * 32 + lane;
     const int      cb = g.cb[(c / NL) * 32 + L0 + (c % NL)];
-    if (cb < 0 || word >= nwords) continue;
+    if (cb < 0 || word >= nwords || (home && home[cb] != (int32_t)gi)) continue;
     const uint32_t nt = min(32u, K - word * 32);  // K is a multiple of 8 but not always of 32
     uint32_t       v  = 0;
     if (noi[cb] & 1u) {
@@ -938,6 +955,135 @@ emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, 
       *reinterpret_cast<uint32_t*>(o) = __byte_perm(v, 0, 0x0123);
     } else {
       for (uint32_t b = 0; b < nb; b++) o[b] = (uint8_t)(v >> (24 - 8 * b));
+    }
+  }
+}
+
+/*
+ * Regrouping of the unfinished code blocks. The 64 code blocks of a group run in lock-step, so a group costs a full
+ * half-iteration as long as ONE of its blocks is unfinished: on the bench workload 87 % of the blocks are done after five
+ * half-iterations, yet every group still runs the sixth. At a regrouping point the survivors of a range of groups are packed
+ * into fresh groups (64 per group) and the old groups retire:
+ *   regroup_plan_kernel   (one block)  counts the survivors; if they fit the slots set aside for the range and at least halve
+ *                         the number of running groups, it writes the new groups' code-block lists, where each lane's state
+ *                         comes from (src), each survivor's new home, and swaps the activity flags;
+ *   extract_kernel        (rg_attempt) refills the channel streams of the new groups from the caller's natural-order LLRs;
+ *   regroup_fill_kernel   moves the ONE stream that carries decoder state across a half-iteration boundary - app2 after a DEC1,
+ *                         xa1 after a DEC2 (rows < K; everything else is rewritten before it is read) - and rebuilds systp.
+ * The decode of a block is the same sequence of operations on the same values in another lane: results are bit-identical.
+ * Only plans of one block size regroup, once per decode and range.
+ */
+__global__ void __launch_bounds__(256)
+regroup_plan_kernel(Group* __restrict__ groups, uint32_t ng, uint32_t second_off, uint32_t cap, uint8_t* __restrict__ active,
+                    const uint8_t* __restrict__ done, int32_t* __restrict__ home, int32_t* __restrict__ src, uint32_t* __restrict__ rg_state,
+                    uint32_t rg_attempt)
+{
+  __shared__ uint32_t s_scan[256], s_tot[2];
+  if (*rg_state) return;  // regrouped at an earlier point of this decode
+  const uint32_t tid = threadIdx.x;
+  auto survivors = [&](uint32_t g) -> uint32_t {
+    if (g >= ng || !active[g]) return 0u;
+    uint32_t c = 0;
+    for (int sl = 0; sl < 64; sl++) {
+      const int cb = groups[g].cb[sl];
+      c += (cb >= 0 && !done[cb]) ? 1u : 0u;
+    }
+    return c;
+  };
+  if (tid < 2) s_tot[tid] = 0u;
+  __syncthreads();
+  {
+    uint32_t c = 0, a = 0;
+    for (uint32_t g = tid; g < ng; g += 256) {
+      const uint32_t v = survivors(g);
+      c += v;
+      a += v ? 1u : 0u;
+    }
+    if (c) atomicAdd(&s_tot[0], c);
+    if (a) atomicAdd(&s_tot[1], a);
+  }
+  __syncthreads();
+  const uint32_t total = s_tot[0], running = s_tot[1], ngn = (total + 63) / 64;
+  if (total == 0 || ngn > cap || 2 * ngn > running) {
+    for (uint32_t i = tid; i < cap; i += 256) active[second_off + i] = 0;  // slots of an earlier decode stay retired
+    return;
+  }
+  uint32_t carry = 0;
+  for (uint32_t g0 = 0; g0 < ng; g0 += 256) {
+    const uint32_t g = g0 + tid, mine = survivors(g);
+    s_scan[tid] = mine;
+    __syncthreads();
+    for (uint32_t d = 1; d < 256; d <<= 1) {  // inclusive scan
+      const uint32_t v = tid >= d ? s_scan[tid - d] : 0u;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    uint32_t q = carry + s_scan[tid] - mine;
+    if (mine) {
+      for (int sl = 0; sl < 64; sl++) {
+        const int cb = groups[g].cb[sl];
+        if (cb >= 0 && !done[cb]) {
+          groups[second_off + (q >> 6)].cb[q & 63u] = cb;
+          src[q]   = (int32_t)((g << 6) | (uint32_t)sl);
+          home[cb] = (int32_t)(second_off + (q >> 6));
+          q++;
+        }
+      }
+    }
+    if (g < ng) active[g] = 0;
+    carry += s_scan[255];
+    __syncthreads();
+  }
+  for (uint32_t q = total + tid; q < ngn * 64; q += 256) {  // the empty lanes of the last new group
+    groups[second_off + (q >> 6)].cb[q & 63u] = -1;
+    src[q] = -1;
+  }
+  for (uint32_t i = tid; i < cap; i += 256) active[second_off + i] = i < ngn ? 1 : 0;
+  if (tid == 0) *rg_state = rg_attempt;
+}
+
+// grid = (R / 64, slots of the range), block = 256: eight rows x 32 lanes per pass. new_groups / new_active / src start at the
+// range's first slot, old_groups at the range's first group; from_app2 = the last half-iteration was a DEC1
+__global__ void __launch_bounds__(256)
+regroup_fill_kernel(const Group* __restrict__ new_groups, const uint8_t* __restrict__ new_active, const Group* __restrict__ old_groups,
+                    const int32_t* __restrict__ src, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws, const uint32_t* __restrict__ rg_state,
+                    uint32_t rg_attempt, int from_app2)
+{
+  if (*rg_state != rg_attempt || !new_active[blockIdx.y]) return;
+  const Group&    g    = new_groups[blockIdx.y];
+  const GroupPtrs gp   = group_ptrs(ws, g);
+  const uint32_t  K    = g.K, lane = threadIdx.x & 31u, rsub = threadIdx.x >> 5;
+  const uint32_t* row2 = ktabs[g.kidx].row2;
+  // the two code blocks of this lane: 16-bit column (slot & 31, half slot >> 5) of the state stream of their old group
+  const uint16_t* col[2];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int32_t sv = src[blockIdx.y * 64 + 32 * h + lane];
+    col[h]           = nullptr;
+    if (sv >= 0) {
+      const GroupPtrs op = group_ptrs(ws, old_groups[(uint32_t)sv >> 6]);
+      col[h] = reinterpret_cast<const uint16_t*>(from_app2 ? op.app2 : op.xa1) + 2u * ((uint32_t)sv & 31u) + (((uint32_t)sv >> 5) & 1u);
+    }
+  }
+  uint32_t* dst = from_app2 ? gp.app2 : gp.xa1;
+  uint32_t  lo[8], hi[8], sp[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t r = blockIdx.x * 64 + rsub + 8 * i;
+    lo[i] = hi[i] = sp[i] = 0u;
+    if (r < K) {
+      if (col[0]) lo[i] = col[0][(size_t)r * 64];
+      if (col[1]) hi[i] = col[1][(size_t)r * 64];
+      sp[i] = gp.syst[(size_t)row2[r] * LANES + lane];  // systp[j] = syst[fwd[j]]
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t r = blockIdx.x * 64 + rsub + 8 * i;
+    if (r < K) {
+      dst[(size_t)r * LANES + lane]      = lo[i] | (hi[i] << 16);
+      gp.systp[(size_t)r * LANES + lane] = sp[i];
     }
   }
 }

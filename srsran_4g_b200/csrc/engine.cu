@@ -196,10 +196,10 @@ struct srsb200_engine {
   size_t h_stage_cap[2] = {0, 0};
 
   // sub-batch streams (see launch_plan)
-  static const int MAX_SUB = 8;
+  static const int MAX_SUB = 16;
   int          n_sub = 8;      // ranges of a host-pointer submission (copy/compute overlap)
   int          n_sub_dev = 4;  // ranges of a device-resident submission (their launch chains overlap a little: +3-4 %)
-  // Device-resident submissions run on one of two LANES (sub[0..3] / sub[4..7]; a plan is bound to a lane when it is built)
+  // Device-resident submissions run on one of two LANES (one half of sub[] each; a plan is bound to a lane when it is built)
   // and are joined back into `stream` lazily (join_pending): the latency-bound last half-iterations of one submission
   // then overlap the bandwidth-bound first ones of the next submission of ANOTHER plan (+11 % on the bench workload).
   static const int N_LANES = 2;
@@ -691,12 +691,9 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   CUDA_TRY(cudaMemcpy(e->d_gold, e->h_gold, sizeof(e->h_gold), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)emit_smem_bytes(((SRSB200_MAX_K + 3 + W - 1) / W) * W, SRSB200_MAX_K + 64)));
-  CUDA_TRY(cudaFuncSetAttribute(job_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
-  CUDA_TRY(cudaFuncSetAttribute(job_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
-  CUDA_TRY(cudaFuncSetAttribute(job_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
-  CUDA_TRY(cudaFuncSetAttribute(job_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
-  CUDA_TRY(cudaFuncSetAttribute(job_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
-  CUDA_TRY(cudaFuncSetAttribute(job_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(job_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(JobWarpSmem))));
   *out = e;
   return SRSB200_SUCCESS;
 }
@@ -929,6 +926,7 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
   if (!no_regroup && buckets.size() == 1 && p->n_groups >= 64) {
     p->n_new = p->n_groups / 4 + srsb200_engine::MAX_SUB + 1;
     Group g  = p->h_groups[0];
+    g.wpj    = WPJ;  // few groups after a regrouping: short job-warp runs (latency)
     for (int j = 0; j < 64; j++) g.cb[j] = -1;
     for (uint32_t i = 0; i < p->n_new; i++) {
       g.ws_off = off;
@@ -1046,7 +1044,8 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
   cudaStream_t   st = r.st;
   const int      mode = (n == 0) ? 0 : ((n & 1u) ? 2 : 1);
   const uint32_t nwin_max = (p->max_R + WC - 1) / WC;
-  const dim3     sgrid((ng + 1) / 2), jgrid((nwin_max + 4 * p->wpj - 1) / (4 * p->wpj), ng);
+  const uint32_t wmin = r.rg_started ? std::min<uint32_t>(p->wpj, WPJ) : p->wpj;  // regrouped groups run WPJ windows per warp
+  const dim3     sgrid((ng + 1) / 2), jgrid((nwin_max + 4 * wmin - 1) / (4 * wmin), ng);
   const size_t   jsm = 4 * sizeof(JobWarpSmem);
   int32_t*       home = r.rg ? p->d_home : nullptr;
   uint32_t*      rgs  = r.rg ? p->d_rg_state + r.rg_idx : nullptr;
@@ -1063,14 +1062,10 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
     } break;
     case 2: {
       ProfScope ps(e, 6, st);
-#define SRSB200_JOB(M, WP)                                                                                                                    \
-  job_kernel<M, WP><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, \
-                                             max_iter, min_iter, early_stop, p->use_cb_max_iter ? p->d_cb_max_iter : nullptr, ng0, so)
-      if (p->wpj == 16) {
-        if (mode == 0) SRSB200_JOB(0, 16); else if (mode == 1) SRSB200_JOB(1, 16); else SRSB200_JOB(2, 16);
-      } else {
-        if (mode == 0) SRSB200_JOB(0, 8); else if (mode == 1) SRSB200_JOB(1, 8); else SRSB200_JOB(2, 8);
-      }
+#define SRSB200_JOB(M)                                                                                                                    \
+  job_kernel<M><<<jgrid, 128, jsm, st>>>(dg, e->d_ktab, p->d_ws, da, p->d_done, p->d_crc_acc, p->d_arrivals + r.g0, d_noi, d_ok, n + 1, \
+                                         max_iter, min_iter, early_stop, p->use_cb_max_iter ? p->d_cb_max_iter : nullptr, ng0, so)
+      if (mode == 0) SRSB200_JOB(0); else if (mode == 1) SRSB200_JOB(1); else SRSB200_JOB(2);
 #undef SRSB200_JOB
     } break;
     case 3: {
@@ -1078,7 +1073,7 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
       // and the state stream of the new groups. n even: the last half-iteration was a DEC1, its output app2 carries the state
       ProfScope ps(e, 0, st);  // (profiled with the extract kernel: layout work)
       const uint32_t attempt = n + 1;
-      regroup_plan_kernel<<<1, 256, 0, st>>>(p->d_groups + r.g0, ng0, so, r.cap, da, p->d_done, p->d_home, p->d_src + 64ull * (r.slot0 - p->n_groups), rgs, attempt);
+      regroup_plan_kernel<<<1, 1024, 0, st>>>(p->d_groups + r.g0, ng0, so, r.cap, da, p->d_done, p->d_home, p->d_src + 64ull * (r.slot0 - p->n_groups), rgs, attempt);
       extract_kernel<<<dim3(p->max_R / XT, r.cap), 256, 0, st>>>(p->d_groups + r.slot0, p->d_ws, d_llr, p->d_llr_off, p->d_active + r.slot0, p->d_done,
                                                                  p->d_crc_acc, nullptr, rgs, attempt);
       regroup_fill_kernel<<<dim3(p->max_R / 64, r.cap), 256, 0, st>>>(p->d_groups + r.slot0, p->d_active + r.slot0, dg, p->d_src + 64ull * (r.slot0 - p->n_groups),

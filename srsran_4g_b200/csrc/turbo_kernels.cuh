@@ -547,7 +547,7 @@ __device__ __forceinline__ uint32_t alpha_llr_step(uint32_t (&a)[8], const uint3
  * Everything a window needs - its input rows, its two beta checkpoints, its step table - arrives in shared memory through
  * one group of bulk asynchronous copies issued one window ahead; the loop itself performs no global loads.
  */
-template <int MODE, int WPJ_T>
+template <int MODE>
 __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, uint8_t* __restrict__ ws,
                                             uint8_t* __restrict__ group_active, uint8_t* __restrict__ done, uint32_t* __restrict__ crc_acc,
                                             uint32_t* __restrict__ arrivals, uint8_t* __restrict__ noi, uint8_t* __restrict__ ok, uint32_t cnt,
@@ -564,7 +564,9 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   const Group&    g    = groups[gi];
   const uint32_t  K    = g.K;
   const int       nwin = (int)((K + WC - 1) / WC);
-  constexpr int   wpj  = WPJ_T;  // == g.wpj (the host picks the instantiation)
+  const int       wpj  = (int)g.wpj;  // windows per warp of THIS group (regrouped groups run shorter warps: few groups, latency)
+  const uint32_t  nblk = (uint32_t)(nwin + 4 * wpj - 1) / (uint32_t)(4 * wpj);  // blocks of the grid that have windows of this group
+  if (blockIdx.x >= nblk) return;
   const int       w0   = (int)(blockIdx.x * 4 + wid) * wpj;
   const int       w1   = min(w0 + wpj, nwin);
   const GroupPtrs gp   = group_ptrs(ws, g);
@@ -734,7 +736,7 @@ __global__ void __maxnreg__(152) job_kernel(const Group* __restrict__ groups, co
   // half-iteration count, CRC == 0 accepted from the min_iter-th on, done flags, group activity for the next launches
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&arrivals[gi], 1u) == gridDim.x - 1) ? 1u : 0u;
+  if (threadIdx.x == 0) s_last = (atomicAdd(&arrivals[gi], 1u) == nblk - 1) ? 1u : 0u;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -973,73 +975,94 @@ emit_kernel(const Group* __restrict__ groups, const KTable* __restrict__ ktabs, 
  * The decode of a block is the same sequence of operations on the same values in another lane: results are bit-identical.
  * Only plans of one block size regroup, once per decode and range.
  */
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 regroup_plan_kernel(Group* __restrict__ groups, uint32_t ng, uint32_t second_off, uint32_t cap, uint8_t* __restrict__ active,
                     const uint8_t* __restrict__ done, int32_t* __restrict__ home, int32_t* __restrict__ src, uint32_t* __restrict__ rg_state,
                     uint32_t rg_attempt)
 {
-  __shared__ uint32_t s_scan[256], s_tot[2];
+  // One block; a thread owns 16 consecutive lanes of a group (a quarter of its code-block list: four 128-bit loads), all loads of
+  // a pass are in flight together - the kernel sits alone on the critical path of its range, so its latency is what counts.
+  __shared__ uint32_t s_warp[32], s_tot[2];
   if (*rg_state) return;  // regrouped at an earlier point of this decode
-  const uint32_t tid = threadIdx.x;
-  auto survivors = [&](uint32_t g) -> uint32_t {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  constexpr uint32_t PER = 16, CHUNK = 1024 * PER;  // list entries per thread / per pass of the block
+  // survivors among this thread's 16 entries of pass c0: bit i set = entry i is an unfinished code block; cb[] = the entries
+  auto survivors = [&](uint32_t c0, int (&cb)[PER]) -> uint32_t {
+    const uint32_t e0 = c0 + tid * PER, g = e0 >> 6;
     if (g >= ng || !active[g]) return 0u;
-    uint32_t c = 0;
-    for (int sl = 0; sl < 64; sl++) {
-      const int cb = groups[g].cb[sl];
-      c += (cb >= 0 && !done[cb]) ? 1u : 0u;
+    const int4* lp = reinterpret_cast<const int4*>(&groups[g].cb[e0 & 63u]);
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const int4 t = lp[v];
+      cb[4 * v] = t.x; cb[4 * v + 1] = t.y; cb[4 * v + 2] = t.z; cb[4 * v + 3] = t.w;
     }
-    return c;
+    uint32_t d[PER], m = 0;
+#pragma unroll
+    for (int i = 0; i < (int)PER; i++) d[i] = cb[i] >= 0 ? (uint32_t)done[cb[i]] : 1u;
+#pragma unroll
+    for (int i = 0; i < (int)PER; i++) m |= (d[i] ? 0u : 1u) << i;
+    return m;
   };
   if (tid < 2) s_tot[tid] = 0u;
   __syncthreads();
   {
     uint32_t c = 0, a = 0;
-    for (uint32_t g = tid; g < ng; g += 256) {
-      const uint32_t v = survivors(g);
-      c += v;
-      a += v ? 1u : 0u;
+    for (uint32_t c0 = 0; c0 < ng * 64; c0 += CHUNK) {
+      int cb[PER];
+      c += __popc(survivors(c0, cb));
+      const uint32_t g = (c0 + tid * PER) >> 6;
+      a += ((tid & 3u) == 0 && g < ng && active[g]) ? 1u : 0u;  // a group is active as long as one of its blocks is unfinished
     }
-    if (c) atomicAdd(&s_tot[0], c);
-    if (a) atomicAdd(&s_tot[1], a);
+    c = __reduce_add_sync(0xffffffffu, c);
+    a = __reduce_add_sync(0xffffffffu, a);
+    if (lane == 0 && c) atomicAdd(&s_tot[0], c);
+    if (lane == 0 && a) atomicAdd(&s_tot[1], a);
   }
   __syncthreads();
   const uint32_t total = s_tot[0], running = s_tot[1], ngn = (total + 63) / 64;
   if (total == 0 || ngn > cap || 2 * ngn > running) {
-    for (uint32_t i = tid; i < cap; i += 256) active[second_off + i] = 0;  // slots of an earlier decode stay retired
+    for (uint32_t i = tid; i < cap; i += 1024) active[second_off + i] = 0;  // slots of an earlier decode stay retired
     return;
   }
   uint32_t carry = 0;
-  for (uint32_t g0 = 0; g0 < ng; g0 += 256) {
-    const uint32_t g = g0 + tid, mine = survivors(g);
-    s_scan[tid] = mine;
-    __syncthreads();
-    for (uint32_t d = 1; d < 256; d <<= 1) {  // inclusive scan
-      const uint32_t v = tid >= d ? s_scan[tid - d] : 0u;
-      __syncthreads();
-      s_scan[tid] += v;
-      __syncthreads();
+  for (uint32_t c0 = 0; c0 < ng * 64; c0 += CHUNK) {
+    int            cb[PER];
+    const uint32_t m = survivors(c0, cb), mine = __popc(m);
+    // exclusive scan of `mine` over the block: shuffles within a warp, the 32 warp totals through shared memory
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+      if ((int)lane >= d) inc += v;
     }
-    uint32_t q = carry + s_scan[tid] - mine;
-    if (mine) {
-      for (int sl = 0; sl < 64; sl++) {
-        const int cb = groups[g].cb[sl];
-        if (cb >= 0 && !done[cb]) {
-          groups[second_off + (q >> 6)].cb[q & 63u] = cb;
-          src[q]   = (int32_t)((g << 6) | (uint32_t)sl);
-          home[cb] = (int32_t)(second_off + (q >> 6));
-          q++;
-        }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, ctot = 0;
+    for (uint32_t w = 0; w < 32; w++) {
+      const uint32_t v = s_warp[w];
+      if (w < wid) wbase += v;
+      ctot += v;
+    }
+    uint32_t       q  = carry + wbase + inc - mine;
+    const uint32_t e0 = c0 + tid * PER, g = e0 >> 6;
+#pragma unroll
+    for (int i = 0; i < (int)PER; i++) {
+      if ((m >> i) & 1u) {
+        groups[second_off + (q >> 6)].cb[q & 63u] = cb[i];
+        src[q]       = (int32_t)((g << 6) | ((e0 & 63u) + (uint32_t)i));
+        home[cb[i]]  = (int32_t)(second_off + (q >> 6));
+        q++;
       }
     }
-    if (g < ng) active[g] = 0;
-    carry += s_scan[255];
-    __syncthreads();
+    carry += ctot;
+    __syncthreads();  // s_warp is rewritten by the next pass; every thread has read active[] of this pass
+    if ((tid & 3u) == 0 && g < ng) active[g] = 0;
   }
-  for (uint32_t q = total + tid; q < ngn * 64; q += 256) {  // the empty lanes of the last new group
+  for (uint32_t q = total + tid; q < ngn * 64; q += 1024) {  // the empty lanes of the last new group
     groups[second_off + (q >> 6)].cb[q & 63u] = -1;
     src[q] = -1;
   }
-  for (uint32_t i = tid; i < cap; i += 256) active[second_off + i] = i < ngn ? 1 : 0;
+  for (uint32_t i = tid; i < cap; i += 1024) active[second_off + i] = i < ngn ? 1 : 0;
   if (tid == 0) *rg_state = rg_attempt;
 }
 

@@ -66,6 +66,7 @@ def lib():
         L.srsb200_tdec_batch.argtypes = [vp, u32, vp, vp, vp, vp, u64, u32, u32, i32, vp, vp, u64, vp, vp]
         L.srsb200_tdec_plan_uniform.argtypes = [vp, u32, u32, i32, C.POINTER(vp)]
         L.srsb200_plan_destroy.argtypes = [vp]
+        L.srsb200_plan_regroup_points.argtypes = [vp, vp, vp, C.c_uint32]
         L.srsb200_plan_destroy.restype = None
         L.srsb200_tdec_run_plan_dev.argtypes = [vp, vp, vp, u32, u32, i32, vp, vp, vp]
         L.srsb200_tdec_init.argtypes = [C.POINTER(vp), vp, u32]
@@ -322,6 +323,15 @@ class Engine:
 
     def plan_destroy(self, p):
         self._L.srsb200_plan_destroy(p)
+
+    def plan_regroup_points(self, p):
+        """per range of the plan's last device-resident decode: the half-iteration count after which its unfinished blocks were
+        regrouped (0: not); [] for plans that never regroup"""
+        pts = (C.c_uint32 * 16)()
+        r = self._L.srsb200_plan_regroup_points(self._h, p, pts, 16)
+        if r < 0:
+            _check(r, "srsb200_plan_regroup_points")
+        return list(pts)[:r]
 
     def run_plan_dev(self, plan, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok):
         _check(self._L.srsb200_tdec_run_plan_dev(self._h, plan, d_llr, max_iter, min_iter, int(early_stop), d_out, d_noi, d_ok),

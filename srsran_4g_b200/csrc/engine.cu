@@ -1001,6 +1001,21 @@ extern "C" void srsb200_plan_destroy(srsb200_plan_t* p)
   delete p;
 }
 
+extern "C" int srsb200_plan_regroup_points(srsb200_engine_t* e, srsb200_plan_t* plan, uint32_t* points, uint32_t n)
+{
+  if (!e || !plan || (!points && n)) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
+  for (uint32_t i = 0; i < n; i++) points[i] = 0;
+  if (!plan->n_new) return 0;
+  std::lock_guard<std::mutex> lk(e->mtx);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (join_pending(e)) return SRSB200_ERROR;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  uint32_t st[srsb200_engine::MAX_SUB];
+  CUDA_TRY(cudaMemcpy(st, plan->d_rg_state, sizeof(st), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n && i < (uint32_t)srsb200_engine::MAX_SUB; i++) points[i] = st[i];
+  return srsb200_engine::MAX_SUB;
+}
+
 extern "C" int srsb200_tdec_plan_uniform(srsb200_engine_t* e, uint32_t n, uint32_t K, int crc_kind, srsb200_plan_t** plan)
 {
   if (!e || !plan) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");

@@ -700,6 +700,52 @@ def test_bench_path_vs_oracle(sb, o):
         e.close()
 
 
+@pytest.mark.parametrize("mix", ["few_hard", "all_hard", "all_easy"])
+def test_regrouping_of_unfinished_blocks_vs_oracle(sb, o, mix):
+    """Plans of one block size with 64+ groups pack the unfinished code blocks of a range into fresh groups once few enough are
+    left (regroup_plan_kernel). Mixed difficulty: most blocks finish after two or three half-iterations, one in ten runs long or
+    never passes - every block of the batch is compared with the oracle (bytes, half-iteration count, CRC verdict). `all_hard`
+    never regroups (too many survivors), `all_easy` has nothing left at the first regrouping point."""
+    import torch
+    K, n = 1024, 64 * 70 + 9
+    dev = torch.device("cuda", 0)
+    e = sb.Engine(0)
+    try:
+        rng = np.random.default_rng(31)
+        bits, _ = vecgen.make_cb_batch(K, 24, 3.0, 777)
+        coded = np.stack([o.encode(b) for b in bits])
+        s = 2.0 * coded[rng.integers(0, 24, n)].astype(np.float64) - 1.0
+        hard = {"few_hard": rng.random(n) < 0.1, "all_hard": np.ones(n, bool), "all_easy": np.zeros(n, bool)}[mix]
+        eb = np.where(hard, rng.choice([0.2, 0.9, 1.3], n), 4.5)
+        sig = np.array([vecgen.sigma_for(x) for x in eb])[:, None]
+        llr = vecgen.quantise(s + sig * rng.standard_normal(s.shape), 60)
+        d_llr = torch.from_numpy(llr).to(dev)
+        plans = [e.plan_uniform(n, K, sb.CRC_24B) for _ in range(2)]
+        outs = [(torch.zeros((n, K // 8), dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev),
+                 torch.zeros(n, dtype=torch.uint8, device=dev)) for _ in range(2)]
+        for step in range(4):  # the second use of a plan starts from the slots the first one left behind
+            i = step % 2
+            e.run_plan_dev(plans[i], d_llr.data_ptr(), 8, 2, True, outs[i][0].data_ptr(), outs[i][1].data_ptr(), outs[i][2].data_ptr())
+        e.sync()
+        torch.cuda.synchronize()
+        _, oo, on, ook = o.tdec_batch(K, llr, 8, True, nthreads=os.cpu_count() or 4)
+        for out_t, noi_t, ok_t in outs:
+            out, noi, ok = out_t.cpu().numpy(), noi_t.cpu().numpy(), ok_t.cpu().numpy()
+            assert (on == noi).all(), np.flatnonzero(on != noi)[:10]
+            assert (ook == ok).all()
+            assert (oo == out).all(), np.flatnonzero((oo != out).any(axis=1))[:10]
+        pts = [e.plan_regroup_points(p) for p in plans]
+        if mix == "few_hard":
+            assert (on[~hard] <= 4).mean() > 0.9 and (on[hard] >= 6).mean() > 0.3  # the case the test is about
+            assert all(sum(1 for x in pp if x == 4) >= 3 for pp in pts), pts       # (nearly) every range regrouped at the first point
+        else:
+            assert all(not any(pp) for pp in pts), pts
+        for p in plans:
+            e.plan_destroy(p)
+    finally:
+        e.close()
+
+
 # ---------------------------------------------------------------- robustness of the C ABI (VERDICT r01 weak 9-11, ADVICE r01)
 def test_decode_tb_batch_error_paths_fault_injection(sb, o):
     """srsb200_engine_inject_alloc_failure: whichever scratch request of a transport-block submission fails, the call returns an

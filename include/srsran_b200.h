@@ -59,6 +59,9 @@ uint64_t srsb200_engine_launch_count(const srsb200_engine_t* e);
  * of launches (the sub-batch overlap of srsb200_engine_set_subbatches is off) so the durations are not inflated. */
 int srsb200_engine_profile(srsb200_engine_t* e, int enable);
 int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[8]);
+/* the same with room for the kinds added later: 8 UL-SCH de-interleaver, 9 soft demodulation / descrambling / gather, 10 regrouping
+ * of unfinished code blocks (with n_kinds = 8 these are reported under 3, 3 and 0 as before) */
+int srsb200_engine_profile_read_kinds(srsb200_engine_t* e, double* ms, uint64_t* cnt, uint32_t n_kinds);
 /* host-pointer submissions of a contiguous equal-size batch are cut into this many ranges whose H2D / decode / D2H
  * overlap on separate streams (default 8, env SRSB200_SUBBATCHES; 1 = off) */
 int srsb200_engine_set_subbatches(srsb200_engine_t* e, int n);

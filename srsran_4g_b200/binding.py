@@ -58,6 +58,7 @@ def lib():
         L.srsb200_engine_set_subbatches.argtypes = [vp, i32]
         L.srsb200_engine_inject_alloc_failure.argtypes = [vp, i32]
         L.srsb200_engine_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.srsb200_engine_profile_read_kinds.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), C.c_uint32]
         L.srsb200_cbsize.argtypes = [u32]
         L.srsb200_cbindex.argtypes = [u32]
         L.srsb200_cbsegm.argtypes = [u32, C.POINTER(u32)]
@@ -257,10 +258,10 @@ class Engine:
 
     def profile_read(self):
         """-> {kernel kind: (summed ms, launches)} since the last read; kinds: extract, decode, emit, rm, tbcrc"""
-        ms = (C.c_double * 8)()
-        cnt = (C.c_uint64 * 8)()
-        _check(self._L.srsb200_engine_profile_read(self._h, ms, cnt), "srsb200_engine_profile_read")
-        names = ["extract", "decode", "emit", "rm", "tbcrc", "scan", "job", "tbenc"]
+        ms = (C.c_double * 11)()
+        cnt = (C.c_uint64 * 11)()
+        _check(self._L.srsb200_engine_profile_read_kinds(self._h, ms, cnt, 11), "srsb200_engine_profile_read_kinds")
+        names = ["extract", "decode", "emit", "rm", "tbcrc", "scan", "job", "tbenc", "deint", "demod", "regroup"]
         return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names)}
 
     # ---- batched decode, host buffers

@@ -735,25 +735,28 @@ extern "C" int srsb200_engine_profile(srsb200_engine_t* e, int enable)
 }
 // ms[kind] += elapsed, cnt[kind] += launches; kinds: 0 extract, 2 emit, 3 rate-dematch, 4 tb-crc, 5 scan, 6 job, 7 tb-encode.
 // Synchronises. While profiling is on, decodes run as a single chain (no sub-batch overlap).
-extern "C" int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[8])
+extern "C" int srsb200_engine_profile_read_kinds(srsb200_engine_t* e, double* ms, uint64_t* cnt, uint32_t n_kinds)
 {
-  if (!e) return SRSB200_ERROR_INVALID_INPUTS;
+  if (!e || !ms || !cnt) return SRSB200_ERROR_INVALID_INPUTS;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
   if (join_pending(e)) return SRSB200_ERROR;
   CUDA_TRY(cudaStreamSynchronize(e->stream));
-  for (int i = 0; i < 8; i++) { ms[i] = 0; cnt[i] = 0; }
+  for (uint32_t i = 0; i < n_kinds; i++) { ms[i] = 0; cnt[i] = 0; }
   for (auto& p : e->prof) {
     float t = 0;
     cudaEventElapsedTime(&t, p.a, p.b);
-    ms[p.kind & 7] += t;
-    cnt[p.kind & 7]++;
+    // kinds the caller's arrays have no room for are folded into the kind they belonged to before they were split off
+    uint32_t k = (uint32_t)p.kind;
+    if (k >= n_kinds) k = (k == 10) ? 0u : 3u;
+    if (k < n_kinds) { ms[k] += t; cnt[k]++; }
     cudaEventDestroy(p.a);
     cudaEventDestroy(p.b);
   }
   e->prof.clear();
   return SRSB200_SUCCESS;
 }
+extern "C" int srsb200_engine_profile_read(srsb200_engine_t* e, double ms[8], uint64_t cnt[8]) { return srsb200_engine_profile_read_kinds(e, ms, cnt, 8); }
 
 extern "C" int srsb200_engine_set_subbatches(srsb200_engine_t* e, int n)
 {
@@ -1086,7 +1089,7 @@ static void launch_one(srsb200_engine* e, srsb200_plan* p, const RangeArgs& r, i
     case 3: {
       // regrouping point after half-iteration n (0-based): plan, then - only if the plan kernel regrouped - the channel streams
       // and the state stream of the new groups. n even: the last half-iteration was a DEC1, its output app2 carries the state
-      ProfScope ps(e, 0, st);  // (profiled with the extract kernel: layout work)
+      ProfScope ps(e, 10, st);
       const uint32_t attempt = n + 1;
       regroup_plan_kernel<<<1, 1024, 0, st>>>(p->d_groups + r.g0, ng0, so, r.cap, da, p->d_done, p->d_home, p->d_src + 64ull * (r.slot0 - p->n_groups), rgs, attempt);
       extract_kernel<<<dim3(p->max_R / XT, r.cap), 256, 0, st>>>(p->d_groups + r.slot0, p->d_ws, d_llr, p->d_llr_off, p->d_active + r.slot0, p->d_done,
@@ -1580,7 +1583,7 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
   CUDA_TRY(stg.flush(e->stream));
   CUDA_TRY(cudaMemsetAsync(d_g, 0, ng * sizeof(int16_t), e->stream));  // the nof_ri_bits values past the data are left stale by the reference
   {
-    ProfScope ps(e, 3);
+    ProfScope ps(e, 8);
     ulsch_deint_kernel<<<dim3(1, std::max(1u, std::min<uint32_t>(128u, (j.rows + DT_ROWS - 1) / DT_ROWS))), 256, 0, e->stream>>>((const DeintJob*)d_dj);
     e->launches++;
   }
@@ -1615,7 +1618,7 @@ extern "C" int srsb200_demod_soft_demodulate_s(srsb200_engine_t* e, uint32_t mod
   CUDA_TRY(stg.h2d(d_job, &j, sizeof(j), e->stream));
   CUDA_TRY(stg.flush(e->stream));
   {
-    ProfScope ps(e, 3);
+    ProfScope ps(e, 9);
     demod_kernel<<<dim3(std::max(1u, std::min(1024u, (nsymbols + 255) / 256)), 1), 256, 0, e->stream>>>((const DemodJob*)d_job);
     e->launches++;
   }

@@ -68,7 +68,7 @@ __device__ __forceinline__ uint32_t warp_gold_jump(const uint32_t* __restrict__ 
 // gold = jump matrices of the two LFSRs ([2][GOLD_POWERS][32] words), only read by jobs with scramble != 0
 // SCR = false: no job of the launch descrambles (the sequence staging and the sign test are compiled out)
 template <bool SCR>
-__global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restrict__ jobs, const uint32_t* __restrict__ gold)
+__global__ void __launch_bounds__(RM_THREADS, 4) rm_rx_kernel(const RmJob* __restrict__ jobs, const uint32_t* __restrict__ gold)
 {
   extern __shared__ __align__(16) int16_t se_raw[];
   __shared__ uint32_t sc[SCR ? RM_SC_WORDS : 1];
@@ -108,9 +108,17 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
     }
   }
   __syncthreads();
+  // The staged copy is read through its 32-bit shared-memory address, computed once: through the shifted generic pointer the
+  // compiler rebuilt the shared window base (S2R + MOV + LEA) in front of every predicated load - 20 instructions per LLR, 6 now.
+  const uint32_t se_addr = (uint32_t)__cvta_generic_to_shared(se);
+  auto lds16 = [&](uint32_t i) -> uint32_t {
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(se_addr + 2u * i));
+    return v;
+  };
   // one received LLR (descrambled if asked for). STAGED: every i < E lies in shared memory (E <= RM_SMEM_ELEMS, the usual case)
   auto llr = [&](uint32_t i, auto staged) -> uint32_t {
-    uint32_t v = (uint16_t)((decltype(staged)::value || i < ns) ? se[i] : j.e[i]);
+    uint32_t v = (decltype(staged)::value || i < ns) ? lds16(i) : (uint32_t)(uint16_t)j.e[i];
     if (SCR && j.scramble) {
       uint32_t c;
       if ((i >> 5) < RM_SC_WORDS) {
@@ -134,8 +142,8 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_kernel(const RmJob* __restri
   const bool     wide = ((reinterpret_cast<uintptr_t>(j.buf) | reinterpret_cast<uintptr_t>(j.table)) & 15u) == 0;
   const uint32_t L8   = wide ? j.L / 8 : 0u;
   auto rmw = [&](auto staged) {
-    // two uint4 per thread and trip: both table loads and both old values are in flight before the first shared-memory read
-    constexpr int U = 2;
+    // U uint4 per thread and trip: the table loads and the old values are in flight before the first shared-memory read
+    constexpr int U = 1;  // (two per trip - four 128-bit loads in flight per thread - measured slower: 0.163 against 0.127 ms)
     for (uint32_t p0 = threadIdx.x; p0 < L8; p0 += U * nthr) {
       uint4 tt[U], old[U];
 #pragma unroll
@@ -253,14 +261,15 @@ struct DeintJob {
 // them, go item by item with the rank found by binary search. Round 1 let every thread read its Qm values straight from q
 // (12 bytes out of every 32-byte sector per request): 1.5 TB/s; 32-row tiles with per-item stores: 2.1 TB/s.
 // grid = (jobs, tiles per job: any number >= 1, tiles are strided over gridDim.y), block = 256
-constexpr int DT_ROWS = 128;  // 32 / 64 / 128 rows per tile: 2.1 / 2.7-3.1 / see profiles TB/s on 512 transport blocks (bytes in flight per SM)
+constexpr int DT_ROWS = 64;   // 32 / 64 / 128 rows per tile: 2.1 / 2.7-3.1 / 2.4 TB/s on 512 transport blocks
 constexpr int DT_MAXC = 14;  // columns = PUSCH symbols carrying data: 12 (normal CP), 10 / 11 with SRS or extended CP
 // floor(n / d) = umulhi(n, magic) while n * d < 2^32 and d >= 2; magic 0 stands for d = 1
 __device__ __forceinline__ uint32_t dt_magic(uint32_t d) { return d < 2 ? 0u : 0xffffffffu / d + 1u; }
 __device__ __forceinline__ uint32_t dt_div(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
 __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __restrict__ jobs)
 {
-  __shared__ __align__(16) int16_t tile[DT_MAXC][DT_ROWS * 8 + 2];
+  constexpr int  PITCH = DT_ROWS * 8 + 8;  // int16 per tile row: a multiple of 8 (128-bit shared stores), 260 words = 4 mod 32 banks
+  __shared__ __align__(16) int16_t tile[DT_MAXC][PITCH];
   const DeintJob j = jobs[blockIdx.x];
   const uint32_t ntiles = (j.rows + DT_ROWS - 1) / DT_ROWS;
   const bool     tiled  = j.cols <= DT_MAXC && j.Qm <= 8 && (j.Qm & 1u) == 0 && ((reinterpret_cast<uintptr_t>(j.q) & 3u) == 0) && ((j.rows * j.Qm) & 1u) == 0;
@@ -274,15 +283,37 @@ __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __rest
     if (tiled) {
       __syncthreads();  // the previous tile has been written out
       const uint32_t rw = run / 2, nw = j.cols * rw, m_rw = dt_magic(rw);  // 32-bit words per column run
-      constexpr int UN = 8;  // loads in flight per thread
-      for (uint32_t i0 = threadIdx.x; i0 < nw; i0 += 256 * UN) {
+      constexpr int UN = 4;  // loads in flight per thread
+      // 128-bit loads when every column run of the tile starts and ends on a 16-byte boundary (the per-word index arithmetic of
+      // the 32-bit version made this kernel issue-bound: sm instruction throughput 73 %, DRAM 25 % in the ncu capture)
+      const bool vec = (run & 7u) == 0 && ((j.rows * j.Qm) & 7u) == 0 && ((row0 * j.Qm) & 7u) == 0 && (reinterpret_cast<uintptr_t>(j.q) & 15u) == 0;
+      if (vec) {
+        const uint32_t rv = run / 8, nv = j.cols * rv, m_rv = dt_magic(rv);  // uint4 per column run
+        for (uint32_t i0 = threadIdx.x; i0 < nv; i0 += 256 * UN) {
+          uint4    v[UN];
+          uint32_t at[UN];
+#pragma unroll
+          for (int u = 0; u < UN; u++) {
+            const uint32_t idx = i0 + 256 * u;
+            if (idx < nv) {
+              const uint32_t col = dt_div(idx, m_rv), wq = idx - col * rv;
+              at[u] = col * PITCH + 8 * wq;
+              v[u]  = __ldg(reinterpret_cast<const uint4*>(j.q + (size_t)col * j.rows * j.Qm + (size_t)row0 * j.Qm) + wq);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UN; u++)
+            if (i0 + 256 * u < nv) *reinterpret_cast<uint4*>(&tile[0][0] + at[u]) = v[u];
+        }
+      }
+      for (uint32_t i0 = threadIdx.x; i0 < (vec ? 0u : nw); i0 += 256 * UN) {
         uint32_t v[UN], at[UN];
 #pragma unroll
         for (int u = 0; u < UN; u++) {
           const uint32_t idx = i0 + 256 * u;
           if (idx < nw) {
             const uint32_t col = dt_div(idx, m_rw), wq = idx - col * rw;
-            at[u] = col * (DT_ROWS * 8 + 2) + 2 * wq;
+            at[u] = col * PITCH + 2 * wq;
             v[u]  = __ldg(reinterpret_cast<const uint32_t*>(j.q + (size_t)col * j.rows * j.Qm + (size_t)row0 * j.Qm) + wq);
           }
         }
@@ -303,6 +334,26 @@ __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __rest
       if (fast) {
         uint32_t*      dst = reinterpret_cast<uint32_t*>(j.g) + (s_lo - c0) / 2;
         const uint32_t now = nr * line_w;
+        if ((now & 3u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+          // four consecutive words per thread, one 128-bit store: the (row, column, word) position is divided out once and then
+          // stepped
+          for (uint32_t w4 = threadIdx.x; w4 < now / 4; w4 += 256) {
+            const uint32_t w = 4 * w4;
+            uint32_t       r = dt_div(w, m_line), rem = w - r * line_w, col = dt_div(rem, m_item), k = rem - col * item_w;
+            uint32_t       v[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              v[i] = *reinterpret_cast<const uint32_t*>(&tile[col][r * j.Qm + 2 * k]);
+              if (++k == item_w) {
+                k = 0;
+                if (++col == j.cols) { col = 0; r++; }
+              }
+            }
+            if (w == 0 && s_lo == c0) v[0] = (v[0] & 0xffff0000u) | (uint16_t)j.q[j.p_star];  // g[0]: see above
+            reinterpret_cast<uint4*>(dst)[w4] = make_uint4(v[0], v[1], v[2], v[3]);
+          }
+          continue;
+        }
         for (uint32_t w = threadIdx.x; w < now; w += 256) {
           const uint32_t r = dt_div(w, m_line), rem = w - r * line_w, col = dt_div(rem, m_item), k = rem - col * item_w;
           uint32_t       v = *reinterpret_cast<const uint32_t*>(&tile[col][r * j.Qm + 2 * k]);

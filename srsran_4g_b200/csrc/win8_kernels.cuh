@@ -572,7 +572,13 @@ __global__ void __launch_bounds__(RM8_THREADS) rm_rx8_kernel(const RmJob8* __res
   }
   __syncthreads();
   const uint32_t reps = (j.E + j.L - 1) / j.L;  // block-uniform trip count over the repetitions (1 without repetition)
-  auto llr = [&](uint32_t i) -> uint32_t { return (uint8_t)(i < ns ? se[i] : j.e[i]); };
+  const uint32_t se_addr = (uint32_t)__cvta_generic_to_shared(se);  // (see rm_rx_kernel: one address computation, not one per load)
+  auto llr = [&](uint32_t i) -> uint32_t {
+    if (i >= ns) return (uint8_t)j.e[i];
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(se_addr + i));
+    return v;
+  };
   // four soft-buffer positions (one 32-bit word, L = 3K + 12 is a multiple of 4) per thread: 64-bit table load, wrapping byte adds
   const bool     wide = (reinterpret_cast<uintptr_t>(j.buf) & 3u) == 0 && (reinterpret_cast<uintptr_t>(j.table) & 7u) == 0;
   const uint32_t L4   = wide ? j.L / 4 : 0u;

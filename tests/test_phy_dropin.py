@@ -140,7 +140,6 @@ def test_dlsch_decode2_8bit_mode_on_the_engine(phy):
     flags AND the average half-iteration count equal the oracle's 8-bit loop (itself pinned to the literal sch.c with llr_is_8bit)
     over a HARQ sequence at an operating point where the first transmission fails; smaller blocks stay in sch.c's own loop."""
     o = ol.oracle()
-    ref = ol.ref()
     for tbs, Qm, G, eb in [(75376, 6, 86400, 1.0), (36696, 6, 6 * 8000, 0.3), (12960, 4, 4 * 5000, 0.5)]:
         h = phy.dlsch_rx_new()
         st = None
@@ -173,13 +172,11 @@ def test_dlsch_decode2_8bit_mode_on_the_engine(phy):
         finally:
             phy.dlsch_rx_free(h)
         assert b["ret"] == 0 and b["tb_crc"] == 1 and np.array_equal(b["data"][:tbs // 8], payload[:tbs // 8])
-        if ref is not None:
-            hc = ref.dlsch_rx_new()
-            try:
-                c = ref.dlsch_decode8(hc, tbs, Qm, 0, e8, 8)
-            finally:
-                ref.dlsch_rx_free(hc)
-            assert c["ret"] == b["ret"] and c["tb_crc"] == b["tb_crc"] and np.array_equal(c["data"][:tbs // 8], b["data"][:tbs // 8])
+        # (No comparison with the literal reference here: for 400 < K <= 800 its 8-bit mode falls back to the 16-bit windowed
+        #  decoder through convert_8_to_16(input, h->input_conv, 3 * K + 12) - turbodecoder.c:477-480 - while the rate de-matcher
+        #  has written the sub-block layout, 3 * (K + 32) + 12 values: the end of the second parity stream and the 12 termination
+        #  values are read from memory nobody initialised. MALLOC_PERTURB_=1 turns its CRC pass into a failure; the result is
+        #  not a function of the input, so it is no parity target.)
 
 
 def test_calls_from_several_threads(phy):

@@ -40,8 +40,7 @@ for ul in (False, True):
         out["rm_ms_launches"] = p["rm"]
     else:
         de_bytes = n_tb * G * 2 * 2
-        rm_ms = out["rm_rx_kernel"]["ms"]
-        de_ms = p["rm"][0] - rm_ms                                # kind 3 = rate de-matching + de-interleaver launches
+        de_ms = p["deint"][0]
         out["ulsch_deint_kernel"] = {"ms": de_ms, "algorithmic_MB": de_bytes / 1e6, "GBps": de_bytes / max(de_ms, 1e-6) / 1e6, "frac_of_hbm_peak": de_bytes / max(de_ms, 1e-6) / 1e6 / 6542.1}
 # descrambling fused into the rate de-matcher: same submission with descramble / c_init set on every TB
 import ctypes as C

@@ -468,6 +468,93 @@ def main():
                 "api": "srsb200_tdec_batch8 (int8 LLRs, scale 12; host pointers, pinned, synchronous) from %d host thread(s); the reference's windowed "
                        "saturating int8 decoder (32 windows at K=6144) reproduced bit for bit - a weaker decoder than the int16 one, hence more half-iterations" % T}
 
+    # ------------------------------------------------------------------ transport blocks end to end (secondary: BASELINE config 5)
+    # 64 cells x one 100-PRB 64QAM uplink transport block (TBS 75376 = 13 code blocks of K=5824, G = 86400 e-bits) per subframe
+    # through srsb200_decode_tb_batch: e-bits from host memory, rate de-matching + HARQ soft buffers resident on the device (reset
+    # every subframe: new data), decode, TB CRC, payload bytes back - 2.3 bytes over PCIe per information bit. Four host threads
+    # with one engine each, the way PHY workers call it. Vectors from the engine's own encoder + AWGN; every payload is checked.
+    e2e_tb = None
+    if not args.no_e2e:
+        import ctypes as C
+        from srsran_4g_b200.binding import _TbStruct
+        L = sb.lib()
+        tbs_t, G_t, Qm_t, cells, T = 75376, 86400, 6, 64, 4
+        rng_t = np.random.default_rng(77 + rank)
+        enc = sb.Engine(local_rank)
+        payloads = [rng_t.integers(0, 256, tbs_t // 8, dtype=np.uint8) for _ in range(4)]
+        e_llr = []
+        for pl in payloads:
+            r_, eb_ = enc.encode_tb(tbs_t, Qm_t, 0, G_t, pl)
+            if r_ != 0:
+                raise SystemExit("encode_tb failed: %s" % L.srsb200_last_error().decode())
+            sym = 2.0 * np.unpackbits(eb_)[:G_t].astype(np.float64) - 1.0
+            e_llr.append(np.clip(np.trunc(40.0 * (sym + 0.42 * rng_t.standard_normal(G_t))), -32768, 32767).astype(np.int16))
+        enc.close()
+        engs_t = [sb.Engine(local_rank) for _ in range(T)]
+        sets = []
+        for t in range(T):
+            engs_t[t].softbuffer_set_resident(True)
+            tbl = [sb.TransportBlock(tbs_t) for _ in range(cells)]
+            arr = (_TbStruct * cells)()
+            for c, (st_, tb) in enumerate(zip(arr, tbl)):
+                tb.fill(st_, Qm_t, 0, e_llr[c % 4])
+            sets.append((tbl, arr, [(tb._bf, tb.max_cb) for tb in tbl]))
+
+        def tb_step(t):
+            tbl, arr, rst = sets[t]
+            h_ = engs_t[t].handle
+            for bf, mc in rst:  # new data in every cell: srsran_softbuffer_rx_reset forwarded to the device mirror
+                L.srsb200_softbuffer_reset(h_, bf, mc)
+            for tb in tbl:
+                tb.cb_crc.fill(0)
+            if L.srsb200_decode_tb_batch(engs_t[t].handle, arr, cells, args.max_iter) != 0:
+                raise SystemExit("srsb200_decode_tb_batch failed: %s" % L.srsb200_last_error().decode())
+
+        for t in range(T):
+            tb_step(t)
+            tb_step(t)
+            tbl, arr, _ = sets[t]
+            for c, st_ in enumerate(arr):
+                if st_.ret != 0 or not np.array_equal(tbl[c].data[:tbs_t // 8], payloads[c % 4]):
+                    raise SystemExit("e2e_tb: transport block %d of thread %d did not decode to its payload" % (c, t))
+        sub_per_thread = 25
+        if dist is not None:
+            dist.barrier()
+        start_t = threading.Barrier(T + 1)
+        errs_t = []
+
+        def worker_t(t):
+            try:
+                start_t.wait()
+                for _ in range(sub_per_thread):
+                    tb_step(t)
+            except BaseException as ex:  # noqa: BLE001
+                errs_t.append(ex)
+
+        ths = [threading.Thread(target=worker_t, args=(t,)) for t in range(T)]
+        for th in ths:
+            th.start()
+        start_t.wait()
+        t0 = time.perf_counter()
+        for th in ths:
+            th.join()
+        dt_t = time.perf_counter() - t0
+        if errs_t:
+            raise SystemExit("e2e_tb worker failed: %r" % errs_t[0])
+        noi_t = float(np.mean([sets[0][0][c].cb_noi[:13].mean() for c in range(cells)]))
+        for e_ in engs_t:
+            e_.close()
+        if dist is not None:
+            tt = torch.tensor([dt_t], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt_t = float(tt.item())
+        nsub = T * sub_per_thread
+        e2e_tb = {"value": world * nsub * cells * tbs_t / dt_t / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": cells * G_t * 2, "d2h_bytes_per_step": cells * (tbs_t // 8 + 13 + 14),
+                  "bytes_over_pcie_per_info_bit": (cells * G_t * 2 + cells * (tbs_t // 8 + 27)) / float(cells * tbs_t), "steps": nsub,
+                  "ms_per_step": dt_t / nsub * 1e3, "host_threads": T, "mean_half_iterations": noi_t,
+                  "workload": "step = one subframe of %d cells x TBS %d (13 code blocks of K=5824, 64QAM, G=%d), HARQ soft buffers resident on the device" % (cells, tbs_t, G_t),
+                  "api": "srsb200_decode_tb_batch (rate de-matching + soft combining + decode + TB CRC) from %d host threads with one engine each; aggregate" % T}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -534,6 +621,8 @@ def main():
         out["e2e"] = e2e
     if e2e8 is not None:
         out["e2e_llr8"] = e2e8
+    if e2e_tb is not None:
+        out["e2e_tb"] = e2e_tb
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = run_cpu(args.max_iter, 10.0, 4321)
     print(json.dumps(out))

@@ -185,8 +185,8 @@ struct srsb200_engine {
   uint16_t* d_rm_inv[LTE_NOF_CB_SIZES][4];  // Tinv (receive side: soft-buffer position p collects e[Tinv[p] + kL])
 
   // scratch for the host-pointer APIs (grown on demand)
-  void*  d_scratch[16]   = {nullptr};  // 0-7 receive side, 8-11 transmit side, 12-13 UL-SCH de-interleaver
-  size_t scratch_cap[16] = {0};
+  void*  d_scratch[20]   = {nullptr};  // 0-7 receive side, 8-11 transmit side, 12-15 UL-SCH de-interleaver / demodulation, 16 reset list
+  size_t scratch_cap[20] = {0};
   uint32_t* d_crc24b_words = nullptr;  // x^(m+24) mod g24B, m < 6144 (tx_cb_kernel)
   uint32_t* d_gold = nullptr;          // jump matrices of the scrambling LFSRs [2][GOLD_POWERS][32] (rm_rx_kernel)
   uint32_t  h_gold[2][GOLD_POWERS][32];
@@ -208,6 +208,7 @@ struct srsb200_engine {
   cudaStream_t sub[MAX_SUB] = {nullptr};
   cudaEvent_t  ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
 
+  std::vector<int16_t*> pending_zero;  // soft-buffer mirrors reset since the last submission (zeroed in front of the next use)
   int fail_alloc_countdown = 0;  // > 0: the n-th ensure_scratch call from now fails (tests of the error paths)
   // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
   bool profiling = false;
@@ -525,6 +526,27 @@ static int softslot_get(srsb200_engine* e, const void* host, int16_t** out, bool
   return 0;
 }
 
+// srsb200_softbuffer_reset only notes which mirrors to zero; one kernel zeroes them in front of the next operation that reads or
+// writes a mirror (a transport-block submission, a copy back to the host, a release). A reset per transport block used to cost a
+// launch and a stream synchronisation each - 64 of them per subframe in the multi-cell case, more host time than the decode.
+static int flush_pending_zero(srsb200_engine* e)
+{
+  if (e->pending_zero.empty()) return 0;
+  const uint32_t n = (uint32_t)e->pending_zero.size();
+  void* d_list;
+  if (ensure_scratch(e, 16, sizeof(int16_t*) * n, &d_list)) return SRSB200_ERROR;
+  // (pageable source: cudaMemcpyAsync returns once the list has been staged, so the vector may be cleared right away)
+  CUDA_TRY(cudaMemcpyAsync(d_list, e->pending_zero.data(), sizeof(int16_t*) * n, cudaMemcpyHostToDevice, e->stream));
+  for (uint32_t c0 = 0; c0 < n; c0 += 65535u) {  // gridDim.y <= 65535
+    zero_slots_kernel<<<dim3((SOFTSLOT_ELEMS / 8 + 255) / 256, std::min(65535u, n - c0)), 256, 0, e->stream>>>((int16_t* const*)d_list + c0,
+                                                                                                           (uint32_t)(SOFTSLOT_ELEMS / 8));
+    e->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  e->pending_zero.clear();
+  return 0;
+}
+
 extern "C" int srsb200_softbuffer_set_resident(srsb200_engine_t* e, int resident)
 {
   if (!e) return SRSB200_ERROR_NO_DEVICE;
@@ -539,21 +561,11 @@ extern "C" int srsb200_softbuffer_reset(srsb200_engine_t* e, int16_t** buffer_f,
   if (!buffer_f) return SRSB200_ERROR_INVALID_INPUTS;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
-  if (join_pending(e)) return SRSB200_ERROR;
-  // one kernel zeroes every listed mirror (a cudaMemsetAsync per code block costs more host time than the decode)
-  std::vector<int16_t*> list(nof_cb);
-  for (uint32_t i = 0; i < nof_cb; i++)
-    if (softslot_get(e, buffer_f[i], &list[i], false)) return SRSB200_ERROR;
-  if (nof_cb == 0) return SRSB200_SUCCESS;
-  void* d_list;
-  if (ensure_scratch(e, 5, sizeof(int16_t*) * nof_cb, &d_list)) return SRSB200_ERROR;
-  CUDA_TRY(cudaMemcpyAsync(d_list, list.data(), sizeof(int16_t*) * nof_cb, cudaMemcpyHostToDevice, e->stream));
-  for (uint32_t c0 = 0; c0 < nof_cb; c0 += 65535u) {  // gridDim.y <= 65535
-    zero_slots_kernel<<<dim3((SOFTSLOT_ELEMS / 8 + 255) / 256, std::min(65535u, nof_cb - c0)), 256, 0, e->stream>>>((int16_t* const*)d_list + c0,
-                                                                                                                 (uint32_t)(SOFTSLOT_ELEMS / 8));
-    e->launches++;
+  for (uint32_t i = 0; i < nof_cb; i++) {
+    int16_t* d = nullptr;
+    if (softslot_get(e, buffer_f[i], &d, false)) return SRSB200_ERROR;
+    e->pending_zero.push_back(d);
   }
-  CUDA_TRY(cudaStreamSynchronize(e->stream));  // `list` (pageable) must stay alive until the copy has been issued and consumed
   return SRSB200_SUCCESS;
 }
 
@@ -564,6 +576,7 @@ extern "C" int srsb200_softbuffer_sync_to_host(srsb200_engine_t* e, int16_t** bu
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
   if (join_pending(e)) return SRSB200_ERROR;
+  if (flush_pending_zero(e)) return SRSB200_ERROR;
   for (uint32_t i = 0; i < nof_cb; i++) {
     auto it = e->softslots.find(buffer_f[i]);
     if (it != e->softslots.end())
@@ -578,9 +591,11 @@ extern "C" int srsb200_softbuffer_release(srsb200_engine_t* e, int16_t** buffer_
   if (!e) return SRSB200_ERROR_NO_DEVICE;
   if (!buffer_f) return SRSB200_ERROR_INVALID_INPUTS;
   std::lock_guard<std::mutex> lk(e->mtx);
+  // a released mirror may be handed to another soft buffer before the next submission: it must not be zeroed under its new owner
   for (uint32_t i = 0; i < nof_cb; i++) {
     auto it = e->softslots.find(buffer_f[i]);
     if (it != e->softslots.end()) {
+      e->pending_zero.erase(std::remove(e->pending_zero.begin(), e->pending_zero.end(), it->second), e->pending_zero.end());
       e->softslot_free.push_back(it->second);
       e->softslots.erase(it);
     }

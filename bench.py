@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (one engine each) calling the synchronous host-pointer API")
     ap.add_argument("--no-pipeline", action="store_true", help="one plan: every step waits for the previous one to finish completely")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--plans", type=int, default=2, help="plans (workspaces) used alternately by the device-resident leg; the engine pipelines consecutive submissions of different plans")
     ap.add_argument("--no-llr8", action="store_true", help="skip the 8-bit LLR leg (e2e_llr8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -232,7 +233,7 @@ def main():
     torch.cuda.synchronize()
     # two plans (each owns a workspace and its outputs) used alternately: consecutive steps are pipelined by the engine -
     # the latency-bound last half-iterations of step i overlap the first ones of step i+1 (include/srsran_b200.h)
-    NPLAN = 1 if args.no_pipeline else 2
+    NPLAN = 1 if args.no_pipeline else max(1, args.plans)
     outs = [(torch.zeros((n_cb, K // 8), dtype=torch.uint8, device=dev), torch.zeros(n_cb, dtype=torch.uint8, device=dev),
              torch.zeros(n_cb, dtype=torch.uint8, device=dev)) for _ in range(NPLAN)]
     plans = [eng.plan_uniform(n_cb, K, sb.CRC_24B) for _ in range(NPLAN)]

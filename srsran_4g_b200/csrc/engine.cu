@@ -202,7 +202,7 @@ struct srsb200_engine {
   // Device-resident submissions run on one of two LANES (one half of sub[] each; a plan is bound to a lane when it is built)
   // and are joined back into `stream` lazily (join_pending): the latency-bound last half-iterations of one submission
   // then overlap the bandwidth-bound first ones of the next submission of ANOTHER plan (+11 % on the bench workload).
-  static const int N_LANES = 2;
+  int          n_lanes = 2;    // env SRSB200_LANES (1..4): MAX_SUB / n_lanes streams each
   int          next_lane = 0;
   bool         pending[MAX_SUB] = {false};
   cudaStream_t sub[MAX_SUB] = {nullptr};
@@ -686,6 +686,7 @@ extern "C" int srsb200_engine_create(srsb200_engine_t** out, int device)
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   if (const char* env = getenv("SRSB200_FAIL_ALLOC")) e->fail_alloc_countdown = std::max(0, atoi(env));
   if (const char* env = getenv("SRSB200_SUBBATCHES")) e->n_sub = std::max(1, std::min((int)srsb200_engine::MAX_SUB, atoi(env)));
+  if (const char* env = getenv("SRSB200_LANES")) e->n_lanes = std::max(1, std::min(4, atoi(env)));
   if (const char* env = getenv("SRSB200_SUBBATCHES_DEV")) e->n_sub_dev = std::max(1, std::min((int)srsb200_engine::MAX_SUB, atoi(env)));
   for (int i = 0; i < srsb200_engine::MAX_SUB; i++) {
     CUDA_TRY(cudaStreamCreateWithFlags(&e->sub[i], cudaStreamNonBlocking));
@@ -902,7 +903,7 @@ static int build_plan(srsb200_engine* e, uint32_t n, const uint32_t* K, const ui
   srsb200_plan* p = new srsb200_plan();
   p->e            = e;
   p->lane         = e->next_lane;
-  e->next_lane    = (e->next_lane + 1) % srsb200_engine::N_LANES;
+  e->next_lane    = (e->next_lane + 1) % e->n_lanes;
   p->n_cb         = n;
   uint64_t off    = 0;
   for (auto& kv : buckets) {
@@ -1149,8 +1150,8 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
   uint32_t S = 1;
   if (!e->profiling) S = std::max(1u, std::min((uint32_t)(io ? e->n_sub : e->n_sub_dev), p->n_groups / 16u));
   if (e->profiling) lazy = false;
-  const uint32_t sbase = lazy ? (uint32_t)p->lane * (srsb200_engine::MAX_SUB / srsb200_engine::N_LANES) : 0u;
-  if (lazy) S = std::min(S, (uint32_t)(srsb200_engine::MAX_SUB / srsb200_engine::N_LANES));
+  const uint32_t sbase = lazy ? (uint32_t)p->lane * (uint32_t)(srsb200_engine::MAX_SUB / e->n_lanes) : 0u;
+  if (lazy) S = std::min(S, (uint32_t)(srsb200_engine::MAX_SUB / e->n_lanes));
   RangeArgs rg[srsb200_engine::MAX_SUB];
   // Host-pointer submissions end with the decode of the LAST range after the last copy has landed, and a decode has a
   // latency floor of ~1 ms however small it is (sequential recursions) - so the ranges shrink geometrically towards the

@@ -120,7 +120,50 @@ def one_pdsch():
         rq.append((tb, Qm, 0, reqs_tx[cw][1][0]))
     eng.decode_tb_batch(rq, 8)
 dt = timeit(one_pdsch, reps=10)
-res["config3_pdsch_2cw_steady"] = {"ms_per_subframe_host_to_host": dt * 1e3, "info_Mbit_s": 2 * tbs / dt / 1e6, "code_blocks": 26}
+res["config3_pdsch_2cw_steady"] = {"ms_per_subframe_host_to_host": dt * 1e3, "info_Mbit_s": 2 * tbs / dt / 1e6, "code_blocks": 26,
+                                   "h2d_bytes_per_info_bit": 2 * (G * 2 + 16 * 18600 * 2) / float(2 * tbs),
+                                   "note": "host-coherent soft buffers: 16 x 18600 int16 per codeword cross PCIe both ways on top of the e-bits"}
+
+# ---- config 3 from equalised SYMBOLS: pdsch.c:693-740 - soft demodulation, descrambling, rate de-matching, decode - in
+# one submission; the LLRs never exist on the host. 8 bytes per resource element in instead of 2 bytes per LLR (12 per 64QAM RE).
+import ctypes as C
+from srsran_4g_b200.binding import _TbStruct
+def modulate64(bits):
+    b = 1.0 - 2.0 * np.asarray(bits, np.float64).reshape(-1, 6)
+    ax = lambda c0: b[:, c0] * (4.0 - b[:, c0 + 2] * (2.0 - b[:, c0 + 4]))
+    return ((ax(0) + 1j * ax(1)) / np.sqrt(42.0)).astype(np.complex64)
+nre = G // Qm
+syms, exp_sym = [], []
+for cw in range(2):
+    c_init = (0x1234 << 14) | (cw << 13) | (3 << 9) | 77
+    payload, e_clean = vecgen.make_tb(tbs, G, Qm, 0, 60.0, 300 + cw, scale=8)
+    scr = o.sequence_apply_s(np.ones(G, np.int16), c_init) < 0
+    sy = modulate64((e_clean > 0).astype(np.uint8) ^ scr.astype(np.uint8))
+    rngs = np.random.default_rng(900 + cw)
+    sg = vecgen.sigma_for(12.5, tbs / float(G)) / np.sqrt(float(Qm))
+    sy = (sy + sg * (rngs.standard_normal(nre) + 1j * rngs.standard_normal(nre))).astype(np.complex64)
+    syms.append((sy, c_init))
+    exp_sym.append(o.decode_tb(tbs, Qm, 0, o.sequence_apply_s(o.demod_soft_demodulate_s(3, sy), c_init), 8))
+eng.softbuffer_set_resident(True)
+tbs_sym = [sb.TransportBlock(tbs) for _ in range(2)]
+arr = (_TbStruct * 2)()
+for cw in range(2):
+    tbs_sym[cw].fill_symbols(arr[cw], Qm, 0, syms[cw][0], 3, G, c_init=syms[cw][1])
+def one_pdsch_symbols():
+    for tb in tbs_sym:
+        eng.softbuffer_reset(tb)
+    assert sb.lib().srsb200_decode_tb_batch(eng.handle, arr, 2, 8) == 0
+one_pdsch_symbols()
+for cw in range(2):
+    assert arr[cw].ret == exp_sym[cw]["ret"] == 0 and (tbs_sym[cw].cb_noi[:13] == exp_sym[cw]["cb_noi"][:13]).all()
+    assert (tbs_sym[cw].data[:tbs // 8] == exp_sym[cw]["data"][:tbs // 8]).all()
+dt = timeit(one_pdsch_symbols, reps=10)
+res["config3_pdsch_2cw_from_symbols_steady"] = {
+    "ms_per_subframe_host_to_host": dt * 1e3, "info_Mbit_s": 2 * tbs / dt / 1e6, "code_blocks": 26,
+    "h2d_bytes_per_info_bit": 2 * nre * 8 / float(2 * tbs), "h2d_bytes_per_info_bit_llr_path": 2 * G * 2 / float(2 * tbs),
+    "parity": "return codes, iteration counts, payload bit-exact vs the oracle chain demodulate -> descramble -> decode_tb",
+    "note": "equalised symbols in (cf_t, 8 B per RE), soft buffers resident on the device: symbols -> LLRs -> descrambling -> rate de-matching -> decode without the LLRs ever existing on the host"}
+eng.softbuffer_set_resident(False)
 
 # ---- config 3, the two-layer single-TB variant (TBS 149776, C = 25, K = 6016, Qm * Nl = 12) and the 8-bit mode of both
 tbs2, G2 = 149776, 12 * 14400

@@ -110,7 +110,7 @@ void srsb200_plan_destroy(srsb200_plan_t* plan);
 /* Diagnostics: plans of one block size with 64 or more groups regroup their unfinished code blocks during a device-resident
  * decode. Writes, per range of the plan's LAST decode (up to n entries, the rest 0), the half-iteration
  * count after which the range was regrouped, 0 if it was not; synchronises the engine. Returns the number of entries a plan
- * of this kind has (0: this plan never regroups). */
+ * of this kind has (0: this plan never regroups). plan == NULL: the engine's latest transport-block submission (16-bit LLRs). */
 int  srsb200_plan_regroup_points(srsb200_engine_t* e, srsb200_plan_t* plan, uint32_t* points, uint32_t n);
 int  srsb200_tdec_run_plan_dev(srsb200_engine_t* e, srsb200_plan_t* plan, const int16_t* d_llr, uint32_t max_iter,
                                uint32_t min_iter, int early_stop, uint8_t* d_out, uint8_t* d_noi, uint8_t* d_crc_ok);

@@ -1022,9 +1022,10 @@ extern "C" void srsb200_plan_destroy(srsb200_plan_t* p)
 
 extern "C" int srsb200_plan_regroup_points(srsb200_engine_t* e, srsb200_plan_t* plan, uint32_t* points, uint32_t n)
 {
-  if (!e || !plan || (!points && n)) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
+  if (!e || (!points && n)) return fail(SRSB200_ERROR_INVALID_INPUTS, "null argument");
   for (uint32_t i = 0; i < n; i++) points[i] = 0;
-  if (!plan->n_new) return 0;
+  if (!plan) plan = e->tb_plan;  // NULL: the plan of the engine's latest transport-block submission
+  if (!plan || !plan->n_new) return 0;
   std::lock_guard<std::mutex> lk(e->mtx);
   CUDA_TRY(cudaSetDevice(e->device));
   if (join_pending(e)) return SRSB200_ERROR;

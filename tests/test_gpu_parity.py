@@ -245,6 +245,50 @@ def test_decode_tb_batch_many_tbs_one_submission(sb, eng, o):
     assert any(r["ret"] == 0 for r in exp) and any(r["ret"] == -1 for r in exp)
 
 
+def test_decode_tb_batch_big_enough_to_regroup(sb, o):
+    """340 transport blocks of 13 code blocks of one size in one submission: 70 groups, so the plan regroups its unfinished code
+    blocks mid-decode. One block in eight runs on a bad channel, the limits differ per transport block, two transmissions with the
+    HARQ buffers on the device - every transport block against the oracle (return code, per-block iteration counts, flags, bytes)"""
+    tbs, G, Qm, n = 75376, 86400, 6, 340
+    rng = np.random.default_rng(1234)
+    e = sb.Engine(0)
+    try:
+        e.softbuffer_set_resident(True)
+        bad = rng.random(n) < 0.125
+        limits = [int(x) for x in rng.choice([6, 8, 10], n)]
+        vec = {}
+        for rv in (0, 2):
+            for b in (False, True):
+                for v in range(3):
+                    vec[(rv, b, v)] = vecgen.make_tb(tbs, G, Qm, rv, 3.8 if b else 6.0, 9000 + 10 * v + (1 if b else 0), scale=400)[1]
+        which = rng.integers(0, 3, n)
+        tbl = [sb.TransportBlock(tbs) for _ in range(n)]
+        for tb in tbl:
+            e.softbuffer_reset(tb)
+        st = [None] * n
+        memo = {}
+        for rv in (0, 2):
+            reqs = [(tbl[i], Qm, rv, vec[(rv, bool(bad[i]), int(which[i]))]) for i in range(n)]
+            assert e.decode_tb_batch(reqs, 8, limits=limits) == 0
+            if rv == 0:
+                assert any(e.plan_regroup_points(None)), "the first transmission (4420 code blocks, one in eight slow) did not regroup"
+            for i in range(n):
+                key = (rv, bool(bad[i]), int(which[i]), limits[i], None if st[i] is None else st[i]["key"])
+                if key not in memo:   # (the oracle result depends on the vector, the limit and the HARQ history only)
+                    memo[key] = o.decode_tb(tbs, Qm, rv, vec[(rv, bool(bad[i]), int(which[i]))], limits[i], None if st[i] is None else st[i]["state"])
+                res = memo[key]
+                tb = tbl[i]
+                assert tb.ret == res["ret"] and int(tb.tb_crc[0]) == res["tb_crc"], (rv, i)
+                assert (tb.cb_noi[:13] == res["cb_noi"][:13]).all() and (tb.cb_crc[:13] == res["state"]["cb_crc"][:13]).all(), (rv, i)
+                if res["ret"] == 0:
+                    assert (tb.data[:tbs // 8] == res["data"][:tbs // 8]).all(), (rv, i)
+                st[i] = {"state": res["state"], "key": key}
+        rets = [tb.ret for tb in tbl]
+        assert 0 in rets
+    finally:
+        e.close()
+
+
 def test_decode_tb_argument_errors(sb, eng):
     """return-code mapping of decode_tb (sch.c:519-545): -2 invalid inputs, 0 for tbs == 0"""
     tb = sb.TransportBlock(6200)

@@ -1601,7 +1601,8 @@ extern "C" int srsb200_ulsch_deinterleave(srsb200_engine_t* e, const int16_t* q_
   CUDA_TRY(cudaMemsetAsync(d_g, 0, ng * sizeof(int16_t), e->stream));  // the nof_ri_bits values past the data are left stale by the reference
   {
     ProfScope ps(e, 8);
-    ulsch_deint_kernel<<<dim3(1, std::max(1u, std::min<uint32_t>(128u, (j.rows + DT_ROWS - 1) / DT_ROWS))), 256, 0, e->stream>>>((const DeintJob*)d_dj);
+    const uint32_t tpj = std::max(1u, std::min<uint32_t>(128u, (j.rows + DT_ROWS - 1) / DT_ROWS));
+    ulsch_deint_kernel<<<tpj, 256, 0, e->stream>>>((const DeintJob*)d_dj, tpj);
     e->launches++;
   }
   CUDA_TRY(stg.d2h(g_bits, d_g, ng * sizeof(int16_t), e->stream));

@@ -260,66 +260,46 @@ struct DeintJob {
 // w's scan position (divisions by multiply-high with per-block constants); tiles with RI positions, or behind an odd number of
 // them, go item by item with the rank found by binary search. Round 1 let every thread read its Qm values straight from q
 // (12 bytes out of every 32-byte sector per request): 1.5 TB/s; 32-row tiles with per-item stores: 2.1 TB/s.
-// grid = (jobs, tiles per job: any number >= 1, tiles are strided over gridDim.y), block = 256
-constexpr int DT_ROWS = 64;   // 32 / 64 / 128 rows per tile: 2.1 / 2.7-3.1 / 2.4 TB/s on 512 transport blocks
+// grid = jobs * tpj (tpj = blocks per job: any number >= 1, the tiles of a job are strided over them), block = 256
+constexpr int DT_ROWS = 128;
 constexpr int DT_MAXC = 14;  // columns = PUSCH symbols carrying data: 12 (normal CP), 10 / 11 with SRS or extended CP
-// floor(n / d) = umulhi(n, magic) while n * d < 2^32 and d >= 2; magic 0 stands for d = 1
-__device__ __forceinline__ uint32_t dt_magic(uint32_t d) { return d < 2 ? 0u : 0xffffffffu / d + 1u; }
-__device__ __forceinline__ uint32_t dt_div(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
-__global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __restrict__ jobs)
+__global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __restrict__ jobs, uint32_t tpj)
 {
   constexpr int  PITCH = DT_ROWS * 8 + 8;  // int16 per tile row: a multiple of 8 (128-bit shared stores), 260 words = 4 mod 32 banks
   __shared__ __align__(16) int16_t tile[DT_MAXC][PITCH];
-  const DeintJob j = jobs[blockIdx.x];
+  // one-dimensional grid, the tpj blocks of a job next to each other: blocks that run at the same time read neighbouring pieces of
+  // the same column runs (DRAM pages) instead of one short run each from many transport blocks
+  const DeintJob j = jobs[blockIdx.x / tpj];
   const uint32_t ntiles = (j.rows + DT_ROWS - 1) / DT_ROWS;
   const bool     tiled  = j.cols <= DT_MAXC && j.Qm <= 8 && (j.Qm & 1u) == 0 && ((reinterpret_cast<uintptr_t>(j.q) & 3u) == 0) && ((j.rows * j.Qm) & 1u) == 0;
   const bool     g32ok  = (reinterpret_cast<uintptr_t>(j.g) & 3u) == 0;
   const uint32_t item_w = j.Qm / 2, line_w = j.cols * item_w;  // 32-bit words per item / per matrix row (tiled: Qm even)
-  const uint32_t m_item = dt_magic(max(item_w, 1u)), m_line = dt_magic(max(line_w, 1u));
-  for (uint32_t tix = blockIdx.y; tix < ntiles; tix += gridDim.y) {
+  for (uint32_t tix = blockIdx.x % tpj; tix < ntiles; tix += tpj) {
     const uint32_t row0 = tix * DT_ROWS, nr = min((uint32_t)DT_ROWS, j.rows - row0), run = nr * j.Qm;  // LLRs per column of this tile
     bool           fast = false;
     uint32_t       c0   = 0;
     if (tiled) {
       __syncthreads();  // the previous tile has been written out
-      const uint32_t rw = run / 2, nw = j.cols * rw, m_rw = dt_magic(rw);  // 32-bit words per column run
-      constexpr int UN = 4;  // loads in flight per thread
-      // 128-bit loads when every column run of the tile starts and ends on a 16-byte boundary (the per-word index arithmetic of
-      // the 32-bit version made this kernel issue-bound: sm instruction throughput 73 %, DRAM 25 % in the ncu capture)
-      const bool vec = (run & 7u) == 0 && ((j.rows * j.Qm) & 7u) == 0 && ((row0 * j.Qm) & 7u) == 0 && (reinterpret_cast<uintptr_t>(j.q) & 15u) == 0;
-      if (vec) {
-        const uint32_t rv = run / 8, nv = j.cols * rv, m_rv = dt_magic(rv);  // uint4 per column run
-        for (uint32_t i0 = threadIdx.x; i0 < nv; i0 += 256 * UN) {
-          uint4    v[UN];
-          uint32_t at[UN];
-#pragma unroll
-          for (int u = 0; u < UN; u++) {
-            const uint32_t idx = i0 + 256 * u;
-            if (idx < nv) {
-              const uint32_t col = dt_div(idx, m_rv), wq = idx - col * rv;
-              at[u] = col * PITCH + 8 * wq;
-              v[u]  = __ldg(reinterpret_cast<const uint4*>(j.q + (size_t)col * j.rows * j.Qm + (size_t)row0 * j.Qm) + wq);
-            }
+      // ---- load: a warp per column run, 128-bit loads when the run starts and ends on 16-byte boundaries. No index arithmetic
+      //      per element: the first versions divided every word index by run / row lengths and were issue-bound (478 instructions
+      //      per thread and tile for 2.25 loads and 2.25 stores; SM instruction throughput 67-73 %, DRAM 25-31 % under ncu).
+      const uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(&tile[0][0]);
+      const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+      const bool     vec = (run & 7u) == 0 && ((j.rows * j.Qm) & 7u) == 0 && ((row0 * j.Qm) & 7u) == 0 && (reinterpret_cast<uintptr_t>(j.q) & 15u) == 0;
+      for (uint32_t col = wid; col < j.cols; col += 8) {
+        const int16_t* src = j.q + ((size_t)col * j.rows + row0) * j.Qm;
+        const uint32_t sa  = tile_sa + col * (uint32_t)(PITCH * 2);
+        if (vec) {
+          for (uint32_t i = lane; i < run / 8; i += 32) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
           }
-#pragma unroll
-          for (int u = 0; u < UN; u++)
-            if (i0 + 256 * u < nv) *reinterpret_cast<uint4*>(&tile[0][0] + at[u]) = v[u];
-        }
-      }
-      for (uint32_t i0 = threadIdx.x; i0 < (vec ? 0u : nw); i0 += 256 * UN) {
-        uint32_t v[UN], at[UN];
-#pragma unroll
-        for (int u = 0; u < UN; u++) {
-          const uint32_t idx = i0 + 256 * u;
-          if (idx < nw) {
-            const uint32_t col = dt_div(idx, m_rw), wq = idx - col * rw;
-            at[u] = col * PITCH + 2 * wq;
-            v[u]  = __ldg(reinterpret_cast<const uint32_t*>(j.q + (size_t)col * j.rows * j.Qm + (size_t)row0 * j.Qm) + wq);
+        } else {
+          for (uint32_t i = lane; i < run / 2; i += 32) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa + 4u * i), "r"(v) : "memory");
           }
         }
-#pragma unroll
-        for (int u = 0; u < UN; u++)
-          if (i0 + 256 * u < nw) *reinterpret_cast<uint32_t*>(&tile[0][0] + at[u]) = v[u];
       }
       // number of RI scan indices before the tile, and whether one lies inside it (every thread the same search: broadcast loads)
       const uint32_t s_lo = row0 * j.cols * j.Qm, s_hi = s_lo + nr * j.cols * j.Qm;
@@ -332,33 +312,39 @@ __global__ void __launch_bounds__(256) ulsch_deint_kernel(const DeintJob* __rest
       fast = g32ok && (c0 & 1u) == 0 && (c0 >= j.nri || __ldg(j.ri_scan + c0) >= s_hi);
       __syncthreads();
       if (fast) {
-        uint32_t*      dst = reinterpret_cast<uint32_t*>(j.g) + (s_lo - c0) / 2;
-        const uint32_t now = nr * line_w;
-        if ((now & 3u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-          // four consecutive words per thread, one 128-bit store: the (row, column, word) position is divided out once and then
-          // stepped
-          for (uint32_t w4 = threadIdx.x; w4 < now / 4; w4 += 256) {
-            const uint32_t w = 4 * w4;
-            uint32_t       r = dt_div(w, m_line), rem = w - r * line_w, col = dt_div(rem, m_item), k = rem - col * item_w;
-            uint32_t       v[4];
+        // ---- store: the tile's part of g is nr consecutive lines of line_w words. A thread owns the same word positions of
+        //      every line it writes, so their places in the tile are worked out once; lines are walked with a fixed stride.
+        uint32_t*      dst   = reinterpret_cast<uint32_t*>(j.g) + (s_lo - c0) / 2;
+        const uint32_t rowb  = j.Qm * 2;  // bytes per matrix row within a column run
+        const bool     first = s_lo == c0;  // this tile holds g[0]: it is q[p_star] (see above)
+        if ((line_w & 3u) == 0 && line_w >= 4 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+          const uint32_t per = line_w / 4, jq = threadIdx.x % per, rr = threadIdx.x / per, rpp = 256 / per;  // 128-bit pieces per line
+          uint32_t       off[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              v[i] = *reinterpret_cast<const uint32_t*>(&tile[col][r * j.Qm + 2 * k]);
-              if (++k == item_w) {
-                k = 0;
-                if (++col == j.cols) { col = 0; r++; }
-              }
-            }
-            if (w == 0 && s_lo == c0) v[0] = (v[0] & 0xffff0000u) | (uint16_t)j.q[j.p_star];  // g[0]: see above
-            reinterpret_cast<uint4*>(dst)[w4] = make_uint4(v[0], v[1], v[2], v[3]);
+          for (int i = 0; i < 4; i++) {
+            const uint32_t w = 4 * jq + i, col = w / item_w, k = w - col * item_w;
+            off[i] = tile_sa + col * (uint32_t)(PITCH * 2) + 4u * k;
           }
-          continue;
-        }
-        for (uint32_t w = threadIdx.x; w < now; w += 256) {
-          const uint32_t r = dt_div(w, m_line), rem = w - r * line_w, col = dt_div(rem, m_item), k = rem - col * item_w;
-          uint32_t       v = *reinterpret_cast<const uint32_t*>(&tile[col][r * j.Qm + 2 * k]);
-          if (w == 0 && s_lo == c0) v = (v & 0xffff0000u) | (uint16_t)j.q[j.p_star];  // g[0]: see above
-          dst[w] = v;
+          if (rr < rpp) {
+            for (uint32_t r = rr; r < nr; r += rpp) {
+              uint32_t v[4];
+#pragma unroll
+              for (int i = 0; i < 4; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[i]) : "r"(off[i] + r * rowb));
+              if (first && r == 0 && jq == 0) v[0] = (v[0] & 0xffff0000u) | (uint16_t)j.q[j.p_star];
+              reinterpret_cast<uint4*>(dst)[r * per + jq] = make_uint4(v[0], v[1], v[2], v[3]);
+            }
+          }
+        } else {
+          // a warp per line, lane l the words l, l + 32, ...
+          for (uint32_t w = lane; w < line_w; w += 32) {
+            const uint32_t col = w / item_w, k = w - col * item_w, off = tile_sa + col * (uint32_t)(PITCH * 2) + 4u * k;
+            for (uint32_t r = wid; r < nr; r += 8) {
+              uint32_t v;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(off + r * rowb));
+              if (first && r == 0 && w == 0) v = (v & 0xffff0000u) | (uint16_t)j.q[j.p_star];
+              dst[r * line_w + w] = v;
+            }
+          }
         }
         continue;
       }

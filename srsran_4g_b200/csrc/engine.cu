@@ -1239,8 +1239,10 @@ static int launch_plan(srsb200_engine* e, srsb200_plan* p, const int16_t* d_llr,
     for (uint32_t n = start_iter; n < max_iter; n++) {
       launch_one(e, p, rg[s], 1, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
       launch_one(e, p, rg[s], 2, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
-      // regrouping points after the 4th, 5th and 6th half-iteration (the first one that finds few enough survivors regroups)
-      if (rg[s].rg && n + 1 >= 4 && n + 1 <= 6 && n + 1 < max_iter) {
+      // regrouping points after the 4th, 5th, ... half-iteration, as long as at least three more can follow (the first point that
+      // finds few enough survivors regroups; a later point would pay the gather for one or two half-iterations)
+      static const uint32_t rg_last = [] { const char* v = getenv("SRSB200_REGROUP_LAST"); return v ? (uint32_t)atoi(v) : 0u; }();
+      if (rg[s].rg && n + 1 >= 4 && n + 1 <= (rg_last ? rg_last : std::max(4u, max_iter - 3)) && n + 1 < max_iter) {
         launch_one(e, p, rg[s], 3, n, d_llr, max_iter, min_iter, early_stop, d_out, d_noi, d_ok);
         rg[s].rg_started = true;
       }

@@ -111,6 +111,41 @@ def kernel_source_sha():
     return h.hexdigest()[:16]
 
 
+def bind_to_gpu_numa_node(torch, device_index):
+    """One process per GPU on a multi-socket box: run on the cores next to this rank's GPU, so that the page-locked host buffers
+    it allocates afterwards (first touch) sit in that socket's memory and the host-to-device copies of eight ranks do not all cross
+    the socket interconnect. Reads the GPU's PCI address and sysfs; does nothing if either is unavailable (SRSB200_NO_NUMA_BIND=1:
+    off). Returns a description for the bench line or None."""
+    if os.environ.get("SRSB200_NO_NUMA_BIND"):
+        return None
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        with open(base + "/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus or cpus == set(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, cpus)
+        node = None
+        try:
+            with open(base + "/numa_node") as f:
+                node = int(f.read().strip())
+        except Exception:  # noqa: BLE001
+            pass
+        return {"gpu": bdf, "numa_node": node, "cpus": len(cpus)}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def cpu_decoder():
     """(library wrapper, kind, impl id, build description): oracle/_ref (the compiled reference, AVX2 windowed decoder, built
     with the reference's release flags) when it travelled with the repo, else the clean-room port. Loaded through
@@ -221,6 +256,7 @@ def main():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -620,6 +656,8 @@ def main():
         "ms_per_step": step_ms}
     if e2e is not None:
         out["e2e"] = e2e
+    if numa is not None:
+        out["config"]["host_binding"] = "each rank runs on the cores local to its GPU (%s: NUMA node %s, %d cores)" % (numa["gpu"], numa["numa_node"], numa["cpus"])
     if e2e8 is not None:
         out["e2e_llr8"] = e2e8
     if e2e_tb is not None:

@@ -305,6 +305,21 @@ class Engine:
                                            _ptr(out), _ptr(ooff), out.size, _ptr(noi), _ptr(ok)), "srsb200_tdec_batch8")
         return out, noi, ok
 
+    def tdec_batch8_mixed(self, Ks, llrs8, max_iter, early_stop=True, min_iter=2, crc_kind=CRC_24B):
+        """8-bit LLR mode, one block size per entry: Ks uint32[n], llrs8 list of int8 arrays (3K+12 each) -> (list of K/8-byte
+        rows, noi, crc_ok)"""
+        Ks = np.ascontiguousarray(Ks, np.uint32)
+        n = len(Ks)
+        parts = [np.ascontiguousarray(a, np.int8).reshape(-1) for a in llrs8]
+        flat = np.concatenate(parts) if n else np.zeros(0, np.int8)
+        loff = np.concatenate([[0], np.cumsum([len(p) for p in parts])[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+        ooff = np.concatenate([[0], np.cumsum(Ks.astype(np.uint64) // 8)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+        kinds = np.full(n, crc_kind, np.uint8) if np.isscalar(crc_kind) else np.ascontiguousarray(crc_kind, np.uint8)
+        out = np.zeros(int((Ks.astype(np.uint64) // 8).sum()), np.uint8); noi = np.zeros(n, np.uint8); ok = np.zeros(n, np.uint8)
+        _check(self._L.srsb200_tdec_batch8(self._h, n, _ptr(Ks), _ptr(kinds), _ptr(flat), _ptr(loff), flat.size, max_iter, min_iter, int(early_stop),
+                                           _ptr(out), _ptr(ooff), out.size, _ptr(noi), _ptr(ok)), "srsb200_tdec_batch8")
+        return [out[int(ooff[i]):int(ooff[i]) + int(Ks[i]) // 8] for i in range(n)], noi, ok
+
     def demod_soft_demodulate_s(self, mod, symbols):
         """mod 0..4 = BPSK, QPSK, 16QAM, 64QAM, 256QAM; symbols complex64[n] -> (ret, int16 LLRs)"""
         s = np.ascontiguousarray(symbols, np.complex64)

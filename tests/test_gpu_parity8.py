@@ -1,6 +1,8 @@
 """8-bit LLR mode on the GPU: the CUDA path through the C ABI against oracle/turbo_oracle8.c - itself pinned to
 the compiled reference's srsran_tdec_iteration_8bit / srsran_rm_turbo_rx_lut_8bit / llr_is_8bit loop (tests/test_oracle8_vs_ref.py).
 Integer work: bit-exact hard bits, half-iteration counts, CRC verdicts, soft buffers."""
+import os
+
 import numpy as np
 import pytest
 
@@ -71,6 +73,26 @@ def test_batch_early_stop_odd_counts(sb, eng, o, K, n):
     out, noi, ok = eng.tdec_batch8(K, l8, 8, early_stop=True)
     assert (noi == on).all() and (ok == ook).all() and (out == oo).all()
     assert ok.mean() > 0.5
+
+
+def test_every_8bit_block_size_in_one_submission(sb, eng, o):
+    """all LTE block sizes the reference decodes in 8-bit arithmetic (K > 800 and K % 16 == 0: 16 windows up to 2048, 32 above where
+    K % 32 == 0), three blocks each in ONE mixed submission (a warp unit per size and pair; window lengths 51..192, the short last
+    recompute block, the wrap-around tail of K % 32 != 0), every block against the 8-bit oracle"""
+    rng = np.random.default_rng(808 + int(os.environ.get("SRSB200_FUZZ_SEED", "0")))
+    sizes = [o.cbsize(i) for i in range(188)]
+    sizes = [k for k in sizes if sb.tdec8_windows(k)]
+    assert len(sizes) > 90 and min(sizes) == 816 and max(sizes) == 6144
+    Ks, llrs = [], []
+    for K in sizes:
+        for j in range(3):
+            _, l = vecgen.make_cb(K, float(rng.choice([0.5, 1.5, 2.5, 4.0])), int(rng.integers(1 << 30)), scale=int(rng.choice([8, 12, 20])))
+            Ks.append(K)
+            llrs.append(np.clip(l, -127, 127).astype(np.int8))
+    outs, noi, ok = eng.tdec_batch8_mixed(np.array(Ks, np.uint32), llrs, 8)
+    for i, K in enumerate(Ks):
+        _, oo, on, ook = o.tdec8_batch(K, llrs[i][None, :], 8, True)
+        assert on[0] == noi[i] and ook[0] == ok[i] and np.array_equal(oo[0], outs[i]), (K, i % 3)
 
 
 def test_rm_rx8(sb, eng, o):

@@ -3,6 +3,7 @@
 result to the path given (a build artefact outside the repository history; nothing of the reference is committed).
 
     python integration/apply_b200_patch.py /root/reference/lib/src/phy/phch/sch.c /tmp/sch_b200.c
+    python integration/apply_b200_patch.py --pdsch /root/reference/lib/src/phy/phch/pdsch.c /tmp/pdsch_b200.c
 
 Three insertions, each keyed on a function signature of the reference:
   decode_tb          -> srsran_b200_decode_tb
@@ -36,7 +37,44 @@ def insert_after_open_brace(src, signature_regex, text):
     return src[:brace + 1] + "\n" + text + src[brace + 1:]
 
 
+PDSCH_PROTOS = '''
+#ifdef SRSRAN_B200
+uint32_t srsran_b200_pdsch_c_init(uint16_t rnti, int codeword_idx, uint32_t nslot, uint32_t cell_id);
+int      srsran_b200_dlsch_takes_symbols(srsran_sch_t* q, srsran_pdsch_cfg_t* cfg, int tb_idx);
+int      srsran_b200_dlsch_decode2_symbols(srsran_sch_t* q, srsran_pdsch_cfg_t* cfg, cf_t* symbols, uint32_t c_init, uint8_t* data, int tb_idx,
+                                           uint32_t nof_layers);
+#endif
+'''
+
+
+def patch_pdsch(src):
+    """srsran_pdsch_codeword_decode (pdsch.c:662-760): demodulate + descramble + srsran_dlsch_decode2 become ONE call with the
+    equalised symbols when nothing else needs the LLRs on the host (no EVM measurement, no CSI correction, 16-bit mode)"""
+    last_inc = [m for m in re.finditer(r'^#include .*$', src, re.M)][-1]
+    src = src[:last_inc.end()] + "\n" + PDSCH_PROTOS + src[last_inc.end():]
+    m = re.search(r'static int srsran_pdsch_codeword_decode\(', src)
+    if not m:
+        raise SystemExit("anchor not found: srsran_pdsch_codeword_decode")
+    a = src.index("    /* demodulate symbols", m.end())
+    b = src.index("    ret = srsran_dlsch_decode2(dl_sch, cfg, q->e[codeword_idx], data[tb_idx].payload, tb_idx, nof_layers);", a)
+    b = src.index("\n", b) + 1
+    head = '''#ifdef SRSRAN_B200
+    if (!(cfg->meas_evm_en && q->evm_buffer[codeword_idx]) && !cfg->csi_enable && srsran_b200_dlsch_takes_symbols(dl_sch, cfg, tb_idx)) {
+      data[tb_idx].evm = NAN;
+      ret = srsran_b200_dlsch_decode2_symbols(dl_sch, cfg, q->d[codeword_idx],
+                                              srsran_b200_pdsch_c_init(cfg->rnti, codeword_idx, 2 * (sf->tti % SRSRAN_NOF_SF_X_FRAME), q->cell.id),
+                                              data[tb_idx].payload, tb_idx, nof_layers);
+    } else {
+#endif
+'''
+    tail = "#ifdef SRSRAN_B200\n    }\n#endif\n"
+    return src[:a] + head + src[a:b] + tail + src[b:]
+
+
 def main():
+    if len(sys.argv) > 3 and sys.argv[1] == "--pdsch":
+        open(sys.argv[3], "w").write(patch_pdsch(open(sys.argv[2]).read()))
+        return
     src = open(sys.argv[1]).read()
     # prototypes after the last #include
     last_inc = [m for m in re.finditer(r'^#include .*$', src, re.M)][-1]

@@ -481,6 +481,63 @@ int srsran_b200_decode_tb_symbols(srsran_sch_t*           q,
   return ret;
 }
 
+/*
+ * What srsran_pdsch_codeword_decode (pdsch.c:662-760) calls under -DSRSRAN_B200 instead of srsran_demod_soft_demodulate_s (:696),
+ * srsran_sequence_pdsch_apply_s (:726-732) and srsran_dlsch_decode2 (:740): the arguments of srsran_dlsch_decode2 (sch.c:580-609)
+ * with the equalised symbols of the codeword in place of its LLRs, plus the four values the scrambling seed is made of
+ * (sequence_pdsch_seed, sequences.c:62-65). Same return codes as srsran_dlsch_decode2.
+ */
+uint32_t srsran_b200_pdsch_c_init(uint16_t rnti, int codeword_idx, uint32_t nslot, uint32_t cell_id)
+{
+  return ((uint32_t)rnti << 14) + ((uint32_t)codeword_idx << 13) + ((nslot / 2) << 9) + cell_id;
+}
+
+/* 1: this codeword can go symbols-in (16-bit LLR mode, a transport block the engine decodes); 0: keep the reference's three calls */
+int srsran_b200_dlsch_takes_symbols(srsran_sch_t* q, srsran_pdsch_cfg_t* cfg, int tb_idx)
+{
+  if (q == NULL || cfg == NULL || tb_idx < 0 || tb_idx >= SRSRAN_MAX_CODEWORDS || q->llr_is_8bit) {
+    return 0;
+  }
+  if (cfg->softbuffers.rx[tb_idx] == NULL || cfg->grant.tb[tb_idx].tbs <= 0 || cfg->grant.nof_re == 0) {
+    return 0;
+  }
+  uint32_t sg[8];
+  return srsb200_cbsegm((uint32_t)cfg->grant.tb[tb_idx].tbs, sg) == SRSB200_SUCCESS && sg[0] == 0; /* no filler bits */
+}
+
+int srsran_b200_dlsch_decode2_symbols(srsran_sch_t*       q,
+                                      srsran_pdsch_cfg_t* cfg,
+                                      cf_t*               symbols,
+                                      uint32_t            c_init,
+                                      uint8_t*            data,
+                                      int                 tb_idx,
+                                      uint32_t            nof_layers)
+{
+  if (q == NULL || cfg == NULL || symbols == NULL || data == NULL || tb_idx < 0 || tb_idx >= SRSRAN_MAX_CODEWORDS) {
+    return SRSRAN_ERROR_INVALID_INPUTS;
+  }
+  uint32_t Nl = (nof_layers != cfg->grant.nof_tb) ? 2 : 1; /* sch.c:587-591 */
+  uint32_t        sg[8];
+  srsran_cbsegm_t cb_segm;
+  memset(&cb_segm, 0, sizeof(cb_segm));
+  if (srsb200_cbsegm((uint32_t)cfg->grant.tb[tb_idx].tbs, sg) != SRSB200_SUCCESS) {
+    ERROR("Error computing Codeword (%d) segmentation for TBS=%d", tb_idx, cfg->grant.tb[tb_idx].tbs);
+    return SRSRAN_ERROR;
+  }
+  cb_segm.F = sg[0]; cb_segm.C = sg[1]; cb_segm.K1 = sg[2]; cb_segm.K2 = sg[3]; cb_segm.K1_idx = sg[4]; cb_segm.K2_idx = sg[5];
+  cb_segm.C1 = sg[6]; cb_segm.C2 = sg[7];
+  cb_segm.tbs = (uint32_t)cfg->grant.tb[tb_idx].tbs; cb_segm.L_tb = 24; cb_segm.L_cb = 24;
+  static const uint32_t bits_x_symbol[5] = {1, 2, 4, 6, 8}; /* srsran_mod_bits_x_symbol (phy_common.c): BPSK .. 256QAM */
+  if ((uint32_t)cfg->grant.tb[tb_idx].mod > 4) {
+    return SRSRAN_ERROR_INVALID_INPUTS;
+  }
+  uint32_t Qm = bits_x_symbol[cfg->grant.tb[tb_idx].mod];
+  /* the reference demodulates cfg->grant.nof_re symbols of q->d[codeword] whatever the number of layers (pdsch.c:696: layer
+   * de-mapping has already gathered the codeword's symbols, :885-887) and hands decode_tb Qm x Nl (sch.c:601-608) */
+  return srsran_b200_decode_tb_symbols(q, cfg->softbuffers.rx[tb_idx], &cb_segm, cfg->grant.tb[tb_idx].mod, Qm * Nl, (uint32_t)cfg->grant.tb[tb_idx].rv,
+                                       cfg->grant.tb[tb_idx].nof_bits, symbols, cfg->grant.nof_re, c_init, data);
+}
+
 /* srsran_demod_soft_demodulate_s (demod_soft.h) on the device, same return codes */
 int srsran_b200_demod_soft_demodulate_s(srsran_mod_t modulation, const cf_t* symbols, short* llr, int nsymbols)
 {
@@ -825,6 +882,58 @@ int srsran_b200_selftest_decode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint3
   free(sb.buffer_f);
   free(sb.data);
   free(sb.cb_crc);
+  free(q);
+  return ret;
+}
+
+/* srsran_b200_dlsch_decode2_symbols through a real srsran_pdsch_cfg_t: what the patched pdsch.c calls (one codeword, tb_idx 0) */
+int srsran_b200_selftest_dlsch_symbols(uint32_t tbs, int mod, uint32_t rv, uint32_t nof_re, uint32_t nof_tb, uint32_t nof_layers, float* symbols,
+                                       uint16_t rnti, int codeword_idx, uint32_t nslot, uint32_t cell_id, uint32_t max_iterations, uint32_t max_cb,
+                                       int16_t* buffer_f, uint8_t* sb_data, uint8_t* cb_crc, uint8_t* tb_crc, uint8_t* data, float* avg_iterations)
+{
+  static const uint32_t bps[5] = {1, 2, 4, 6, 8};
+  srsran_sch_t* q = calloc(1, sizeof(srsran_sch_t));
+  if (!q || mod < 0 || mod > 4) {
+    free(q);
+    return SRSRAN_ERROR;
+  }
+  q->max_iterations = max_iterations ? max_iterations : 10;
+  srsran_softbuffer_rx_t sb;
+  memset(&sb, 0, sizeof(sb));
+  sb.max_cb      = max_cb;
+  sb.max_cb_size = SOFTBUFFER_SIZE;
+  sb.buffer_f    = calloc(max_cb, sizeof(int16_t*));
+  sb.data        = calloc(max_cb, sizeof(uint8_t*));
+  sb.cb_crc      = calloc(max_cb, sizeof(bool));
+  for (uint32_t i = 0; i < max_cb; i++) {
+    sb.buffer_f[i] = &buffer_f[(size_t)i * SOFTBUFFER_SIZE];
+    sb.data[i]     = &sb_data[(size_t)i * (SOFTBUFFER_SIZE / 8)];
+    sb.cb_crc[i]   = cb_crc[i] != 0;
+  }
+  srsran_pdsch_cfg_t* cfg = calloc(1, sizeof(srsran_pdsch_cfg_t));
+  cfg->grant.nof_tb         = nof_tb;
+  cfg->grant.nof_layers     = nof_layers;
+  cfg->grant.nof_re         = nof_re;
+  cfg->grant.tb[0].tbs      = (int)tbs;
+  cfg->grant.tb[0].mod      = (srsran_mod_t)mod;
+  cfg->grant.tb[0].rv       = (int)rv;
+  cfg->grant.tb[0].nof_bits = nof_re * bps[mod];
+  cfg->grant.tb[0].enabled  = true;
+  cfg->softbuffers.rx[0]    = &sb;
+  cfg->rnti                 = rnti;
+  int ret = SRSRAN_ERROR_INVALID_INPUTS;
+  if (srsran_b200_dlsch_takes_symbols(q, cfg, 0)) {
+    ret = srsran_b200_dlsch_decode2_symbols(q, cfg, (cf_t*)symbols, srsran_b200_pdsch_c_init(rnti, codeword_idx, nslot, cell_id), data, 0, nof_layers);
+  }
+  for (uint32_t i = 0; i < max_cb; i++) {
+    cb_crc[i] = sb.cb_crc[i] ? 1 : 0;
+  }
+  *tb_crc         = sb.tb_crc ? 1 : 0;
+  *avg_iterations = q->avg_iterations;
+  free(sb.buffer_f);
+  free(sb.data);
+  free(sb.cb_crc);
+  free(cfg);
   free(q);
   return ret;
 }

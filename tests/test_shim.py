@@ -21,7 +21,7 @@ def test_shim_builds_against_reference_headers():
     import __graft_entry__ as g
     g.build()
     out = subprocess.check_output(["make", "-s", "-C", os.path.join(ROOT, "integration"), "check"]).decode()
-    assert "exports all 24" in out
+    assert "exports all 27" in out
 
 
 @pytest.fixture(scope="module")
@@ -207,3 +207,46 @@ def test_shim_thread_engines_are_destroyed_at_thread_exit(shim):
     assert not errs, errs[0]
     assert free0 - free1 < 32 * 2 ** 20, "device memory grew by %.1f MB over 20 thread lifetimes" % ((free0 - free1) / 2 ** 20)
     assert shim.srsran_b200_nof_devices() >= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tbs,nre,mod,eb,layers", [(75376, 14400, 3, 12.5, 1), (12216, 4803, 2, 6.5, 1), (6120, 7200, 1, 2.5, 1), (36696, 7200, 3, 12.0, 2)])
+def test_pdsch_codeword_from_symbols(shim, tbs, nre, mod, eb, layers):
+    """what the patched srsran_pdsch_codeword_decode calls (pdsch.c:693-740 under -DSRSRAN_B200): srsran_b200_dlsch_decode2_symbols on
+    a real srsran_pdsch_cfg_t - equalised symbols in, payload out - against the oracle chain soft demodulation -> descrambling with
+    the PDSCH seed (sequences.c:62-65) -> decode_tb; one codeword on one and on two layers (Qm x Nl for the rate de-matcher)"""
+    o = ol.oracle()
+    Qm = (1, 2, 4, 6, 8)[mod]
+    G = nre * Qm
+    rnti, cw, nslot, cell = 0x4601, 0, 2 * 7, 301
+    c_init = (rnti << 14) + (cw << 13) + ((nslot // 2) << 9) + cell
+    assert shim.srsran_b200_pdsch_c_init(rnti, cw, nslot, cell) == c_init
+    rng = np.random.default_rng(tbs + mod + layers)
+    payload, e_clean = vecgen.make_tb(tbs, G, Qm * layers, 0, 60.0, 15 + mod, scale=8)
+    scr = o.sequence_apply_s(np.ones(G, np.int16), c_init) < 0
+    bits = (e_clean > 0).astype(np.uint8) ^ scr.astype(np.uint8)
+    b = 1.0 - 2.0 * bits.astype(np.float64).reshape(-1, Qm)
+    if mod == 1:
+        sym = (b[:, 0] + 1j * b[:, 1]) / np.sqrt(2.0)
+    elif mod == 2:
+        sym = (b[:, 0] * (2.0 - b[:, 2]) + 1j * b[:, 1] * (2.0 - b[:, 3])) / np.sqrt(10.0)
+    else:
+        sym = (b[:, 0] * (4.0 - b[:, 2] * (2.0 - b[:, 4])) + 1j * b[:, 1] * (4.0 - b[:, 3] * (2.0 - b[:, 5]))) / np.sqrt(42.0)
+    sigma = vecgen.sigma_for(eb, tbs / float(G)) / np.sqrt(float(Qm))
+    sym = (sym + sigma * (rng.standard_normal(nre) + 1j * rng.standard_normal(nre))).astype(np.complex64)
+    llr = o.sequence_apply_s(o.demod_soft_demodulate_s(mod, sym), c_init)
+    res = o.decode_tb(tbs, Qm * layers, 0, llr, 8)
+    Cn = res["seg"]["C"]
+    buf = np.zeros((Cn, ol.SOFTBUFFER_SIZE), np.int16); sbd = np.zeros((Cn, ol.SOFTBUFFER_SIZE // 8), np.uint8)
+    cbc = np.zeros(Cn, np.uint8); tbc = np.zeros(1, np.uint8); avg = C.c_float(0)
+    data = np.zeros(tbs // 8 + 64, np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    shim.srsran_b200_selftest_dlsch_symbols.argtypes = [C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint16, C.c_int,
+                                                        C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                        C.c_void_p]
+    ret = shim.srsran_b200_selftest_dlsch_symbols(tbs, mod, 0, nre, 1, layers, p(sym), rnti, cw, nslot, cell, 8, Cn, p(buf), p(sbd), p(cbc), p(tbc), p(data),
+                                                  C.cast(C.byref(avg), C.c_void_p))
+    assert ret == res["ret"] == 0 and int(tbc[0]) == res["tb_crc"] and (cbc == res["state"]["cb_crc"][:Cn]).all()
+    assert np.float32(avg.value) == np.float32(res["avg_iterations"])
+    assert (buf == res["state"]["buffer_f"][:Cn]).all()
+    assert (data[:tbs // 8] == res["data"][:tbs // 8]).all() and (data[:tbs // 8] == payload[:tbs // 8]).all()

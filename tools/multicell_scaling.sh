@@ -5,7 +5,8 @@ max=${1:-8}
 nproc >&2
 for g in 1 2 4 8; do
   [ $g -le $max ] || break
-  for t in 2 4; do
+  for t in 2 4 8; do
+    [ $((g * t)) -le 64 ] || continue
     for rep in 1 2; do
       timeout 120 examples/multicell_uplink $t 64 50 1 $g
     done

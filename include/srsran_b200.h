@@ -255,6 +255,8 @@ typedef struct {
  * reference's reset points (srsran_softbuffer_rx_reset / _reset_tbs / _reset_cb, softbuffer.c:139-169) to
  * srsb200_softbuffer_reset, may fetch the contents with srsb200_softbuffer_sync_to_host, and frees the mirror in
  * srsran_softbuffer_rx_free via srsb200_softbuffer_release. A buffer first seen without a reset adopts the host content.
+ * srsb200_softbuffer_reset costs no launch of its own: the mirrors it names are zeroed by one kernel in front of the next call that
+ * reads or writes a mirror (a transport-block submission, sync_to_host), so a reset per transport block and subframe is cheap.
  */
 int srsb200_softbuffer_set_resident(srsb200_engine_t* e, int resident);
 int srsb200_softbuffer_reset(srsb200_engine_t* e, int16_t** buffer_f, uint32_t nof_cb);

@@ -2,6 +2,7 @@
 container, exercised on the GPU through the reference's symbol names and struct layouts."""
 import ctypes as C
 import os
+import sys
 import subprocess
 
 import numpy as np
@@ -22,6 +23,30 @@ def test_shim_builds_against_reference_headers():
     g.build()
     out = subprocess.check_output(["make", "-s", "-C", os.path.join(ROOT, "integration"), "check"]).decode()
     assert "exports all 27" in out
+
+
+@pytest.mark.ref
+def test_pdsch_hook_applies_to_the_reference_and_compiles(tmp_path):
+    """integration/apply_b200_patch.py --pdsch on the reference's own pdsch.c: the patched file compiles against the reference
+    headers with -DSRSRAN_B200 and calls the three symbol-input hooks; without the define it is the reference's code (the
+    hooks vanish)"""
+    ref = os.environ.get("SRSRAN_REF", "/root/reference")
+    if not os.path.isdir(ref):
+        pytest.skip("no reference tree")
+    import __graft_entry__ as g
+    g.build()  # oracle/_ref/gen holds the generated config headers the reference sources include
+    src = os.path.join(ref, "lib", "src", "phy", "phch", "pdsch.c")
+    out_c = str(tmp_path / "pdsch_b200.c")
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "integration", "apply_b200_patch.py"), "--pdsch", src, out_c])
+    patched = open(out_c).read()
+    assert patched.count("#ifdef SRSRAN_B200") == 3 and "srsran_b200_dlsch_decode2_symbols(dl_sch, cfg, q->d[codeword_idx]" in patched
+    flags = ["-O1", "-std=gnu99", "-mavx2", "-mfma", "-DLV_HAVE_SSE", "-DLV_HAVE_AVX", "-DLV_HAVE_AVX2", "-fPIC", "-w", "-I" + os.path.join(ref, "lib", "include"),
+             "-I" + os.path.join(ROOT, "oracle", "_ref", "gen"), "-I" + os.path.join(ref, "lib", "src", "phy", "phch")]
+    for define, n_hooks in (("-DSRSRAN_B200", 3), ("-USRSRAN_B200", 0)):
+        obj = str(tmp_path / ("pdsch%d.o" % n_hooks))
+        subprocess.check_call([os.environ.get("CC", "gcc")] + flags + [define, "-c", out_c, "-o", obj])
+        syms = subprocess.check_output(["nm", obj]).decode()
+        assert sum(1 for line in syms.splitlines() if " U srsran_b200_" in line) == n_hooks
 
 
 @pytest.fixture(scope="module")
